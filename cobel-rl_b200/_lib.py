@@ -1,0 +1,104 @@
+"""ctypes binding of the C ABI declared in include/cobel_b200.h.
+
+There is no CPU fallback: if ``libcobel_b200.so`` has not been built (see
+``__graft_entry__.build()``) every compute entry point raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libcobel_b200.so')
+ABI_VERSION = 1
+
+c_f64p = C.c_void_p   # device pointers travel as raw addresses
+c_ptr = C.c_void_p
+
+
+class World(C.Structure):
+    _fields_ = [('n_states', C.c_int32), ('n_actions', C.c_int32), ('n_starts', C.c_int32),
+                ('reserved', C.c_int32), ('succ', c_ptr), ('reward', c_ptr), ('terminal', c_ptr),
+                ('starts', c_ptr)]
+
+
+class Stream(C.Structure):
+    _fields_ = [('seed', C.c_uint64), ('agent_id_base', C.c_int64), ('draw_count', c_ptr),
+                ('user_stream', c_ptr), ('user_stream_len', C.c_int64)]
+
+
+class Policy(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('reserved', C.c_int32), ('param', c_ptr)]
+
+
+class Trace(C.Structure):
+    _fields_ = [('trial_steps', c_ptr), ('trial_reward', c_ptr), ('n_steps', c_ptr), ('n_replay', c_ptr),
+                ('step_sa', c_ptr), ('step_cap', C.c_int64), ('replay_idx', c_ptr), ('replay_cap', C.c_int64),
+                ('replay_len', c_ptr), ('replay_calls_cap', C.c_int64), ('flags', c_ptr)]
+
+
+class DynaQParams(C.Structure):
+    _fields_ = [('n_agents', C.c_int64), ('world', World), ('stream', Stream), ('policy', Policy),
+                ('trace', Trace), ('Q', c_ptr), ('Mr', c_ptr), ('Ms', c_ptr), ('Mt', c_ptr),
+                ('action_mask', c_ptr), ('mask_agent_stride', C.c_int64), ('lr', c_ptr), ('gamma', c_ptr),
+                ('mem_lr', c_ptr), ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32),
+                ('learn', C.c_int32), ('no_replay', C.c_int32), ('episodic_replay', C.c_int32)]
+
+
+STRUCTS = {'CobelWorld': World, 'CobelStream': Stream, 'CobelPolicy': Policy, 'CobelTrace': Trace,
+           'CobelDynaQParams': DynaQParams}
+
+_SIGNATURES = {
+    'cobel_sizeof': (C.c_size_t, [C.c_char_p]),
+    'cobel_abi_version': (C.c_int, []),
+    'cobel_last_error': (None, [C.c_char_p, C.c_size_t]),
+    'cobel_launch_count': (C.c_int64, []),
+    'cobel_draw_uniforms': (C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, c_ptr, c_ptr]),
+    'cobel_stream_next': (C.c_int, [C.POINTER(Stream), C.c_int64, C.c_int64, c_ptr, c_ptr]),
+    'cobel_dynaq_run': (C.c_int, [C.POINTER(DynaQParams), c_ptr]),
+}
+
+_lib = None
+
+
+class CobelError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (once).  Raises if it is missing -- no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CobelError(
+                '%s not found: build the CUDA extension first (python -c "import __graft_entry__ as g; '
+                'g.build()"); cobel_rl_b200 has no CPU fallback' % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.cobel_abi_version() != ABI_VERSION:
+            raise CobelError('ABI version mismatch: library %d, binding %d' % (L.cobel_abi_version(), ABI_VERSION))
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def check(rc):
+    """Translate a C status into the exception the reference would raise."""
+    if rc == 0:
+        return
+    buf = C.create_string_buffer(512)
+    lib().cobel_last_error(buf, 512)
+    msg = buf.value.decode()
+    if rc == -1:
+        raise AssertionError(msg)
+    if rc == -2:
+        raise NotImplementedError(msg)
+    raise CobelError(msg)
+
+
+def ptr(t):
+    """Device address of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,3 @@
+"""Tabular agents of the hot path (reference: cobel/agent/__init__.py)."""
+from .agent import Agent, Callbacks  # noqa: F401
+from .dyna_q import DynaQ  # noqa: F401

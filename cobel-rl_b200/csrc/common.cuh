@@ -1,0 +1,189 @@
+// common.cuh -- shared device helpers: exact fp64 arithmetic, the Philox stream,
+// action selection and NumPy-order reductions.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/cobel_b200.h"
+
+#define COBEL_DEV __device__ __forceinline__
+
+// ---------------------------------------------------------------------------
+// Exact arithmetic.  Integer trajectories depend on exact float equality
+// (policy/greedy.py:85 `np.amax(values) == values`, memory/pma.py:251), so every
+// parity-relevant +,-,*,/ is a single IEEE round-to-nearest operation in the
+// reference's order.  The __d*_rn intrinsics are never contracted into DFMA
+// (the library is additionally compiled with -fmad=false).
+// ---------------------------------------------------------------------------
+COBEL_DEV double xadd(double a, double b) { return __dadd_rn(a, b); }
+COBEL_DEV double xsub(double a, double b) { return __dsub_rn(a, b); }
+COBEL_DEV double xmul(double a, double b) { return __dmul_rn(a, b); }
+COBEL_DEV double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+// np.amax / Python max on non-NaN doubles (sign of zero is irrelevant to every consumer)
+COBEL_DEV double xmax(double a, double b) { return a < b ? b : a; }
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), same constants as oracle/philox.py.
+// ---------------------------------------------------------------------------
+COBEL_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                             uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+COBEL_DEV double u53(uint32_t a, uint32_t b) {
+  // ((a>>5)*2^26 + (b>>6)) * 2^-53 : every step is exact in fp64
+  const double hi = (double)(a >> 5), lo = (double)(b >> 6);
+  return xmul(xadd(xmul(hi, 67108864.0), lo), 1.1102230246251565404e-16);
+}
+
+// One agent's uniform stream, consumed in program order.
+struct Rng {
+  uint64_t k;              // index of the next draw
+  uint64_t agent;          // global agent id
+  uint32_t key0, key1;
+  uint32_t w2, w3;         // second half of the block of draw k (valid when k is odd and `have`)
+  bool have;
+  const double* user;      // optional pre-drawn stream of this agent
+  int64_t user_len;
+
+  COBEL_DEV void init(const CobelStream& s, int64_t local_agent) {
+    agent = (uint64_t)(s.agent_id_base + local_agent);
+    k = (uint64_t)s.draw_count[local_agent];
+    key0 = (uint32_t)s.seed; key1 = (uint32_t)(s.seed >> 32);
+    have = false; w2 = w3 = 0;
+    user = s.user_stream ? s.user_stream + local_agent * s.user_stream_len : nullptr;
+    user_len = s.user_stream_len;
+  }
+  COBEL_DEV double at(uint64_t kk) const {       // random access (lane-parallel generation)
+    if (user) return kk < (uint64_t)user_len ? user[kk] : 0.0;
+    uint32_t o[4];
+    const uint64_t b = kk >> 1;
+    philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)agent, (uint32_t)(agent >> 32), key0, key1, o);
+    return (kk & 1) ? u53(o[2], o[3]) : u53(o[0], o[1]);
+  }
+  COBEL_DEV double next() {
+    if (user) { const double v = k < (uint64_t)user_len ? user[k] : 0.0; ++k; return v; }
+    double v;
+    if ((k & 1) && have) {
+      v = u53(w2, w3); have = false;
+    } else {
+      uint32_t o[4];
+      const uint64_t b = k >> 1;
+      philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)agent, (uint32_t)(agent >> 32), key0, key1, o);
+      if (k & 1) { v = u53(o[2], o[3]); }
+      else { v = u53(o[0], o[1]); w2 = o[2]; w3 = o[3]; have = true; }
+    }
+    ++k;
+    return v;
+  }
+};
+
+// Generator.integers(n) / choice(a) from one uniform: min(floor(u*n), n-1)
+COBEL_DEV int draw_integer(double u, int n) {
+  const int i = (int)xmul(u, (double)n);   // u*n >= 0: truncation == floor
+  return i < n - 1 ? i : n - 1;
+}
+
+// ---------------------------------------------------------------------------
+// Action selection for A actions held in registers.
+//   probabilities: policy/greedy.py:60-88, 117-147; policy/softmax.py:60-88
+//   draw: Generator.choice(p=probs) == searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right')
+// mask bit a set = action a valid.
+// ---------------------------------------------------------------------------
+template <int A>
+COBEL_DEV void action_probs(const double (&v)[A], uint32_t mask, int kind, double par, double (&p)[A]) {
+  int nv = 0;
+  double m = 0.0;
+  bool first = true;
+#pragma unroll
+  for (int a = 0; a < A; ++a)
+    if (mask >> a & 1u) { ++nv; m = first ? v[a] : xmax(m, v[a]); first = false; }
+  if (kind == COBEL_POLICY_SOFTMAX) {
+    double sum = 0.0;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      p[a] = 0.0;
+      if (mask >> a & 1u) { p[a] = exp(xmul(xsub(v[a], m), par)); sum = xadd(sum, p[a]); }
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a)
+      if (mask >> a & 1u) p[a] = xdiv(p[a], sum);
+    return;
+  }
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < A; ++a) k += ((mask >> a & 1u) && v[a] == m) ? 1 : 0;
+  const double om = xsub(1.0, par);
+  if (kind == COBEL_POLICY_EPS_GREEDY) {
+    const double base = xdiv(par, (double)nv);
+    const double tie = xdiv(om, (double)k);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      const bool valid = mask >> a & 1u;
+      p[a] = valid ? xadd(base, v[a] == m ? tie : 0.0) : 0.0;
+    }
+  } else {  // exclusive epsilon-greedy
+    const int d = nv - k > 1 ? nv - k : 1;
+    const double tie = xdiv(om, (double)k);
+    const double expl = xdiv(par, (double)d);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      const bool valid = mask >> a & 1u;
+      p[a] = valid ? (v[a] == m ? xadd(tie, 0.0) : xadd(0.0, expl)) : 0.0;
+    }
+  }
+}
+
+template <int A>
+COBEL_DEV int draw_categorical(const double (&p)[A], double u) {
+  double c[A];
+  c[0] = p[0];
+#pragma unroll
+  for (int a = 1; a < A; ++a) c[a] = xadd(c[a - 1], p[a]);
+  int idx = 0;
+#pragma unroll
+  for (int a = 0; a < A - 1; ++a) idx += (xdiv(c[a], c[A - 1]) <= u) ? 1 : 0;
+  return idx;    // c[A-1]/c[A-1] == 1 > u always
+}
+
+template <int A>
+COBEL_DEV int select_action(const double (&v)[A], uint32_t mask, int kind, double par, double u) {
+  double p[A];
+  action_probs<A>(v, mask, kind, par, p);
+  return draw_categorical<A>(p, u);
+}
+
+template <int A>
+COBEL_DEV double row_max(const double (&v)[A]) {
+  double m = v[0];
+#pragma unroll
+  for (int a = 1; a < A; ++a) m = xmax(m, v[a]);
+  return m;
+}
+
+// ---------------------------------------------------------------------------
+// Host-side error plumbing shared by the entry points.
+// ---------------------------------------------------------------------------
+void cobel_set_error(const char* fmt, ...);
+void cobel_count_launch(int n = 1);
+#define COBEL_REQUIRE(cond, code, ...)                 \
+  do {                                                 \
+    if (!(cond)) { cobel_set_error(__VA_ARGS__); return (code); } \
+  } while (0)
+#define COBEL_CUDA_OK(expr)                                                        \
+  do {                                                                             \
+    cudaError_t e__ = (expr);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      cobel_set_error("%s failed: %s", #expr, cudaGetErrorString(e__));            \
+      return COBEL_ECUDA;                                                          \
+    }                                                                              \
+  } while (0)

@@ -1,0 +1,77 @@
+"""Gridworld environment (reference: interface/gridworld.py:33-156).
+
+The reference steps one agent through a dense ``sas[S,4,S]`` row (arg-max scan).
+Here the world is compiled once to ``succ[S,4]`` / ``reward[S]`` / ``terminal[S]``
+/ ``starts[K]`` device tables that the fused agent kernels read; ``step``/``reset``
+are kept as batched table lookups for interactive use.
+"""
+from typing import Any, TypedDict
+
+import numpy as np
+import torch
+
+from .interface import Interface
+from ..spaces import Discrete
+
+
+class WorldDict(TypedDict, total=False):   # interface/gridworld.py:17-30
+    width: int
+    height: int
+    states: int
+    rewards: Any
+    terminals: Any
+    sas: Any
+    succ: Any          # extension: successor table; `sas` may be None for very large worlds
+    starting_states: Any
+    invalid_transitions: list
+    invalid_states: list
+    wind: Any
+    goals: list
+    coordinates: Any
+    deterministic: bool
+
+
+def successor_table(world):
+    """``argmax(sas[s, a, :])`` for every (s, a) (gridworld.py:116-117), or the
+    builder-provided ``succ`` when the dense tensor was not materialised."""
+    if world.get('succ') is not None:
+        return np.asarray(world['succ'], dtype=np.int32)
+    return np.argmax(np.asarray(world['sas']), axis=2).astype(np.int32)
+
+
+class Gridworld(Interface):
+    def __init__(self, world, widget=None, rng=None):
+        super().__init__(widget, rng)
+        assert world.get('deterministic', True), \
+            'non-deterministic gridworlds are not supported by the B200 path yet'
+        self.world = world
+        self.observation_space = Discrete(world['states'])
+        self.action_space = Discrete(4)
+        self._set_tables(successor_table(world), world['rewards'], world['terminals'], world['starting_states'])
+        self._coordinates = torch.as_tensor(np.asarray(world['coordinates']), dtype=torch.float64).to(self.rng.device)
+        self._current = torch.zeros(self.rng.n_agents, dtype=torch.int64, device=self.rng.device)
+        self.reset()      # gridworld.py:89 -- consumes one draw per agent, like the reference
+
+    @property
+    def current_state(self):
+        return self._out(self._current)
+
+    @property
+    def current_coordinates(self):
+        return self._out(self._coordinates[self._current])
+
+    def step(self, action):
+        """gridworld.py:92-129 for all agents: (state, reward, end_trial, False, {})."""
+        a = torch.as_tensor(action, device=self.rng.device).reshape(-1).to(torch.int64)
+        self._current = self._succ[self._current, a].to(torch.int64)
+        reward = self._reward[self._current]
+        end = self._terminal[self._current].bool()
+        return self._out(self._current), self._out(reward), self._out(end), False, {}
+
+    def reset(self):
+        """gridworld.py:131-145: uniform draw over the starting states."""
+        self._current = self._starts[self.rng.integers(self._starts.numel())].to(torch.int64)
+        return self._out(self._current), {}
+
+    def get_position(self):
+        return self._out(self._coordinates[self._current].clone())

@@ -1,0 +1,60 @@
+"""Abstract environment (reference: interface/interface.py:37-86).
+
+Batched convention: every method acts on all N agents of the attached
+``BatchStream`` at once; with a single-agent stream the return values have the
+reference's scalar types.
+"""
+import abc
+
+import torch
+
+from .. import _lib
+from ..stream import BatchStream
+
+
+class Interface(abc.ABC):
+    def __init__(self, widget=None, rng=None):
+        assert widget is None, 'visualisation widgets are out of scope of the B200 path'
+        self.widget = None
+        self.rng = BatchStream() if rng is None else rng
+        assert isinstance(self.rng, BatchStream), 'rng must be a cobel_rl_b200.BatchStream'
+
+    @abc.abstractmethod
+    def step(self, action):
+        ...
+
+    @abc.abstractmethod
+    def reset(self):
+        ...
+
+    @abc.abstractmethod
+    def get_position(self):
+        ...
+
+    # -- table view consumed by the fused kernels (include/cobel_b200.h: CobelWorld)
+    def _set_tables(self, succ, reward, terminal, starts):
+        dev = self.rng.device
+        self._succ = torch.as_tensor(succ, dtype=torch.int32).contiguous().to(dev)
+        self._reward = torch.as_tensor(reward, dtype=torch.float64).contiguous().to(dev)
+        self._terminal = torch.as_tensor(terminal).to(torch.uint8).contiguous().to(dev)
+        self._starts = torch.as_tensor(starts, dtype=torch.int32).contiguous().to(dev)
+        assert self._succ.dim() == 2 and self._starts.numel() > 0
+
+    @property
+    def n_states(self):
+        return self._succ.shape[0]
+
+    @property
+    def n_actions(self):
+        return self._succ.shape[1]
+
+    def c_world(self):
+        return _lib.World(self.n_states, self.n_actions, self._starts.numel(), 0, self._succ.data_ptr(),
+                          self._reward.data_ptr(), self._terminal.data_ptr(), self._starts.data_ptr())
+
+    def _out(self, t):
+        """Squeeze the agent axis for single-agent streams (reference return types)."""
+        if not self.rng.single:
+            return t
+        v = t[0]
+        return v.item() if v.dim() == 0 else v

@@ -1,0 +1,2 @@
+"""Memory modules of the hot path (reference: cobel/memory/__init__.py)."""
+from .dyna_q import DynaQMemory  # noqa: F401

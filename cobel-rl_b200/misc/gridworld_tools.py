@@ -1,0 +1,82 @@
+"""Gridworld builders (reference: misc/gridworld_tools.py:10-234).
+
+Produces the same ``WorldDict`` (keys, dtypes and state numbering
+``state = row*width + column``; actions 0 left, 1 up, 2 right, 3 down) as the
+reference, built with vectorised index arithmetic instead of the reference's
+S x 4 Python loop.  The successor table ``succ[S,4]`` is always included;
+the dense one-hot ``sas[S,4,S]`` (needed by ``PMAMemory`` / the DR and SR
+metrics) can be skipped with ``dense_sas=False`` for very large worlds
+(100 x 100 would need 3.2 GB).
+"""
+import numpy as np
+
+
+def make_gridworld(height, width, terminals=None, rewards=None, goals=None, starting_states=None,
+                   invalid_states=None, invalid_transitions=None, wind=None, deterministic=True,
+                   dense_sas=True):
+    S = height * width
+    world = {'height': height, 'width': width, 'states': S, 'goals': [] if goals is None else goals}
+    world['terminals'] = np.zeros(S).astype(int)
+    if terminals is not None:
+        world['terminals'][terminals] = 1
+    world['rewards'] = np.zeros(S).astype(float)
+    if rewards is not None:
+        rewards = np.asarray(rewards)
+        world['rewards'][rewards[:, 0].astype(int)] = rewards[:, 1]
+    # starting states default to all non-terminal states (gridworld_tools.py:76-82)
+    if starting_states is not None and len(starting_states) > 0:
+        world['starting_states'] = np.array(starting_states)
+    else:
+        term = set([] if terminals is None else terminals)
+        world['starting_states'] = np.array(list(set(range(S)) - term))
+    world['wind'] = np.zeros((S, 2)).astype(int)
+    if wind is not None:
+        wind = np.asarray(wind)
+        world['wind'][wind[:, 0].astype(int)] = wind[:, 1:].astype(int)
+    world['invalid_states'] = [] if invalid_states is None else invalid_states
+    world['invalid_transitions'] = [] if invalid_transitions is None else invalid_transitions
+    # coordinates: x = column, y counted from the bottom row (gridworld_tools.py:98-102)
+    idx = np.arange(S)
+    row, col = idx // width, idx % width
+    world['coordinates'] = np.stack([col, height - 1 - row], axis=1).astype(float)
+    # successor of every (state, action): move, apply wind, clip, then undo forbidden moves
+    dh = np.array([0, -1, 0, 1])
+    dw = np.array([-1, 0, 1, 0])
+    h = np.clip(row[:, None] + dh[None, :], 0, height - 1) + world['wind'][:, 0:1]
+    w = np.clip(col[:, None] + dw[None, :], 0, width - 1) + world['wind'][:, 1:2]
+    succ = np.clip(h, 0, height - 1) * width + np.clip(w, 0, width - 1)
+    blocked = np.isin(succ, np.asarray(world['invalid_states'], dtype=int))
+    if len(world['invalid_transitions']) > 0:
+        pairs = np.asarray(world['invalid_transitions'], dtype=np.int64).reshape(-1, 2)
+        code = pairs[:, 0] * S + pairs[:, 1]
+        blocked |= np.isin(idx[:, None] * S + succ, code)
+    succ = np.where(blocked, idx[:, None], succ).astype(np.int32)
+    world['succ'] = succ
+    if dense_sas:
+        sas = np.zeros((S, 4, S))
+        sas[idx[:, None], np.arange(4)[None, :], succ] = 1
+        world['sas'] = sas
+    else:
+        world['sas'] = None
+    world['deterministic'] = deterministic
+    return world
+
+
+def make_open_field(height, width, goal_state=0, reward=1, dense_sas=True):
+    """Open field with one terminal goal state (gridworld_tools.py:139-167)."""
+    return make_gridworld(height, width, terminals=[goal_state], rewards=np.array([[goal_state, reward]]),
+                          goals=[goal_state], dense_sas=dense_sas)
+
+
+def make_empty_field(height, width):
+    """Open field without goal (gridworld_tools.py:170-186)."""
+    return make_gridworld(height, width)
+
+
+def make_windy_gridworld(height, width, columns, goal_state=0, reward=1, direction='up'):
+    """Column-wise wind applied to the row coordinate (gridworld_tools.py:189-234)."""
+    sign = {'up': 1, 'down': -1}[direction]
+    idx = np.arange(height * width)
+    wind = np.stack([idx, np.asarray(columns)[idx % width] * sign, np.zeros_like(idx)], axis=1)
+    return make_gridworld(height, width, terminals=[goal_state], rewards=np.array([[goal_state, reward]]),
+                          goals=[goal_state], wind=wind)

@@ -1,0 +1,78 @@
+"""Topology-graph builders (reference: misc/topology_tools.py:14-172, 275-373).
+
+Same node dictionaries as the reference (``{'id','pose','terminal','reward','neighbors'}``,
+ids ``str(n)``, neighbour order left / up / right / down, missing neighbours point to the
+node itself), built from integer lattice arithmetic instead of all-pairs distance scans.
+"""
+import numpy as np
+
+
+def _lattice_nodes(cells, spacing):
+    """Nodes on integer lattice cells ``[(x, y), ...]`` with 4-neighbourhoods (up = larger y)."""
+    index = {c: str(n) for n, c in enumerate(cells)}
+    nodes = {}
+    for n, (x, y) in enumerate(cells):
+        nid = str(n)
+        nb = [index.get((x - 1, y), nid), index.get((x, y + 1), nid),
+              index.get((x + 1, y), nid), index.get((x, y - 1), nid)]
+        nodes[nid] = {'id': nid, 'pose': (float(x) * spacing, float(y) * spacing, 0.0, 0.0, 0.0, 0.0),
+                      'terminal': False, 'reward': 0.0, 'neighbors': nb}
+    return nodes
+
+
+def linear_track(nb_nodes_track, nb_nodes_width, spacing=1.0, reward=1.0, location='right'):
+    """topology_tools.py:14-100: nodes numbered row-major ``n = j*L + i``; reward and terminal
+    flag on the ``location`` end of every row, starting nodes on the opposite end."""
+    assert nb_nodes_track > 1, 'Track has to be at least 2 states long!'
+    assert nb_nodes_width > 0, 'Track has to be at least 1 state wide!'
+    assert spacing > 0, 'Node spacing must be positive!'
+    assert location in ['left', 'right'], 'Invalid reward location!'
+    L, Wd = nb_nodes_track, nb_nodes_width
+    nodes = _lattice_nodes([(i, Wd - j - 1) for j in range(Wd) for i in range(L)], spacing)
+    starting_nodes = []
+    for j in range(Wd):
+        goal = str(j * L + (L - 1) * (location == 'right'))
+        nodes[goal].update({'terminal': True, 'reward': reward})
+        starting_nodes.append(str(j * L + (L - 1) * (location == 'left')))
+    return nodes, starting_nodes
+
+
+def grid(nb_nodes, limits=(0.0, 1.0), reward=1.0, location=None):
+    """topology_tools.py:103-172: rectangular grid graph; the goal defaults to the top-right node."""
+    nx = nb_nodes if isinstance(nb_nodes, int) else nb_nodes[0]
+    ny = nb_nodes if isinstance(nb_nodes, int) else nb_nodes[1]
+    assert (nx > 1 and ny >= 1) or (nx >= 1 and ny > 1), 'Invalid environment dimensions!'
+    lim_x = limits if isinstance(limits[0], float) else limits[0]
+    lim_y = limits if isinstance(limits[0], float) else limits[1]
+    assert lim_x[1] > lim_x[0], 'Invalid x coordinate range!'
+    assert lim_y[1] > lim_y[0], 'Invalid y coordinate range!'
+    xs, ys = np.linspace(lim_x[0], lim_x[1], nx), np.linspace(lim_y[0], lim_y[1], ny)
+    nodes = {}
+    for n in range(nx * ny):
+        j, i = divmod(n, nx)
+        nb = [str(j * nx + max(i - 1, 0)), str(max(j - 1, 0) * nx + i),
+              str(j * nx + min(i + 1, nx - 1)), str(min(j + 1, ny - 1) * nx + i)]
+        pose = (float(xs[i]), float(lim_y[1] - (ys[j] - lim_y[0])), 0.0, 0.0, 0.0, 0.0)
+        nodes[str(n)] = {'id': str(n), 'pose': pose, 'terminal': False, 'reward': 0.0, 'neighbors': nb}
+    if location is None or location not in nodes:
+        location = str(nx - 1)
+    nodes[location].update({'terminal': True, 'reward': reward})
+    starting_nodes = [n for n in nodes if n != location]
+    return nodes, starting_nodes
+
+
+def t_maze(nb_nodes_stem, nb_nodes_arm, nb_nodes_width, spacing=1.0, reward=1.0, location='right'):
+    """topology_tools.py:275-373: arms first (row-major from the top), then the stem; goal at
+    the end of the ``location`` arm, starting nodes = bottom row of the stem."""
+    assert nb_nodes_arm > 0, 'Invalid arm length!'
+    assert nb_nodes_stem > 0, 'Invalid stem length!'
+    assert nb_nodes_width > 0, 'Invalid corridor width!'
+    assert location in ['left', 'right'], 'The goal can only be located left or right!'
+    span = nb_nodes_arm * 2 + nb_nodes_width
+    cells = [(j, nb_nodes_stem + nb_nodes_width - 1 - i) for i in range(nb_nodes_width) for j in range(span)]
+    cells += [(nb_nodes_arm + j, nb_nodes_stem - 1 - i) for i in range(nb_nodes_stem) for j in range(nb_nodes_width)]
+    nodes = _lattice_nodes(cells, spacing)
+    for i in range(nb_nodes_width):
+        nodes[str(span * i + (span - 1) * int(location == 'right'))].update({'terminal': True, 'reward': reward})
+    starting_nodes = list(nodes.keys())[-nb_nodes_width:]
+    return nodes, starting_nodes

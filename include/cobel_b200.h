@@ -1,0 +1,145 @@
+/*
+ * cobel_b200.h -- C ABI of the B200-native batched tabular simulator.
+ *
+ * Drop-in boundary for CoBeL-RL's tabular closed loop (reference: sencheng/CoBeL-RL
+ * v3.0.1, paths below are relative to src/cobel/).  The reference has no FFI: its
+ * boundary is the Python class API.  Each entry point here replaces one
+ * `Agent.train()/test()` loop of the reference for N independent agents and is
+ * bound from Python with ctypes (cobel-rl_b200/_lib.py); INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated otherwise; the caller
+ *    (PyTorch) owns all buffers, kernels never allocate or free;
+ *  - all reals are IEEE fp64 and are combined in the reference's operation
+ *    order without FMA contraction, so tables are bit-equal to NumPy's;
+ *  - N = n_agents, S = n_states, A = n_actions; leading axis of every per-agent
+ *    tensor is the agent; tensors are C-contiguous;
+ *  - entry points return 0 on success or a negative COBEL_E* code;
+ *    cobel_last_error() returns the message of the calling thread's last failure.
+ *    Launches are asynchronous on `stream` (a cudaStream_t passed as void*).
+ */
+#ifndef COBEL_B200_H
+#define COBEL_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COBEL_ABI_VERSION 1
+
+enum {
+  COBEL_OK = 0,
+  COBEL_EINVAL = -1,      /* bad argument (the AssertionError / ValueError cases of the reference) */
+  COBEL_EUNSUPPORTED = -2,/* shape outside what the kernels were built for */
+  COBEL_ECUDA = -3        /* CUDA runtime error at launch */
+};
+
+/* Action-selection policies: policy/greedy.py:60-88 (EpsilonGreedy), 117-147
+ * (ExclusiveEpsilonGreedy), policy/softmax.py:60-88 (Softmax). */
+enum { COBEL_POLICY_EPS_GREEDY = 0, COBEL_POLICY_EXCL_EPS_GREEDY = 1, COBEL_POLICY_SOFTMAX = 2 };
+
+/* Environment tables: interface/gridworld.py:92-145 (`sas` compiled to its arg-max
+ * successor, rewards/terminals looked up at the arrival state) and
+ * interface/topology.py:126-172 (`neighbors` lists). */
+typedef struct CobelWorld {
+  int32_t n_states;
+  int32_t n_actions;
+  int32_t n_starts;
+  int32_t reserved;
+  const int32_t* succ;      /* [S*A]  successor of (s,a) */
+  const double*  reward;    /* [S]    reward on arrival */
+  const uint8_t* terminal;  /* [S]    1 = trial ends on arrival */
+  const int32_t* starts;    /* [K]    starting states, reset draws uniformly */
+} CobelWorld;
+
+/* Random-stream contract (one uniform stream per agent, consumed in program
+ * order by environment, policies, memory and agent alike -- the reference run
+ * with one shared numpy Generator).  Draw k of agent g is Philox4x32-10 with
+ * key = seed, counter = (k>>1, g), 53-bit mantissa construction; see
+ * oracle/philox.py.  If user_stream != NULL draws are read from it instead. */
+typedef struct CobelStream {
+  uint64_t seed;
+  int64_t  agent_id_base;    /* global id of local agent 0 (multi-GPU shards) */
+  int64_t* draw_count;       /* [N] in/out: number of draws consumed so far */
+  const double* user_stream; /* optional [N, user_stream_len] uniforms in [0,1) */
+  int64_t  user_stream_len;
+} CobelStream;
+
+typedef struct CobelPolicy {
+  int32_t kind;              /* COBEL_POLICY_* */
+  int32_t reserved;
+  const double* param;       /* [N] epsilon or beta per agent */
+} CobelPolicy;
+
+/* Per-agent outputs that replace the reference's `logs` dict / callbacks
+ * (agent/dyna_q.py:165-212).  Optional members may be NULL. */
+typedef struct CobelTrace {
+  int32_t* trial_steps;      /* [N, trials] logs['steps'] = index of the last step */
+  double*  trial_reward;     /* [N, trials] logs['trial_reward'] */
+  int64_t* n_steps;          /* [N] in/out: environment steps executed (accumulates) */
+  int64_t* n_replay;         /* [N] in/out: replayed updates executed (accumulates) */
+  int32_t* step_sa;          /* optional [N, step_cap]: s*A + a of every step */
+  int64_t  step_cap;
+  int32_t* replay_idx;       /* optional [N, replay_cap]: flat index of every replayed experience */
+  int64_t  replay_cap;
+  int32_t* replay_len;       /* optional [N, replay_calls_cap]: length of every replay call */
+  int64_t  replay_calls_cap;
+  int32_t* flags;            /* optional [N] in/out: COBEL_FLAG_* bits raised by the agent */
+} CobelTrace;
+
+enum {
+  COBEL_FLAG_TRACE_OVERFLOW = 1,  /* a step_sa / replay_idx / replay_len buffer was too small */
+  COBEL_FLAG_CDF_NEAR_TIE   = 2,  /* an inverse-CDF draw fell within rounding distance of a bin edge */
+  COBEL_FLAG_LOG_OVERFLOW   = 4,  /* QAgent experience log full */
+  COBEL_FLAG_SINGULAR       = 8   /* PMA: (I - gamma T) pivot underflow */
+};
+
+/* ---- Dyna-Q: agent/dyna_q.py:140-330 + memory/dyna_q.py:62-157 ------------- */
+typedef struct CobelDynaQParams {
+  int64_t n_agents;
+  CobelWorld world;
+  CobelStream stream;
+  CobelPolicy policy;
+  CobelTrace trace;
+  double*  Q;                /* [N,S,A] agent.Q */
+  double*  Mr;               /* [N,S,A] M.rewards */
+  int32_t* Ms;               /* [N,S,A] M.states (init: self-loops) */
+  int32_t* Mt;               /* [N,S,A] M.terminals (holds 1 - end_trial) */
+  const uint8_t* action_mask;/* [S,A] or [N,S,A] (see mask_agent_stride); NULL = mask_actions False */
+  int64_t  mask_agent_stride;/* 0 = one mask shared by all agents, S*A = per agent */
+  const double* lr;          /* [N] agent.learning_rate */
+  const double* gamma;       /* [N] agent.gamma */
+  const double* mem_lr;      /* [N] M.learning_rate */
+  int32_t trials, steps, batch;
+  int32_t learn;             /* 1 = train(), 0 = test() (policy only; no store/update/replay) */
+  int32_t no_replay;         /* train(..., no_replay=True) */
+  int32_t episodic_replay;   /* agent.episodic_replay */
+} CobelDynaQParams;
+
+int cobel_dynaq_run(const CobelDynaQParams* p, void* stream);
+
+/* ---- utilities -------------------------------------------------------------- */
+int  cobel_abi_version(void);
+/* Copy the last error message of this thread into buf (NUL-terminated). */
+void cobel_last_error(char* buf, size_t len);
+/* Fill out[N, n_draws] with draws first..first+n_draws-1 of agents
+ * agent_id_base..+N-1 (device buffer).  Used to check the stream contract. */
+int  cobel_draw_uniforms(uint64_t seed, int64_t agent_id_base, int64_t n_agents,
+                         int64_t first, int64_t n_draws, double* out, void* stream);
+/* Draw the next n_draws uniforms of every agent at its own draw_count (out[N, n_draws], device)
+ * and advance draw_count -- serves Interface.reset()/Policy.select_action() outside train(). */
+int  cobel_stream_next(const CobelStream* s, int64_t n_agents, int64_t n_draws, double* out, void* stream);
+/* sizeof() of an ABI struct by name ("CobelDynaQParams", ...), 0 if unknown: lets a binding
+ * verify its mirror of the layout. */
+size_t cobel_sizeof(const char* struct_name);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t cobel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COBEL_B200_H */

@@ -54,7 +54,7 @@ def _gridworld(cobel, world, rng):
 
 def run_dynaq(world, u, trials, steps, batch, *, policy=('eps', 0.1), policy_test=None, lr=0.99,
               gamma=0.99, mem_lr=0.9, mask_actions=False, no_replay=False, episodic_replay=False,
-              test_trials=0):
+              test_trials=0, action_mask=None):
     cobel = ref_loader.load()
     rng = StreamRNG(u)
     env = _gridworld(cobel, world, rng)
@@ -74,6 +74,8 @@ def run_dynaq(world, u, trials, steps, batch, *, policy=('eps', 0.1), policy_tes
                               None if policy_test is None else _policy(cobel, policy_test, rng),
                               lr, gamma, mem, cap.callbacks())
     agent.mask_actions = mask_actions
+    if action_mask is not None:
+        agent.action_mask = np.array(action_mask, dtype=bool)
     agent.episodic_replay = episodic_replay
     agent.train(env, trials, steps, batch, no_replay)
     out = cap.arrays()
@@ -143,7 +145,8 @@ def run_q_topology(nodes, starting_nodes, u, trials, steps, batch, *, policy=('e
     return out
 
 
-def run_sr(world, u, trials, steps, *, policy=('eps', 0.1), lr=0.1, gamma=0.99, mask_actions=False):
+def run_sr(world, u, trials, steps, *, policy=('eps', 0.1), lr=0.1, gamma=0.99, mask_actions=False,
+           action_mask=None):
     cobel = ref_loader.load()
     rng = StreamRNG(u)
     env = _gridworld(cobel, world, rng)
@@ -151,6 +154,8 @@ def run_sr(world, u, trials, steps, *, policy=('eps', 0.1), lr=0.1, gamma=0.99, 
     agent = cobel.agent.SR(env.observation_space, env.action_space, _policy(cobel, policy, rng),
                            None, lr, gamma, cap.callbacks())
     agent.mask_actions = mask_actions
+    if action_mask is not None:
+        agent.action_mask = np.array(action_mask, dtype=bool)
     agent.train(env, trials, steps)
     out = cap.arrays()
     out.update(SR=agent.SR.copy(), rew=agent.rewards.copy(),
@@ -160,7 +165,7 @@ def run_sr(world, u, trials, steps, *, policy=('eps', 0.1), lr=0.1, gamma=0.99, 
 
 def run_sfma(world, D, u, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99, gamma=0.99,
              mem_lr=0.9, mask_actions=False, mode='default', recency=False, start_replay=False,
-             nb_replays=1, metric=None):
+             nb_replays=1, metric=None, action_mask=None):
     cobel = ref_loader.load()
     rng = StreamRNG(u)
     env = _gridworld(cobel, world, rng)
@@ -184,6 +189,8 @@ def run_sfma(world, D, u, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99,
     agent = cobel.agent.SFMA(env.observation_space, env.action_space, _policy(cobel, policy, rng),
                              mem, None, lr, gamma, cbs, rng=rng)
     agent.mask_actions = mask_actions
+    if action_mask is not None:
+        agent.action_mask = np.array(action_mask, dtype=bool)
     agent.start_replay = start_replay
     agent.nb_replays = nb_replays
     agent.train(env, trials, steps, batch)
@@ -196,7 +203,7 @@ def run_sfma(world, D, u, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99,
 
 def run_pma(world, u, trials, steps, batch, *, policy=('eps', 0.1), mem_policy=('eps', 0.1), lr=0.9,
             gamma=0.99, mem_lr=0.9, lr_q=0.9, gamma_sr=0.9, gamma_q=0.99, mask_actions=True,
-            prefill=False, min_gain_mode='original'):
+            prefill=False, min_gain_mode='original', action_mask=None):
     cobel = ref_loader.load()
     rng = StreamRNG(u)
     env = _gridworld(cobel, world, rng)
@@ -219,6 +226,8 @@ def run_pma(world, u, trials, steps, batch, *, policy=('eps', 0.1), mem_policy=(
     agent = cobel.agent.PMA(env.observation_space, env.action_space, _policy(cobel, policy, rng),
                             mem, None, lr, gamma, cbs)
     agent.mask_actions = mask_actions
+    if action_mask is not None:
+        agent.action_mask = np.array(action_mask, dtype=bool)
     agent.train(env, trials, steps, batch)
     out = cap.arrays()
     out.update(Q=agent.Q.copy(), Mr=mem.rewards.copy(), Ms=mem.states.astype(np.int32),

@@ -100,6 +100,12 @@ def compile_topology(nodes, starting_nodes=None):
     }
 
 
+def valid_move_mask(succ):
+    """Action mask used by the parity cases: an action is valid iff it changes the state."""
+    succ = np.asarray(succ)
+    return succ != np.arange(succ.shape[0]).reshape(-1, 1)
+
+
 def env_reset(W, rng):
     """interface/gridworld.py:131-145, interface/topology.py:159-172: one draw."""
     return int(W['starts'][draw_integer(rng.next(), len(W['starts']))])

@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def reference():
+    """The real reference package (only present in the build container)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference sources not present (GPU box)')
+    return ref_loader.load()

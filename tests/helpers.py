@@ -1,0 +1,182 @@
+"""Shared helpers of the parity tests: run one case of oracle/cases.py through the
+oracle (CPU) or through the CUDA path, and compare records field by field."""
+import os
+
+import numpy as np
+
+from oracle import cases, tabular as tb
+from oracle.philox import LazyStream
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+TRAJ = ['states', 'actions', 'next_states', 'rewards', 'trial_steps', 'trial_reward']
+KEYS = {
+    'dynaq': TRAJ + ['replay', 'replay_len', 'Q', 'Mr', 'Ms', 'Mt', 'draws'],
+    'q_grid': TRAJ + ['replay', 'replay_len', 'Q', 'draws'],
+    'q_topo': TRAJ + ['replay', 'replay_len', 'Q', 'draws'],
+    'sr': TRAJ + ['SR', 'rew', 'model', 'draws'],
+    'sfma': TRAJ + ['replay', 'replay_len', 'Q', 'Mr', 'Ms', 'Mt', 'C', 'T', 'I', 'draws'],
+    'pma': TRAJ + ['replay', 'replay_len', 'Q', 'Mr', 'Ms', 'Mt', 'T', 'SR', 'update_mask', 'draws'],
+}
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN, name + '.npz')) as z:
+        return {k: z[k] for k in z.files}
+
+
+def make_world(name, tools=None):
+    """WorldDict of a named case world, built with the product's builder by default."""
+    if tools is None:
+        from cobel_rl_b200.misc import gridworld_tools as tools
+    h, w, kw = cases.world_args(name)
+    return tools.make_gridworld(h, w, **kw)
+
+
+def make_topology(spec, tools=None):
+    if tools is None:
+        from cobel_rl_b200.misc import topology_tools as tools
+    fn, args = spec
+    return getattr(tools, fn)(*args)
+
+
+def assert_equal_records(got, want, keys, rtol=None, what=''):
+    for k in keys:
+        g, w = np.asarray(got[k]), np.asarray(want[k])
+        assert g.shape == w.shape, '%s %s: shape %s vs %s' % (what, k, g.shape, w.shape)
+        if rtol is not None and k in rtol:
+            np.testing.assert_allclose(g, w, rtol=rtol[k], atol=0, err_msg='%s %s' % (what, k))
+        else:
+            assert np.array_equal(g, w), '%s %s differs (max abs diff %s)' % (
+                what, k, np.abs(g.astype(np.float64) - w.astype(np.float64)).max() if g.size else '')
+
+
+def oracle_case(name, agent=None, golden=None):
+    """Run the oracle restatement on a case; returns a record shaped like the goldens."""
+    kind, wname, case_agent, args = cases.CASES[name]
+    agent = case_agent if agent is None else agent
+    a = dict(args)
+    trials, steps = a.pop('trials'), a.pop('steps')
+    valid_mask = a.pop('valid_mask', False)
+    rng = tb.Draws(LazyStream(cases.SEED, agent), 1)      # env constructor consumed draw 0
+    if kind in ('q_topo',):
+        W = tb.compile_topology(*make_topology(wname))
+    else:
+        world = make_world(wname)
+        W = tb.compile_gridworld(world)
+    S, A = W['S'], W['A']
+    if kind == 'dynaq':
+        st = tb.dynaq_init(S, A)
+        if valid_mask:
+            st['action_mask'] = tb.valid_move_mask(W['succ'])
+        out = tb.dynaq_train(W, st, rng, trials, steps, a.pop('batch'), **a).arrays()
+        out.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], draws=rng.k)
+        t = tb.tabular_test(W, st['Q'], rng, 5, steps, policy=('eps', 0.0),
+                            action_mask=st['action_mask'] if a.get('mask_actions') else None).arrays()
+        out.update({'test_' + k: v for k, v in t.items() if not k.startswith('replay')})
+        out['draws_after_test'] = rng.k
+    elif kind in ('q_grid', 'q_topo'):
+        st = tb.q_init(S, A)
+        out = tb.q_train(W, st, rng, trials, steps, a.pop('batch'), **a).arrays()
+        out.update(Q=st['Q'], draws=rng.k, log_len=len(st['log']))
+    elif kind == 'sr':
+        st = tb.sr_init(S, A)
+        if valid_mask:
+            st['action_mask'] = tb.valid_move_mask(W['succ'])
+        out = tb.sr_train(W, st, rng, trials, steps, **a).arrays()
+        out.update(SR=st['SR'], rew=st['rew'], model=st['model'], draws=rng.k)
+    elif kind == 'sfma':
+        st = tb.sfma_init(S, A)
+        if valid_mask:
+            st['action_mask'] = tb.valid_move_mask(W['succ'])
+        D = (golden if golden is not None else load_golden(name))['D']
+        rk = {'recency': a.pop('recency')} if 'recency' in a else {}
+        out = tb.sfma_train(W, st, D, rng, trials, steps, a.pop('batch'), replay_kwargs=rk, **a).arrays()
+        out.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], C=st['C'], T=st['T'], I=st['I'], draws=rng.k)
+    elif kind == 'pma':
+        st = tb.pma_init(tb.t0_from_succ(W['succ']), S, A)
+        if valid_mask:
+            st['action_mask'] = tb.valid_move_mask(W['succ'])
+        if a.pop('prefill', False):
+            st['Ms'][:] = W['succ']
+            st['update_mask'] = tb.pma_compute_update_mask(st)
+        cert = []
+        out = tb.pma_train(W, st, rng, trials, steps, a.pop('batch'), cert=cert, **a).arrays()
+        out.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], T=st['T'], SR=st['SR'],
+                   update_mask=st['update_mask'], draws=rng.k, min_gap=min(cert))
+    else:
+        raise ValueError(kind)
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# CUDA side
+# --------------------------------------------------------------------------- #
+
+def policy_obj(spec, stream):
+    from cobel_rl_b200 import policy as P
+    kind, par = spec
+    cls = {'eps': P.EpsilonGreedy, 'xeps': P.ExclusiveEpsilonGreedy, 'softmax': P.Softmax}[kind]
+    return cls(par, rng=stream)
+
+
+def unpack_run(res, i, A, succ, reward):
+    """Record of local agent ``i`` from a RunResult with recorded traces."""
+    ns = int(res['n_steps'][i])
+    sa = res['step_sa'][i, :ns].cpu().numpy()
+    s, a = sa // A, sa % A
+    s2 = np.asarray(succ)[s, a]
+    nrep = int(res['n_replay'][i])
+    rl = res['replay_len'][i].cpu().numpy()
+    rl = rl[rl >= 0]
+    return {
+        'states': s.astype(np.int32), 'actions': a.astype(np.int32), 'next_states': s2.astype(np.int32),
+        'rewards': np.asarray(reward, dtype=np.float64)[s2],
+        'trial_steps': res['trial_steps'][i].cpu().numpy(), 'trial_reward': res['trial_reward'][i].cpu().numpy(),
+        'replay': res['replay_idx'][i, :nrep].cpu().numpy(), 'replay_len': rl.astype(np.int32),
+    }
+
+
+def cuda_case(name, n_extra=2, device='cuda:0'):
+    """Run a case of oracle/cases.py through the CUDA path.  The case's agent is local agent 0 of
+    a batch of ``1 + n_extra`` agents (global ids agent .. agent+n_extra)."""
+    import torch
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld, Topology
+    from cobel_rl_b200 import agent as AG
+    kind, wname, case_agent, args = cases.CASES[name]
+    a = dict(args)
+    trials, steps = a.pop('trials'), a.pop('steps')
+    valid_mask = a.pop('valid_mask', False)
+    stream = cb.BatchStream(1 + n_extra, seed=cases.SEED, device=device, agent_id_base=case_agent)
+    if kind == 'q_topo':
+        env = Topology(*make_topology(wname), rng=stream)
+    else:
+        env = Gridworld(make_world(wname), rng=stream)
+    succ = env._succ.cpu().numpy()
+    reward = env._reward.cpu().numpy()
+    A = succ.shape[1]
+    pol = policy_obj(a.pop('policy', ('eps', 0.1)), stream)
+    if kind == 'dynaq':
+        from cobel_rl_b200.memory import DynaQMemory
+        mem = DynaQMemory(env.n_states, A, a.pop('mem_lr', 0.9), rng=stream)
+        ag = AG.DynaQ(env.observation_space, env.action_space, pol, policy_obj(('eps', 0.0), stream),
+                      a.pop('lr', 0.99), a.pop('gamma', 0.99), mem)
+        ag.mask_actions = a.pop('mask_actions', False)
+        ag.episodic_replay = a.pop('episodic_replay', False)
+        if valid_mask:
+            ag.action_mask = tb.valid_move_mask(succ)
+        ag.record = True
+        res = ag.train(env, trials, steps, a.pop('batch'), a.pop('no_replay', False))
+        torch.cuda.synchronize()
+        out = unpack_run(res, 0, A, succ, reward)
+        out.update(Q=ag._Q[0].cpu().numpy(), Mr=mem._rewards[0].cpu().numpy(), Ms=mem._states[0].cpu().numpy(),
+                   Mt=mem._terminals[0].cpu().numpy(), draws=int(stream.draw_count[0]))
+        rt = ag.test(env, 5, steps)
+        torch.cuda.synchronize()
+        t = unpack_run(rt, 0, A, succ, reward)
+        out.update({'test_' + k: v for k, v in t.items() if not k.startswith('replay')})
+        out['draws_after_test'] = int(stream.draw_count[0])
+        assert not a, 'unused case arguments %s' % a
+        return out
+    raise ValueError(kind)

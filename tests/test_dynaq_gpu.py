@@ -1,0 +1,156 @@
+"""GPU: Dyna-Q CUDA path (cobel_dynaq_run through the Python class API) against the golden
+vectors generated from the reference and against the oracle, bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, tabular as tb
+from oracle.philox import LazyStream, uniforms
+from helpers import KEYS, assert_equal_records, cuda_case, load_golden, make_world, unpack_run
+
+pytestmark = pytest.mark.gpu
+
+DYNAQ_CASES = sorted(n for n, c in cases.CASES.items() if c[0] == 'dynaq')
+
+
+def test_stream_contract():
+    """Device Philox stream == host definition (oracle/philox.py), random access and sequential."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200 import _lib
+    out = torch.empty((5, 33), dtype=torch.float64, device='cuda:0')
+    _lib.check(_lib.lib().cobel_draw_uniforms(cases.SEED, 7, 5, 3, 33, out.data_ptr(), None))
+    torch.cuda.synchronize()
+    for i in range(5):
+        assert np.array_equal(out[i].cpu().numpy(), uniforms(cases.SEED, 7 + i, 33, first=3))
+    st = cb.BatchStream(4, seed=123456789012345, device='cuda:0', agent_id_base=2**33)
+    a = st.next(3).cpu().numpy()
+    b = st.next(4).cpu().numpy()
+    for i in range(4):
+        assert np.array_equal(np.concatenate([a[i], b[i]]), uniforms(123456789012345, 2**33 + i, 7))
+    assert st.draw_count.tolist() == [7] * 4
+
+
+@pytest.mark.parametrize('name', DYNAQ_CASES)
+def test_dynaq_matches_reference_golden(name):
+    want = load_golden(name)
+    got = cuda_case(name)
+    keys = KEYS['dynaq'] + ['test_states', 'test_actions', 'test_trial_steps', 'test_trial_reward', 'draws_after_test']
+    assert_equal_records(got, want, keys, what=name)
+
+
+def test_dynaq_sweep_batch_matches_oracle():
+    """256 agents with per-agent hyper-parameters (a sweep); a sample is replayed by the oracle."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.memory import DynaQMemory
+    from cobel_rl_b200.policy import EpsilonGreedy
+    n, trials, steps, batch = 256, 12, 30, 32
+    world = make_world('walls5')
+    stream = cb.BatchStream(n, seed=99, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    eps = np.linspace(0.0, 0.5, n)
+    lr = np.linspace(0.5, 1.0, n)
+    gamma = np.linspace(0.8, 0.99, n)
+    mlr = np.linspace(0.1, 0.9, n)
+    mem = DynaQMemory(25, 4, mlr, rng=stream)
+    ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(eps, rng=stream), None, lr, gamma, mem)
+    ag.record = True
+    res = ag.train(env, trials, steps, batch)
+    torch.cuda.synchronize()
+    W = tb.compile_gridworld(world)
+    for i in (0, 1, 31, 32, 100, 255):
+        rng = tb.Draws(LazyStream(99, i), 1)
+        st = tb.dynaq_init(25, 4)
+        rec = tb.dynaq_train(W, st, rng, trials, steps, batch, policy=('eps', eps[i]), lr=lr[i], gamma=gamma[i],
+                             mem_lr=mlr[i]).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got.update(Q=ag.Q[i].cpu().numpy(), Mr=mem.rewards[i].cpu().numpy(), draws=int(stream.draw_count[i]))
+        rec.update(Q=st['Q'], Mr=st['Mr'], draws=rng.k)
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'trial_reward', 'replay', 'Q', 'Mr', 'draws'],
+                             what='agent %d' % i)
+
+
+def test_dynaq_results_independent_of_sharding():
+    """Agent g's result depends only on (seed, g): a 40-agent shard at base 100 equals the same
+    agents inside a 200-agent run."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.policy import EpsilonGreedy
+    world = make_world('open5')
+
+    def run(n, base):
+        stream = cb.BatchStream(n, seed=5, device='cuda:0', agent_id_base=base)
+        env = Gridworld(world, rng=stream)
+        ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream))
+        res = ag.train(env, 20, 50, 32)
+        return ag.Q.clone(), res['trial_steps'].clone(), stream.draw_count.clone()
+    q1, s1, d1 = run(200, 0)
+    q2, s2, d2 = run(40, 100)
+    assert torch.equal(q1[100:140], q2) and torch.equal(s1[100:140], s2) and torch.equal(d1[100:140], d2)
+
+
+def test_dynaq_large_state_space_global_path():
+    """S*A too large for the staged shared-memory layout -> tables stay in global memory."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.policy import EpsilonGreedy
+    from cobel_rl_b200.misc.gridworld_tools import make_open_field
+    world = make_open_field(12, 12, 0, 1)
+    stream = cb.BatchStream(3, seed=11, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream))
+    ag.record = True
+    res = ag.train(env, 4, 60, 16)
+    torch.cuda.synchronize()
+    W = tb.compile_gridworld(world)
+    for i in range(3):
+        rng = tb.Draws(LazyStream(11, i), 1)
+        st = tb.dynaq_init(144, 4)
+        rec = tb.dynaq_train(W, st, rng, 4, 60, 16).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got['Q'] = ag.Q[i].cpu().numpy(); rec['Q'] = st['Q']
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'Q'], what='agent %d' % i)
+
+
+def test_dynaq_user_stream():
+    """Arbitrary pre-drawn uniforms instead of Philox ("load stream from HBM" mode)."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.policy import EpsilonGreedy
+    world = make_world('open5')
+    u = np.random.default_rng(3).random((2, 20000))
+    stream = cb.BatchStream(2, device='cuda:0', user_stream=u)
+    env = Gridworld(world, rng=stream)
+    ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream))
+    ag.record = True
+    res = ag.train(env, 10, 30, 32)
+    torch.cuda.synchronize()
+    W = tb.compile_gridworld(world)
+    for i in range(2):
+        rng = tb.Draws(u[i], 1)
+        st = tb.dynaq_init(25, 4)
+        rec = tb.dynaq_train(W, st, rng, 10, 30, 32).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got['Q'] = ag.Q[i].cpu().numpy(); rec['Q'] = st['Q']
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'Q'], what='agent %d' % i)
+
+
+def test_bad_arguments_raise():
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.policy import EpsilonGreedy
+    from cobel_rl_b200.spaces import Box
+    stream = cb.BatchStream(2, device='cuda:0')
+    env = Gridworld(make_world('open5'), rng=stream)
+    with pytest.raises(AssertionError):
+        DynaQ(Box([0.], [1.]), env.action_space, EpsilonGreedy(0.1, rng=stream))
+    with pytest.raises(AssertionError):
+        EpsilonGreedy(1.5)
+    ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream))
+    with pytest.raises(AssertionError):
+        ag.train(env, 3, 0, 32)          # steps must be positive
