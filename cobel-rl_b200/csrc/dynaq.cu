@@ -4,141 +4,120 @@
 // memory/dyna_q.py:62-157 (store, retrieve_batch), policy/greedy.py, policy/softmax.py,
 // interface/gridworld.py:92-145.  Semantics: SURVEY.md Appendix A.4.
 //
-// Mapping: ONE THREAD PER AGENT.  The 33 TD updates of a step (1 online + 32
-// replayed) form a strictly sequential fp64 dependency chain per agent, so the
-// only parallelism is across agents; a thread per agent keeps 32 agents per warp
-// busy instead of one.  Each warp stages the tables of its 32 agents in shared
-// memory in a lane-interleaved layout (see SmemTables): whatever state each of
-// the 32 lanes looks up, lane l always hits "its" banks, so the per-lane random
-// row accesses of 32 different agents are conflict-free (a row of A=4 doubles is
-// two LDS.128).  HBM is touched once per launch (stage in / stage out, coalesced).
-#include "common.cuh"
+// Mapping: ONE WARP PER AGENT, agent tables resident in shared memory for the whole launch
+// (HBM is touched once: coalesced stage-in / stage-out).  Per environment step the warp
+//   * generates the step's 34 uniforms lane-parallel (one Philox block per lane),
+//   * selects the action and steps the environment warp-uniformly,
+//   * draws the 32 replay indices one per lane, gathers the 32 experiences in parallel and
+//     applies the 32 TD updates in dependency levels (td_batch_level_parallel): updates that
+//     do not touch each other's rows run in the same round, so the reference's strictly
+//     sequential 32-update chain collapses to ~6-8 rounds with bit-identical results.
+// (v1 of this kernel used one thread per agent: 180 warp-instructions per update at one
+//  instruction per 5 cycles, profiles/r1_dynaq_v1_thread_per_agent.txt.)
+#include "warp_agent.cuh"
 
 namespace {
 
-constexpr int kWarp = 32;
+constexpr int kWarpsPerCta = 4;
 
-// ---- table accessors -------------------------------------------------------
-// Shared-memory resident block of 32 agents.  Q rows are split into 16-byte
-// vectors laid out [state][vector][lane] (A even) so that a warp-wide LDS.128
-// of "my agent's row of state s_lane" is conflict-free whatever s_lane is; Mr is
-// [state*A+action][lane] doubles, and the memory's (next state, non-terminal
-// flag) pair is packed into one u16 per (s,a), [state*A+action][lane].
+struct AgentSmem {      // byte offsets inside one agent's shared-memory block
+  int q, mr, mx, wm, rm, bytes;
+  __host__ __device__ AgentSmem(int S, int A) {
+    const int SA = S * A;
+    q = 0;
+    mr = q + SA * 8;
+    wm = mr + SA * 8;
+    rm = wm + S * 4;
+    mx = rm + S * 4;
+    bytes = (mx + SA * 2 + 15) & ~15;
+  }
+};
+
+struct WorldSmem {      // byte offsets of the CTA-shared environment tables
+  int rew, succ, starts, term, bytes;
+  __host__ __device__ WorldSmem(int S, int A, int K) {
+    rew = 0;
+    succ = rew + S * 8;
+    starts = succ + S * A * 4;
+    term = starts + K * 4;
+    bytes = (term + S + 15) & ~15;
+  }
+};
+
 template <int A>
-struct SmemTables {
-  static constexpr int V = (A % 2 == 0) ? 2 : 1;   // doubles per vector
-  static constexpr int NV = A / V;                 // vectors per row
-  double* q;
-  double* mr;
-  uint16_t* mx;
-  int lane;
-  COBEL_DEV int qidx(int s, int a) const { return ((s * NV + a / V) * kWarp + lane) * V + a % V; }
-  COBEL_DEV void load_qrow(int s, double (&v)[A]) const {
-    if constexpr (V == 2) {
-#pragma unroll
-      for (int c = 0; c < NV; ++c) {
-        const double2 t = *reinterpret_cast<const double2*>(q + ((s * NV + c) * kWarp + lane) * 2);
-        v[2 * c] = t.x; v[2 * c + 1] = t.y;
-      }
-    } else {
-#pragma unroll
-      for (int a = 0; a < A; ++a) v[a] = q[(s * A + a) * kWarp + lane];
-    }
-  }
-  COBEL_DEV double q_get(int s, int a) const { return q[qidx(s, a)]; }
-  COBEL_DEV void q_set(int s, int a, double x) const { q[qidx(s, a)] = x; }
-  COBEL_DEV double mr_get(int s, int a) const { return mr[(s * A + a) * kWarp + lane]; }
-  COBEL_DEV void mr_set(int s, int a, double x) const { mr[(s * A + a) * kWarp + lane] = x; }
-  COBEL_DEV void mem_get(int s, int a, int& s2, int& nt) const {
-    const uint16_t v = mx[(s * A + a) * kWarp + lane];
-    s2 = v & 0x7FFF; nt = v >> 15;
-  }
-  COBEL_DEV void mem_set(int s, int a, int s2, int nt) const {
-    mx[(s * A + a) * kWarp + lane] = (uint16_t)(s2 | (nt << 15));
-  }
-  // index of element (s,a) of local agent `al` in the staged Q / flat layouts
-  COBEL_DEV static int stage_q(int s, int a, int al) { return ((s * NV + a / V) * kWarp + al) * V + a % V; }
-  COBEL_DEV static int stage_flat(int s, int a, int al) { return (s * A + a) * kWarp + al; }
-};
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const __grid_constant__ CobelDynaQParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int S = p.world.n_states, K = p.world.n_starts, SA = S * A;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const WorldSmem wo(S, A, K);
+  const AgentSmem ao(S, A);
 
-// Tables left in global memory (state spaces too large for the staged layout).
-template <int A>
-struct GmemTables {
-  double* q;      // this agent's [S,A]
-  double* mr;
-  int32_t* ms;
-  int32_t* mt;
-  COBEL_DEV void load_qrow(int s, double (&v)[A]) const {
-#pragma unroll
-    for (int a = 0; a < A; ++a) v[a] = q[s * A + a];
+  double* rew_s = reinterpret_cast<double*>(smem + wo.rew);
+  int32_t* succ_s = reinterpret_cast<int32_t*>(smem + wo.succ);
+  int32_t* starts_s = reinterpret_cast<int32_t*>(smem + wo.starts);
+  uint8_t* term_s = smem + wo.term;
+  for (int e = threadIdx.x; e < SA; e += blockDim.x) succ_s[e] = p.world.succ[e];
+  for (int e = threadIdx.x; e < S; e += blockDim.x) { rew_s[e] = p.world.reward[e]; term_s[e] = p.world.terminal[e]; }
+  for (int e = threadIdx.x; e < K; e += blockDim.x) starts_s[e] = p.world.starts[e];
+  __syncthreads();
+
+  const int64_t n = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+  if (n >= p.n_agents) return;                      // whole warp leaves; no block-wide sync below
+
+  unsigned char* blk = smem + wo.bytes + (size_t)warp * ao.bytes;
+  double* Q = reinterpret_cast<double*>(blk + ao.q);
+  double* Mr = reinterpret_cast<double*>(blk + ao.mr);
+  uint16_t* Mx = reinterpret_cast<uint16_t*>(blk + ao.mx);     // next state | non-terminal << 15
+  uint32_t* wm = reinterpret_cast<uint32_t*>(blk + ao.wm);
+  uint32_t* rm = reinterpret_cast<uint32_t*>(blk + ao.rm);
+
+  const size_t g0 = (size_t)n * SA;
+  for (int e = lane; e < SA; e += 32) {
+    Q[e] = p.Q[g0 + e];
+    Mr[e] = p.Mr[g0 + e];
+    Mx[e] = (uint16_t)(p.Ms[g0 + e] | ((p.Mt[g0 + e] ? 1 : 0) << 15));
   }
-  COBEL_DEV double q_get(int s, int a) const { return q[s * A + a]; }
-  COBEL_DEV void q_set(int s, int a, double x) const { q[s * A + a] = x; }
-  COBEL_DEV double mr_get(int s, int a) const { return mr[s * A + a]; }
-  COBEL_DEV void mr_set(int s, int a, double x) const { mr[s * A + a] = x; }
-  COBEL_DEV void mem_get(int s, int a, int& s2, int& nt) const { s2 = ms[s * A + a]; nt = mt[s * A + a]; }
-  COBEL_DEV void mem_set(int s, int a, int s2, int nt) const { ms[s * A + a] = s2; mt[s * A + a] = nt; }
-};
+  __syncwarp();
 
-// One-step TD update, agent/dyna_q.py:275-301:
-//   td = r; td += gamma * nt * max(Q[s2]); td -= Q[s,a]; Q[s,a] += lr * td
-template <int A, class Tab>
-COBEL_DEV void td_update(const Tab& t, int s, int a, double r, int s2, int nt, double lr, double gamma) {
-  double row[A];
-  t.load_qrow(s2, row);
-  const double q = t.q_get(s, a);
-  const double g = nt ? gamma : 0.0;                  // gamma * nt, nt in {0,1}
-  double td = xadd(r, xmul(g, row_max<A>(row)));
-  td = xsub(td, q);
-  t.q_set(s, a, xadd(q, xmul(lr, td)));
-}
-
-struct WorldView {
-  const int32_t* succ; const double* reward; const uint8_t* terminal; const int32_t* starts;
-  int S, K;
-};
-
-template <int A, class Tab>
-COBEL_DEV void run_agent(const CobelDynaQParams& p, const WorldView& w, const Tab& t, int64_t n) {
-  Rng rng; rng.init(p.stream, n);
+  DrawWindow win; win.init(p.stream, n);
+  uint64_t k = (uint64_t)p.stream.draw_count[n];
   const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
-  const double par = p.policy.param[n];
-  const int kind = p.policy.kind;
-  const int S = w.S, B = p.batch;
+  PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
   const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
+  const int B = p.batch;
   const bool learn = p.learn != 0;
   const bool step_replay = learn && !p.no_replay && !p.episodic_replay && B > 0;
   const bool trial_replay = learn && !p.no_replay && p.episodic_replay && B > 0;
+  const CobelTrace& tr = p.trace;
   int64_t nsteps = 0, nrep = 0, ncalls = 0;
   int flags = 0;
-  const CobelTrace& tr = p.trace;
 
+  // memory/dyna_q.py:137-157 + agent/dyna_q.py:329-330: B uniform draws over S*A (C-order
+  // unravel), applied in order; 32 at a time, one per lane.
   auto replay = [&]() {
-    // memory/dyna_q.py:137-157 then agent/dyna_q.py:329-330: B uniform draws over
-    // S*A (C order), applied strictly in order.  Experiences are fetched 8 at a
-    // time (the memory does not change during a replay), the Q chain is serial.
-    for (int b0 = 0; b0 < B; b0 += 8) {
-      int rs[8], ra[8], rs2[8], rnt[8];
-      double rr[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (b0 + j < B) {
-          const int i = draw_integer(rng.next(), S * A);
-          rs[j] = i / A; ra[j] = i - rs[j] * A;
-          rr[j] = t.mr_get(rs[j], ra[j]);
-          t.mem_get(rs[j], ra[j], rs2[j], rnt[j]);
-          if (tr.replay_idx) {
-            if (nrep + j < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + j] = i;
-            else flags |= COBEL_FLAG_TRACE_OVERFLOW;
-          }
+    for (int b0 = 0; b0 < B; b0 += 32) {
+      const int nb = B - b0 < 32 ? B - b0 : 32;
+      win.ensure(k, nb, lane);
+      const bool active = lane < nb;
+      const double u = win.get(k + (active ? lane : 0));
+      k += nb;
+      int rs = 0, ra = 0, rs2 = 0, rnt = 0;
+      double rr = 0.0;
+      if (active) {
+        const int i = draw_integer(u, SA);
+        rs = i / A; ra = i - rs * A;
+        rr = Mr[i];
+        const uint16_t v = Mx[i];
+        rs2 = v & 0x7FFF; rnt = v >> 15;
+        if (tr.replay_idx) {
+          if (nrep + lane < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + lane] = i;
+          else flags |= COBEL_FLAG_TRACE_OVERFLOW;
         }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (b0 + j < B) td_update<A>(t, rs[j], ra[j], rr[j], rs2[j], rnt[j], lr, gamma);
-      nrep += (B - b0 < 8 ? B - b0 : 8);
+      td_batch_level_parallel<A>(Q, wm, rm, S, lane, active, rs, ra, rr, rs2, rnt, lr, gamma);
+      nrep += nb;
     }
-    if (tr.replay_len) {
+    if (tr.replay_len && lane == 0) {
       if (ncalls < tr.replay_calls_cap) tr.replay_len[n * tr.replay_calls_cap + ncalls] = B;
       else flags |= COBEL_FLAG_TRACE_OVERFLOW;
     }
@@ -146,143 +125,95 @@ COBEL_DEV void run_agent(const CobelDynaQParams& p, const WorldView& w, const Ta
   };
 
   for (int trial = 0; trial < p.trials; ++trial) {
-    int s = w.starts[draw_integer(rng.next(), w.K)];       // interface/gridworld.py:142
+    // interface/gridworld.py:142: one uniform draw over the starting states
+    win.ensure(k, 2 + (step_replay && B < 32 ? B : 0), lane);
+    int s = starts_s[draw_integer(win.get(k), K)];
+    ++k;
     double treward = 0.0;
     int step = 0;
-    for (; step < p.steps; ++step) {
+    for (;; ++step) {
+      win.ensure(k, 1 + (step_replay && B < 32 ? B : 0), lane);
       double row[A];
-      t.load_qrow(s, row);
+      load_row<A>(Q + s * A, row);
       uint32_t mask = (1u << A) - 1u;
       if (amask) {
         mask = 0;
 #pragma unroll
         for (int a = 0; a < A; ++a) mask |= (amask[s * A + a] ? 1u : 0u) << a;
       }
-      const int a = select_action<A>(row, mask, kind, par, rng.next());
-      const int s2 = w.succ[s * A + a];
-      const double r = w.reward[s2];
-      const int end = w.terminal[s2];
+      const int a = select_action_warp<A>(row, mask, pt, win.get(k), lane);
+      ++k;
+      const int s2 = succ_s[s * A + a];
+      const double r = rew_s[s2];
+      const int end = term_s[s2];
       const int nt = 1 - end;
-      if (tr.step_sa) {
+      if (tr.step_sa && lane == 0) {
         if (nsteps < tr.step_cap) tr.step_sa[n * tr.step_cap + nsteps] = s * A + a;
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
       ++nsteps;
       if (learn) {
-        // memory/dyna_q.py:92-96 -- store first, then the online update
-        const double m0 = t.mr_get(s, a);
-        t.mr_set(s, a, xadd(m0, xmul(mlr, xsub(r, m0))));
-        t.mem_set(s, a, s2, nt);
-        td_update<A>(t, s, a, r, s2, nt, lr, gamma);
+        // memory/dyna_q.py:92-96 (store first), then agent/dyna_q.py:275-301 (online update);
+        // every lane computes the same values, lane 0 commits them
+        const double m0 = Mr[s * A + a];
+        const double m1 = xadd(m0, xmul(mlr, xsub(r, m0)));
+        double row2[A];
+        load_row<A>(Q + s2 * A, row2);
+        const double q = Q[s * A + a];
+        const double g = nt ? gamma : 0.0;
+        double td = xadd(r, xmul(g, row_max<A>(row2)));
+        td = xsub(td, q);
+        const double qn = xadd(q, xmul(lr, td));
+        __syncwarp();
+        if (lane == 0) {
+          Mr[s * A + a] = m1;
+          Mx[s * A + a] = (uint16_t)(s2 | (nt << 15));
+          Q[s * A + a] = qn;
+        }
+        __syncwarp();
       }
       s = s2;
       if (step_replay) replay();
       treward = xadd(treward, r);
-      if (end) break;
+      if (end || step + 1 == p.steps) break;
     }
-    if (step == p.steps) step = p.steps - 1;               // logs['steps'] = last loop index
-    tr.trial_steps[n * p.trials + trial] = step;
-    tr.trial_reward[n * p.trials + trial] = treward;
+    if (lane == 0) {                                 // logs['steps'] = index of the last step
+      tr.trial_steps[n * p.trials + trial] = step;
+      tr.trial_reward[n * p.trials + trial] = treward;
+    }
     if (trial_replay) replay();
   }
-  p.stream.draw_count[n] = (int64_t)rng.k;
-  tr.n_steps[n] += nsteps;
-  tr.n_replay[n] += nrep;
-  if (tr.flags && flags) tr.flags[n] |= flags;
-}
 
-// ---- staged (shared-memory) kernel: one warp per CTA, 32 agents ------------
-template <int A>
-__global__ void __launch_bounds__(kWarp) dynaq_smem_kernel(const __grid_constant__ CobelDynaQParams p) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int S = p.world.n_states, K = p.world.n_starts, SA = S * A;
-  const int lane = threadIdx.x;
-  const int64_t base = (int64_t)blockIdx.x * kWarp;
-  const int64_t n = base + lane;
-  const int nloc = (int)((p.n_agents - base) < kWarp ? (p.n_agents - base) : kWarp);
-
-  double* q_s = reinterpret_cast<double*>(smem);
-  double* mr_s = q_s + (size_t)SA * kWarp;
-  double* rew_s = mr_s + (size_t)SA * kWarp;
-  int32_t* succ_s = reinterpret_cast<int32_t*>(rew_s + S);
-  int32_t* starts_s = succ_s + SA;
-  uint16_t* mx_s = reinterpret_cast<uint16_t*>(starts_s + K);
-  uint8_t* term_s = reinterpret_cast<uint8_t*>(mx_s + (size_t)SA * kWarp);
-
-  // stage in: coalesced reads of [agent][s][a], scattered into [s][lane][a]
-  for (int e = lane; e < SA * kWarp; e += kWarp) {
-    const int al = e / SA, idx = e - al * SA;
-    const int s = idx / A, a = idx - s * A;
-    const int dq = SmemTables<A>::stage_q(s, a, al), df = SmemTables<A>::stage_flat(s, a, al);
-    if (al < nloc) {
-      const size_t g = (size_t)(base + al) * SA + idx;
-      q_s[dq] = p.Q[g];
-      mr_s[df] = p.Mr[g];
-      mx_s[df] = (uint16_t)(p.Ms[g] | ((p.Mt[g] ? 1 : 0) << 15));
-    } else {
-      q_s[dq] = 0.0; mr_s[df] = 0.0; mx_s[df] = 0;
+  __syncwarp();
+  if (learn) {
+    for (int e = lane; e < SA; e += 32) {
+      p.Q[g0 + e] = Q[e];
+      p.Mr[g0 + e] = Mr[e];
+      p.Ms[g0 + e] = Mx[e] & 0x7FFF;
+      p.Mt[g0 + e] = Mx[e] >> 15;
     }
   }
-  for (int e = lane; e < SA; e += kWarp) succ_s[e] = p.world.succ[e];
-  for (int e = lane; e < S; e += kWarp) { rew_s[e] = p.world.reward[e]; term_s[e] = p.world.terminal[e]; }
-  for (int e = lane; e < K; e += kWarp) starts_s[e] = p.world.starts[e];
-  __syncwarp();
-
-  if (n < p.n_agents) {
-    SmemTables<A> t{q_s, mr_s, mx_s, lane};
-    WorldView w{succ_s, rew_s, term_s, starts_s, S, K};
-    run_agent<A>(p, w, t, n);
+  flags = __reduce_or_sync(kFull, flags);
+  if (lane == 0) {
+    p.stream.draw_count[n] = (int64_t)k;
+    tr.n_steps[n] += nsteps;
+    tr.n_replay[n] += nrep;
+    if (tr.flags && flags) tr.flags[n] |= flags;
   }
-  __syncwarp();
-
-  if (p.learn) {
-    for (int e = lane; e < SA * kWarp; e += kWarp) {
-      const int al = e / SA, idx = e - al * SA;
-      if (al >= nloc) break;
-      const int s = idx / A, a = idx - s * A;
-      const int dq = SmemTables<A>::stage_q(s, a, al), df = SmemTables<A>::stage_flat(s, a, al);
-      const size_t g = (size_t)(base + al) * SA + idx;
-      p.Q[g] = q_s[dq];
-      p.Mr[g] = mr_s[df];
-      p.Ms[g] = mx_s[df] & 0x7FFF;
-      p.Mt[g] = mx_s[df] >> 15;
-    }
-  }
-}
-
-// ---- fallback: tables stay in global memory (S*A too large to stage) --------
-template <int A>
-__global__ void __launch_bounds__(128) dynaq_gmem_kernel(const __grid_constant__ CobelDynaQParams p) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= p.n_agents) return;
-  const size_t SA = (size_t)p.world.n_states * A;
-  GmemTables<A> t{p.Q + n * SA, p.Mr + n * SA, p.Ms + n * SA, p.Mt + n * SA};
-  WorldView w{p.world.succ, p.world.reward, p.world.terminal, p.world.starts, p.world.n_states, p.world.n_starts};
-  run_agent<A>(p, w, t, n);
-}
-
-size_t smem_bytes(int S, int A, int K) {
-  const size_t SA = (size_t)S * A;
-  size_t b = 2 * SA * kWarp * sizeof(double);      // Q, Mr
-  b += (size_t)S * sizeof(double);                 // reward
-  b += SA * sizeof(int32_t) + (size_t)K * sizeof(int32_t);
-  b += SA * kWarp * sizeof(uint16_t);              // packed memory
-  b += (size_t)S;                                  // terminal
-  return (b + 15) & ~(size_t)15;
 }
 
 template <int A>
 int launch(const CobelDynaQParams& p, cudaStream_t st) {
   const int S = p.world.n_states, K = p.world.n_starts;
-  const size_t sm = smem_bytes(S, A, K);
-  if (sm <= 227 * 1024 && S <= 0x7FFF) {
-    COBEL_CUDA_OK(cudaFuncSetAttribute(dynaq_smem_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    const unsigned grid = (unsigned)((p.n_agents + kWarp - 1) / kWarp);
-    dynaq_smem_kernel<A><<<grid, kWarp, sm, st>>>(p);
-  } else {
-    const unsigned grid = (unsigned)((p.n_agents + 127) / 128);
-    dynaq_gmem_kernel<A><<<grid, 128, 0, st>>>(p);
-  }
+  COBEL_REQUIRE(S <= 0x7FFF, COBEL_EUNSUPPORTED, "Dyna-Q kernel supports at most 32767 states");
+  const WorldSmem wo(S, A, K);
+  const AgentSmem ao(S, A);
+  const size_t sm = (size_t)wo.bytes + (size_t)kWarpsPerCta * ao.bytes;
+  COBEL_REQUIRE(sm <= 227 * 1024, COBEL_EUNSUPPORTED,
+                "Dyna-Q tables of %d states x %d actions do not fit in shared memory (%zu bytes per CTA)", S, A, sm);
+  COBEL_CUDA_OK(cudaFuncSetAttribute(dynaq_warp_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const unsigned grid = (unsigned)((p.n_agents + kWarpsPerCta - 1) / kWarpsPerCta);
+  dynaq_warp_kernel<A><<<grid, kWarpsPerCta * 32, sm, st>>>(p);
   cobel_count_launch();
   COBEL_CUDA_OK(cudaGetLastError());
   return COBEL_OK;

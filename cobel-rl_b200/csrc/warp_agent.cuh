@@ -1,0 +1,193 @@
+// warp_agent.cuh -- building blocks shared by the warp-per-agent kernels (Dyna-Q, QAgent, SFMA...):
+// a 64-draw window of the agent's Philox stream generated lane-parallel, warp-uniform action
+// selection with the (few) fp64 divisions spread over lanes, and the conflict-free
+// level-parallel execution of a batch of sequential one-step TD updates.
+#pragma once
+#include "common.cuh"
+
+constexpr unsigned kFull = 0xffffffffu;
+
+COBEL_DEV double shfl_f64(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(kFull, lo, src);
+  hi = __shfl_sync(kFull, hi, src);
+  return __hiloint2double(hi, lo);
+}
+
+// Row of A doubles from a 16-byte aligned table (A even -> LDS.128 / LDG.128).
+template <int A>
+COBEL_DEV void load_row(const double* r, double (&v)[A]) {
+  if constexpr (A % 2 == 0) {
+#pragma unroll
+    for (int x = 0; x < A; x += 2) {
+      const double2 t = *reinterpret_cast<const double2*>(r + x);
+      v[x] = t.x; v[x + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int x = 0; x < A; ++x) v[x] = r[x];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// DrawWindow: lane l holds draws 2*(b0+l) and 2*(b0+l)+1 of the agent's stream, i.e. the warp
+// holds the 64 consecutive draws starting at 2*b0.  One Philox block per lane per refill
+// instead of one per draw per agent.
+// ---------------------------------------------------------------------------
+struct DrawWindow {
+  uint64_t agent;
+  uint32_t key0, key1;
+  uint64_t b0;            // first block held
+  double ua, ub;          // this lane's two draws
+  const double* user;     // optional pre-drawn stream of this agent
+  int64_t user_len;
+  bool valid;
+
+  COBEL_DEV void init(const CobelStream& s, int64_t local_agent) {
+    agent = (uint64_t)(s.agent_id_base + local_agent);
+    key0 = (uint32_t)s.seed; key1 = (uint32_t)(s.seed >> 32);
+    user = s.user_stream ? s.user_stream + local_agent * s.user_stream_len : nullptr;
+    user_len = s.user_stream_len;
+    valid = false; b0 = 0; ua = ub = 0.0;
+  }
+  // make draws k .. k+need-1 available (need <= 63)
+  COBEL_DEV void ensure(uint64_t k, int need, int lane) {
+    if (user) return;
+    if (valid && k >= 2 * b0 && k + need <= 2 * b0 + 64) return;
+    b0 = k >> 1;
+    const uint64_t b = b0 + lane;
+    uint32_t o[4];
+    philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)agent, (uint32_t)(agent >> 32), key0, key1, o);
+    ua = u53(o[0], o[1]); ub = u53(o[2], o[3]);
+    valid = true;
+  }
+  // draw kk (may differ per lane); all 32 lanes must call
+  COBEL_DEV double get(uint64_t kk) const {
+    if (user) return kk < (uint64_t)user_len ? user[kk] : 0.0;
+    const int off = (int)(kk - 2 * b0);
+    const double a = shfl_f64(ua, off >> 1), b = shfl_f64(ub, off >> 1);
+    return (off & 1) ? b : a;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Warp-uniform action selection (all lanes hold the same v[], mask, u and get the same action).
+//   probabilities: policy/greedy.py:60-88, 117-147; policy/softmax.py:60-88
+//   draw: searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right')   (policy/greedy.py:58)
+// PolicyTab caches, per agent, the quotients eps/n and (1-eps)/n for n = 1..A in lane n-1.
+// ---------------------------------------------------------------------------
+struct PolicyTab {
+  int kind;
+  double par;
+  double q_par;   // lane l: par / (l+1)
+  double q_om;    // lane l: (1 - par) / (l+1)
+  COBEL_DEV void init(int kind_, double par_, int lane) {
+    kind = kind_; par = par_;
+    q_par = xdiv(par_, (double)(lane + 1));
+    q_om = xdiv(xsub(1.0, par_), (double)(lane + 1));
+  }
+};
+
+template <int A>
+COBEL_DEV int select_action_warp(const double (&v)[A], uint32_t mask, const PolicyTab& pt, double u, int lane) {
+  int nv = 0;
+  double m = 0.0;
+  bool first = true;
+#pragma unroll
+  for (int a = 0; a < A; ++a)
+    if (mask >> a & 1u) { ++nv; m = first ? v[a] : xmax(m, v[a]); first = false; }
+  double p[A];
+  if (pt.kind == COBEL_POLICY_SOFTMAX) {
+    double sum = 0.0;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      p[a] = 0.0;
+      if (mask >> a & 1u) { p[a] = exp(xmul(xsub(v[a], m), pt.par)); sum = xadd(sum, p[a]); }
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a)
+      if (mask >> a & 1u) p[a] = xdiv(p[a], sum);
+  } else {
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < A; ++a) k += ((mask >> a & 1u) && v[a] == m) ? 1 : 0;
+    const double tie = shfl_f64(pt.q_om, k - 1);                      // (1-eps)/k
+    if (pt.kind == COBEL_POLICY_EPS_GREEDY) {
+      const double base = shfl_f64(pt.q_par, nv - 1);                 // eps/n_valid
+#pragma unroll
+      for (int a = 0; a < A; ++a)
+        p[a] = (mask >> a & 1u) ? xadd(base, v[a] == m ? tie : 0.0) : 0.0;
+    } else {
+      const int d = nv - k > 1 ? nv - k : 1;
+      const double expl = shfl_f64(pt.q_par, d - 1);                  // eps/max(n_valid-k,1)
+#pragma unroll
+      for (int a = 0; a < A; ++a)
+        p[a] = (mask >> a & 1u) ? (v[a] == m ? xadd(tie, 0.0) : xadd(0.0, expl)) : 0.0;
+    }
+  }
+  // inverse CDF: lane a tests cdf[a]/cdf[A-1] <= u, one division per lane instead of A-1 in series
+  double c = p[0], mine = p[0];
+#pragma unroll
+  for (int a = 1; a < A; ++a) { c = xadd(c, p[a]); if (lane == a) mine = c; }
+  const bool le = (lane < A - 1) && (xdiv(mine, c) <= u);
+  return __popc(__ballot_sync(kFull, le));
+}
+
+// ---------------------------------------------------------------------------
+// Level-parallel execution of a batch of one-step TD updates that the reference applies
+// strictly in order (agent/dyna_q.py:329-330, agent/q.py:353-354).
+//
+// Lane j holds update j: it reads row Q[s2_j,:] and entry Q[s_j,a_j] and writes Q[s_j,a_j].
+// For i < j:   i writes what j reads or writes  -> j must run in a LATER round  (strict)
+//              j writes what i reads            -> j must not run in an EARLIER round (weak;
+//              same round is fine because every round reads, syncs, then writes)
+// Rounds execute all currently ready lanes at once; each update sees exactly the values it
+// would see in sequential order, so the result is bit-identical to the sequential loop.
+// `wm`/`rm` are per-agent scratch arrays of S words in shared memory.
+// ---------------------------------------------------------------------------
+template <int A>
+COBEL_DEV void td_batch_level_parallel(double* Q, uint32_t* wm, uint32_t* rm, int S, int lane, bool active,
+                                       int s, int a, double r, int s2, int nt, double lr, double gamma) {
+  const unsigned act = __ballot_sync(kFull, active);
+  const unsigned below = (1u << lane) - 1u;
+  // writers / readers per state
+  for (int e = lane; e < S; e += 32) { wm[e] = 0; rm[e] = 0; }
+  __syncwarp();
+  if (active) {
+    // all lanes with the same key store the same mask: a benign same-value race
+    wm[s] = __match_any_sync(act, s);
+    rm[s2] = __match_any_sync(act, s2);
+  }
+  __syncwarp();
+  unsigned strict = 0, weak = 0;
+  if (active) {
+    const unsigned same_sa = __match_any_sync(act, s * A + a);      // i writes the entry j reads+writes
+    strict = (wm[s2] | same_sa) & below;                            // i writes into the row j reads
+    weak = rm[s] & below;                                           // j writes into the row i reads
+  }
+  const double g = nt ? gamma : 0.0;
+  unsigned done = ~act;
+  while (done != kFull) {
+    bool ready = active && !(done >> lane & 1u) && (strict & ~done) == 0;
+    unsigned R = __ballot_sync(kFull, ready);
+    for (;;) {
+      ready = ready && (weak & ~(done | R)) == 0;
+      const unsigned R2 = __ballot_sync(kFull, ready);
+      if (R2 == R) break;
+      R = R2;
+    }
+    double qn = 0.0;
+    if (ready) {
+      double row[A];
+      load_row<A>(Q + s2 * A, row);
+      const double q = Q[s * A + a];
+      double td = xadd(r, xmul(g, row_max<A>(row)));
+      td = xsub(td, q);
+      qn = xadd(q, xmul(lr, td));
+    }
+    __syncwarp();
+    if (ready) Q[s * A + a] = qn;
+    __syncwarp();
+    done |= R;
+  }
+}
