@@ -40,9 +40,13 @@ COBEL_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
 }
 
 COBEL_DEV double u53(uint32_t a, uint32_t b) {
-  // ((a>>5)*2^26 + (b>>6)) * 2^-53 : every step is exact in fp64
-  const double hi = (double)(a >> 5), lo = (double)(b >> 6);
-  return xmul(xadd(xmul(hi, 67108864.0), lo), 1.1102230246251565404e-16);
+  // ((a>>5)*2^26 + (b>>6)) * 2^-53, built without int->fp64 conversions (which are slow
+  // multi-instruction sequences): placing an integer m < 2^32 in the low mantissa word of a
+  // double with biased exponent 0x433-e gives (2^52 + m) * 2^-e exactly; subtracting 2^(52-e)
+  // leaves m * 2^-e.  hi*2^-27 and lo*2^-53 occupy disjoint bit ranges, so the sum is exact.
+  const double hi = xsub(__hiloint2double(0x43300000 - (27 << 20), (int)(a >> 5)), 33554432.0);   // (a>>5) * 2^-27
+  const double lo = xsub(__hiloint2double(0x43300000 - (53 << 20), (int)(b >> 6)), 0.5);          // (b>>6) * 2^-53
+  return xadd(hi, lo);
 }
 
 // One agent's uniform stream, consumed in program order.
@@ -88,8 +92,14 @@ struct Rng {
 };
 
 // Generator.integers(n) / choice(a) from one uniform: min(floor(u*n), n-1)
+// Exact int -> double for 0 <= n < 2^31 without a conversion instruction.
+COBEL_DEV double int_to_f64(int n) { return xsub(__hiloint2double(0x43300000, n), 4503599627370496.0); }
+
 COBEL_DEV int draw_integer(double u, int n) {
-  const int i = (int)xmul(u, (double)n);   // u*n >= 0: truncation == floor
+  // floor(u*n): adding 2^52 with round-toward-minus-infinity leaves floor(x) in the low
+  // mantissa word (0 <= x < 2^31); avoids the slow fp64 -> int conversion sequence.
+  const double x = xmul(u, int_to_f64(n));
+  const int i = __double2loint(__dadd_rd(x, 4503599627370496.0));
   return i < n - 1 ? i : n - 1;
 }
 

@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   }
   __syncwarp();
 
-  DrawWindow win; win.init(p.stream, n);
-  uint64_t k = (uint64_t)p.stream.draw_count[n];
+  for (int e = lane; e < S; e += 32) { wm[e] = 0; rm[e] = 0; }
+  DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
   const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
   const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
@@ -97,10 +97,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   auto replay = [&]() {
     for (int b0 = 0; b0 < B; b0 += 32) {
       const int nb = B - b0 < 32 ? B - b0 : 32;
-      win.ensure(k, nb, lane);
+      win.ensure(nb, lane);
       const bool active = lane < nb;
-      const double u = win.get(k + (active ? lane : 0));
-      k += nb;
+      const double u = win.peek(active ? lane : 0);
+      win.advance(nb);
       int rs = 0, ra = 0, rs2 = 0, rnt = 0;
       double rr = 0.0;
       if (active) {
@@ -126,13 +126,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
 
   for (int trial = 0; trial < p.trials; ++trial) {
     // interface/gridworld.py:142: one uniform draw over the starting states
-    win.ensure(k, 2 + (step_replay && B < 32 ? B : 0), lane);
-    int s = starts_s[draw_integer(win.get(k), K)];
-    ++k;
+    win.ensure(2 + (step_replay && B <= 32 ? B : 0), lane);
+    int s = starts_s[draw_integer(win.next(), K)];
     double treward = 0.0;
     int step = 0;
     for (;; ++step) {
-      win.ensure(k, 1 + (step_replay && B < 32 ? B : 0), lane);
+      win.ensure(1 + (step_replay && B <= 32 ? B : 0), lane);
       double row[A];
       load_row<A>(Q + s * A, row);
       uint32_t mask = (1u << A) - 1u;
@@ -141,8 +140,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
 #pragma unroll
         for (int a = 0; a < A; ++a) mask |= (amask[s * A + a] ? 1u : 0u) << a;
       }
-      const int a = select_action_warp<A>(row, mask, pt, win.get(k), lane);
-      ++k;
+      const int a = select_action_warp<A>(row, mask, pt, win.next(), lane);
       const int s2 = succ_s[s * A + a];
       const double r = rew_s[s2];
       const int end = term_s[s2];
@@ -195,7 +193,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   }
   flags = __reduce_or_sync(kFull, flags);
   if (lane == 0) {
-    p.stream.draw_count[n] = (int64_t)k;
+    p.stream.draw_count[n] = (int64_t)win.position();
     tr.n_steps[n] += nsteps;
     tr.n_replay[n] += nrep;
     if (tr.flags && flags) tr.flags[n] |= flags;

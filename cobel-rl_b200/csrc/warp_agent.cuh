@@ -37,37 +37,43 @@ COBEL_DEV void load_row(const double* r, double (&v)[A]) {
 struct DrawWindow {
   uint64_t agent;
   uint32_t key0, key1;
-  uint64_t b0;            // first block held
-  double ua, ub;          // this lane's two draws
+  uint64_t base;          // stream index of window slot 0 (even)
+  int off;                // window slot of the next draw: k = base + off
+  double ua, ub;          // this lane's two draws: slots 2*lane and 2*lane+1
   const double* user;     // optional pre-drawn stream of this agent
   int64_t user_len;
-  bool valid;
 
-  COBEL_DEV void init(const CobelStream& s, int64_t local_agent) {
+  COBEL_DEV void init(const CobelStream& s, int64_t local_agent, uint64_t k) {
     agent = (uint64_t)(s.agent_id_base + local_agent);
     key0 = (uint32_t)s.seed; key1 = (uint32_t)(s.seed >> 32);
     user = s.user_stream ? s.user_stream + local_agent * s.user_stream_len : nullptr;
     user_len = s.user_stream_len;
-    valid = false; b0 = 0; ua = ub = 0.0;
+    base = k; off = 64;     // empty: the first ensure() refills
+    ua = ub = 0.0;
   }
-  // make draws k .. k+need-1 available (need <= 63)
-  COBEL_DEV void ensure(uint64_t k, int need, int lane) {
-    if (user) return;
-    if (valid && k >= 2 * b0 && k + need <= 2 * b0 + 64) return;
-    b0 = k >> 1;
-    const uint64_t b = b0 + lane;
+  COBEL_DEV uint64_t position() const { return base + (uint64_t)off; }
+  // make the next `need` draws available (need <= 63); warp-uniform
+  COBEL_DEV void ensure(int need, int lane) {
+    if (user || off + need <= 64) return;
+    const uint64_t k = base + (uint64_t)off;
+    base = k & ~1ull; off = (int)(k & 1ull);
+    const uint64_t b = (base >> 1) + lane;
     uint32_t o[4];
     philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)agent, (uint32_t)(agent >> 32), key0, key1, o);
     ua = u53(o[0], o[1]); ub = u53(o[2], o[3]);
-    valid = true;
   }
-  // draw kk (may differ per lane); all 32 lanes must call
-  COBEL_DEV double get(uint64_t kk) const {
-    if (user) return kk < (uint64_t)user_len ? user[kk] : 0.0;
-    const int off = (int)(kk - 2 * b0);
-    const double a = shfl_f64(ua, off >> 1), b = shfl_f64(ub, off >> 1);
-    return (off & 1) ? b : a;
+  // draw number (next + ahead), `ahead` may differ per lane; all 32 lanes must call
+  COBEL_DEV double peek(int ahead) const {
+    if (user) {
+      const uint64_t kk = base + (uint64_t)(off + ahead);
+      return kk < (uint64_t)user_len ? user[kk] : 0.0;
+    }
+    const int slot = off + ahead;
+    const double a = shfl_f64(ua, slot >> 1), b = shfl_f64(ub, slot >> 1);
+    return (slot & 1) ? b : a;
   }
+  COBEL_DEV void advance(int n) { off += n; }
+  COBEL_DEV double next() { const double u = peek(0); ++off; return u; }
 };
 
 // ---------------------------------------------------------------------------
@@ -90,12 +96,17 @@ struct PolicyTab {
 
 template <int A>
 COBEL_DEV int select_action_warp(const double (&v)[A], uint32_t mask, const PolicyTab& pt, double u, int lane) {
-  int nv = 0;
-  double m = 0.0;
-  bool first = true;
+  constexpr uint32_t kAll = (1u << A) - 1u;
+  double m;
+  int nv = A;
+  if (mask == kAll) {
+    m = row_max<A>(v);
+  } else {
+    nv = __popc(mask);
+    m = -__longlong_as_double(0x7FF0000000000000ll);
 #pragma unroll
-  for (int a = 0; a < A; ++a)
-    if (mask >> a & 1u) { ++nv; m = first ? v[a] : xmax(m, v[a]); first = false; }
+    for (int a = 0; a < A; ++a) m = (mask >> a & 1u) ? xmax(m, v[a]) : m;
+  }
   double p[A];
   if (pt.kind == COBEL_POLICY_SOFTMAX) {
     double sum = 0.0;
@@ -108,28 +119,34 @@ COBEL_DEV int select_action_warp(const double (&v)[A], uint32_t mask, const Poli
     for (int a = 0; a < A; ++a)
       if (mask >> a & 1u) p[a] = xdiv(p[a], sum);
   } else {
-    int k = 0;
+    uint32_t ties = 0;
 #pragma unroll
-    for (int a = 0; a < A; ++a) k += ((mask >> a & 1u) && v[a] == m) ? 1 : 0;
+    for (int a = 0; a < A; ++a) ties |= (v[a] == m ? 1u : 0u) << a;
+    ties &= mask;
+    const int k = __popc(ties);
     const double tie = shfl_f64(pt.q_om, k - 1);                      // (1-eps)/k
     if (pt.kind == COBEL_POLICY_EPS_GREEDY) {
       const double base = shfl_f64(pt.q_par, nv - 1);                 // eps/n_valid
+      const double top = xadd(base, tie), low = xadd(base, 0.0);
 #pragma unroll
       for (int a = 0; a < A; ++a)
-        p[a] = (mask >> a & 1u) ? xadd(base, v[a] == m ? tie : 0.0) : 0.0;
+        p[a] = (mask >> a & 1u) ? ((ties >> a & 1u) ? top : low) : 0.0;
     } else {
       const int d = nv - k > 1 ? nv - k : 1;
       const double expl = shfl_f64(pt.q_par, d - 1);                  // eps/max(n_valid-k,1)
+      const double top = xadd(tie, 0.0), low = xadd(0.0, expl);
 #pragma unroll
       for (int a = 0; a < A; ++a)
-        p[a] = (mask >> a & 1u) ? (v[a] == m ? xadd(tie, 0.0) : xadd(0.0, expl)) : 0.0;
+        p[a] = (mask >> a & 1u) ? ((ties >> a & 1u) ? top : low) : 0.0;
     }
   }
-  // inverse CDF: lane a tests cdf[a]/cdf[A-1] <= u, one division per lane instead of A-1 in series
+  // inverse CDF: lane a tests cdf[a]/cdf[A-1] <= u -- one division per lane instead of A-1 in
+  // series, and none when the total is exactly 1.0 (x/1.0 == x)
   double c = p[0], mine = p[0];
 #pragma unroll
   for (int a = 1; a < A; ++a) { c = xadd(c, p[a]); if (lane == a) mine = c; }
-  const bool le = (lane < A - 1) && (xdiv(mine, c) <= u);
+  if (c != 1.0) mine = xdiv(mine, c);
+  const bool le = (lane < A - 1) && (mine <= u);
   return __popc(__ballot_sync(kFull, le));
 }
 
@@ -143,16 +160,14 @@ COBEL_DEV int select_action_warp(const double (&v)[A], uint32_t mask, const Poli
 //              same round is fine because every round reads, syncs, then writes)
 // Rounds execute all currently ready lanes at once; each update sees exactly the values it
 // would see in sequential order, so the result is bit-identical to the sequential loop.
-// `wm`/`rm` are per-agent scratch arrays of S words in shared memory.
+// `wm`/`rm` are per-agent scratch arrays of S words in shared memory, zero between calls.
 // ---------------------------------------------------------------------------
 template <int A>
 COBEL_DEV void td_batch_level_parallel(double* Q, uint32_t* wm, uint32_t* rm, int S, int lane, bool active,
                                        int s, int a, double r, int s2, int nt, double lr, double gamma) {
   const unsigned act = __ballot_sync(kFull, active);
   const unsigned below = (1u << lane) - 1u;
-  // writers / readers per state
-  for (int e = lane; e < S; e += 32) { wm[e] = 0; rm[e] = 0; }
-  __syncwarp();
+  // writers / readers per state (wm / rm are all-zero on entry and are re-zeroed on exit)
   if (active) {
     // all lanes with the same key store the same mask: a benign same-value race
     wm[s] = __match_any_sync(act, s);
@@ -165,6 +180,8 @@ COBEL_DEV void td_batch_level_parallel(double* Q, uint32_t* wm, uint32_t* rm, in
     strict = (wm[s2] | same_sa) & below;                            // i writes into the row j reads
     weak = rm[s] & below;                                           // j writes into the row i reads
   }
+  __syncwarp();
+  if (active) { wm[s] = 0; rm[s2] = 0; }
   const double g = nt ? gamma : 0.0;
   unsigned done = ~act;
   while (done != kFull) {
