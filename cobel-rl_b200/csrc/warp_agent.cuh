@@ -39,6 +39,7 @@ struct DrawWindow {
   uint32_t key0, key1;
   uint64_t base;          // stream index of window slot 0 (even)
   int off;                // window slot of the next draw: k = base + off
+  int cap;                // slots filled (0 = empty, 64 after a refill)
   double ua, ub;          // this lane's two draws: slots 2*lane and 2*lane+1
   const double* user;     // optional pre-drawn stream of this agent
   int64_t user_len;
@@ -48,15 +49,15 @@ struct DrawWindow {
     key0 = (uint32_t)s.seed; key1 = (uint32_t)(s.seed >> 32);
     user = s.user_stream ? s.user_stream + local_agent * s.user_stream_len : nullptr;
     user_len = s.user_stream_len;
-    base = k; off = 64;     // empty: the first ensure() refills
+    base = k; off = 0; cap = 0;     // empty: the first ensure() refills
     ua = ub = 0.0;
   }
   COBEL_DEV uint64_t position() const { return base + (uint64_t)off; }
   // make the next `need` draws available (need <= 63); warp-uniform
   COBEL_DEV void ensure(int need, int lane) {
-    if (user || off + need <= 64) return;
+    if (user || off + need <= cap) return;
     const uint64_t k = base + (uint64_t)off;
-    base = k & ~1ull; off = (int)(k & 1ull);
+    base = k & ~1ull; off = (int)(k & 1ull); cap = 64;
     const uint64_t b = (base >> 1) + lane;
     uint32_t o[4];
     philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)agent, (uint32_t)(agent >> 32), key0, key1, o);
