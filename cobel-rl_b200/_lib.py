@@ -43,8 +43,15 @@ class DynaQParams(C.Structure):
                 ('learn', C.c_int32), ('no_replay', C.c_int32), ('episodic_replay', C.c_int32)]
 
 
+class QParams(C.Structure):
+    _fields_ = [('n_agents', C.c_int64), ('world', World), ('stream', Stream), ('policy', Policy),
+                ('trace', Trace), ('Q', c_ptr), ('obs_key', c_ptr), ('n_keys', C.c_int32), ('reserved', C.c_int32),
+                ('log', c_ptr), ('log_cap', C.c_int64), ('log_len', c_ptr), ('lr', c_ptr), ('gamma', c_ptr),
+                ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32), ('learn', C.c_int32)]
+
+
 STRUCTS = {'CobelWorld': World, 'CobelStream': Stream, 'CobelPolicy': Policy, 'CobelTrace': Trace,
-           'CobelDynaQParams': DynaQParams}
+           'CobelDynaQParams': DynaQParams, 'CobelQParams': QParams}
 
 _SIGNATURES = {
     'cobel_sizeof': (C.c_size_t, [C.c_char_p]),
@@ -54,6 +61,7 @@ _SIGNATURES = {
     'cobel_draw_uniforms': (C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, c_ptr, c_ptr]),
     'cobel_stream_next': (C.c_int, [C.POINTER(Stream), C.c_int64, C.c_int64, c_ptr, c_ptr]),
     'cobel_dynaq_run': (C.c_int, [C.POINTER(DynaQParams), c_ptr]),
+    'cobel_q_run': (C.c_int, [C.POINTER(QParams), c_ptr]),
 }
 
 _lib = None

@@ -1,3 +1,4 @@
 """Tabular agents of the hot path (reference: cobel/agent/__init__.py)."""
 from .agent import Agent, Callbacks  # noqa: F401
 from .dyna_q import DynaQ  # noqa: F401
+from .q import QAgent  # noqa: F401

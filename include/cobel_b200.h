@@ -122,6 +122,29 @@ typedef struct CobelDynaQParams {
 
 int cobel_dynaq_run(const CobelDynaQParams* p, void* stream);
 
+/* ---- QAgent: agent/q.py:115-354 (tabular Q-learning, append-only experience log) -------- */
+typedef struct CobelQParams {
+  int64_t n_agents;
+  CobelWorld world;          /* Gridworld tables or Topology graph (neighbors -> succ) */
+  CobelStream stream;
+  CobelPolicy policy;
+  CobelTrace trace;          /* replay_idx holds log indices */
+  double*  Q;                /* [N, n_keys, A] rows keyed by observation (agent.Q dict, q.py:142,197-204) */
+  const int32_t* obs_key;    /* [S] node/state -> Q row; NULL = identity */
+  int32_t  n_keys;
+  int32_t  reserved;
+  void*    log;              /* [N, log_cap] 16-byte records {f64 reward; u16 state, next_state; u8 action,
+                                nonterminal; u16 pad} = agent.M (q.py:143,213) */
+  int64_t  log_cap;
+  int64_t* log_len;          /* [N] in/out: experiences stored so far */
+  const double* lr;          /* [N] */
+  const double* gamma;       /* [N] */
+  int32_t trials, steps, batch;
+  int32_t learn;             /* 1 = train(), 0 = test() */
+} CobelQParams;
+
+int cobel_q_run(const CobelQParams* p, void* stream);
+
 /* ---- utilities -------------------------------------------------------------- */
 int  cobel_abi_version(void);
 /* Copy the last error message of this thread into buf (NUL-terminated). */

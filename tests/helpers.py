@@ -179,4 +179,14 @@ def cuda_case(name, n_extra=2, device='cuda:0'):
         out['draws_after_test'] = int(stream.draw_count[0])
         assert not a, 'unused case arguments %s' % a
         return out
+    if kind in ('q_grid', 'q_topo'):
+        ag = AG.QAgent(env.observation_space, env.action_space, pol, None, a.pop('lr', 0.9), a.pop('gamma', 0.8),
+                       rng=stream)
+        ag.record = True
+        res = ag.train(env, trials, steps, a.pop('batch'))
+        torch.cuda.synchronize()
+        out = unpack_run(res, 0, A, succ, reward)
+        out.update(Q=ag._Q[0].cpu().numpy(), draws=int(stream.draw_count[0]), log_len=int(ag._log_len[0]))
+        assert not a, 'unused case arguments %s' % a
+        return out
     raise ValueError(kind)
