@@ -50,8 +50,15 @@ class QParams(C.Structure):
                 ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32), ('learn', C.c_int32)]
 
 
+class SRParams(C.Structure):
+    _fields_ = [('n_agents', C.c_int64), ('world', World), ('stream', Stream), ('policy', Policy),
+                ('trace', Trace), ('SR', c_ptr), ('rewards', c_ptr), ('model', c_ptr), ('action_mask', c_ptr),
+                ('mask_agent_stride', C.c_int64), ('lr', c_ptr), ('gamma', c_ptr), ('trials', C.c_int32),
+                ('steps', C.c_int32), ('learn', C.c_int32), ('reserved', C.c_int32)]
+
+
 STRUCTS = {'CobelWorld': World, 'CobelStream': Stream, 'CobelPolicy': Policy, 'CobelTrace': Trace,
-           'CobelDynaQParams': DynaQParams, 'CobelQParams': QParams}
+           'CobelDynaQParams': DynaQParams, 'CobelQParams': QParams, 'CobelSRParams': SRParams}
 
 _SIGNATURES = {
     'cobel_sizeof': (C.c_size_t, [C.c_char_p]),
@@ -62,6 +69,7 @@ _SIGNATURES = {
     'cobel_stream_next': (C.c_int, [C.POINTER(Stream), C.c_int64, C.c_int64, c_ptr, c_ptr]),
     'cobel_dynaq_run': (C.c_int, [C.POINTER(DynaQParams), c_ptr]),
     'cobel_q_run': (C.c_int, [C.POINTER(QParams), c_ptr]),
+    'cobel_sr_run': (C.c_int, [C.POINTER(SRParams), c_ptr]),
 }
 
 _lib = None

@@ -1,0 +1,244 @@
+// sr.cu -- K3: SR.train()/test() (tabular successor-representation agent) for N independent
+// agents in one launch.
+//
+// Reference: agent/sr.py:142-308.  Per step
+//   Q[a] = np.sum(SR * rewards, axis=1)[m(s,a)]  with m = the learned one-hot transition model
+//          (sr.py:288-308; only the A modelled-successor rows are evaluated here, each as the
+//          same NumPy pairwise sum -- SURVEY.md Appendix A.3/A.5),
+//   action selection, environment step,
+//   rewards[s'] += (r - rewards[s']) * lr;  model[s,a] = s'                      (sr.py:272-274)
+//   td = e_s + gamma * (SR[s'] if non-terminal else e_s') - SR[s];  SR[s] += lr * td   (276-284)
+//
+// Mapping: one CTA per agent, threads parallel over the S columns of a row.  SR stays in HBM
+// (S*S*8 bytes per agent: 5 KB at 5x5, 1.28 MB at 20x20) and is streamed through L1/L2 with
+// coalesced fp64 row accesses: A+2 row reads and one row write per step (8S(A+4) algorithmic
+// bytes); rewards / model / Q scratch live in shared memory.
+#include "warp_agent.cuh"
+
+namespace {
+
+constexpr int kMaxLeaves = 64;     // pairwise-sum leaves of <=128 elements: S <= 8192
+
+// NumPy's pairwise summation (DOUBLE_add reduce) as a plan: leaves of 8..128 elements are summed
+// with 8 strided accumulators + a sequential tail; leaf results are combined by the recursion
+// `sum(n) = sum(first n2) + sum(rest)`, n2 = n/2 - (n/2)%8, flattened here in post-order.
+struct PairwisePlan {
+  int n, nl, nc;
+  int start[kMaxLeaves + 1];
+  short left[kMaxLeaves], right[kMaxLeaves];
+};
+
+int plan_rec(PairwisePlan& pl, int lo, int n) {
+  if (n <= 128) {
+    if (pl.nl >= kMaxLeaves) return -1;
+    pl.start[pl.nl] = lo;
+    pl.start[pl.nl + 1] = lo + n;
+    return pl.nl++;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  const int l = plan_rec(pl, lo, n2);
+  const int r = plan_rec(pl, lo + n2, n - n2);
+  if (l < 0 || r < 0) return -1;
+  pl.left[pl.nc] = (short)l; pl.right[pl.nc] = (short)r;
+  ++pl.nc;
+  return l;              // the sum of the subtree is accumulated into its left-most leaf slot
+}
+
+bool make_plan(PairwisePlan& pl, int n) {
+  pl.n = n; pl.nl = 0; pl.nc = 0;
+  return plan_rec(pl, 0, n) >= 0;
+}
+
+struct SRSmem {
+  int rew, prod, acc, leaf, q, model, bytes;
+  __host__ __device__ SRSmem(int S, int A, int nl) {
+    rew = 0;
+    prod = rew + S * 8;
+    acc = prod + A * S * 8;
+    leaf = acc + A * nl * 8 * 8;
+    q = leaf + A * nl * 8;
+    model = q + A * 8;
+    bytes = (model + S * A * 4 + 15) & ~15;
+  }
+};
+
+template <int A>
+__global__ void __launch_bounds__(256) sr_kernel(const __grid_constant__ CobelSRParams p, const __grid_constant__ PairwisePlan pl) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int S = p.world.n_states, K = p.world.n_starts;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+  const int64_t n = blockIdx.x;
+  const SRSmem so(S, A, pl.nl);
+  double* rew = reinterpret_cast<double*>(smem + so.rew);
+  double* prod = reinterpret_cast<double*>(smem + so.prod);      // [A][S] products SR[m_a, j] * rew[j]
+  double* acc = reinterpret_cast<double*>(smem + so.acc);        // [A][nl][8]
+  double* leaf = reinterpret_cast<double*>(smem + so.leaf);      // [A][nl]
+  double* qv = reinterpret_cast<double*>(smem + so.q);           // [A]
+  int32_t* model = reinterpret_cast<int32_t*>(smem + so.model);  // [S][A] modelled successor
+
+  double* SR = p.SR + (size_t)n * S * S;
+  for (int e = tid; e < S; e += T) rew[e] = p.rewards[(size_t)n * S + e];
+  for (int e = tid; e < S * A; e += T) model[e] = p.model[(size_t)n * S * A + e];
+  __syncthreads();
+
+  DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
+  const double lr = p.lr[n], gamma = p.gamma[n];
+  PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
+  const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
+  const bool learn = p.learn != 0;
+  const CobelTrace& tr = p.trace;
+  int64_t nsteps = 0;
+  int flags = 0;
+  const int nl = pl.nl;
+
+  for (int trial = 0; trial < p.trials; ++trial) {
+    win.ensure(2, lane);
+    int s = __ldg(p.world.starts + draw_integer(win.next(), K));
+    double treward = 0.0;
+    int step = 0;
+    for (;; ++step) {
+      // ---- retrieve_q: A row dots in NumPy's pairwise order --------------------------------
+      for (int e = tid; e < A * S; e += T) {
+        const int a = e / S, j = e - a * S;
+        prod[e] = xmul(SR[(size_t)model[s * A + a] * S + j], rew[j]);
+      }
+      __syncthreads();
+      for (int t = tid; t < A * nl * 8; t += T) {          // 8 strided accumulators per leaf
+        const int a = t / (nl * 8), l = (t / 8) % nl, k = t & 7;
+        const int lo = pl.start[l], len = pl.start[l + 1] - lo;
+        const double* x = prod + a * S + lo;
+        double r = 0.0;
+        if (len >= 8) {
+          r = x[k];
+          for (int i = 8 + k; i < len - (len & 7); i += 8) r = xadd(r, x[i]);
+        }
+        acc[t] = r;
+      }
+      __syncthreads();
+      for (int t = tid; t < A * nl; t += T) {              // combine + sequential tail
+        const int a = t / nl, l = t - a * nl;
+        const int lo = pl.start[l], len = pl.start[l + 1] - lo;
+        const double* x = prod + a * S + lo;
+        const double* r = acc + t * 8;
+        double res;
+        int i;
+        if (len < 8) {
+          res = 0.0; i = 0;
+        } else {
+          res = xadd(xadd(xadd(r[0], r[1]), xadd(r[2], r[3])), xadd(xadd(r[4], r[5]), xadd(r[6], r[7])));
+          i = len - (len & 7);
+        }
+        for (; i < len; ++i) res = xadd(res, x[i]);
+        leaf[t] = res;
+      }
+      __syncthreads();
+      if (tid < A) {                                       // recursion over the leaves, post-order
+        double* L = leaf + tid * nl;
+        for (int c = 0; c < pl.nc; ++c) L[pl.left[c]] = xadd(L[pl.left[c]], L[pl.right[c]]);
+        qv[tid] = L[0];
+      }
+      __syncthreads();
+      // ---- action selection and environment step: every warp computes the same (warp-uniform)
+      // result, which keeps all warps' stream windows in lock-step without a broadcast ---------
+      win.ensure(1, lane);
+      double row[A];
+#pragma unroll
+      for (int x = 0; x < A; ++x) row[x] = qv[x];
+      uint32_t mask = (1u << A) - 1u;
+      if (amask) {
+        mask = 0;
+#pragma unroll
+        for (int x = 0; x < A; ++x) mask |= (amask[s * A + x] ? 1u : 0u) << x;
+      }
+      const int a = select_action_warp<A>(row, mask, pt, win.next(), lane);
+      const int s2 = __ldg(p.world.succ + s * A + a);
+      const double r = __ldg(p.world.reward + s2);
+      const int end = __ldg(p.world.terminal + s2);
+      if (tr.step_sa && tid == 0) {
+        if (nsteps < tr.step_cap) tr.step_sa[n * tr.step_cap + nsteps] = s * A + a;
+        else flags |= COBEL_FLAG_TRACE_OVERFLOW;
+      }
+      ++nsteps;
+      if (learn) {
+        // ---- SR.update (sr.py:255-286): every thread owns columns j = tid, tid+T, ... ----------
+        const double* rs = SR + (size_t)s * S;
+        const double* rs2 = SR + (size_t)s2 * S;
+        double* wr = SR + (size_t)s * S;
+        for (int j = tid; j < S; j += T) {
+          const double old = rs[j];
+          const double x = end ? (j == s2 ? 1.0 : 0.0) : rs2[j];
+          double td = xadd(j == s ? 1.0 : 0.0, xmul(gamma, x));
+          td = xsub(td, old);
+          // all reads of row s (as SR[s] and, when s2 == s, as SR[s2]) precede this write of column j
+          wr[j] = xadd(old, xmul(lr, td));
+        }
+        if (tid == 0) {
+          const double r0 = rew[s2];
+          rew[s2] = xadd(r0, xmul(xsub(r, r0), lr));
+          model[s * A + a] = s2;
+        }
+        __syncthreads();
+      }
+      s = s2;
+      treward = xadd(treward, r);
+      if (end || step + 1 == p.steps) break;
+    }
+    if (tid == 0) {
+      tr.trial_steps[n * p.trials + trial] = step;
+      tr.trial_reward[n * p.trials + trial] = treward;
+    }
+  }
+
+  __syncthreads();
+  if (learn) {
+    for (int e = tid; e < S; e += T) p.rewards[(size_t)n * S + e] = rew[e];
+    for (int e = tid; e < S * A; e += T) p.model[(size_t)n * S * A + e] = model[e];
+  }
+  if (tid == 0) {
+    p.stream.draw_count[n] = (int64_t)win.position();
+    tr.n_steps[n] += nsteps;
+    if (tr.flags && flags) tr.flags[n] |= flags;
+  }
+}
+
+template <int A>
+int launch(const CobelSRParams& p, cudaStream_t st) {
+  const int S = p.world.n_states;
+  PairwisePlan pl;
+  COBEL_REQUIRE(make_plan(pl, S), COBEL_EUNSUPPORTED, "dense SR kernel supports at most %d states", kMaxLeaves * 128);
+  const SRSmem so(S, A, pl.nl);
+  COBEL_REQUIRE(so.bytes <= 227 * 1024, COBEL_EUNSUPPORTED, "dense SR kernel: %d states need %d bytes of shared memory",
+                S, so.bytes);
+  COBEL_CUDA_OK(cudaFuncSetAttribute(sr_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, so.bytes));
+  const int T = S <= 32 ? 32 : S <= 64 ? 64 : S <= 256 ? 128 : 256;
+  sr_kernel<A><<<(unsigned)p.n_agents, T, so.bytes, st>>>(p, pl);
+  cobel_count_launch();
+  COBEL_CUDA_OK(cudaGetLastError());
+  return COBEL_OK;
+}
+
+}  // namespace
+
+int cobel_validate_common(int64_t n_agents, const CobelWorld& w, const CobelStream& s, const CobelPolicy& pol,
+                          const CobelTrace& tr, int trials, int steps);
+
+extern "C" int cobel_sr_run(const CobelSRParams* pp, void* stream) {
+  COBEL_REQUIRE(pp != nullptr, COBEL_EINVAL, "null params");
+  const CobelSRParams& p = *pp;
+  int rc = cobel_validate_common(p.n_agents, p.world, p.stream, p.policy, p.trace, p.trials, p.steps);
+  if (rc) return rc;
+  COBEL_REQUIRE(p.SR && p.rewards && p.model && p.lr && p.gamma, COBEL_EINVAL, "agent tables missing");
+  if (p.trials == 0) return COBEL_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (p.world.n_actions) {
+    case 2: return launch<2>(p, st);
+    case 3: return launch<3>(p, st);
+    case 4: return launch<4>(p, st);
+    case 6: return launch<6>(p, st);
+    case 8: return launch<8>(p, st);
+    default:
+      cobel_set_error("unsupported number of actions %d (built for 2,3,4,6,8)", p.world.n_actions);
+      return COBEL_EUNSUPPORTED;
+  }
+}

@@ -145,6 +145,27 @@ typedef struct CobelQParams {
 
 int cobel_q_run(const CobelQParams* p, void* stream);
 
+/* ---- SR agent: agent/sr.py:109-324 (dense successor representation) ---------------------- */
+typedef struct CobelSRParams {
+  int64_t n_agents;
+  CobelWorld world;
+  CobelStream stream;
+  CobelPolicy policy;
+  CobelTrace trace;
+  double*  SR;               /* [N,S,S] agent.SR (init: identity) */
+  double*  rewards;          /* [N,S]   agent.rewards (learned reward per state) */
+  int32_t* model;            /* [N,S,A] arg-max of agent.transitions[s,a,:] (init: s) */
+  const uint8_t* action_mask;/* [S,A] or [N,S,A]; NULL = mask_actions False */
+  int64_t  mask_agent_stride;
+  const double* lr;          /* [N] */
+  const double* gamma;       /* [N] */
+  int32_t trials, steps;
+  int32_t learn;             /* 1 = train(), 0 = test() */
+  int32_t reserved;
+} CobelSRParams;
+
+int cobel_sr_run(const CobelSRParams* p, void* stream);
+
 /* ---- utilities -------------------------------------------------------------- */
 int  cobel_abi_version(void);
 /* Copy the last error message of this thread into buf (NUL-terminated). */

@@ -189,4 +189,17 @@ def cuda_case(name, n_extra=2, device='cuda:0'):
         out.update(Q=ag._Q[0].cpu().numpy(), draws=int(stream.draw_count[0]), log_len=int(ag._log_len[0]))
         assert not a, 'unused case arguments %s' % a
         return out
+    if kind == 'sr':
+        ag = AG.SR(env.observation_space, env.action_space, pol, None, a.pop('lr', 0.1), a.pop('gamma', 0.99))
+        ag.mask_actions = a.pop('mask_actions', False)
+        if valid_mask:
+            ag.action_mask = tb.valid_move_mask(succ)
+        ag.record = True
+        res = ag.train(env, trials, steps)
+        torch.cuda.synchronize()
+        out = unpack_run(res, 0, A, succ, reward)
+        out.update(SR=ag._SR[0].cpu().numpy(), rew=ag._rewards[0].cpu().numpy(), model=ag._model[0].cpu().numpy(),
+                   draws=int(stream.draw_count[0]))
+        assert not a, 'unused case arguments %s' % a
+        return out
     raise ValueError(kind)
