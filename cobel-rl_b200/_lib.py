@@ -57,8 +57,20 @@ class SRParams(C.Structure):
                 ('steps', C.c_int32), ('learn', C.c_int32), ('reserved', C.c_int32)]
 
 
+class SFMAParams(C.Structure):
+    _fields_ = [('n_agents', C.c_int64), ('world', World), ('stream', Stream), ('policy', Policy),
+                ('trace', Trace), ('Q', c_ptr), ('Mr', c_ptr), ('Ms', c_ptr), ('Mt', c_ptr), ('C', c_ptr),
+                ('T', c_ptr), ('I', c_ptr), ('D', c_ptr), ('action_mask', c_ptr), ('mask_agent_stride', C.c_int64),
+                ('lr', c_ptr), ('gamma', c_ptr), ('mem_lr', c_ptr), ('beta', C.c_double), ('threshold', C.c_double),
+                ('decay_inhibition', C.c_double), ('decay_strength', C.c_double), ('decay_recency', C.c_double),
+                ('c_step', C.c_double), ('i_step', C.c_double), ('blend', C.c_double), ('interp_fwd', C.c_double),
+                ('interp_rev', C.c_double), ('mode', C.c_int32), ('recency', C.c_int32), ('deterministic', C.c_int32),
+                ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32), ('nb_replays', C.c_int32),
+                ('start_replay', C.c_int32), ('no_replay', C.c_int32), ('learn', C.c_int32)]
+
+
 STRUCTS = {'CobelWorld': World, 'CobelStream': Stream, 'CobelPolicy': Policy, 'CobelTrace': Trace,
-           'CobelDynaQParams': DynaQParams, 'CobelQParams': QParams, 'CobelSRParams': SRParams}
+           'CobelDynaQParams': DynaQParams, 'CobelQParams': QParams, 'CobelSRParams': SRParams, 'CobelSFMAParams': SFMAParams}
 
 _SIGNATURES = {
     'cobel_sizeof': (C.c_size_t, [C.c_char_p]),
@@ -70,6 +82,7 @@ _SIGNATURES = {
     'cobel_dynaq_run': (C.c_int, [C.POINTER(DynaQParams), c_ptr]),
     'cobel_q_run': (C.c_int, [C.POINTER(QParams), c_ptr]),
     'cobel_sr_run': (C.c_int, [C.POINTER(SRParams), c_ptr]),
+    'cobel_sfma_run': (C.c_int, [C.POINTER(SFMAParams), c_ptr]),
 }
 
 _lib = None

@@ -3,3 +3,4 @@ from .agent import Agent, Callbacks  # noqa: F401
 from .dyna_q import DynaQ  # noqa: F401
 from .q import QAgent  # noqa: F401
 from .sr import SR  # noqa: F401
+from .sfma import SFMA  # noqa: F401

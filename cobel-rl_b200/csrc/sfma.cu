@@ -1,0 +1,438 @@
+// sfma.cu -- K5: SFMA.train()/test() (Dyna-Q with SFMA replay: strength x similarity x
+// inhibition sampling over a state-similarity metric D) for N independent agents in one launch.
+//
+// Reference: agent/sfma.py:233-458 (trial loop, replay, masked update_q) and
+// memory/sfma.py:195-373 (store, replay, softmax).  Semantics: SURVEY.md Appendix A.6.
+//
+// Mapping: one CTA per agent; all per-agent tables (Q, M.rewards, M.states|terminals, C, I and
+// the priority scratch R) live in shared memory, the shared similarity matrix D[S,S] is read
+// from HBM/L2 one row at a time (coalesced).  The online steps of a trial are executed by
+// warp 0 (warp-uniform, as in the Dyna-Q kernel); each replay reactivation is a CTA-wide pass
+// over the S*A experiences: priority R = C*D*(1-I) -> threshold -> max -> exp -> inverse-CDF
+// draw by a block scan -> inhibition update.  The replayed TD updates are applied afterwards,
+// in order, by the level-parallel batch of warp_agent.cuh.
+//
+// Exactness: every quantity that reaches Q, C, I or an integer is computed with the
+// reference's operation order; exp() and the CDF prefix sums are not bit-identical to NumPy's
+// and only decide the sampled index, so a draw that falls within 1e-12 of a bin edge raises
+// COBEL_FLAG_CDF_NEAR_TIE instead of silently risking a different index.
+#include "warp_agent.cuh"
+
+namespace {
+
+enum { MODE_DEFAULT = 0, MODE_FORWARD, MODE_REVERSE, MODE_BLEND_FORWARD, MODE_BLEND_REVERSE, MODE_INTERPOLATE, MODE_SWEEPING };
+
+struct SfmaSmem {
+  int q, mr, c, t, r, inh, part, mx, mbits, rep, bytes;
+  __host__ __device__ SfmaSmem(int S, int A, int T, int B, bool recency) {
+    const int N = S * A;
+    q = 0;
+    mr = q + N * 8;
+    c = mr + N * 8;
+    t = c + N * 8;
+    r = t + (recency ? N * 8 : 0);
+    inh = r + N * 8;
+    part = inh + S * 8;
+    rep = part + (T + 32) * 8;
+    mx = rep + ((B + 1) & ~1) * 4;
+    mbits = mx + N * 2;
+    bytes = (mbits + S + 15) & ~15;
+  }
+};
+
+struct BlockShared {
+  double u, total, target;
+  int idx, flag, action, last, brk;
+};
+
+// Exclusive block scan of one double per thread (T <= 1024); also returns the grand total.
+COBEL_DEV double block_exclusive_scan(double v, double* part, int tid, int T, double& total) {
+  const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  double inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double o = shfl_f64_up(inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) part[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    double w = lane < nw ? part[lane] : 0.0;
+    double winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double o = shfl_f64_up(winc, d);
+      if (lane >= d) winc += o;
+    }
+    if (lane < nw) part[lane] = winc - w;          // exclusive offset of each warp
+    if (lane == 31) part[32] = winc;               // grand total
+  }
+  __syncthreads();
+  total = part[32];
+  const double res = part[warp] + (inc - v);
+  __syncthreads();                                  // part[] may be reused by the caller
+  return res;
+}
+
+// Inverse-CDF draw over non-negative weights w[0..N): the first i whose running sum / total
+// exceeds u  (NumPy: searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right') with p = w/sum(w)).
+COBEL_DEV int block_sample(const double* w, int N, double u, double* part, BlockShared* sh, int tid, int T, int& flags) {
+  const int chunk = (N + T - 1) / T;
+  const int lo = tid * chunk < N ? tid * chunk : N, hi = lo + chunk < N ? lo + chunk : N;
+  double local = 0.0;
+  for (int i = lo; i < hi; ++i) local += w[i];
+  double total;
+  const double excl = block_exclusive_scan(local, part, tid, T, total);
+  const double target = u * total;
+  const double tol = 1e-12 * total;
+  if (tid == 0) { sh->idx = 0x7fffffff; sh->flag = 0; }
+  __syncthreads();
+  // owner = the first thread whose running sum passes the target
+  if (local > 0.0 && excl + local > target) atomicMin(&sh->idx, tid);
+  __syncthreads();
+  const int owner = sh->idx;
+  __syncthreads();
+  if (owner == 0x7fffffff) {                       // u*total rounded up to the total: the last positive weight
+    if (tid == 0) {
+      int f = N - 1;
+      while (f > 0 && !(w[f] > 0.0)) --f;
+      sh->idx = f; sh->flag = 1;
+    }
+  } else if (tid == owner) {
+    double acc = excl;
+    int found = -1, lastpos = lo;
+    bool near = fabs(excl - target) < tol;
+    for (int i = lo; i < hi; ++i) {
+      if (!(w[i] > 0.0)) continue;
+      lastpos = i;
+      acc += w[i];
+      if (fabs(acc - target) < tol) near = true;
+      if (found < 0 && acc > target) found = i;
+    }
+    sh->idx = found >= 0 ? found : lastpos;
+    if (near || found < 0) sh->flag = 1;
+  }
+  __syncthreads();
+  const int idx = sh->idx;
+  if (sh->flag) flags |= COBEL_FLAG_CDF_NEAR_TIE;
+  __syncthreads();
+  return idx;
+}
+
+template <int A>
+__global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ CobelSFMAParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ BlockShared sh;
+  const int S = p.world.n_states, K = p.world.n_starts, N = S * A, B = p.batch;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n = blockIdx.x;
+  const bool recency = p.recency != 0;
+  const SfmaSmem so(S, A, T, B, recency);
+  double* Q = reinterpret_cast<double*>(smem + so.q);        // [s][a]
+  double* Mr = reinterpret_cast<double*>(smem + so.mr);      // [s][a]
+  double* C = reinterpret_cast<double*>(smem + so.c);        // [a*S + s]
+  double* Tr = reinterpret_cast<double*>(smem + so.t);       // [a*S + s] (only when recency)
+  double* R = reinterpret_cast<double*>(smem + so.r);        // scratch [a*S + s]
+  double* I = reinterpret_cast<double*>(smem + so.inh);      // [s]
+  double* part = reinterpret_cast<double*>(smem + so.part);
+  int32_t* rep = reinterpret_cast<int32_t*>(smem + so.rep);  // reactivated flat indices of one replay
+  uint16_t* Mx = reinterpret_cast<uint16_t*>(smem + so.mx);  // [s][a] next state | non-terminal << 15
+  uint8_t* mbits = smem + so.mbits;                          // [s] valid-action bits
+  // dependency scratch of the level-parallel batch aliases the (then idle) priority scratch
+  uint32_t* wm = reinterpret_cast<uint32_t*>(R);
+  uint32_t* rm = wm + S;
+
+  const size_t g0 = (size_t)n * N;
+  const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
+  for (int e = tid; e < N; e += T) {
+    Q[e] = p.Q[g0 + e];
+    Mr[e] = p.Mr[g0 + e];
+    Mx[e] = (uint16_t)(p.Ms[g0 + e] | ((p.Mt[g0 + e] ? 1 : 0) << 15));
+    C[e] = p.C[g0 + e];
+    if (recency) Tr[e] = p.T[g0 + e];
+  }
+  for (int e = tid; e < S; e += T) {
+    I[e] = p.I[(size_t)n * S + e];
+    uint32_t mb = (1u << A) - 1u;
+    if (amask) {
+      mb = 0;
+      for (int a = 0; a < A; ++a) mb |= (amask[e * A + a] ? 1u : 0u) << a;
+    }
+    mbits[e] = (uint8_t)mb;
+  }
+  __syncthreads();
+
+  DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);      // used by warp 0 only
+  const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
+  PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
+  const bool learn = p.learn != 0;
+  const bool masked = amask != nullptr;
+  const bool do_replay = learn && !p.no_replay;
+  const double beta = p.beta, thr = p.threshold, dinh = p.decay_inhibition, dstr = p.decay_strength, drec = p.decay_recency;
+  const CobelTrace& tr = p.trace;
+  int64_t nsteps = 0, nrep = 0, ncalls = 0;
+  int flags = 0;
+  const double* D = p.D;
+
+  // similarity of experience i = (a, s') to the current experience, by replay mode
+  // (memory/sfma.py:283-306)
+  auto dvec = [&](int i, int cur, int nxt) -> double {
+    const int a = i / S, sp = i - a * S;
+    const int ms = Mx[sp * A + a] & 0x7FFF;                 // states.flatten('F')[i]
+    const double* Dc = D + (size_t)cur * S;
+    const double* Dn = D + (size_t)nxt * S;
+    switch (p.mode) {
+      case MODE_FORWARD: return Dn[sp];
+      case MODE_REVERSE: return Dc[ms];
+      case MODE_BLEND_FORWARD: return xadd(Dc[sp], xmul(p.blend, Dn[sp]));
+      case MODE_BLEND_REVERSE: return xadd(Dc[sp], xmul(p.blend, Dc[ms]));
+      case MODE_INTERPOLATE: return xadd(xmul(p.interp_fwd, Dn[sp]), xmul(p.interp_rev, Dc[ms]));
+      case MODE_SWEEPING: return Dn[ms];
+      default: return Dc[sp];
+    }
+  };
+
+  // SFMAMemory.replay (memory/sfma.py:238-347) + the Q updates of SFMA.replay (agent/sfma.py:416-419)
+  auto replay = [&](int last) {
+    if (warp == 0) {
+      win.ensure(2, lane);
+      const int act0 = draw_integer(win.next(), A);                        // sfma.py:264 (always drawn)
+      double u = 0.0;
+      if (last < 0) u = win.next();                                        // sfma.py:272
+      if (lane == 0) { sh.action = act0; sh.u = u; }
+    }
+    __syncthreads();
+    int cur = last, action = sh.action;
+    if (cur < 0) {                                                         // start ~ clip(C, 0) / sum
+      for (int e = tid; e < N; e += T) R[e] = C[e] > 0.0 ? C[e] : 0.0;
+      __syncthreads();
+      const int e = block_sample(R, N, sh.u, part, &sh, tid, T, flags);
+      cur = e % S; action = e / S;
+    }
+    int nxt = Mx[cur * A + action] & 0x7FFF;
+    for (int e = tid; e < S; e += T) I[e] = 0.0;                           // sfma.py:277
+    __syncthreads();
+    int count = 0;
+    for (int it = 0; it < B; ++it) {
+      double lmax = 0.0;
+      for (int i = tid; i < N; i += T) {
+        const int a = i / S, sp = i - a * S;
+        double r = xmul(xmul(C[i], dvec(i, cur, nxt)), xsub(1.0, I[sp]));  // C * D * (1 - I)
+        if (recency) r = xmul(r, Tr[i]);
+        if (r < thr) r = 0.0;
+        R[i] = r;
+        lmax = r > lmax ? r : lmax;
+      }
+      // block max (R >= 0): all-zero <=> np.sum(R) == 0 (sfma.py:316)
+      for (int d = 16; d > 0; d >>= 1) { const double o = shfl_f64_xor(lmax, d); lmax = o > lmax ? o : lmax; }
+      if (lane == 0) part[warp] = lmax;
+      __syncthreads();
+      double m = part[0];
+      for (int w = 1; w < (T >> 5); ++w) m = part[w] > m ? part[w] : m;
+      __syncthreads();
+      if (!(m > 0.0)) break;
+      int e;
+      if (p.deterministic) {                                               // argmax(R): first maximum
+        if (tid == 0) sh.idx = 0x7fffffff;
+        __syncthreads();
+        for (int i = tid; i < N; i += T) if (R[i] == m) { atomicMin(&sh.idx, i); break; }
+        __syncthreads();
+        e = sh.idx;
+        __syncthreads();
+      } else {
+        // probs ~ exp(beta * R / max) - 1  (softmax(R, -1, beta), sfma.py:349-373)
+        for (int i = tid; i < N; i += T) R[i] = xadd(exp(xmul(xdiv(R[i], m), beta)), -1.0);
+        if (warp == 0) {
+          win.ensure(1, lane);
+          const double u = win.next();
+          if (lane == 0) sh.u = u;
+        }
+        __syncthreads();
+        e = block_sample(R, N, sh.u, part, &sh, tid, T, flags);
+      }
+      action = e / S;
+      cur = e - action * S;
+      nxt = Mx[cur * A + action] & 0x7FFF;
+      for (int s = tid; s < S; s += T) {                                   // sfma.py:333-335
+        double v = xmul(I[s], dinh);
+        if (s == cur) { v = xadd(v, p.i_step); v = v < 1.0 ? v : 1.0; }
+        I[s] = v;
+      }
+      if (tid == 0) rep[count] = e;
+      ++count;
+      __syncthreads();
+    }
+    // apply the reactivated experiences to Q in order (agent/sfma.py:416-419)
+    if (tr.replay_idx)
+      for (int j = tid; j < count; j += T) {
+        if (nrep + j < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + j] = rep[j];
+        else flags |= COBEL_FLAG_TRACE_OVERFLOW;
+      }
+    for (int e = tid; e < 2 * S; e += T) wm[e] = 0;                        // wm, rm alias R
+    __syncthreads();
+    if (warp == 0) {
+      for (int b0 = 0; b0 < count; b0 += 32) {
+        const bool active = b0 + lane < count;
+        int es = 0, ea = 0, es2 = 0, ent = 0;
+        double er = 0.0;
+        if (active) {
+          const int e = rep[b0 + lane];
+          ea = e / S; es = e - ea * S;
+          er = Mr[es * A + ea];
+          const uint16_t v = Mx[es * A + ea];
+          es2 = v & 0x7FFF; ent = v >> 15;
+        }
+        td_batch_level_parallel<A>(Q, wm, rm, S, lane, active, es, ea, er, es2, ent, lr, gamma,
+                                   masked ? mbits : nullptr);
+      }
+    }
+    if (tr.replay_len && tid == 0) {
+      if (ncalls < tr.replay_calls_cap) tr.replay_len[n * tr.replay_calls_cap + ncalls] = count;
+      else flags |= COBEL_FLAG_TRACE_OVERFLOW;
+    }
+    nrep += count;
+    ++ncalls;
+    __syncthreads();
+  };
+
+  for (int trial = 0; trial < p.trials; ++trial) {
+    // ---- reset (+ optional replay at trial start, agent/sfma.py:272-275) ------------------------
+    if (warp == 0) {
+      win.ensure(2, lane);
+      const int s0 = __ldg(p.world.starts + draw_integer(win.next(), K));
+      if (lane == 0) sh.last = s0;
+    }
+    __syncthreads();
+    int s = sh.last;
+    __syncthreads();
+    if (do_replay && p.start_replay) replay(s);
+    // ---- the online steps of the trial: warp 0, warp-uniform ---------------------------------
+    if (warp == 0) {
+      double treward = 0.0;
+      int step = 0, last = -1;
+      for (;; ++step) {
+        win.ensure(1, lane);
+        double row[A];
+        load_row<A>(Q + s * A, row);
+        const int a = select_action_warp<A>(row, mbits[s], pt, win.next(), lane);
+        const int s2 = __ldg(p.world.succ + s * A + a);
+        const double r = __ldg(p.world.reward + s2);
+        const int end = __ldg(p.world.terminal + s2);
+        const int nt = 1 - end;
+        if (tr.step_sa && lane == 0) {
+          if (nsteps < tr.step_cap) tr.step_sa[n * tr.step_cap + nsteps] = s * A + a;
+          else flags |= COBEL_FLAG_TRACE_OVERFLOW;
+        }
+        ++nsteps;
+        if (learn) {
+          // SFMAMemory.store (memory/sfma.py:206-215): EMA reward, next state, flag, strengths, recency
+          if (dstr != 1.0) for (int e = lane; e < N; e += 32) C[e] = xmul(C[e], dstr);
+          if (recency) for (int e = lane; e < N; e += 32) Tr[e] = xmul(Tr[e], drec);
+          const double m0 = Mr[s * A + a];
+          const double m1 = xadd(m0, xmul(mlr, xsub(r, m0)));
+          // SFMA.update_q (agent/sfma.py:423-458): max over the unmasked actions of s'
+          double row2[A];
+          load_row<A>(Q + s2 * A, row2);
+          const uint32_t mb = mbits[s2];
+          double mx = -__longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll
+          for (int x = 0; x < A; ++x) mx = (mb >> x & 1u) ? xmax(mx, row2[x]) : mx;
+          const double q = Q[s * A + a];
+          double td = xadd(r, xmul(nt ? gamma : 0.0, mx));
+          td = xsub(td, q);
+          const double qn = xadd(q, xmul(lr, td));
+          __syncwarp();
+          if (lane == 0) {
+            Mr[s * A + a] = m1;
+            Mx[s * A + a] = (uint16_t)(s2 | (nt << 15));
+            C[a * S + s] = xadd(C[a * S + s], p.c_step);
+            if (recency) Tr[a * S + s] = 1.0;
+            Q[s * A + a] = qn;
+          }
+          __syncwarp();
+        }
+        s = s2;
+        treward = xadd(treward, r);
+        if (end) last = s2;
+        if (end || step + 1 == p.steps) break;
+      }
+      if (lane == 0) {
+        tr.trial_steps[n * p.trials + trial] = step;
+        tr.trial_reward[n * p.trials + trial] = treward;
+        sh.last = last;
+      }
+    }
+    __syncthreads();
+    if (do_replay) {
+      const int last = sh.last;
+      for (int rpl = 0; rpl < p.nb_replays; ++rpl) replay(last);
+      if (recency) for (int e = tid; e < N; e += T) Tr[e] = 0.0;           // M.T.fill(0), agent/sfma.py:324
+      __syncthreads();
+    }
+  }
+
+  __syncthreads();
+  if (learn) {
+    for (int e = tid; e < N; e += T) {
+      p.Q[g0 + e] = Q[e];
+      p.Mr[g0 + e] = Mr[e];
+      p.Ms[g0 + e] = Mx[e] & 0x7FFF;
+      p.Mt[g0 + e] = Mx[e] >> 15;
+      p.C[g0 + e] = C[e];
+      // without the recency option T is never read; it is zero after every trial with replay
+      if (recency) p.T[g0 + e] = Tr[e];
+      else if (do_replay && p.trials > 0) p.T[g0 + e] = 0.0;
+    }
+    for (int e = tid; e < S; e += T) p.I[(size_t)n * S + e] = I[e];
+  }
+  flags = __syncthreads_or(flags);
+  if (tid == 0) {
+    p.stream.draw_count[n] = (int64_t)win.position();
+    tr.n_steps[n] += nsteps;
+    tr.n_replay[n] += nrep;
+    if (tr.flags && flags) tr.flags[n] |= flags;
+  }
+}
+
+template <int A>
+int launch(const CobelSFMAParams& p, cudaStream_t st) {
+  const int S = p.world.n_states, N = S * A;
+  COBEL_REQUIRE(S <= 0x7FFF, COBEL_EUNSUPPORTED, "SFMA kernel supports at most 32767 states");
+  const int T = N <= 128 ? 64 : N <= 512 ? 128 : 256;
+  const SfmaSmem so(S, A, T, p.batch, p.recency != 0);
+  COBEL_REQUIRE(so.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
+                "SFMA tables of %d states x %d actions need %d bytes of shared memory", S, A, so.bytes);
+  COBEL_CUDA_OK(cudaFuncSetAttribute(sfma_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, so.bytes));
+  sfma_kernel<A><<<(unsigned)p.n_agents, T, so.bytes, st>>>(p);
+  cobel_count_launch();
+  COBEL_CUDA_OK(cudaGetLastError());
+  return COBEL_OK;
+}
+
+}  // namespace
+
+int cobel_validate_common(int64_t n_agents, const CobelWorld& w, const CobelStream& s, const CobelPolicy& pol,
+                          const CobelTrace& tr, int trials, int steps);
+
+extern "C" int cobel_sfma_run(const CobelSFMAParams* pp, void* stream) {
+  COBEL_REQUIRE(pp != nullptr, COBEL_EINVAL, "null params");
+  const CobelSFMAParams& p = *pp;
+  int rc = cobel_validate_common(p.n_agents, p.world, p.stream, p.policy, p.trace, p.trials, p.steps);
+  if (rc) return rc;
+  COBEL_REQUIRE(p.Q && p.Mr && p.Ms && p.Mt && p.C && p.T && p.I && p.D && p.lr && p.gamma && p.mem_lr, COBEL_EINVAL,
+                "agent tables missing");
+  COBEL_REQUIRE(p.batch >= 0 && p.nb_replays >= 0, COBEL_EINVAL, "batch and nb_replays must be >= 0");
+  COBEL_REQUIRE(p.mode >= MODE_DEFAULT && p.mode <= MODE_SWEEPING, COBEL_EINVAL, "unknown replay mode %d", p.mode);
+  if (p.trials == 0) return COBEL_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (p.world.n_actions) {
+    case 2: return launch<2>(p, st);
+    case 3: return launch<3>(p, st);
+    case 4: return launch<4>(p, st);
+    case 6: return launch<6>(p, st);
+    case 8: return launch<8>(p, st);
+    default:
+      cobel_set_error("unsupported number of actions %d (built for 2,3,4,6,8)", p.world.n_actions);
+      return COBEL_EUNSUPPORTED;
+  }
+}

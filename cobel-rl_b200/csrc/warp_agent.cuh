@@ -14,6 +14,20 @@ COBEL_DEV double shfl_f64(double v, int src) {
   return __hiloint2double(hi, lo);
 }
 
+COBEL_DEV double shfl_f64_up(double v, int delta) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(kFull, lo, delta);
+  hi = __shfl_up_sync(kFull, hi, delta);
+  return __hiloint2double(hi, lo);
+}
+
+COBEL_DEV double shfl_f64_xor(double v, int m) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(kFull, lo, m);
+  hi = __shfl_xor_sync(kFull, hi, m);
+  return __hiloint2double(hi, lo);
+}
+
 // Row of A doubles from a 16-byte aligned table (A even -> LDS.128 / LDG.128).
 template <int A>
 COBEL_DEV void load_row(const double* r, double (&v)[A]) {
@@ -163,9 +177,12 @@ COBEL_DEV int select_action_warp(const double (&v)[A], uint32_t mask, const Poli
 // would see in sequential order, so the result is bit-identical to the sequential loop.
 // `wm`/`rm` are per-agent scratch arrays of S words in shared memory, zero between calls.
 // ---------------------------------------------------------------------------
+// `mbits` (optional) holds one byte per state with bit a set = action a may enter the max over
+// Q[s2,:] (SFMA.update_q honours the action mask, agent/sfma.py:440-449; DynaQ / QAgent do not).
 template <int A>
 COBEL_DEV void td_batch_level_parallel(double* Q, uint32_t* wm, uint32_t* rm, int S, int lane, bool active,
-                                       int s, int a, double r, int s2, int nt, double lr, double gamma) {
+                                       int s, int a, double r, int s2, int nt, double lr, double gamma,
+                                       const uint8_t* mbits = nullptr) {
   const unsigned act = __ballot_sync(kFull, active);
   const unsigned below = (1u << lane) - 1u;
   // writers / readers per state (wm / rm are all-zero on entry and are re-zeroed on exit)
@@ -199,7 +216,16 @@ COBEL_DEV void td_batch_level_parallel(double* Q, uint32_t* wm, uint32_t* rm, in
       double row[A];
       load_row<A>(Q + s2 * A, row);
       const double q = Q[s * A + a];
-      double td = xadd(r, xmul(g, row_max<A>(row)));
+      double mx;
+      if (mbits) {
+        const uint32_t mb = mbits[s2];
+        mx = -__longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll
+        for (int x = 0; x < A; ++x) mx = (mb >> x & 1u) ? xmax(mx, row[x]) : mx;
+      } else {
+        mx = row_max<A>(row);
+      }
+      double td = xadd(r, xmul(g, mx));
       td = xsub(td, q);
       qn = xadd(q, xmul(lr, td));
     }

@@ -166,6 +166,48 @@ typedef struct CobelSRParams {
 
 int cobel_sr_run(const CobelSRParams* p, void* stream);
 
+/* ---- SFMA: agent/sfma.py:189-474 + memory/sfma.py:21-416 --------------------------------- */
+enum { COBEL_SFMA_DEFAULT = 0, COBEL_SFMA_FORWARD = 1, COBEL_SFMA_REVERSE = 2, COBEL_SFMA_BLEND_FORWARD = 3,
+       COBEL_SFMA_BLEND_REVERSE = 4, COBEL_SFMA_INTERPOLATE = 5, COBEL_SFMA_SWEEPING = 6 };
+
+typedef struct CobelSFMAParams {
+  int64_t n_agents;
+  CobelWorld world;
+  CobelStream stream;
+  CobelPolicy policy;
+  CobelTrace trace;          /* replay_idx holds flat indices a*S + s; replay_len the length of each replay */
+  double*  Q;                /* [N,S,A] */
+  double*  Mr;               /* [N,S,A] M.rewards */
+  int32_t* Ms;               /* [N,S,A] M.states (init: self-loops) */
+  int32_t* Mt;               /* [N,S,A] M.terminals */
+  double*  C;                /* [N,S*A] M.C experience strengths, index a*S + s */
+  double*  T;                /* [N,S*A] M.T recency */
+  double*  I;                /* [N,S]   M.I inhibition */
+  const double* D;           /* [S,S]   metric.D similarity matrix, shared by all agents */
+  const uint8_t* action_mask;/* [S,A] or [N,S,A]; NULL = mask_actions False */
+  int64_t  mask_agent_stride;
+  const double* lr;          /* [N] agent.learning_rate */
+  const double* gamma;       /* [N] agent.gamma */
+  const double* mem_lr;      /* [N] M.learning_rate */
+  double beta;               /* M.beta (20) */
+  double threshold;          /* M.R_threshold (1e-6) */
+  double decay_inhibition;   /* M.decay_inhibition (0.9) */
+  double decay_strength;     /* M.decay_strength (1.0) */
+  double decay_recency;      /* M.decay_recency (0.9) */
+  double c_step, i_step;     /* M.C_step, M.I_step (1.0) */
+  double blend, interp_fwd, interp_rev;   /* M.blend, M.interpolation_fwd / _rev */
+  int32_t mode;              /* COBEL_SFMA_* (M.mode) */
+  int32_t recency;           /* M.recency */
+  int32_t deterministic;     /* M.deterministic */
+  int32_t trials, steps, batch;
+  int32_t nb_replays;        /* agent.nb_replays */
+  int32_t start_replay;      /* agent.start_replay */
+  int32_t no_replay;
+  int32_t learn;             /* 1 = train(), 0 = test() */
+} CobelSFMAParams;
+
+int cobel_sfma_run(const CobelSFMAParams* p, void* stream);
+
 /* ---- utilities -------------------------------------------------------------- */
 int  cobel_abi_version(void);
 /* Copy the last error message of this thread into buf (NUL-terminated). */

@@ -202,4 +202,26 @@ def cuda_case(name, n_extra=2, device='cuda:0'):
                    draws=int(stream.draw_count[0]))
         assert not a, 'unused case arguments %s' % a
         return out
+    if kind == 'sfma':
+        from cobel_rl_b200.memory import SFMAMemory
+
+        class _Metric:
+            D = load_golden(name)['D']
+        mem = SFMAMemory(_Metric(), env.n_states, A, learning_rate=a.pop('mem_lr', 0.9), rng=stream)
+        mem.mode = a.pop('mode', 'default')
+        mem.recency = a.pop('recency', False)
+        ag = AG.SFMA(env.observation_space, env.action_space, pol, mem, None, a.pop('lr', 0.99), a.pop('gamma', 0.99),
+                     rng=stream)
+        ag.mask_actions = a.pop('mask_actions', False)
+        if valid_mask:
+            ag.action_mask = tb.valid_move_mask(succ)
+        ag.record = True
+        res = ag.train(env, trials, steps, a.pop('batch'))
+        torch.cuda.synchronize()
+        out = unpack_run(res, 0, A, succ, reward)
+        out.update(Q=ag._Q[0].cpu().numpy(), Mr=mem._rewards[0].cpu().numpy(), Ms=mem._states[0].cpu().numpy(),
+                   Mt=mem._terminals[0].cpu().numpy(), C=mem._C[0].cpu().numpy(), T=mem._T[0].cpu().numpy(),
+                   I=mem._I[0].cpu().numpy(), draws=int(stream.draw_count[0]), flags=int(res['flags'][0]))
+        assert not a, 'unused case arguments %s' % a
+        return out
     raise ValueError(kind)

@@ -1,0 +1,73 @@
+"""GPU: SFMA CUDA path (cobel_sfma_run) against the reference goldens and the oracle.
+Integer sequences (trajectory, reactivated experiences, draw counts) and the fp64 tables must be
+bit-equal; a draw within 1e-12 of a CDF bin edge would raise COBEL_FLAG_CDF_NEAR_TIE (asserted
+absent), because exp() and the CDF prefix sums are the only quantities not bit-identical to NumPy's."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, tabular as tb
+from oracle.philox import LazyStream
+from helpers import KEYS, assert_equal_records, cuda_case, load_golden, make_world, unpack_run
+
+pytestmark = pytest.mark.gpu
+
+SFMA_CASES = sorted(n for n, c in cases.CASES.items() if c[0] == 'sfma')
+
+
+@pytest.mark.parametrize('name', SFMA_CASES)
+def test_sfma_matches_reference_golden(name):
+    want = load_golden(name)
+    got = cuda_case(name)
+    assert got['flags'] & 2 == 0, 'a CDF draw fell within 1e-12 of a bin edge'
+    assert_equal_records(got, want, KEYS['sfma'], what=name)
+
+
+@pytest.mark.parametrize('mode', ['default', 'reverse', 'forward', 'blend_forward', 'blend_reverse', 'interpolate', 'sweeping'])
+def test_sfma_modes_batch_vs_oracle(mode):
+    """All replay modes, 20x20-like larger table (12x12), several agents, start_replay and 2 replays per trial."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import SFMA
+    from cobel_rl_b200.memory import SFMAMemory
+    from cobel_rl_b200.memory.utils.metrics import DR
+    from cobel_rl_b200.policy import EpsilonGreedy
+    from cobel_rl_b200.misc.gridworld_tools import make_gridworld
+    walls = [(5, 6), (6, 5), (17, 18), (18, 17), (29, 30), (30, 29), (70, 82), (82, 70)]
+    world = make_gridworld(12, 12, terminals=[11], rewards=np.array([[11, 5.0]]), starting_states=[132, 77],
+                           invalid_transitions=walls)
+    metric = DR(12, 12, world['sas'], 0.9, walls)
+    n, trials, steps, batch = 4, 5, 70, 24
+    stream = cb.BatchStream(n, seed=31337, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = SFMAMemory(metric, 144, 4, rng=stream)
+    mem.mode = mode
+    ag = SFMA(env.observation_space, env.action_space, EpsilonGreedy(0.15, rng=stream), mem, rng=stream)
+    ag.mask_actions = True
+    W = tb.compile_gridworld(world)
+    ag.action_mask = tb.valid_move_mask(W['succ'])
+    ag.start_replay = True
+    ag.nb_replays = 2
+    ag.record = True
+    res = ag.train(env, trials, steps, batch)
+    torch.cuda.synchronize()
+    assert int((res['flags'] & 2).sum()) == 0
+    for i in range(n):
+        rng = tb.Draws(LazyStream(31337, i), 1)
+        st = tb.sfma_init(144, 4)
+        st['action_mask'] = tb.valid_move_mask(W['succ'])
+        rec = tb.sfma_train(W, st, metric.D, rng, trials, steps, batch, policy=('eps', 0.15), mode=mode,
+                            mask_actions=True, start_replay=True, nb_replays=2).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got.update(Q=ag.Q[i].cpu().numpy(), C=mem.C[i].cpu().numpy(), I=mem.I[i].cpu().numpy(), draws=int(stream.draw_count[i]))
+        rec.update(Q=st['Q'], C=st['C'], I=st['I'], draws=rng.k)
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q', 'C', 'I', 'draws'],
+                             what='%s agent %d' % (mode, i))
+
+
+def test_metrics_match_reference_fixture():
+    """DR computed by the product's metrics module equals the D stored with the golden (same LAPACK)."""
+    from cobel_rl_b200.memory.utils.metrics import DR
+    world = make_world('walls5')
+    D = DR(5, 5, world['sas'], 0.9, world['invalid_transitions']).D
+    np.testing.assert_allclose(D, load_golden('sfma_walls5_default')['D'], rtol=1e-12, atol=1e-15)
