@@ -69,8 +69,22 @@ class SFMAParams(C.Structure):
                 ('start_replay', C.c_int32), ('no_replay', C.c_int32), ('learn', C.c_int32)]
 
 
+PMA_MAX_SEQ = 64
+
+
+class PMAParams(C.Structure):
+    _fields_ = [('n_agents', C.c_int64), ('world', World), ('stream', Stream), ('policy', Policy),
+                ('mem_policy', Policy), ('trace', Trace), ('Q', c_ptr), ('Mr', c_ptr), ('Ms', c_ptr), ('Mt', c_ptr),
+                ('T', c_ptr), ('SR', c_ptr), ('update_mask', c_ptr), ('action_mask', c_ptr),
+                ('mask_agent_stride', C.c_int64), ('lr', c_ptr), ('gamma', c_ptr), ('mem_lr', c_ptr), ('lr_q', c_ptr),
+                ('gamma_q', c_ptr), ('gamma_sr', c_ptr), ('pow_gamma_sr', c_ptr), ('pow_gamma_q', c_ptr),
+                ('pow_stride', C.c_int64), ('min_gap', c_ptr), ('lr_T', C.c_double), ('min_gain', C.c_double),
+                ('min_gain_original', C.c_int32), ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32),
+                ('no_replay', C.c_int32), ('learn', C.c_int32)]
+
+
 STRUCTS = {'CobelWorld': World, 'CobelStream': Stream, 'CobelPolicy': Policy, 'CobelTrace': Trace,
-           'CobelDynaQParams': DynaQParams, 'CobelQParams': QParams, 'CobelSRParams': SRParams, 'CobelSFMAParams': SFMAParams}
+           'CobelDynaQParams': DynaQParams, 'CobelQParams': QParams, 'CobelSRParams': SRParams, 'CobelSFMAParams': SFMAParams, 'CobelPMAParams': PMAParams}
 
 _SIGNATURES = {
     'cobel_sizeof': (C.c_size_t, [C.c_char_p]),
@@ -83,6 +97,7 @@ _SIGNATURES = {
     'cobel_q_run': (C.c_int, [C.POINTER(QParams), c_ptr]),
     'cobel_sr_run': (C.c_int, [C.POINTER(SRParams), c_ptr]),
     'cobel_sfma_run': (C.c_int, [C.POINTER(SFMAParams), c_ptr]),
+    'cobel_pma_run': (C.c_int, [C.POINTER(PMAParams), c_ptr]),
 }
 
 _lib = None

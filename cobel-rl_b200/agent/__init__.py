@@ -4,3 +4,4 @@ from .dyna_q import DynaQ  # noqa: F401
 from .q import QAgent  # noqa: F401
 from .sr import SR  # noqa: F401
 from .sfma import SFMA  # noqa: F401
+from .pma import PMA  # noqa: F401

@@ -1,0 +1,646 @@
+// pma.cu -- K4: PMA.train()/test() (Dyna-Q with Mattar & Daw prioritized memory access:
+// replay of the backup with the largest gain x need) for N independent agents in one launch.
+//
+// Reference: agent/pma.py:167-353 (trial loop, online n-step update_q) and
+// memory/pma.py:104-496 (store, replay, compute_gain_batch, compute_gain, compute_need,
+// update_sr, update_q).  Semantics: SURVEY.md Appendix A.7.
+//
+// Mapping: one CTA per agent.
+//   * Q, M.rewards, M.states|terminals, the gain vector and the utility scratch live in shared
+//     memory together with ONE S x S fp64 matrix buffer that holds the successor
+//     representation SR = (I - gamma T)^-1 (the `need` rows) between its per-trial
+//     recomputation; T stays in HBM (one row read+written per step, one full read per trial).
+//   * update_sr: in-place Gauss-Jordan inversion in shared memory (I - gamma T is strictly
+//     diagonally dominant, so no pivoting is needed); the stationary distribution used as
+//     `need` after a timed-out trial comes from the subtraction-free GTH elimination.
+//   * replay: the gain of all S*A one-step backups is a function of two Q rows each, so after
+//     the first iteration of a replay call only the backups whose rows were touched by the
+//     previous update are re-evaluated (bit-identical to the reference's full recomputation);
+//     gain x need x mask, the tie-aware arg-max draw and the n-step update are CTA-wide passes.
+// Exactness: everything except SR / the stationary vector follows the reference's operation
+// order bit for bit; those two come from a different (but 1e-13-accurate) factorisation than
+// LAPACK's, which only matters if two distinct utilities are closer than that -- the smallest
+// relative gap seen is reported per agent (`min_gap`) as a certificate.
+#include "warp_agent.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kMaxSeq = 64;          // longest n-step sequence (replay batch) supported
+
+struct PmaSmem {
+  int mat, q, mr, gain, util, need, pk, umask, mbits, dirty, seq, perf, psr, pq, part, qpar, qom, bytes;
+  __host__ __device__ PmaSmem(int S, int A, int B) {
+    const int N = S * A;
+    mat = 0;
+    q = (mat + S * S * 8 + 15) & ~15;       // Q rows are read with 16-byte vector loads
+    mr = q + N * 8;
+    gain = mr + N * 8;
+    util = gain + N * 8;
+    need = util + N * 8;
+    psr = (need + S * 8 + 15) & ~15;
+    pq = psr + (kMaxSeq + 2) * 8;
+    part = pq + (kMaxSeq + 2) * 8;
+    qpar = part + (kThreads + 40) * 8;
+    qom = qpar + 8 * 8;
+    seq = qom + 8 * 8;
+    perf = seq + (kMaxSeq + 2) * 4;
+    pk = perf + (B + 2) * 4;
+    umask = pk + N * 2;
+    mbits = umask + N;
+    dirty = mbits + S;
+    bytes = (dirty + S + 15) & ~15;
+  }
+};
+
+struct PmaShared {
+  double u, val, fv, gap;
+  int idx, ext, cand_len, last_seq, count, flag, last, a;
+};
+
+// Policy probabilities for one Q row (thread-local): policy/greedy.py:60-88,117-147, policy/softmax.py:60-88.
+// qpar[n-1] = par/n and qom[n-1] = (1-par)/n are the cached quotients.
+template <int A>
+COBEL_DEV void probs_row(const double (&v)[A], uint32_t mask, int kind, double par, const double* qpar, const double* qom,
+                         double (&p)[A]) {
+  double m = -__longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll
+  for (int a = 0; a < A; ++a) m = (mask >> a & 1u) ? xmax(m, v[a]) : m;
+  const int nv = __popc(mask);
+  if (kind == COBEL_POLICY_SOFTMAX) {
+    double sum = 0.0;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      p[a] = 0.0;
+      if (mask >> a & 1u) { p[a] = exp(xmul(xsub(v[a], m), par)); sum = xadd(sum, p[a]); }
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a)
+      if (mask >> a & 1u) p[a] = xdiv(p[a], sum);
+    return;
+  }
+  uint32_t ties = 0;
+#pragma unroll
+  for (int a = 0; a < A; ++a) ties |= (v[a] == m ? 1u : 0u) << a;
+  ties &= mask;
+  const int k = __popc(ties);
+  const double tie = qom[k - 1];
+  double top, low;
+  if (kind == COBEL_POLICY_EPS_GREEDY) {
+    const double base = qpar[nv - 1];
+    top = xadd(base, tie); low = xadd(base, 0.0);
+  } else {
+    const int d = nv - k > 1 ? nv - k : 1;
+    top = xadd(tie, 0.0); low = xadd(0.0, qpar[d - 1]);
+  }
+#pragma unroll
+  for (int a = 0; a < A; ++a) p[a] = (mask >> a & 1u) ? ((ties >> a & 1u) ? top : low) : 0.0;
+}
+
+template <int A>
+COBEL_DEV double sum_seq(const double (&x)[A]) {     // np.sum over < 8 elements: sequential
+  double s = x[0];
+#pragma unroll
+  for (int a = 1; a < A; ++a) s = xadd(s, x[a]);
+  return s;
+}
+
+// integer exclusive scan over the block (contiguous chunks per thread are summed by the caller)
+COBEL_DEV int block_exclusive_scan_int(int v, int* part, int tid, int T, int& total) {
+  const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(kFull, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) part[warp] = inc;
+  __syncthreads();
+  int off = 0, tot = 0;
+  for (int w = 0; w < nw; ++w) { if (w < warp) off += part[w]; tot += part[w]; }
+  total = tot;
+  __syncthreads();
+  return off + inc - v;
+}
+
+COBEL_DEV double block_max(double v, double* part, int tid, int T) {
+  for (int d = 16; d > 0; d >>= 1) { const double o = shfl_f64_xor(v, d); v = o > v ? o : v; }
+  if ((tid & 31) == 0) part[tid >> 5] = v;
+  __syncthreads();
+  double m = part[0];
+  for (int w = 1; w < (T >> 5); ++w) m = part[w] > m ? part[w] : m;
+  __syncthreads();
+  return m;
+}
+
+COBEL_DEV double block_sum(double v, double* part, int tid, int T) {
+  for (int d = 16; d > 0; d >>= 1) v += shfl_f64_xor(v, d);
+  if ((tid & 31) == 0) part[tid >> 5] = v;
+  __syncthreads();
+  double m = 0.0;
+  for (int w = 0; w < (T >> 5); ++w) m += part[w];
+  __syncthreads();
+  return m;
+}
+
+template <int A>
+__global__ void __launch_bounds__(kThreads) pma_kernel(const __grid_constant__ CobelPMAParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ PmaShared sh;
+  const int S = p.world.n_states, K = p.world.n_starts, N = S * A, B = p.batch;
+  const int tid = threadIdx.x, T = kThreads, lane = tid & 31, warp = tid >> 5;
+  const int64_t n = blockIdx.x;
+  const PmaSmem so(S, A, B);
+  double* Mat = reinterpret_cast<double*>(smem + so.mat);     // SR (need rows) / elimination scratch
+  double* Q = reinterpret_cast<double*>(smem + so.q);         // [s][a]
+  double* Mr = reinterpret_cast<double*>(smem + so.mr);       // [s][a]
+  double* gain = reinterpret_cast<double*>(smem + so.gain);   // [a*S+s] one-step gains
+  double* util = reinterpret_cast<double*>(smem + so.util);   // [a*S+s] scratch
+  double* needv = reinterpret_cast<double*>(smem + so.need);  // [s] stationary need (time-out case)
+  double* powsr = reinterpret_cast<double*>(smem + so.psr);   // M.gamma ** k
+  double* powq = reinterpret_cast<double*>(smem + so.pq);     // M.gamma_q ** k
+  double* part = reinterpret_cast<double*>(smem + so.part);
+  double* qpar = reinterpret_cast<double*>(smem + so.qpar);
+  double* qom = reinterpret_cast<double*>(smem + so.qom);
+  int32_t* seq = reinterpret_cast<int32_t*>(smem + so.seq);   // candidate n-step sequence (flat indices)
+  int32_t* perf = reinterpret_cast<int32_t*>(smem + so.perf); // performed updates of this replay call
+  uint16_t* Pk = reinterpret_cast<uint16_t*>(smem + so.pk);   // [s][a] M.states | M.terminals << 15
+  uint8_t* umask = smem + so.umask;                           // [a*S+s] M.update_mask
+  uint8_t* mbits = smem + so.mbits;                           // [s] valid-action bits (all ones if unmasked)
+  uint8_t* dirty = smem + so.dirty;                           // [s] Q row changed since the gains were computed
+
+  const size_t g0 = (size_t)n * N;
+  double* Tg = p.T + (size_t)n * S * S;
+  double* SRg = p.SR + (size_t)n * S * S;
+  const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
+  for (int e = tid; e < N; e += T) {
+    Q[e] = p.Q[g0 + e];
+    Mr[e] = p.Mr[g0 + e];
+    Pk[e] = (uint16_t)(p.Ms[g0 + e] | ((p.Mt[g0 + e] ? 1 : 0) << 15));
+    umask[e] = p.update_mask[g0 + e];
+  }
+  for (int e = tid; e < S * S; e += T) Mat[e] = SRg[e];
+  for (int e = tid; e < S; e += T) {
+    uint32_t mb = (1u << A) - 1u;
+    if (amask) {
+      mb = 0;
+      for (int a = 0; a < A; ++a) mb |= (amask[e * A + a] ? 1u : 0u) << a;
+    }
+    mbits[e] = (uint8_t)mb;
+  }
+  for (int e = tid; e < kMaxSeq + 2; e += T) {
+    powsr[e] = p.pow_gamma_sr[n * p.pow_stride + e];
+    powq[e] = p.pow_gamma_q[n * p.pow_stride + e];
+  }
+  const int mkind = p.mem_policy.kind;
+  const double mpar = p.mem_policy.param[n];
+  if (tid < A) {
+    qpar[tid] = xdiv(mpar, (double)(tid + 1));
+    qom[tid] = xdiv(xsub(1.0, mpar), (double)(tid + 1));
+  }
+  __syncthreads();
+
+  DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);      // used by warp 0 only
+  const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
+  const double lrq = p.lr_q[n], gq = p.gamma_q[n], gsr = p.gamma_sr[n];
+  const double min_gain = p.min_gain;
+  const bool original = p.min_gain_original != 0;
+  PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
+  PolicyTab mpt; mpt.init(mkind, mpar, lane);
+  const bool learn = p.learn != 0;
+  const bool do_replay = learn && !p.no_replay;
+  const CobelTrace& tr = p.trace;
+  int64_t nsteps = 0, nrep = 0, ncalls = 0;
+  int flags = 0;
+  double min_gap = __longlong_as_double(0x7FF0000000000000ll);
+
+  // gain of the one-step backup i = (a, s): PMAMemory.compute_gain_batch, memory/pma.py:333-386
+  auto gain_one = [&](int i) -> double {
+    const int a = i / S, s = i - a * S;
+    double q[A], qn[A], po[A], pn[A], t[A];
+    load_row<A>(Q + s * A, q);
+    const uint16_t pk = Pk[s * A + a];
+    const int ms = pk & 0x7FFF, mt = pk >> 15;
+    double tr_[A];
+    load_row<A>(Q + ms * A, tr_);
+    const double boot = xmul(xmul(gq, row_max<A>(tr_)), mt ? 1.0 : 0.0);
+#pragma unroll
+    for (int c = 0; c < A; ++c) qn[c] = q[c];
+    {
+      double qa = q[0], ra = Mr[s * A];
+#pragma unroll
+      for (int c = 1; c < A; ++c) { qa = c == a ? q[c] : qa; ra = c == a ? Mr[s * A + c] : ra; }
+      const double upd = xadd(qa, xmul(lrq, xsub(xadd(ra, boot), qa)));
+#pragma unroll
+      for (int c = 0; c < A; ++c) qn[c] = c == a ? upd : q[c];
+    }
+    const uint32_t mb = mbits[s];
+    probs_row<A>(q, mb, mkind, mpar, qpar, qom, po);
+    probs_row<A>(qn, mb, mkind, mpar, qpar, qom, pn);
+    const double so_ = sum_seq<A>(po), sn_ = sum_seq<A>(pn);
+#pragma unroll
+    for (int c = 0; c < A; ++c) t[c] = xmul(xdiv(pn[c], sn_), qn[c]);
+    const double gnew = sum_seq<A>(t);
+#pragma unroll
+    for (int c = 0; c < A; ++c) t[c] = xmul(xdiv(po[c], so_), qn[c]);
+    const double gold = sum_seq<A>(t);
+    const double g = xsub(gnew, gold);
+    return g > min_gain ? g : min_gain;
+  };
+
+  // SR = inv(I - gamma T): PMAMemory.update_sr, memory/pma.py:413-415 (in-place Gauss-Jordan)
+  auto update_sr = [&]() {
+    for (int e = tid; e < S * S; e += T) {
+      const int i = e / S, j = e - i * S;
+      Mat[e] = xsub(i == j ? 1.0 : 0.0, xmul(gsr, Tg[e]));
+    }
+    __syncthreads();
+    for (int k = 0; k < S; ++k) {
+      const double piv = Mat[k * S + k];
+      if (!(fabs(piv) > 1e-300)) flags |= COBEL_FLAG_SINGULAR;
+      const double ipiv = 1.0 / piv;
+      __syncthreads();
+      for (int j = tid; j < S; j += T) Mat[k * S + j] = j == k ? ipiv : Mat[k * S + j] * ipiv;
+      __syncthreads();
+      for (int e = tid; e < S * S; e += T) {
+        const int i = e / S, j = e - i * S;
+        if (i == k) continue;
+        const double f = Mat[i * S + k];
+        // column k is read by every thread of row i: update it last, from the saved factor
+        if (j != k) Mat[e] = Mat[e] - f * Mat[k * S + j];
+      }
+      __syncthreads();
+      for (int i = tid; i < S; i += T)
+        if (i != k) Mat[i * S + k] = -Mat[i * S + k] * ipiv;
+      __syncthreads();
+    }
+    for (int e = tid; e < S * S; e += T) SRg[e] = Mat[e];
+    __syncthreads();
+  };
+
+  // |left Perron vector| of T with unit 2-norm (memory/pma.py:401-408) by GTH elimination;
+  // uses (and destroys) the matrix buffer, the caller restores SR from HBM afterwards.
+  auto stationary = [&]() {
+    for (int e = tid; e < S * S; e += T) Mat[e] = Tg[e];
+    __syncthreads();
+    for (int k = S - 1; k >= 1; --k) {
+      double ssum = 0.0;
+      for (int j = tid; j < k; j += T) ssum += Mat[k * S + j];
+      ssum = block_sum(ssum, part, tid, T);
+      if (!(ssum > 0.0)) { flags |= COBEL_FLAG_SINGULAR; ssum = 1.0; }
+      for (int i = tid; i < k; i += T) Mat[i * S + k] /= ssum;
+      __syncthreads();
+      for (int e = tid; e < k * k; e += T) {
+        const int i = e / k, j = e - i * k;
+        Mat[i * S + j] += Mat[i * S + k] * Mat[k * S + j];
+      }
+      __syncthreads();
+    }
+    if (tid == 0) needv[0] = 1.0;
+    __syncthreads();
+    for (int k = 1; k < S; ++k) {
+      double acc = 0.0;
+      for (int i = tid; i < k; i += T) acc += needv[i] * Mat[i * S + k];
+      acc = block_sum(acc, part, tid, T);
+      if (tid == 0) needv[k] = acc;
+      __syncthreads();
+    }
+    double sq = 0.0;
+    for (int i = tid; i < S; i += T) sq += needv[i] * needv[i];
+    sq = block_sum(sq, part, tid, T);
+    const double nrm = sqrt(sq);
+    for (int i = tid; i < S; i += T) needv[i] = fabs(needv[i]) / nrm;
+    __syncthreads();
+    for (int e = tid; e < S * S; e += T) Mat[e] = SRg[e];
+    __syncthreads();
+  };
+
+  // PMAMemory.replay, memory/pma.py:168-267
+  auto replay = [&](int cur) {
+    const double* need = cur >= 0 ? Mat + (size_t)cur * S : needv;
+    if (cur < 0) stationary();
+    for (int e = tid; e < S; e += T) dirty[e] = 1;                     // first iteration: evaluate every backup
+    if (tid == 0) { sh.count = 0; sh.last_seq = 0; }
+    __syncthreads();
+    for (int it = 0; it < B; ++it) {
+      // ---- (1) extension of the current sequence (memory/pma.py:219-235); warp 0 -------------
+      if (warp == 0) {
+        int ext = -1, clen = 0;
+        const int count = sh.count, last_seq = sh.last_seq;
+        if (count > 0) {
+          const int lp = perf[count - 1];
+          ext = Pk[(lp % S) * A + lp / S] & 0x7FFF;                    // next_state of the last update
+          bool loop = false;
+          for (int j = last_seq + lane; j < count; j += 32) loop |= (perf[j] % S) == ext;
+          loop = __any_sync(kFull, loop);
+          if (!loop) {
+            win.ensure(2, lane);
+            double row[A];
+            load_row<A>(Q + ext * A, row);
+            const int ea = select_action_warp<A>(row, mbits[ext], mpt, win.next(), lane);
+            ext += ea * S;
+            clen = count - last_seq + 1;
+            for (int j = lane; j < clen - 1; j += 32) seq[j] = perf[last_seq + j];
+            if (lane == 0) seq[clen - 1] = ext;
+          } else if (lane == 0) {
+            seq[0] = ext;                                              // failed extension: one-step(ext, action 0)
+          }
+        }
+        if (lane == 0) { sh.ext = ext; sh.cand_len = clen; }
+      }
+      __syncthreads();
+      const int ext = sh.ext, clen = sh.cand_len;
+      if (clen > kMaxSeq) flags |= COBEL_FLAG_TRACE_OVERFLOW;
+      // ---- (2) one-step gains, re-evaluated only where a Q row they read has changed ----------
+      for (int i = tid; i < N; i += T) {
+        const int a = i / S, s = i - a * S;
+        if (dirty[s] || dirty[Pk[s * A + a] & 0x7FFF]) gain[i] = gain_one(i);
+      }
+      __syncthreads();
+      for (int e = tid; e < S; e += T) dirty[e] = 0;
+      // ---- (3) n-step gain of the candidate (memory/pma.py:269-331), lane j = element j ----------
+      if (warp == 0 && ext >= 0) {
+        const int nseq = clen > 0 ? clen : 1;
+        const int lastI = seq[nseq - 1];
+        const uint16_t lpk = Pk[(lastI % S) * A + lastI / S];
+        double lrow[A];
+        load_row<A>(Q + (lpk & 0x7FFF) * A, lrow);
+        const double fv = xmul(row_max<A>(lrow), (lpk >> 15) ? 1.0 : 0.0);
+        double total = 0.0;
+        for (int j0 = 0; j0 < nseq; j0 += 32) {
+          const int j = j0 + lane;
+          double sg = 0.0;
+          if (j < nseq) {
+            const int i = seq[j];
+            const int a = i / S, s = i - a * S;
+            double q[A], qn[A], pb[A], pa[A], t[A];
+            load_row<A>(Q + s * A, q);
+            const uint32_t mb = mbits[s];
+            probs_row<A>(q, mb, mkind, mpar, qpar, qom, pb);
+            double r = 0.0;
+            for (int f = 0; f < nseq - j; ++f) {
+              const int k = seq[j + f];
+              r = xadd(r, xmul(Mr[(k % S) * A + k / S], powsr[f]));
+            }
+            const double target = xadd(r, xmul(fv, powq[nseq - j]));
+#pragma unroll
+            for (int c = 0; c < A; ++c) {
+              const double qt = c == a ? target : q[c];
+              qn[c] = xadd(q[c], xmul(lrq, xsub(qt, q[c])));
+            }
+            probs_row<A>(qn, mb, mkind, mpar, qpar, qom, pa);
+#pragma unroll
+            for (int c = 0; c < A; ++c) t[c] = xmul(qn[c], pa[c]);
+            const double ga = sum_seq<A>(t);
+#pragma unroll
+            for (int c = 0; c < A; ++c) t[c] = xmul(qn[c], pb[c]);
+            sg = xsub(ga, sum_seq<A>(t));
+            if (original) sg = sg > min_gain ? sg : min_gain;
+          }
+          const int m = nseq - j0 < 32 ? nseq - j0 : 32;
+          for (int l = 0; l < m; ++l) total = xadd(total, shfl_f64(sg, l));       // gain += step_gain, in order
+        }
+        if (lane == 0) sh.val = total > min_gain ? total : min_gain;
+      }
+      __syncthreads();
+      // ---- (4) utility = gain * need * update_mask; arg-max with exact ties (memory/pma.py:247-254)
+      const double gext = sh.val;
+      double lmax = -__longlong_as_double(0x7FF0000000000000ll);
+      for (int i = tid; i < N; i += T) {
+        const int s = i % S;
+        const double g = (i == ext) ? gext : gain[i];
+        const double u_ = xmul(xmul(g, need[s]), umask[i] ? 1.0 : 0.0);
+        util[i] = u_;
+        lmax = u_ > lmax ? u_ : lmax;
+      }
+      const double umax = block_max(lmax, part, tid, T);
+      // certificate: relative gap to the largest utility below the maximum
+      double l2 = -__longlong_as_double(0x7FF0000000000000ll);
+      for (int i = tid; i < N; i += T) { const double v = util[i]; if (v < umax && v > l2) l2 = v; }
+      const double u2 = block_max(l2, part, tid, T);
+      if (umax != 0.0 && u2 > -1e300) { const double gp = (umax - u2) / fabs(umax); min_gap = gp < min_gap ? gp : min_gap; }
+      // ties in flat-index order: contiguous chunks per thread + integer scan
+      const int chunk = (N + T - 1) / T;
+      const int lo = tid * chunk < N ? tid * chunk : N, hi = lo + chunk < N ? lo + chunk : N;
+      int cnt = 0;
+      for (int i = lo; i < hi; ++i) cnt += util[i] == umax ? 1 : 0;
+      int ktot;
+      const int before = block_exclusive_scan_int(cnt, reinterpret_cast<int*>(part), tid, T, ktot);
+      if (warp == 0) {
+        win.ensure(1, lane);
+        const double u = win.next();
+        if (lane == 0) {
+          // Generator.choice(p = ties / k): cdf_m = m-fold sequential sum of fl(1/k), normalised by cdf_k
+          const double pk_ = xdiv(1.0, (double)ktot);
+          double ck = 0.0;
+          for (int m = 0; m < ktot; ++m) ck = xadd(ck, pk_);
+          double c = 0.0;
+          int pick = ktot - 1;
+          for (int m = 0; m < ktot; ++m) {
+            c = xadd(c, pk_);
+            if (xdiv(c, ck) > u) { pick = m; break; }
+          }
+          sh.idx = pick;
+        }
+      }
+      __syncthreads();
+      const int pick = sh.idx;
+      __syncthreads();
+      if (pick >= before && pick < before + cnt) {
+        int r = pick - before;
+        for (int i = lo; i < hi; ++i)
+          if (util[i] == umax && r-- == 0) { sh.a = i; break; }
+      }
+      __syncthreads();
+      const int chosen = sh.a;
+      // ---- (5) apply the chosen (n-step) update: PMAMemory.update_q, memory/pma.py:452-496 ----------
+      if (warp == 0) {
+        const bool use_seq = clen > 0 && chosen == ext;
+        const int nseq = use_seq ? clen : 1;
+        if (!use_seq && lane == 0) seq[0] = chosen;
+        __syncwarp();
+        const int lastI = seq[nseq - 1];
+        const uint16_t lpk = Pk[(lastI % S) * A + lastI / S];
+        double lrow[A];
+        load_row<A>(Q + (lpk & 0x7FFF) * A, lrow);
+        const double fv = xmul(row_max<A>(lrow), (lpk >> 15) ? 1.0 : 0.0);
+        bool ok = true;                                 // n >= 2: every transition must be non-terminal & experienced
+        if (nseq >= 2) {
+          bool bad = false;
+          for (int j = lane; j < nseq; j += 32) { const int k = seq[j]; bad |= (Pk[(k % S) * A + k / S] >> 15) == 0; }
+          ok = !__any_sync(kFull, bad);
+        }
+        __syncwarp();
+        if (ok) {
+          for (int j = lane; j < nseq; j += 32) {
+            const int i = seq[j];
+            const int a = i / S, s = i - a * S;
+            double r = 0.0;
+            for (int f = 0; f < nseq - j; ++f) {
+              const int k = seq[j + f];
+              r = xadd(r, xmul(Mr[(k % S) * A + k / S], powq[f]));
+            }
+            double td = xadd(r, xmul(fv, powq[nseq - j]));
+            const double q = Q[s * A + a];
+            td = xsub(td, q);
+            Q[s * A + a] = xadd(q, xmul(lrq, td));       // states of a sequence are distinct (no loops)
+            dirty[s] = 1;
+          }
+        }
+        if (lane == 0) {
+          const int count = sh.count;
+          perf[count] = chosen;
+          sh.count = count + 1;
+          if (ext != chosen) sh.last_seq = it;
+        }
+      }
+      __syncthreads();
+    }
+    const int count = sh.count;
+    if (tr.replay_idx)
+      for (int j = tid; j < count; j += T) {
+        if (nrep + j < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + j] = perf[j];
+        else flags |= COBEL_FLAG_TRACE_OVERFLOW;
+      }
+    if (tr.replay_len && tid == 0) {
+      if (ncalls < tr.replay_calls_cap) tr.replay_len[n * tr.replay_calls_cap + ncalls] = count;
+      else flags |= COBEL_FLAG_TRACE_OVERFLOW;
+    }
+    nrep += count;
+    ++ncalls;
+    __syncthreads();
+  };
+
+  for (int trial = 0; trial < p.trials; ++trial) {
+    if (warp == 0) {
+      win.ensure(2, lane);
+      const int s0 = __ldg(p.world.starts + draw_integer(win.next(), K));
+      if (lane == 0) sh.last = s0;
+    }
+    __syncthreads();
+    int s = sh.last;
+    __syncthreads();
+    if (do_replay) replay(s);                                       // awake replay, need = SR[start] (agent/pma.py:206-213)
+    if (warp == 0) {
+      double treward = 0.0;
+      int step = 0, last = -1;
+      for (;; ++step) {
+        win.ensure(1, lane);
+        double row[A];
+        load_row<A>(Q + s * A, row);
+        const int a = select_action_warp<A>(row, mbits[s], pt, win.next(), lane);
+        const int s2 = __ldg(p.world.succ + s * A + a);
+        const double r = __ldg(p.world.reward + s2);
+        const int end = __ldg(p.world.terminal + s2);
+        const int nt = 1 - end;
+        if (tr.step_sa && lane == 0) {
+          if (nsteps < tr.step_cap) tr.step_sa[n * tr.step_cap + nsteps] = s * A + a;
+          else flags |= COBEL_FLAG_TRACE_OVERFLOW;
+        }
+        ++nsteps;
+        if (learn) {
+          // PMA.update_q([experience]) (agent/pma.py:319-353), then M.store (memory/pma.py:148-166)
+          double row2[A];
+          load_row<A>(Q + s2 * A, row2);
+          const double fv = xmul(row_max<A>(row2), nt ? 1.0 : 0.0);
+          const double rr = xadd(0.0, xmul(r, 1.0));
+          double td = xadd(rr, xmul(fv, gamma));
+          const double q = Q[s * A + a];
+          td = xsub(td, q);
+          const double qn = xadd(q, xmul(lr, td));
+          const double m0 = Mr[s * A + a];
+          const double m1 = xadd(m0, xmul(mlr, xsub(r, m0)));
+          for (int j = lane; j < S; j += 32) {           // T[s] += 0.9 * (onehot(s') - T[s])
+            const double t0 = Tg[(size_t)s * S + j];
+            Tg[(size_t)s * S + j] = xadd(t0, xmul(p.lr_T, xsub(j == s2 ? 1.0 : 0.0, t0)));
+          }
+          __syncwarp();
+          if (lane == 0) {
+            Q[s * A + a] = qn;
+            Mr[s * A + a] = m1;
+            Pk[s * A + a] = (uint16_t)(s2 | (nt << 15));
+          }
+          __syncwarp();
+        }
+        s = s2;
+        treward = xadd(treward, r);
+        if (end) last = s2;
+        if (end || step + 1 == p.steps) break;
+      }
+      if (lane == 0) {
+        tr.trial_steps[n * p.trials + trial] = step;
+        tr.trial_reward[n * p.trials + trial] = treward;
+        sh.last = last;
+      }
+    }
+    __syncthreads();
+    if (do_replay) {
+      const int last = sh.last;
+      __syncthreads();
+      update_sr();
+      replay(last);                                                  // need from the terminal state, or stationary
+    }
+  }
+
+  __syncthreads();
+  if (learn) {
+    for (int e = tid; e < N; e += T) {
+      p.Q[g0 + e] = Q[e];
+      p.Mr[g0 + e] = Mr[e];
+      p.Ms[g0 + e] = Pk[e] & 0x7FFF;
+      p.Mt[g0 + e] = Pk[e] >> 15;
+    }
+  }
+  flags = __syncthreads_or(flags);
+  min_gap = block_max(-min_gap, part, tid, T);
+  if (tid == 0) {
+    p.stream.draw_count[n] = (int64_t)win.position();
+    tr.n_steps[n] += nsteps;
+    tr.n_replay[n] += nrep;
+    if (tr.flags && flags) tr.flags[n] |= flags;
+    if (p.min_gap) p.min_gap[n] = fmin(p.min_gap[n], -min_gap);
+  }
+}
+
+template <int A>
+int launch(const CobelPMAParams& p, cudaStream_t st) {
+  const int S = p.world.n_states;
+  COBEL_REQUIRE(S <= 0x7FFF, COBEL_EUNSUPPORTED, "PMA kernel supports at most 32767 states");
+  const PmaSmem so(S, A, p.batch);
+  COBEL_REQUIRE(so.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
+                "PMA: %d states need %d bytes of shared memory (the S x S successor representation must fit)", S, so.bytes);
+  COBEL_CUDA_OK(cudaFuncSetAttribute(pma_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, so.bytes));
+  pma_kernel<A><<<(unsigned)p.n_agents, kThreads, so.bytes, st>>>(p);
+  cobel_count_launch();
+  COBEL_CUDA_OK(cudaGetLastError());
+  return COBEL_OK;
+}
+
+}  // namespace
+
+int cobel_validate_common(int64_t n_agents, const CobelWorld& w, const CobelStream& s, const CobelPolicy& pol,
+                          const CobelTrace& tr, int trials, int steps);
+
+extern "C" int cobel_pma_run(const CobelPMAParams* pp, void* stream) {
+  COBEL_REQUIRE(pp != nullptr, COBEL_EINVAL, "null params");
+  const CobelPMAParams& p = *pp;
+  int rc = cobel_validate_common(p.n_agents, p.world, p.stream, p.policy, p.trace, p.trials, p.steps);
+  if (rc) return rc;
+  COBEL_REQUIRE(p.Q && p.Mr && p.Ms && p.Mt && p.T && p.SR && p.update_mask && p.lr && p.gamma && p.mem_lr && p.lr_q &&
+                p.gamma_q && p.gamma_sr && p.pow_gamma_sr && p.pow_gamma_q && p.mem_policy.param, COBEL_EINVAL,
+                "agent tables missing");
+  COBEL_REQUIRE(p.mem_policy.kind >= 0 && p.mem_policy.kind <= 2, COBEL_EINVAL, "bad memory policy");
+  COBEL_REQUIRE(p.batch >= 0 && p.batch <= kMaxSeq, COBEL_EUNSUPPORTED, "PMA replay batch must be in 0..%d", kMaxSeq);
+  if (p.trials == 0) return COBEL_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (p.world.n_actions) {
+    case 2: return launch<2>(p, st);
+    case 3: return launch<3>(p, st);
+    case 4: return launch<4>(p, st);
+    case 6: return launch<6>(p, st);
+    case 8: return launch<8>(p, st);
+    default:
+      cobel_set_error("unsupported number of actions %d (built for 2,3,4,6,8)", p.world.n_actions);
+      return COBEL_EUNSUPPORTED;
+  }
+}

@@ -1,0 +1,103 @@
+"""PMA memory (reference: memory/pma.py:20-496): prioritized memory access after Mattar & Daw (2018).
+
+Holds, per agent, the experience tables, the learned state-state transition matrix ``T``, the
+successor representation ``SR = inv(I - gamma T)`` and ``update_mask``; the replay
+(gain x need arg-max with n-step sequences) runs inside ``PMA.train()`` (csrc/pma.cu).
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+from .dyna_q import TableMemory
+
+
+class PMAMemory(TableMemory):
+    def __init__(self, sas, policy, learning_rate=0.9, learning_rate_q=0.9, gamma=0.9, gamma_q=0.9, rng=None):
+        sas = np.asarray(sas)
+        if sas.ndim == 3:                       # dense one-hot sas[S,A,S] (memory/pma.py:139)
+            self.nb_states, self.nb_actions = sas.shape[0], sas.shape[1]
+            self._T0 = np.sum(sas, axis=1) / self.nb_actions
+        else:                                   # extension: successor table succ[S,A]
+            self.nb_states, self.nb_actions = sas.shape
+            T0 = np.zeros((self.nb_states, self.nb_states))
+            np.add.at(T0, (np.repeat(np.arange(self.nb_states), self.nb_actions), sas.reshape(-1)), 1.0)
+            self._T0 = T0 / self.nb_actions
+        self.sas = sas
+        self.policy = policy
+        self.learning_rate_q = learning_rate_q
+        self.learning_rate_T = 0.9
+        self.gamma = gamma
+        self.gamma_q = gamma_q
+        self.min_gain = 10 ** -6
+        self.min_gain_mode = 'original'
+        # options of the reference that the B200 path does not implement (must stay at their defaults)
+        self.equal_need = False
+        self.equal_gain = False
+        self.ignore_barriers = True
+        self.allow_loops = False
+        if rng is None and getattr(policy, 'rng', None) is not None:
+            rng = policy.rng
+        super().__init__(self.nb_states, self.nb_actions, learning_rate, rng, init_self_loops=False)
+
+    def _allocate_extra(self, stream):
+        n, S, dev = stream.n_agents, self.nb_states, stream.device
+        self._T = torch.as_tensor(self._T0, dtype=torch.float64).to(dev).repeat(n, 1, 1).contiguous()
+        g = stream.param(self.gamma, 'gamma').cpu().numpy()
+        eye = np.eye(S)
+        cache = {}
+        SR = np.empty((n, S, S))
+        for i, gi in enumerate(g):              # memory/pma.py:141, same LAPACK call as the reference
+            if gi not in cache:
+                cache[gi] = np.linalg.inv(eye - gi * self._T0)
+            SR[i] = cache[gi]
+        self._SR = torch.as_tensor(SR).to(dev).contiguous()
+        self._update_mask = torch.zeros((n, S * self.nb_actions), dtype=torch.uint8, device=dev)
+        self._min_gap = torch.full((n,), float('inf'), dtype=torch.float64, device=dev)
+        self.compute_update_mask()
+
+    T = property(lambda self: self._view(self._T))
+    SR = property(lambda self: self._view(self._SR))
+    update_mask = property(lambda self: self._view(self._update_mask).bool())
+    min_gap = property(lambda self: self._view(self._min_gap))
+
+    def compute_update_mask(self):
+        """memory/pma.py:417-421: backups that lead into their own state are ignored."""
+        S, A = self.nb_states, self.nb_actions
+        flatF = self._states.permute(0, 2, 1).reshape(-1, S * A)          # states.flatten(order='F')
+        own = torch.arange(S, device=flatF.device, dtype=flatF.dtype).repeat(A).unsqueeze(0)
+        self._update_mask.copy_((flatF != own).to(torch.uint8))
+
+    def update_sr(self):
+        """memory/pma.py:413-415 (host-side convenience; train() refreshes SR on the device)."""
+        S = self.nb_states
+        g = self._alloc_for.param(self.gamma, 'gamma').reshape(-1, 1, 1)
+        eye = torch.eye(S, dtype=torch.float64, device=self._T.device)
+        self._SR.copy_(torch.linalg.inv(eye - g * self._T))
+
+    def check_supported(self):
+        bad = [k for k in ('equal_need', 'equal_gain', 'allow_loops') if getattr(self, k)]
+        if bad or not self.ignore_barriers:
+            raise NotImplementedError('PMAMemory options not implemented by the B200 path: %s'
+                                      % (bad or ['ignore_barriers=False']))
+
+    def power_tables(self, stream, keep):
+        """``float(gamma) ** k`` for k = 0..MAX_SEQ+1 with Python's pow, like the reference
+        (memory/pma.py:310,315,485,491).  Returns (sr table, q table, per-agent stride)."""
+        L = _lib.PMA_MAX_SEQ + 2
+
+        def table(x):
+            v = stream.param(x, 'gamma').cpu().numpy()
+            if np.all(v == v[0]):
+                rows = [[float(v[0]) ** k for k in range(L)]]
+            else:
+                cache = {}
+                rows = [cache.setdefault(float(g), [float(g) ** k for k in range(L)]) for g in v]
+            return np.array(rows, dtype=np.float64)
+        a, b = table(self.gamma), table(self.gamma_q)
+        if a.shape[0] != b.shape[0]:
+            n = stream.n_agents
+            a, b = np.broadcast_to(a, (n, L)).copy(), np.broadcast_to(b, (n, L)).copy()
+        ta = torch.as_tensor(a).to(stream.device).contiguous()
+        tb = torch.as_tensor(b).to(stream.device).contiguous()
+        keep += [ta, tb]
+        return ta, tb, (0 if a.shape[0] == 1 else L)

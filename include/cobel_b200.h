@@ -208,6 +208,45 @@ typedef struct CobelSFMAParams {
 
 int cobel_sfma_run(const CobelSFMAParams* p, void* stream);
 
+/* ---- PMA: agent/pma.py:137-369 + memory/pma.py:20-496 (Mattar & Daw gain x need replay) ---- */
+#define COBEL_PMA_MAX_SEQ 64      /* longest n-step sequence = largest replay batch */
+
+typedef struct CobelPMAParams {
+  int64_t n_agents;
+  CobelWorld world;
+  CobelStream stream;
+  CobelPolicy policy;        /* agent.policy (online action selection) */
+  CobelPolicy mem_policy;    /* M.policy (gain evaluation and sequence extension) */
+  CobelTrace trace;          /* replay_idx holds flat indices a*S + s of the performed updates */
+  double*  Q;                /* [N,S,A] */
+  double*  Mr;               /* [N,S,A] M.rewards */
+  int32_t* Ms;               /* [N,S,A] M.states (init: 0, memory/pma.py:136) */
+  int32_t* Mt;               /* [N,S,A] M.terminals */
+  double*  T;                /* [N,S,S] M.T learned state-state transition matrix */
+  double*  SR;               /* [N,S,S] M.SR = inv(I - gamma T), refreshed every trial */
+  const uint8_t* update_mask;/* [N,S*A] M.update_mask, index a*S + s */
+  const uint8_t* action_mask;/* [S,A] or [N,S,A]; NULL = mask_actions False */
+  int64_t  mask_agent_stride;
+  const double* lr;          /* [N] agent.learning_rate */
+  const double* gamma;       /* [N] agent.gamma */
+  const double* mem_lr;      /* [N] M.learning_rate */
+  const double* lr_q;        /* [N] M.learning_rate_q */
+  const double* gamma_q;     /* [N] M.gamma_q */
+  const double* gamma_sr;    /* [N] M.gamma */
+  const double* pow_gamma_sr;/* [COBEL_PMA_MAX_SEQ+2] (or per agent, see pow_stride): float(M.gamma) ** k */
+  const double* pow_gamma_q; /* same for M.gamma_q (the reference uses Python's float pow) */
+  int64_t  pow_stride;       /* 0 = one table for all agents, COBEL_PMA_MAX_SEQ+2 = one per agent */
+  double*  min_gap;          /* optional [N] in/out: smallest relative gap between the two largest distinct utilities */
+  double   lr_T;             /* M.learning_rate_T (0.9) */
+  double   min_gain;         /* M.min_gain (1e-6) */
+  int32_t  min_gain_original;/* M.min_gain_mode == 'original' */
+  int32_t trials, steps, batch;
+  int32_t no_replay;
+  int32_t learn;             /* 1 = train(), 0 = test() */
+} CobelPMAParams;
+
+int cobel_pma_run(const CobelPMAParams* p, void* stream);
+
 /* ---- utilities -------------------------------------------------------------- */
 int  cobel_abi_version(void);
 /* Copy the last error message of this thread into buf (NUL-terminated). */

@@ -1,0 +1,64 @@
+"""GPU: PMA CUDA path (cobel_pma_run) against the reference goldens and the oracle.
+
+Integer sequences (trajectory, performed updates, draw counts) and Q / M tables must be
+bit-equal.  SR and the stationary `need` vector come from an in-kernel Gauss-Jordan / GTH
+factorisation instead of LAPACK: tolerance 1e-12 relative to the matrix scale (BASELINE.json
+north_star: "within 1e-12 relative"; see helpers.assert_equal_records), and the kernel's top-2
+utility gap certificate must stay far above that tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, tabular as tb
+from oracle.philox import LazyStream
+from helpers import KEYS, assert_equal_records, cuda_case, load_golden, make_world, unpack_run
+
+pytestmark = pytest.mark.gpu
+
+PMA_CASES = sorted(n for n, c in cases.CASES.items() if c[0] == 'pma')
+RTOL = {'SR': 1e-12}
+
+
+@pytest.mark.parametrize('name', PMA_CASES)
+def test_pma_matches_reference_golden(name):
+    want = load_golden(name)
+    got = cuda_case(name)
+    assert got['flags'] == 0
+    assert got['min_gap'] > 1e-9, 'utilities too close for a 1e-12-accurate need vector'
+    assert_equal_records(got, want, KEYS['pma'], rtol=RTOL, what=name)
+
+
+def test_pma_batch_sweep_vs_oracle():
+    """Several agents with per-agent hyper-parameters on the 10x10 walled world (config C3 shape),
+    including timed-out trials (stationary need)."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import PMA
+    from cobel_rl_b200.memory import PMAMemory
+    from cobel_rl_b200.policy import EpsilonGreedy
+    world = make_world('walls10')
+    n, trials, steps, batch = 4, 2, 40, 24
+    gq = [0.99, 0.95, 0.9, 0.99]
+    lrq = [0.9, 0.8, 0.9, 0.5]
+    stream = cb.BatchStream(n, seed=4242, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = PMAMemory(world['sas'], EpsilonGreedy(0.1, rng=stream), 0.9, lrq, 0.9, gq, rng=stream)
+    ag = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem)
+    ag.mask_actions = True
+    W = tb.compile_gridworld(world)
+    ag.action_mask = tb.valid_move_mask(W['succ'])
+    ag.record = True
+    res = ag.train(env, trials, steps, batch)
+    torch.cuda.synchronize()
+    assert int(res['flags'].sum()) == 0
+    for i in range(n):
+        rng = tb.Draws(LazyStream(4242, i), 1)
+        st = tb.pma_init(tb.t0_from_succ(W['succ']), 100, 4)
+        st['action_mask'] = tb.valid_move_mask(W['succ'])
+        rec = tb.pma_train(W, st, rng, trials, steps, batch, lr_q=lrq[i], gamma_q=gq[i], mask_actions=True).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got.update(Q=ag.Q[i].cpu().numpy(), T=mem.T[i].cpu().numpy(), SR=mem.SR[i].cpu().numpy(), draws=int(stream.draw_count[i]))
+        rec.update(Q=st['Q'], T=st['T'], SR=st['SR'], draws=rng.k)
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q', 'T', 'SR', 'draws'],
+                             rtol=RTOL, what='agent %d' % i)
+    assert float(mem.min_gap.min()) > 1e-9
