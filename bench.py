@@ -1,16 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200-native tabular simulator.
+"""bench.py -- headline benchmarks of the B200-native tabular simulator.
 
-Metric (BASELINE.json): agent-steps/sec including replay.  Workload at N GPUs
-(weak scaling): BASELINE.json configs[1] per GPU -- 4096 independent Dyna-Q
-agents on the 5x5 open gridworld, the reference demo's setting
-(demo/gridworld/demo_dyna_q.py:36-56: 500 trials x <=50 steps, replay batch 32,
-epsilon 0.1, lr 0.99, gamma 0.99).  One "step" of this benchmark = one complete
-``DynaQ.train(env, 500, 50, 32)`` of all agents from freshly initialised tables.
+Metric (BASELINE.json): "agent-steps/sec incl. replay at 1/2/4/8 B200; PMA replay updates/sec".
+The JSON line's top-level fields are the first metric on BASELINE.json configs[1]:
+  4096 independent Dyna-Q agents per GPU (weak scaling) on the 5x5 open gridworld, the reference
+  demo's setting (demo/gridworld/demo_dyna_q.py:36-56: 500 trials x <=50 steps, replay batch 32,
+  epsilon 0.1, lr 0.99, gamma 0.99).  One "step" of the benchmark = one complete
+  ``DynaQ.train(env, 500, 50, 32)`` of all agents from freshly initialised tables.
+The second metric (PMA replay-updates/s on configs[2]: 10x10 walled gridworld, 16384 agents per
+GPU) is measured in the same run and reported under the key "pma".  Other workloads
+(--workload sfma|sr|q) print their own line with the same schema.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload dynaq|...]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload dynaq|pma|sfma|sr|q]
 
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+Prints ONE JSON line (rank 0).  DESIGN.md "Measurement" documents every field.
 """
 import argparse
 import json
@@ -20,6 +23,11 @@ import sys
 import threading
 import time
 
+# the CPU baseline runs one process per core: keep LAPACK single-threaded (must be set before NumPy loads)
+os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
+os.environ.setdefault('OMP_NUM_THREADS', '1')
+os.environ.setdefault('MKL_NUM_THREADS', '1')
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -27,12 +35,35 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 SEED = 0x5EED
-# algorithmic bytes per unit, SURVEY.md section 8d / DESIGN.md
-DYNAQ_BYTES_PER_STEP = 2066
 
+# Workloads.  bytes_per_unit = algorithmic bytes per unit.
 WORKLOADS = {
-    'dynaq': dict(desc='C2: 4096 Dyna-Q agents/GPU, 5x5 open field, 500 trials x <=50 steps, batch 32',
-                  agents_per_gpu=4096, trials=500, steps=50, batch=32, S=25, A=4),
+    'dynaq': dict(
+        desc='C2: 4096 Dyna-Q agents/GPU, 5x5 open field, 500 trials x <=50 steps, batch 32',
+        metric='agent-steps/sec incl. replay', unit='agent-steps/s', kernel='dynaq_warp_kernel<4>',
+        agents_per_gpu=4096, trials=500, steps=50, batch=32, world='open5', bytes_per_unit=2066,
+        unit_key='n_steps', cpu_trials=500),
+    'pma': dict(
+        desc='C3: 16384 PMA agents/GPU, 10x10 gridworld with walls, 4 trials x <=100 steps, replay batch 32 at '
+             'trial start and end',
+        metric='PMA replay updates/sec', unit='replay-updates/s', kernel='pma_kernel<4>',
+        agents_per_gpu=16384, trials=4, steps=100, batch=32, world='walls10', bytes_per_unit=23 * 400 + 8 * 100,
+        unit_key='n_replay', cpu_trials=4),
+    'sfma': dict(
+        desc='C4: 65536 SFMA agents/GPU, 20x20 open field, DR metric, default mode, 4 trials x <=200 steps, batch 32',
+        metric='agent-steps/sec incl. replay', unit='agent-steps/s', kernel='sfma_kernel<4>',
+        agents_per_gpu=65536, trials=4, steps=200, batch=32, world='open20', bytes_per_unit=138,
+        unit_key='n_steps', cpu_trials=4),
+    'sr': dict(
+        desc='SR agents (dense S x S), 20x20 open field, 4096 agents/GPU, 4 trials x <=64 steps',
+        metric='agent-steps/sec', unit='agent-steps/s', kernel='sr_kernel<4>',
+        agents_per_gpu=4096, trials=4, steps=64, batch=0, world='open20', bytes_per_unit=8 * 400 * 8 + 24,
+        unit_key='n_steps', cpu_trials=4),
+    'q': dict(
+        desc='QAgent on the linear_track(10,2) topology graph, 4096 agents/GPU, 500 trials x <=50 steps, batch 32',
+        metric='agent-steps/sec incl. replay', unit='agent-steps/s', kernel='q_warp_kernel<4>',
+        agents_per_gpu=4096, trials=500, steps=50, batch=32, world='track', bytes_per_unit=2223,
+        unit_key='n_steps', cpu_trials=500),
 }
 
 
@@ -44,6 +75,15 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def make_world(name):
+    from cobel_rl_b200.misc.gridworld_tools import make_gridworld, make_open_field
+    from oracle.cases import world_args
+    if name == 'open20':
+        return make_open_field(20, 20, 0, 1)
+    h, w, kw = world_args(name)
+    return make_gridworld(h, w, **kw)
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
@@ -51,17 +91,15 @@ class ClockSampler:
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.gpu, self.proc, self.lines = gpu_index, None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            threading.Thread(target=self._read, daemon=True).start()
+            time.sleep(0.3)
         except OSError:
             self.proc = None
 
@@ -100,71 +138,94 @@ class ClockSampler:
 # --------------------------------------------------------------------------- #
 
 def _cpu_worker(args):
-    agent_ids, trials, steps, batch = args
+    name, agent_ids, trials = args
     os.environ['OPENBLAS_NUM_THREADS'] = '1'
     from oracle import tabular as tb
     from oracle.philox import LazyStream
-    from oracle.cases import world_args
-    from cobel_rl_b200.misc.gridworld_tools import make_gridworld
-    h, w, kw = world_args('open5')
-    W = tb.compile_gridworld(make_gridworld(h, w, **kw))
-    total = 0
+    wl = WORKLOADS[name]
+    steps, batch = wl['steps'], wl['batch']
+    if name == 'q':
+        from cobel_rl_b200.misc.topology_tools import linear_track
+        W = tb.compile_topology(*linear_track(10, 2, 1.0, 20.0, 'right'))
+    else:
+        world = make_world(wl['world'])
+        W = tb.compile_gridworld(world)
+    S, A = W['S'], W['A']
+    units = 0
     for g in agent_ids:
         rng = tb.Draws(LazyStream(SEED, g), 1)
-        st = tb.dynaq_init(W['S'], W['A'])
-        rec = tb.dynaq_train(W, st, rng, trials, steps, batch)
-        total += len(rec.s)
-    return total
+        if name == 'dynaq':
+            rec = tb.dynaq_train(W, tb.dynaq_init(S, A), rng, trials, steps, batch)
+            units += len(rec.s)
+        elif name == 'q':
+            rec = tb.q_train(W, tb.q_init(S, A), rng, trials, steps, batch)
+            units += len(rec.s)
+        elif name == 'sr':
+            rec = tb.sr_train(W, tb.sr_init(S, A), rng, trials, steps)
+            units += len(rec.s)
+        elif name == 'sfma':
+            from cobel_rl_b200.memory.utils.metrics import DR
+            D = DR(world['width'], world['height'], world['sas'], 0.9, world['invalid_transitions']).D
+            rec = tb.sfma_train(W, tb.sfma_init(S, A), D, rng, trials, steps, batch, mask_actions=True)
+            units += len(rec.s)
+        elif name == 'pma':
+            st = tb.pma_init(tb.t0_from_succ(W['succ']), S, A)
+            rec = tb.pma_train(W, st, rng, trials, steps, batch, gamma_q=0.99, mask_actions=True)
+            units += len(rec.replay)
+    return units
 
 
-def cpu_dynaq(wl, agents_per_core=2, pool=None, cores=None):
-    """Oracle port of the reference loop, one process per host core, each running a slice of
-    agents of the SAME workload (same world, hyper-parameters and per-agent streams)."""
+def cpu_run(name, agents_per_core=1, pool=None, cores=None, trials=None):
+    """Oracle port of the reference loop, one process per host core, each running a slice of agents
+    of the SAME workload (same world, hyper-parameters and per-agent streams)."""
     import multiprocessing as mp
+    wl = WORKLOADS[name]
+    trials = trials or wl['cpu_trials']
     cores = cores or os.cpu_count() or 1
     ids = [list(range(c * agents_per_core, (c + 1) * agents_per_core)) for c in range(cores)]
     own = pool is None
     if own:
         pool = mp.get_context('spawn').Pool(cores)
-        pool.map(_cpu_worker, [([0], 2, 5, 4)] * cores)       # import / warm the workers
+        pool.map(_cpu_worker, [('dynaq', [0], 1)] * cores)       # import / warm the workers
     t0 = time.perf_counter()
-    steps = sum(pool.map(_cpu_worker, [(i, wl['trials'], wl['steps'], wl['batch']) for i in ids]))
+    units = sum(pool.map(_cpu_worker, [(name, i, trials) for i in ids]))
     dt = time.perf_counter() - t0
     if own:
         pool.close()
-    return {'value': steps / dt, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d agents (%d per core) of the same workload, full %d trials x <=%d steps, batch %d; '
-                      '%d agent-steps in %.1f s; oracle/tabular.py (NumPy restatement validated bit-exact '
-                      'against the reference)' % (cores * agents_per_core, agents_per_core, wl['trials'],
-                                                   wl['steps'], wl['batch'], steps, dt),
-            'seconds': dt, 'agent_steps': steps}
+    return {'value': units / dt, 'unit': wl['unit'], 'cores': cores, 'kind': 'port',
+            'sample': '%d agents (%d per core) of the same workload, %d trials x <=%d steps, batch %d: %d units in '
+                      '%.1f s; oracle/tabular.py (NumPy restatement validated bit-exact against the reference)'
+                      % (cores * agents_per_core, agents_per_core, trials, wl['steps'], wl['batch'], units, dt),
+            'seconds': dt, 'units': units}
 
 
-def run_reference(args, wl):
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
+def run_reference(args):
+    if int(os.environ.get('RANK', '0')) != 0:
         return
     import multiprocessing as mp
+    name = args.workload
+    wl = WORKLOADS[name]
     cores = os.cpu_count() or 1
     pool = mp.get_context('spawn').Pool(cores)
-    pool.map(_cpu_worker, [([0], 2, 5, 4)] * cores)
+    pool.map(_cpu_worker, [('dynaq', [0], 1)] * cores)
     for _ in range(args.warmup):
-        cpu_dynaq(wl, 1, pool, cores)
-    t_tot, s_tot, last = 0.0, 0, None
+        cpu_run(name, 1, pool, cores)
+    t_tot, u_tot, last = 0.0, 0, None
     for _ in range(args.steps):
-        last = cpu_dynaq(wl, 1, pool, cores)
-        t_tot += last['seconds']; s_tot += last['agent_steps']
+        last = cpu_run(name, 1, pool, cores)
+        t_tot += last['seconds']; u_tot += last['units']
     pool.close()
-    val = s_tot / t_tot
-    cb = dict(last); cb['value'] = val
-    cb.pop('seconds'); cb.pop('agent_steps')
+    val = u_tot / t_tot
+    cb = {k: v for k, v in last.items() if k not in ('seconds', 'units')}
+    cb['value'] = val
     print(json.dumps({
-        'impl': 'reference', 'metric': 'agent-steps/sec incl. replay', 'value': val, 'unit': 'agent-steps/s',
+        'impl': 'reference', 'metric': wl['metric'], 'value': val, 'unit': wl['unit'],
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': wl['desc'], 'note': 'each step = one agent per host core run through the full workload'},
+        'config': {'workload': wl['desc'], 'note': 'each step = one agent per host core run through the workload '
+                   '(%d trials)' % wl['cpu_trials']},
         'cpu_baseline': cb,
-        'e2e': {'value': val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'e2e': {'value': val, 'unit': wl['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }))
 
@@ -173,140 +234,230 @@ def run_reference(args, wl):
 # our arm
 # --------------------------------------------------------------------------- #
 
-def run_ours(args, wl):
-    import torch
-    import cobel_rl_b200 as cb
-    from cobel_rl_b200 import _lib, dist as cdist
-    from cobel_rl_b200.agent import DynaQ
-    from cobel_rl_b200.interface import Gridworld
-    from cobel_rl_b200.memory import DynaQMemory
-    from cobel_rl_b200.misc.gridworld_tools import make_open_field
-    from cobel_rl_b200.policy import EpsilonGreedy
+class Job:
+    """One workload on one rank: builds the agents through the public class API, exposes
+    ``step()`` (kernel-only, inputs resident in HBM) and ``step_e2e()`` (host buffers in, results out)."""
 
-    rank, world, local = cdist.init_from_env()
-    assert world == args.gpus, 'launch with torchrun --nproc-per-node %d for --gpus %d' % (args.gpus, args.gpus)
-    dev = torch.device('cuda', local)
-    torch.cuda.set_device(dev)
-    L = _lib.lib()
-    n_local = wl['agents_per_gpu']
-    n_total = n_local * world
-    lo, hi = cdist.shard_range(n_total, rank, world)
-    S, A, trials, steps, batch = wl['S'], wl['A'], wl['trials'], wl['steps'], wl['batch']
+    def __init__(self, name, dev, lo, n_local):
+        import torch
+        import cobel_rl_b200 as cb
+        from cobel_rl_b200 import agent as AG, memory as MEM
+        from cobel_rl_b200.interface import Gridworld, Topology
+        from cobel_rl_b200.policy import EpsilonGreedy
+        self.torch, self.name, self.wl, self.dev = torch, name, WORKLOADS[name], dev
+        wl = self.wl
+        self.stream = st = cb.BatchStream(n_local, seed=SEED, device=dev, agent_id_base=lo)
+        if name == 'q':
+            from cobel_rl_b200.misc.topology_tools import linear_track
+            self.env = Topology(*linear_track(10, 2, 1.0, 20.0, 'right'), rng=st)
+        else:
+            self.world = make_world(wl['world'])
+            self.env = Gridworld(self.world, rng=st)
+        env = self.env
+        pol = EpsilonGreedy(0.1, rng=st)
+        if name == 'dynaq':
+            mem = MEM.DynaQMemory(env.n_states, 4, 0.9, rng=st)
+            self.agent = AG.DynaQ(env.observation_space, env.action_space, pol, None, 0.99, 0.99, mem)
+            self.state = {'Q': self.agent._Q, 'Mr': mem._rewards, 'Ms': mem._states, 'Mt': mem._terminals}
+        elif name == 'q':
+            self.agent = AG.QAgent(env.observation_space, env.action_space, pol, None, 0.9, 0.8, rng=st)
+            self.agent._alloc_q(env.n_states)
+            self.agent._ensure_log(wl['trials'] * wl['steps'])
+            self.state = {'Q': self.agent._Q, 'log_len': self.agent._log_len}
+        elif name == 'sr':
+            self.agent = AG.SR(env.observation_space, env.action_space, pol, None, 0.1, 0.99)
+            self.state = {'SR': self.agent._SR, 'rew': self.agent._rewards, 'model': self.agent._model}
+        elif name == 'sfma':
+            from cobel_rl_b200.memory.utils.metrics import DR
+            w = self.world
+            mem = MEM.SFMAMemory(DR(w['width'], w['height'], w['sas'], 0.9, w['invalid_transitions']),
+                                 env.n_states, 4, rng=st)
+            self.agent = AG.SFMA(env.observation_space, env.action_space, pol, mem, None, 0.99, 0.99, rng=st)
+            self.agent.mask_actions = True
+            self.state = {'Q': self.agent._Q, 'Mr': mem._rewards, 'Ms': mem._states, 'Mt': mem._terminals,
+                          'C': mem._C, 'T': mem._T, 'I': mem._I}
+        elif name == 'pma':
+            mem = MEM.PMAMemory(self.world['sas'], EpsilonGreedy(0.1, rng=st), 0.9, 0.9, 0.9, 0.99, rng=st)
+            self.agent = AG.PMA(env.observation_space, env.action_space, pol, mem, None, 0.9, 0.99)
+            self.agent.mask_actions = True
+            self.state = {'Q': self.agent._Q, 'Mr': mem._rewards, 'Ms': mem._states, 'Mt': mem._terminals,
+                          'T': mem._T, 'SR': mem._SR}
+        # per-agent state small enough to keep pristine device + pinned host copies of (everything except the
+        # S x S matrices, which are re-broadcast on the device from one pristine matrix)
+        self.big = {k: v[0].clone() for k, v in self.state.items() if v.dim() == 3 and v[0].numel() >= 2500}
+        self.init = {k: v.clone() for k, v in self.state.items() if k not in self.big}
+        self.host_in = {k: v.cpu().pin_memory() for k, v in self.init.items()}
+        self.host_big = {k: v.cpu().pin_memory() for k, v in self.big.items()}
+        tr = wl['trials']
+        self.host_out = {'trial_steps': torch.empty((n_local, tr), dtype=torch.int32).pin_memory(),
+                         'trial_reward': torch.empty((n_local, tr), dtype=torch.float64).pin_memory()}
+        key = 'Q' if 'Q' in self.state else 'rew'
+        self.out_key = key
+        self.host_out[key] = torch.empty(self.state[key].shape, dtype=self.state[key].dtype).pin_memory()
 
-    stream = cb.BatchStream(n_local, seed=SEED, device=dev, agent_id_base=lo)
-    env = Gridworld(make_open_field(5, 5, 0, 1), rng=stream)
-    mem = DynaQMemory(S, A, 0.9, rng=stream)
-    agent = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), None, 0.99, 0.99, mem)
+    def _train(self):
+        wl, a = self.wl, self.agent
+        if self.name == 'sr':
+            return a.train(self.env, wl['trials'], wl['steps'])
+        return a.train(self.env, wl['trials'], wl['steps'], wl['batch'])
 
-    # pristine tables: device copies for the kernel-only loop, pinned host copies for the e2e loop
-    init = {'Q': agent._Q.clone(), 'Mr': mem._rewards.clone(), 'Ms': mem._states.clone(), 'Mt': mem._terminals.clone()}
-    host_in = {k: v.cpu().pin_memory() for k, v in init.items()}
-    live = {'Q': agent._Q, 'Mr': mem._rewards, 'Ms': mem._states, 'Mt': mem._terminals}
-    host_out = {'Q': torch.empty_like(host_in['Q']).pin_memory(),
-                'trial_steps': torch.empty((n_local, trials), dtype=torch.int32).pin_memory(),
-                'trial_reward': torch.empty((n_local, trials), dtype=torch.float64).pin_memory()}
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    def reset(self):
+        for k, v in self.init.items():
+            self.state[k].copy_(v)
+        for k, v in self.big.items():
+            self.state[k].copy_(v.unsqueeze(0).expand_as(self.state[k]))
+        self.stream.draw_count.fill_(1)        # draw 0 was consumed by the environment constructor
 
-    def reset_device():
-        for k in live:
-            live[k].copy_(init[k])
-        stream.draw_count.fill_(1)          # draw 0 was consumed by the environment constructor
+    def step(self):
+        return self._train()
 
-    def step_device():
-        reset_device()
-        return agent.train(env, trials, steps, batch)
-
-    def step_e2e():
-        for k in live:
-            live[k].copy_(host_in[k], non_blocking=True)
-        stream.draw_count.fill_(1)
-        res = agent.train(env, trials, steps, batch)
-        host_out['Q'].copy_(agent._Q, non_blocking=True)
-        host_out['trial_steps'].copy_(res['trial_steps'], non_blocking=True)
-        host_out['trial_reward'].copy_(res['trial_reward'], non_blocking=True)
+    def step_e2e(self):
+        """Host buffers in (pinned), results out: per-agent tables + hyper-parameters H2D, train(), D2H."""
+        for k, v in self.host_in.items():
+            self.state[k].copy_(v, non_blocking=True)
+        for k, v in self.host_big.items():
+            self.state[k].copy_(v.to(self.dev, non_blocking=True).unsqueeze(0).expand_as(self.state[k]))
+        self.stream.draw_count.fill_(1)
+        res = self._train()
+        self.host_out[self.out_key].copy_(self.state[self.out_key], non_blocking=True)
+        self.host_out['trial_steps'].copy_(res['trial_steps'], non_blocking=True)
+        self.host_out['trial_reward'].copy_(res['trial_reward'], non_blocking=True)
         return res
 
-    def timed(fn, k):
-        """K steps; device time per step from CUDA events on the launching (current) stream,
-        L2 flushed between steps outside the event pairs; wall clock kept as a cross-check."""
+    def h2d_bytes(self):
+        return sum(v.numel() * v.element_size() for v in list(self.host_in.values()) + list(self.host_big.values()))
+
+    def d2h_bytes(self):
+        return sum(v.numel() * v.element_size() for v in self.host_out.values())
+
+
+def measure(job, k, warmup, cdist, dev, flush, e2e=True):
+    """Returns dict(ms kernel-only, ms e2e, per-rank units of one step, launches, wall)."""
+    import torch
+    from cobel_rl_b200 import _lib
+    L = _lib.lib()
+
+    def timed(fn, pre):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
         res = None
         cdist.barrier(); torch.cuda.synchronize(dev)
         w0 = time.perf_counter()
         for s, e in evs:
-            flush.fill_(1)
+            flush.fill_(1)                      # evict L2 (256 MiB write), outside the event pair
+            if pre:
+                pre()
             s.record()
             res = fn()
             e.record()
         torch.cuda.synchronize(dev); cdist.barrier()
         wall = time.perf_counter() - w0
-        ms = [s.elapsed_time(e) for s, e in evs]
-        return ms, wall, res
+        return [s.elapsed_time(e) for s, e in evs], wall, res
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
+    for _ in range(max(warmup, 3)):
+        job.reset(); job.step()
     torch.cuda.synchronize(dev)
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = L.cobel_launch_count()
-    ms, wall, res = timed(step_device, args.steps)
+    ms, wall, res = timed(job.step, job.reset)
     launches = L.cobel_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    steps_local = float(res['n_steps'].sum().item())           # agent-steps of ONE bench step on this rank
-    replays_local = float(res['n_replay'].sum().item())
+    units = float(res[job.wl['unit_key']].sum().item())
+    out = {'ms': sum(ms) / len(ms), 'wall': wall, 'units': units, 'launches': int(launches), 'res': res,
+           'steps_units': float(res['n_steps'].sum().item()), 'replay_units': float(res['n_replay'].sum().item())}
+    if e2e:
+        for _ in range(2):
+            job.step_e2e()
+        torch.cuda.synchronize(dev)
+        ms2, _, res2 = timed(job.step_e2e, None)
+        assert float(res2[job.wl['unit_key']].sum().item()) == units
+        out['ms_e2e'] = sum(ms2) / len(ms2)
+    return out
 
-    for _ in range(2):
-        step_e2e()
-    torch.cuda.synchronize(dev)
-    ms_e2e, wall_e2e, res_e = timed(step_e2e, args.steps)
-    assert float(res_e['n_steps'].sum().item()) == steps_local
 
-    # the only collective of the path: final all-gather of per-agent statistics
-    torch.cuda.synchronize(dev)
-    g0 = time.perf_counter()
-    gathered = cdist.gather_results(res, n_total)
-    torch.cuda.synchronize(dev)
-    gather_ms = 1e3 * (time.perf_counter() - g0)
-    assert gathered['n_steps'].shape[0] == n_total
+def result_block(name, m, world, peak, peak_src, job, t_step, t_e2e, units_total):
+    wl = WORKLOADS[name]
+    achieved = wl['bytes_per_unit'] * m['units'] / (m['ms'] * 1e-3) / 1e9
+    blk = {
+        'metric': wl['metric'], 'value': units_total / (t_step * 1e-3), 'unit': wl['unit'], 'ms_per_step': t_step,
+        'config': {'workload': wl['desc'], 'agents_total': wl['agents_per_gpu'] * world,
+                   'units_per_bench_step': units_total,
+                   'l2': 'flushed between steps with a 256 MiB write (outside the event pairs)',
+                   'timing': 'CUDA events on the launching stream per step (table reset outside), mean of K, max over ranks',
+                   'seed': SEED},
+        'roofline': {'bound': 'hbm', 'kernel': wl['kernel'], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_unit': wl['bytes_per_unit'],
+                     'note': 'per-agent tables stay in shared memory for the whole launch, so DRAM traffic is far '
+                             'below the algorithmic bytes; the kernels are issue / dependency-latency bound '
+                             '(DESIGN.md, profiles/)'},
+        'gpu_launches': m['launches'],
+    }
+    if t_e2e is not None:
+        blk['e2e'] = {'value': units_total / (t_e2e * 1e-3), 'unit': wl['unit'], 'h2d_bytes_per_step': job.h2d_bytes(),
+                      'd2h_bytes_per_step': job.d2h_bytes(), 'ms_per_step': t_e2e}
+    return blk
 
-    t_step = cdist.max_over_ranks(sum(ms) / len(ms), dev)              # ms, max over ranks
-    t_e2e = cdist.max_over_ranks(sum(ms_e2e) / len(ms_e2e), dev)
-    steps_total = cdist.sum_over_ranks(steps_local, dev)
-    replays_total = cdist.sum_over_ranks(replays_local, dev)
-    wall_max = cdist.max_over_ranks(wall, dev)
 
+def run_ours(args):
+    import torch
+    from cobel_rl_b200 import dist as cdist
+
+    rank, world, local = cdist.init_from_env()
+    assert world == args.gpus, 'launch with torchrun --nproc-per-node %d for --gpus %d' % (args.gpus, args.gpus)
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    peak, peak_src = peaks()
+    names = [args.workload] + (['pma'] if args.workload == 'dynaq' and not args.no_pma else [])
+    blocks, clocks = {}, None
+    for name in names:
+        wl = WORKLOADS[name]
+        n_local = wl['agents_per_gpu']
+        lo, hi = cdist.shard_range(n_local * world, rank, world)
+        job = Job(name, dev, lo, n_local)
+        sampler = ClockSampler(local)
+        if rank == 0 and name == names[0]:
+            sampler.start()
+        k = args.steps if name == names[0] else max(3, min(args.steps, 5))
+        m = measure(job, k, args.warmup, cdist, dev, flush)
+        if rank == 0 and name == names[0]:
+            clocks = sampler.stop()
+        # the only collective of the path: final all-gather of per-agent statistics
+        torch.cuda.synchronize(dev)
+        g0 = time.perf_counter()
+        gathered = cdist.gather_results(m['res'], n_local * world)
+        torch.cuda.synchronize(dev)
+        gather_ms = 1e3 * (time.perf_counter() - g0)
+        assert gathered['n_steps'].shape[0] == n_local * world
+        t_step = cdist.max_over_ranks(m['ms'], dev)
+        t_e2e = cdist.max_over_ranks(m['ms_e2e'], dev)
+        units_total = cdist.sum_over_ranks(m['units'], dev)
+        steps_total = cdist.sum_over_ranks(m['steps_units'], dev)
+        replay_total = cdist.sum_over_ranks(m['replay_units'], dev)
+        if rank == 0:
+            blk = result_block(name, m, world, peak, peak_src, job, t_step, t_e2e, units_total)
+            blk['config'].update(agent_steps_per_bench_step=steps_total, replay_updates_per_bench_step=replay_total,
+                                 final_all_gather_ms=gather_ms, wall_s_incl_flush_and_reset=m['wall'])
+            blocks[name] = blk
+        del job, gathered, m
+        torch.cuda.empty_cache()
     if rank != 0:
         return
-    value = steps_total / (t_step * 1e-3)
-    peak, peak_src = peaks()
-    # roofline of the dominant (only) kernel, dynaq_smem_kernel: one launch per bench step per GPU
-    achieved = DYNAQ_BYTES_PER_STEP * steps_local / (ms and (sum(ms) / len(ms)) * 1e-3) / 1e9
-    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
-    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+    head = blocks[names[0]]
     out = {
-        'metric': 'agent-steps/sec incl. replay', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': t_step, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': wl['desc'], 'agents_total': n_total, 'agent_steps_per_bench_step': steps_total,
-                   'replay_updates_per_bench_step': replays_total,
-                   'l2': 'flushed between steps with a 256 MiB write (outside the event pairs); inputs are 7 MB',
-                   'timing': 'CUDA events on the launching stream per step, mean of K, max over ranks',
-                   'wall_s_incl_flush': wall_max, 'final_all_gather_ms': gather_ms, 'seed': SEED},
-        'roofline': {'bound': 'hbm', 'kernel': 'dynaq_smem_kernel<4>', 'achieved': achieved, 'peak': peak,
-                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-                     'peak_source': peak_src, 'algorithmic_bytes_per_agent_step': DYNAQ_BYTES_PER_STEP,
-                     'note': 'tables live in shared memory for the whole launch: real DRAM traffic is the one-off '
-                             'stage-in/out; the kernel is bound by the serial fp64 TD-update chain (see DESIGN.md)'},
-        'e2e': {'value': steps_total / (t_e2e * 1e-3), 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h, 'ms_per_step': t_e2e},
-        'gpu_launches': int(launches), 'clocks': clocks,
+        'metric': head['metric'], 'value': head['value'], 'unit': head['unit'], 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': head['ms_per_step'],
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': head['config'], 'roofline': head['roofline'], 'e2e': head['e2e'],
+        'gpu_launches': head['gpu_launches'], 'clocks': clocks,
     }
     if world == 1 and not args.no_cpu:
-        cbase = cpu_dynaq(wl, 2)
-        cbase.pop('seconds'); cbase.pop('agent_steps')
-        out['cpu_baseline'] = cbase
+        cb = cpu_run(names[0], 2 if names[0] == 'dynaq' else 1)
+        out['cpu_baseline'] = {k: v for k, v in cb.items() if k not in ('seconds', 'units')}
+    for name in names[1:]:
+        blk = blocks[name]
+        if world == 1 and not args.no_cpu:
+            cb = cpu_run(name, 1)
+            blk['cpu_baseline'] = {k: v for k, v in cb.items() if k not in ('seconds', 'units')}
+        out[name] = blk
     print(json.dumps(out))
 
 
@@ -318,12 +469,12 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='dynaq', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-pma', action='store_true', help='skip the second headline metric (PMA replay-updates/s)')
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
     if args.impl == 'reference':
-        run_reference(args, wl)
+        run_reference(args)
     else:
-        run_ours(args, wl)
+        run_ours(args)
     try:
         import torch.distributed as dist
         if dist.is_initialized():

@@ -543,8 +543,25 @@ def t0_from_succ(succ):
 
 
 def _probs_rows(policy, Qrows, mask_rows):
-    return np.array([action_probs(policy, q, None if mask_rows is None else mask_rows[j])
-                     for j, q in enumerate(Qrows)])
+    """Row-wise ``get_action_probs`` (memory/pma.py:440-449).  The epsilon-greedy kinds are
+    evaluated for all rows at once with the same element-wise IEEE operations as the per-row
+    call (``eps/n + ((1-eps)*tie)/k``), which keeps the result bit-identical and the oracle usable
+    as a CPU baseline; other kinds fall back to the per-row restatement."""
+    kind, par = policy
+    if kind not in ('eps', 'xeps'):
+        return np.array([action_probs(policy, q, None if mask_rows is None else mask_rows[j])
+                         for j, q in enumerate(Qrows)])
+    Qrows = np.asarray(Qrows, dtype=np.float64)
+    valid = np.ones(Qrows.shape, dtype=bool) if mask_rows is None else np.asarray(mask_rows, dtype=bool)
+    vmax = np.max(np.where(valid, Qrows, -np.inf), axis=1, keepdims=True)
+    ties = (Qrows == vmax) & valid
+    nv = valid.sum(axis=1, keepdims=True)
+    k = ties.sum(axis=1, keepdims=True)
+    if kind == 'eps':
+        p = par / nv + ((1.0 - par) * ties) / k
+    else:
+        p = ((1.0 - par) * ties) / k + (par * (~ties & valid)) / np.maximum(nv - k, 1)
+    return np.where(valid, p, 0.0)
 
 
 def pma_gain_batch(st, Qx, mask, policy, lr_q, gamma_q, min_gain):
