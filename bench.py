@@ -67,6 +67,10 @@ WORKLOADS = {
 }
 
 
+# agents per host core in the cpu_baseline leg: sized for roughly 10-20 s of CPU work per workload
+CPU_AGENTS_PER_CORE = {'dynaq': 16, 'pma': 12, 'q': 16, 'sr': 8, 'sfma': 4}
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -450,12 +454,12 @@ def run_ours(args):
         'gpu_launches': head['gpu_launches'], 'clocks': clocks,
     }
     if world == 1 and not args.no_cpu:
-        cb = cpu_run(names[0], 2 if names[0] == 'dynaq' else 1)
+        cb = cpu_run(names[0], CPU_AGENTS_PER_CORE.get(names[0], 1))
         out['cpu_baseline'] = {k: v for k, v in cb.items() if k not in ('seconds', 'units')}
     for name in names[1:]:
         blk = blocks[name]
         if world == 1 and not args.no_cpu:
-            cb = cpu_run(name, 1)
+            cb = cpu_run(name, CPU_AGENTS_PER_CORE.get(name, 1))
             blk['cpu_baseline'] = {k: v for k, v in cb.items() if k not in ('seconds', 'units')}
         out[name] = blk
     print(json.dumps(out))
