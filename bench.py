@@ -473,8 +473,13 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='dynaq', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--agents', type=int, default=0, help='override agents per GPU (profiling only; not the headline config)')
     ap.add_argument('--no-pma', action='store_true', help='skip the second headline metric (PMA replay-updates/s)')
     args = ap.parse_args()
+    if args.agents:
+        for w in WORKLOADS.values():
+            w['agents_per_gpu'] = args.agents
+            w['desc'] += ' [agents per GPU overridden to %d]' % args.agents
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -25,12 +25,12 @@
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;        // 16 x 16 thread grid for the register-tiled eliminations
 constexpr int kMaxSeq = 64;          // longest n-step sequence (replay batch) supported
 
 struct PmaSmem {
-  int mat, q, mr, gain, util, need, pk, umask, mbits, dirty, seq, perf, psr, pq, part, qpar, qom, bytes;
-  __host__ __device__ PmaSmem(int S, int A, int B) {
+  int mat, q, mr, gain, util, need, pk, umask, mbits, dirty, seq, perf, psr, pq, part, qpar, qom, elim, bytes;
+  __host__ __device__ PmaSmem(int S, int A, int B, int tile) {
     const int N = S * A;
     mat = 0;
     q = (mat + S * S * 8 + 15) & ~15;       // Q rows are read with 16-byte vector loads
@@ -41,7 +41,8 @@ struct PmaSmem {
     psr = (need + S * 8 + 15) & ~15;
     pq = psr + (kMaxSeq + 2) * 8;
     part = pq + (kMaxSeq + 2) * 8;
-    qpar = part + (kThreads + 40) * 8;
+    elim = part + (kThreads + 40) * 8;       // 2 x (pivot row + pivot column) of the tiled eliminations
+    qpar = elim + 4 * tile * 16 * 8;
     qom = qpar + 8 * 8;
     seq = qom + 8 * 8;
     perf = seq + (kMaxSeq + 2) * 4;
@@ -143,14 +144,183 @@ COBEL_DEV double block_sum(double v, double* part, int tid, int T) {
   return m;
 }
 
-template <int A>
-__global__ void __launch_bounds__(kThreads) pma_kernel(const __grid_constant__ CobelPMAParams p) {
+// ---------------------------------------------------------------------------
+// Register-tiled dense eliminations on an S x S matrix distributed over the 16 x 16 thread
+// grid of the CTA: thread (ty, tx) owns elements (ty + 16 r, tx + 16 c), r, c < TILE.  Each
+// elimination step broadcasts one pivot row and one pivot column through shared memory
+// (double-buffered: one barrier per step) and updates the tiles with TILE*TILE DFMAs per
+// thread, i.e. the S^3 work runs out of registers at the fp64 pipe rate instead of the
+// shared-memory rate.  These two routines are the only non-bit-exact arithmetic of the kernel
+// (the reference calls LAPACK here), so FMA contraction is used deliberately.
+// ---------------------------------------------------------------------------
+template <int TILE>
+struct Tile {
+  double m[TILE][TILE];
+};
+
+// SR = inv(I - gamma T) by in-place Gauss-Jordan without pivoting (I - gamma T is strictly
+// diagonally dominant).  The pivot row / column need no special-casing: with f_k := piv - 1 and
+// rowk_k := 1 + 1/piv the generic update m -= f_i * rowk_j / piv also produces the scaled pivot
+// row, -f_i/piv in the pivot column and 1/piv on the pivot.
+template <int TILE>
+__device__ __forceinline__ void gauss_jordan_inverse(const double* __restrict__ Tg, double gsr, double* Mat, double* SRg,
+                                                     int S, double* buf, int tid, int& flags) {
+  const int ty = tid >> 4, tx = tid & 15;
+  const int SP = TILE * 16;
+  Tile<TILE> t;
+#pragma unroll
+  for (int r = 0; r < TILE; ++r)
+#pragma unroll
+    for (int c = 0; c < TILE; ++c) {
+      const int i = ty + 16 * r, j = tx + 16 * c;
+      double v = i == j ? 1.0 : 0.0;
+      if (i < S && j < S) v -= gsr * Tg[(size_t)i * S + j];
+      t.m[r][c] = v;
+    }
+  for (int k = 0; k < S; ++k) {
+    double* rowk = buf + (k & 1) * 2 * SP;
+    double* colk = rowk + SP;
+    const int r0 = k >> 4, c0 = k >> 4;
+    if (ty == (k & 15)) {
+#pragma unroll
+      for (int r = 0; r < TILE; ++r)
+        if (r == r0) {
+#pragma unroll
+          for (int c = 0; c < TILE; ++c) rowk[tx + 16 * c] = t.m[r][c];
+        }
+    }
+    if (tx == (k & 15)) {
+#pragma unroll
+      for (int c = 0; c < TILE; ++c)
+        if (c == c0) {
+#pragma unroll
+          for (int r = 0; r < TILE; ++r) colk[ty + 16 * r] = t.m[r][c];
+        }
+    }
+    __syncthreads();
+    const double piv = rowk[k];
+    if (!(fabs(piv) > 1e-300)) flags |= COBEL_FLAG_SINGULAR;
+    const double ipiv = 1.0 / piv;
+    double rk[TILE];
+#pragma unroll
+    for (int c = 0; c < TILE; ++c) {
+      const int j = tx + 16 * c;
+      rk[c] = j == k ? 1.0 + ipiv : rowk[j] * ipiv;
+    }
+#pragma unroll
+    for (int r = 0; r < TILE; ++r) {
+      const int i = ty + 16 * r;
+      const double f = i == k ? piv - 1.0 : colk[i];
+#pragma unroll
+      for (int c = 0; c < TILE; ++c) t.m[r][c] = fma(-f, rk[c], t.m[r][c]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < TILE; ++r)
+#pragma unroll
+    for (int c = 0; c < TILE; ++c) {
+      const int i = ty + 16 * r, j = tx + 16 * c;
+      if (i < S && j < S) { Mat[i * S + j] = t.m[r][c]; SRg[(size_t)i * S + j] = t.m[r][c]; }
+    }
+  __syncthreads();
+}
+
+// Stationary distribution of the row-stochastic T by GTH (Grassmann-Taksar-Heyman) elimination,
+// returned in x[0..S) scaled to unit 2-norm.  Mat receives the eliminated matrix (scratch).
+template <int TILE>
+__device__ __forceinline__ void gth_stationary(const double* __restrict__ Tg, double* Mat, double* x, int S, double* buf,
+                                               int tid, int& flags) {
+  const int ty = tid >> 4, tx = tid & 15, lane = tid & 31;
+  const int SP = TILE * 16;
+  Tile<TILE> t;
+#pragma unroll
+  for (int r = 0; r < TILE; ++r)
+#pragma unroll
+    for (int c = 0; c < TILE; ++c) {
+      const int i = ty + 16 * r, j = tx + 16 * c;
+      t.m[r][c] = (i < S && j < S) ? Tg[(size_t)i * S + j] : 0.0;
+    }
+  for (int k = S - 1; k >= 1; --k) {
+    double* rowk = buf + (k & 1) * 2 * SP;
+    double* colk = rowk + SP;
+    const int r0 = k >> 4, c0 = k >> 4;
+    if (ty == (k & 15)) {
+#pragma unroll
+      for (int r = 0; r < TILE; ++r)
+        if (r == r0) {
+#pragma unroll
+          for (int c = 0; c < TILE; ++c) rowk[tx + 16 * c] = t.m[r][c];
+        }
+    }
+    if (tx == (k & 15)) {
+#pragma unroll
+      for (int c = 0; c < TILE; ++c)
+        if (c == c0) {
+#pragma unroll
+          for (int r = 0; r < TILE; ++r) colk[ty + 16 * r] = t.m[r][c];
+        }
+    }
+    __syncthreads();
+    // every warp forms s = sum_{j<k} P[k][j] with the same reduction tree
+    double ssum = 0.0;
+    for (int j = lane; j < k; j += 32) ssum += rowk[j];
+    for (int d = 16; d > 0; d >>= 1) ssum += shfl_f64_xor(ssum, d);
+    if (!(ssum > 0.0)) { flags |= COBEL_FLAG_SINGULAR; ssum = 1.0; }
+    const double inv = 1.0 / ssum;
+    double rk[TILE];
+#pragma unroll
+    for (int c = 0; c < TILE; ++c) {
+      const int j = tx + 16 * c;
+      rk[c] = j < k ? rowk[j] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < TILE; ++r) {
+      const int i = ty + 16 * r;
+      const double f = i < k ? colk[i] * inv : 0.0;
+#pragma unroll
+      for (int c = 0; c < TILE; ++c) {
+        const int j = tx + 16 * c;
+        t.m[r][c] = j == k ? (i < k ? f : t.m[r][c]) : fma(f, rk[c], t.m[r][c]);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < TILE; ++r)
+#pragma unroll
+    for (int c = 0; c < TILE; ++c) {
+      const int i = ty + 16 * r, j = tx + 16 * c;
+      if (i < S && j < S) Mat[i * S + j] = t.m[r][c];
+    }
+  __syncthreads();
+  if (tid < 32) {                                   // x_0 = 1, x_k = sum_{i<k} x_i P[i][k]: one warp, no block barriers
+    if (lane == 0) x[0] = 1.0;
+    __syncwarp();
+    for (int k = 1; k < S; ++k) {
+      double acc = 0.0;
+      for (int i = lane; i < k; i += 32) acc = fma(x[i], Mat[i * S + k], acc);
+      for (int d = 16; d > 0; d >>= 1) acc += shfl_f64_xor(acc, d);
+      if (lane == 0) x[k] = acc;
+      __syncwarp();
+    }
+    double sq = 0.0;
+    for (int i = lane; i < S; i += 32) sq = fma(x[i], x[i], sq);
+    for (int d = 16; d > 0; d >>= 1) sq += shfl_f64_xor(sq, d);
+    const double nrm = sqrt(sq);
+    for (int i = lane; i < S; i += 32) x[i] = fabs(x[i]) / nrm;
+  }
+  __syncthreads();
+}
+
+template <int A, int TILE>
+__global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_kernel(const __grid_constant__ CobelPMAParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ PmaShared sh;
   const int S = p.world.n_states, K = p.world.n_starts, N = S * A, B = p.batch;
   const int tid = threadIdx.x, T = kThreads, lane = tid & 31, warp = tid >> 5;
   const int64_t n = blockIdx.x;
-  const PmaSmem so(S, A, B);
+  const PmaSmem so(S, A, B, TILE);
   double* Mat = reinterpret_cast<double*>(smem + so.mat);     // SR (need rows) / elimination scratch
   double* Q = reinterpret_cast<double*>(smem + so.q);         // [s][a]
   double* Mr = reinterpret_cast<double*>(smem + so.mr);       // [s][a]
@@ -160,6 +330,7 @@ __global__ void __launch_bounds__(kThreads) pma_kernel(const __grid_constant__ C
   double* powsr = reinterpret_cast<double*>(smem + so.psr);   // M.gamma ** k
   double* powq = reinterpret_cast<double*>(smem + so.pq);     // M.gamma_q ** k
   double* part = reinterpret_cast<double*>(smem + so.part);
+  double* elim = reinterpret_cast<double*>(smem + so.elim);
   double* qpar = reinterpret_cast<double*>(smem + so.qpar);
   double* qom = reinterpret_cast<double*>(smem + so.qom);
   int32_t* seq = reinterpret_cast<int32_t*>(smem + so.seq);   // candidate n-step sequence (flat indices)
@@ -248,69 +419,13 @@ __global__ void __launch_bounds__(kThreads) pma_kernel(const __grid_constant__ C
     return g > min_gain ? g : min_gain;
   };
 
-  // SR = inv(I - gamma T): PMAMemory.update_sr, memory/pma.py:413-415 (in-place Gauss-Jordan)
-  auto update_sr = [&]() {
-    for (int e = tid; e < S * S; e += T) {
-      const int i = e / S, j = e - i * S;
-      Mat[e] = xsub(i == j ? 1.0 : 0.0, xmul(gsr, Tg[e]));
-    }
-    __syncthreads();
-    for (int k = 0; k < S; ++k) {
-      const double piv = Mat[k * S + k];
-      if (!(fabs(piv) > 1e-300)) flags |= COBEL_FLAG_SINGULAR;
-      const double ipiv = 1.0 / piv;
-      __syncthreads();
-      for (int j = tid; j < S; j += T) Mat[k * S + j] = j == k ? ipiv : Mat[k * S + j] * ipiv;
-      __syncthreads();
-      for (int e = tid; e < S * S; e += T) {
-        const int i = e / S, j = e - i * S;
-        if (i == k) continue;
-        const double f = Mat[i * S + k];
-        // column k is read by every thread of row i: update it last, from the saved factor
-        if (j != k) Mat[e] = Mat[e] - f * Mat[k * S + j];
-      }
-      __syncthreads();
-      for (int i = tid; i < S; i += T)
-        if (i != k) Mat[i * S + k] = -Mat[i * S + k] * ipiv;
-      __syncthreads();
-    }
-    for (int e = tid; e < S * S; e += T) SRg[e] = Mat[e];
-    __syncthreads();
-  };
+  // SR = inv(I - gamma T): PMAMemory.update_sr, memory/pma.py:413-415
+  auto update_sr = [&]() { gauss_jordan_inverse<TILE>(Tg, gsr, Mat, SRg, S, elim, tid, flags); };
 
-  // |left Perron vector| of T with unit 2-norm (memory/pma.py:401-408) by GTH elimination;
-  // uses (and destroys) the matrix buffer, the caller restores SR from HBM afterwards.
+  // |left Perron vector| of T with unit 2-norm (memory/pma.py:401-408); uses (and destroys) the
+  // matrix buffer, SR is restored from HBM afterwards.
   auto stationary = [&]() {
-    for (int e = tid; e < S * S; e += T) Mat[e] = Tg[e];
-    __syncthreads();
-    for (int k = S - 1; k >= 1; --k) {
-      double ssum = 0.0;
-      for (int j = tid; j < k; j += T) ssum += Mat[k * S + j];
-      ssum = block_sum(ssum, part, tid, T);
-      if (!(ssum > 0.0)) { flags |= COBEL_FLAG_SINGULAR; ssum = 1.0; }
-      for (int i = tid; i < k; i += T) Mat[i * S + k] /= ssum;
-      __syncthreads();
-      for (int e = tid; e < k * k; e += T) {
-        const int i = e / k, j = e - i * k;
-        Mat[i * S + j] += Mat[i * S + k] * Mat[k * S + j];
-      }
-      __syncthreads();
-    }
-    if (tid == 0) needv[0] = 1.0;
-    __syncthreads();
-    for (int k = 1; k < S; ++k) {
-      double acc = 0.0;
-      for (int i = tid; i < k; i += T) acc += needv[i] * Mat[i * S + k];
-      acc = block_sum(acc, part, tid, T);
-      if (tid == 0) needv[k] = acc;
-      __syncthreads();
-    }
-    double sq = 0.0;
-    for (int i = tid; i < S; i += T) sq += needv[i] * needv[i];
-    sq = block_sum(sq, part, tid, T);
-    const double nrm = sqrt(sq);
-    for (int i = tid; i < S; i += T) needv[i] = fabs(needv[i]) / nrm;
-    __syncthreads();
+    gth_stationary<TILE>(Tg, Mat, needv, S, elim, tid, flags);
     for (int e = tid; e < S * S; e += T) Mat[e] = SRg[e];
     __syncthreads();
   };
@@ -602,18 +717,26 @@ __global__ void __launch_bounds__(kThreads) pma_kernel(const __grid_constant__ C
   }
 }
 
-template <int A>
-int launch(const CobelPMAParams& p, cudaStream_t st) {
+template <int A, int TILE>
+int launch_tile(const CobelPMAParams& p, cudaStream_t st) {
   const int S = p.world.n_states;
-  COBEL_REQUIRE(S <= 0x7FFF, COBEL_EUNSUPPORTED, "PMA kernel supports at most 32767 states");
-  const PmaSmem so(S, A, p.batch);
+  const PmaSmem so(S, A, p.batch, TILE);
   COBEL_REQUIRE(so.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
                 "PMA: %d states need %d bytes of shared memory (the S x S successor representation must fit)", S, so.bytes);
-  COBEL_CUDA_OK(cudaFuncSetAttribute(pma_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, so.bytes));
-  pma_kernel<A><<<(unsigned)p.n_agents, kThreads, so.bytes, st>>>(p);
+  COBEL_CUDA_OK(cudaFuncSetAttribute(pma_kernel<A, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, so.bytes));
+  pma_kernel<A, TILE><<<(unsigned)p.n_agents, kThreads, so.bytes, st>>>(p);
   cobel_count_launch();
   COBEL_CUDA_OK(cudaGetLastError());
   return COBEL_OK;
+}
+
+template <int A>
+int launch(const CobelPMAParams& p, cudaStream_t st) {
+  const int S = p.world.n_states;
+  if (S <= 7 * 16) return launch_tile<A, 7>(p, st);
+  if (S <= 10 * 16) return launch_tile<A, 10>(p, st);
+  cobel_set_error("PMA kernel supports at most 160 states (S x S successor representation in shared memory), got %d", S);
+  return COBEL_EUNSUPPORTED;
 }
 
 }  // namespace

@@ -45,21 +45,28 @@ def main():
     rows = list(csv.reader(io.StringIO(raw)))
     hdr = rows[1]
     ci = {n: i for i, n in enumerate(hdr)}
-    prof = [(r[ci['Source']].strip(), int(r[ci['Instructions Executed']] or 0)) for r in rows[2:] if len(r) >= len(hdr)]
+    prof = [(r[ci['Source']].strip(), int(r[ci['Instructions Executed']] or 0), int(r[ci['# Samples']] or 0))
+            for r in rows[2:] if len(r) >= len(hdr)]
     sass = sass_lines(so, cubsub, ksub)
     assert len(sass) == len(prof), (len(sass), len(prof))
-    inner, outer = Counter(), Counter()
-    tot = 0
-    for (off, txt, loc), (ptxt, n) in zip(sass, prof):
+    inner, outer, sinner, souter = Counter(), Counter(), Counter(), Counter()
+    tot = stot = 0
+    for (off, txt, loc), (ptxt, n, smp) in zip(sass, prof):
         tot += n
+        stot += smp
         if loc:
             inner['%s:%d' % loc[0]] += n
             outer['%s:%d' % loc[-1]] += n
-    print('total warp-instructions %d (%.1f per unit)' % (tot, tot / units))
-    for name, c in (('innermost source line', inner), ('outermost (kernel body) line', outer)):
-        print('--- by %s' % name)
-        for k, v in c.most_common(28):
-            print('  %5.1f%%  %8.1f/unit  %s' % (100.0 * v / tot, v / units, k))
+            sinner['%s:%d' % loc[0]] += smp
+            souter['%s:%d' % loc[-1]] += smp
+    print('total warp-instructions %d (%.1f per unit); %d stall samples' % (tot, tot / units, stot))
+    for name, c, sc in (('innermost source line', inner, sinner), ('outermost (kernel body) line', outer, souter)):
+        print('--- by %s: %%instructions, instructions/unit, %%stall samples (~time)' % name)
+        keys = sorted(set(k for k, _ in c.most_common(24)) | set(k for k, _ in sc.most_common(24)),
+                      key=lambda k: -sc[k])
+        for k in keys[:30]:
+            print('  %5.1f%%  %9.1f/unit  %5.1f%%  %s' % (100.0 * c[k] / max(tot, 1), c[k] / units,
+                                                        100.0 * sc[k] / max(stot, 1), k))
 
 
 if __name__ == '__main__':
