@@ -78,7 +78,8 @@ class PMAParams(C.Structure):
                 ('T', c_ptr), ('SR', c_ptr), ('update_mask', c_ptr), ('action_mask', c_ptr),
                 ('mask_agent_stride', C.c_int64), ('lr', c_ptr), ('gamma', c_ptr), ('mem_lr', c_ptr), ('lr_q', c_ptr),
                 ('gamma_q', c_ptr), ('gamma_sr', c_ptr), ('pow_gamma_sr', c_ptr), ('pow_gamma_q', c_ptr),
-                ('pow_stride', C.c_int64), ('min_gap', c_ptr), ('lr_T', C.c_double), ('min_gain', C.c_double),
+                ('pow_stride', C.c_int64), ('min_gap', c_ptr), ('carry', c_ptr), ('need_scratch', c_ptr),
+                ('lr_T', C.c_double), ('min_gain', C.c_double),
                 ('min_gain_original', C.c_int32), ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32),
                 ('no_replay', C.c_int32), ('learn', C.c_int32)]
 

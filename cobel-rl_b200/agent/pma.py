@@ -74,7 +74,8 @@ class PMA(Agent):
                 M._T.data_ptr(), M._SR.data_ptr(), M._update_mask.data_ptr(), mptr, mstride,
                 par['lr'].data_ptr(), par['gamma'].data_ptr(), par['mem_lr'].data_ptr(), par['lr_q'].data_ptr(),
                 par['gamma_q'].data_ptr(), par['gamma_sr'].data_ptr(), psr.data_ptr(), pq.data_ptr(), pstride,
-                M._min_gap.data_ptr(), float(M.learning_rate_T), float(M.min_gain),
+                M._min_gap.data_ptr(), M._carry.data_ptr(), M._need_scratch.data_ptr(),
+                float(M.learning_rate_T), float(M.min_gain),
                 1 if M.min_gain_mode == 'original' else 0, n_tr, steps, batch_size, 1 if no_replay else 0,
                 1 if learn else 0)
             keep.append(par)

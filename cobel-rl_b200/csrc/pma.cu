@@ -1,22 +1,32 @@
 // pma.cu -- K4: PMA.train()/test() (Dyna-Q with Mattar & Daw prioritized memory access:
-// replay of the backup with the largest gain x need) for N independent agents in one launch.
+// replay of the backup with the largest gain x need) for N independent agents.
 //
 // Reference: agent/pma.py:167-353 (trial loop, online n-step update_q) and
 // memory/pma.py:104-496 (store, replay, compute_gain_batch, compute_gain, compute_need,
 // update_sr, update_q).  Semantics: SURVEY.md Appendix A.7.
 //
-// Mapping: one CTA per agent.
-//   * Q, M.rewards, M.states|terminals, the gain vector and the utility scratch live in shared
-//     memory together with ONE S x S fp64 matrix buffer that holds the successor
-//     representation SR = (I - gamma T)^-1 (the `need` rows) between its per-trial
-//     recomputation; T stays in HBM (one row read+written per step, one full read per trial).
-//   * update_sr: in-place Gauss-Jordan inversion in shared memory (I - gamma T is strictly
-//     diagonally dominant, so no pivoting is needed); the stationary distribution used as
-//     `need` after a timed-out trial comes from the subtraction-free GTH elimination.
-//   * replay: the gain of all S*A one-step backups is a function of two Q rows each, so after
-//     the first iteration of a replay call only the backups whose rows were touched by the
-//     previous update are re-evaluated (bit-identical to the reference's full recomputation);
-//     gain x need x mask, the tie-aware arg-max draw and the n-step update are CTA-wide passes.
+// The trial loop is split into two kernels launched alternately by cobel_pma_run (all agents
+// advance trial by trial; per-agent state is carried in HBM between launches):
+//
+//   pma_main_kernel  ONE WARP PER AGENT.  [end-of-trial replay of the previous trial] + reset +
+//                    start-of-trial replay + the online steps.  Q, M.rewards, M.states|terminals,
+//                    the gain vector and the need row live in shared memory (13 KB per agent at
+//                    10x10, 16 agents per SM); T stays in HBM (one row read+written per step).
+//                    Replay: the gain of every one-step backup depends on two Q rows, so after the
+//                    first iteration of a replay call only the backups whose rows were touched by
+//                    the previous update are re-evaluated (compacted to one lane-parallel pass) --
+//                    bit-identical to the reference's full recomputation; gain x need x mask,
+//                    the exact-tie arg-max draw and the n-step update are warp passes with
+//                    shuffle reductions (no block barriers).
+//   pma_sr_kernel    ONE CTA PER AGENT.  update_sr: SR = inv(I - gamma T) by register-tiled
+//                    Gauss-Jordan (no pivoting: I - gamma T is strictly diagonally dominant), T
+//                    read from and SR written to HBM; for agents whose trial timed out also the
+//                    stationary distribution (the reference's LAPACK dgeev `need`) by the
+//                    subtraction-free GTH elimination.
+//
+// (v1 ran everything in one CTA per agent and was barrier-bound: 7 of 8 warps waited for warp 0
+//  through ~12 block barriers per replay iteration, profiles/r1_pma_v1_cta_per_agent.txt.)
+//
 // Exactness: everything except SR / the stationary vector follows the reference's operation
 // order bit for bit; those two come from a different (but 1e-13-accurate) factorisation than
 // LAPACK's, which only matters if two distinct utilities are closer than that -- the smallest
@@ -25,39 +35,9 @@
 
 namespace {
 
-constexpr int kThreads = 256;        // 16 x 16 thread grid for the register-tiled eliminations
+constexpr int kThreads = 256;        // pma_sr_kernel: 16 x 16 thread grid for the register-tiled eliminations
+constexpr int kMainWarps = 4;        // pma_main_kernel: agents (warps) per CTA
 constexpr int kMaxSeq = 64;          // longest n-step sequence (replay batch) supported
-
-struct PmaSmem {
-  int mat, q, mr, gain, util, need, pk, umask, mbits, dirty, seq, perf, psr, pq, part, qpar, qom, elim, bytes;
-  __host__ __device__ PmaSmem(int S, int A, int B, int tile) {
-    const int N = S * A;
-    mat = 0;
-    q = (mat + S * S * 8 + 15) & ~15;       // Q rows are read with 16-byte vector loads
-    mr = q + N * 8;
-    gain = mr + N * 8;
-    util = gain + N * 8;
-    need = util + N * 8;
-    psr = (need + S * 8 + 15) & ~15;
-    pq = psr + (kMaxSeq + 2) * 8;
-    part = pq + (kMaxSeq + 2) * 8;
-    elim = part + (kThreads + 40) * 8;       // 2 x (pivot row + pivot column) of the tiled eliminations
-    qpar = elim + 4 * tile * 16 * 8;
-    qom = qpar + 8 * 8;
-    seq = qom + 8 * 8;
-    perf = seq + (kMaxSeq + 2) * 4;
-    pk = perf + (B + 2) * 4;
-    umask = pk + N * 2;
-    mbits = umask + N;
-    dirty = mbits + S;
-    bytes = (dirty + S + 15) & ~15;
-  }
-};
-
-struct PmaShared {
-  double u, val, fv, gap;
-  int idx, ext, cand_len, last_seq, count, flag, last, a;
-};
 
 // Policy probabilities for one Q row (thread-local): policy/greedy.py:60-88,117-147, policy/softmax.py:60-88.
 // qpar[n-1] = par/n and qom[n-1] = (1-par)/n are the cached quotients.
@@ -163,8 +143,8 @@ struct Tile {
 // rowk_k := 1 + 1/piv the generic update m -= f_i * rowk_j / piv also produces the scaled pivot
 // row, -f_i/piv in the pivot column and 1/piv on the pivot.
 template <int TILE>
-__device__ __forceinline__ void gauss_jordan_inverse(const double* __restrict__ Tg, double gsr, double* Mat, double* SRg,
-                                                     int S, double* buf, int tid, int& flags) {
+__device__ __forceinline__ void gauss_jordan_inverse(const double* __restrict__ Tg, double gsr, double* SRg, int S,
+                                                     double* buf, int tid, int& flags) {
   const int ty = tid >> 4, tx = tid & 15;
   const int SP = TILE * 16;
   Tile<TILE> t;
@@ -221,7 +201,7 @@ __device__ __forceinline__ void gauss_jordan_inverse(const double* __restrict__ 
 #pragma unroll
     for (int c = 0; c < TILE; ++c) {
       const int i = ty + 16 * r, j = tx + 16 * c;
-      if (i < S && j < S) { Mat[i * S + j] = t.m[r][c]; SRg[(size_t)i * S + j] = t.m[r][c]; }
+      if (i < S && j < S) SRg[(size_t)i * S + j] = t.m[r][c];
     }
   __syncthreads();
 }
@@ -313,45 +293,97 @@ __device__ __forceinline__ void gth_stationary(const double* __restrict__ Tg, do
   __syncthreads();
 }
 
-template <int A, int TILE>
-__global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_kernel(const __grid_constant__ CobelPMAParams p) {
+// ---------------------------------------------------------------------------
+// pma_sr_kernel: one CTA per agent.  SR <- inv(I - gamma T); if the agent's last trial timed
+// out (carry[.,0] < 0) also the stationary `need` vector into need_scratch[n].
+// ---------------------------------------------------------------------------
+template <int TILE>
+__global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_sr_kernel(const __grid_constant__ CobelPMAParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ PmaShared sh;
-  const int S = p.world.n_states, K = p.world.n_starts, N = S * A, B = p.batch;
-  const int tid = threadIdx.x, T = kThreads, lane = tid & 31, warp = tid >> 5;
+  const int S = p.world.n_states, tid = threadIdx.x;
   const int64_t n = blockIdx.x;
-  const PmaSmem so(S, A, B, TILE);
-  double* Mat = reinterpret_cast<double*>(smem + so.mat);     // SR (need rows) / elimination scratch
-  double* Q = reinterpret_cast<double*>(smem + so.q);         // [s][a]
-  double* Mr = reinterpret_cast<double*>(smem + so.mr);       // [s][a]
-  double* gain = reinterpret_cast<double*>(smem + so.gain);   // [a*S+s] one-step gains
-  double* util = reinterpret_cast<double*>(smem + so.util);   // [a*S+s] scratch
-  double* needv = reinterpret_cast<double*>(smem + so.need);  // [s] stationary need (time-out case)
-  double* powsr = reinterpret_cast<double*>(smem + so.psr);   // M.gamma ** k
-  double* powq = reinterpret_cast<double*>(smem + so.pq);     // M.gamma_q ** k
-  double* part = reinterpret_cast<double*>(smem + so.part);
-  double* elim = reinterpret_cast<double*>(smem + so.elim);
-  double* qpar = reinterpret_cast<double*>(smem + so.qpar);
-  double* qom = reinterpret_cast<double*>(smem + so.qom);
-  int32_t* seq = reinterpret_cast<int32_t*>(smem + so.seq);   // candidate n-step sequence (flat indices)
-  int32_t* perf = reinterpret_cast<int32_t*>(smem + so.perf); // performed updates of this replay call
-  uint16_t* Pk = reinterpret_cast<uint16_t*>(smem + so.pk);   // [s][a] M.states | M.terminals << 15
-  uint8_t* umask = smem + so.umask;                           // [a*S+s] M.update_mask
-  uint8_t* mbits = smem + so.mbits;                           // [s] valid-action bits (all ones if unmasked)
-  uint8_t* dirty = smem + so.dirty;                           // [s] Q row changed since the gains were computed
+  double* elim = reinterpret_cast<double*>(smem);                 // 2 x (pivot row + pivot column)
+  double* xv = elim + 4 * TILE * 16;                              // [S] stationary vector
+  double* Mat = xv + ((S + 1) & ~1);                              // [S*S] GTH scratch
+  int flags = 0;
+  const double* Tg = p.T + (size_t)n * S * S;
+  gauss_jordan_inverse<TILE>(Tg, p.gamma_sr[n], p.SR + (size_t)n * S * S, S, elim, tid, flags);
+  if (p.carry[n * 4 + 0] < 0) {
+    gth_stationary<TILE>(Tg, Mat, xv, S, elim, tid, flags);
+    for (int e = tid; e < S; e += kThreads) p.need_scratch[(size_t)n * S + e] = xv[e];
+  }
+  flags = __syncthreads_or(flags);
+  if (tid == 0 && flags && p.trace.flags) p.trace.flags[n] |= flags;
+}
+
+// ---------------------------------------------------------------------------
+// pma_main_kernel: one warp per agent.
+// ---------------------------------------------------------------------------
+struct MainSmem {      // byte offsets inside one agent's shared-memory block
+  int q, mr, gain, need, pk, list, seq, perf, umask, mbits, dirty, bytes;
+  __host__ __device__ MainSmem(int S, int A) {
+    const int N = S * A;
+    q = 0;
+    mr = q + N * 8;
+    gain = mr + N * 8;
+    need = gain + N * 8;
+    seq = need + ((S + 1) & ~1) * 8;
+    perf = seq + (kMaxSeq + 2) * 4;
+    pk = perf + (kMaxSeq + 2) * 4;
+    list = pk + N * 2;
+    umask = list + N * 2;
+    mbits = umask + N;
+    dirty = mbits + S;
+    bytes = (dirty + S + 15) & ~15;
+  }
+};
+
+COBEL_DEV double warp_max_f64(double v) {
+  for (int d = 16; d > 0; d >>= 1) { const double o = shfl_f64_xor(v, d); v = o > v ? o : v; }
+  return v;
+}
+
+// launch phases of pma_main_kernel
+struct MainPhase {
+  int init_carry;       // first launch of a run: reset the per-agent carry
+  int end_replay;       // replay(last) of the previous trial first (SR / need_scratch are fresh)
+  int trial_first;      // index of the first trial run by this launch
+  int n_trials;         // trials run by this launch (0 or 1 when replays are enabled)
+};
+
+template <int A>
+__global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __grid_constant__ CobelPMAParams p,
+                                                                      const __grid_constant__ MainPhase ph) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int S = p.world.n_states, K = p.world.n_starts, N = S * A, B = p.batch;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n = (int64_t)blockIdx.x * kMainWarps + warp;
+  if (n >= p.n_agents) return;                         // whole warp leaves; no block-wide barrier is used
+  const MainSmem so(S, A);
+  unsigned char* blk = smem + (size_t)warp * so.bytes;
+  double* Q = reinterpret_cast<double*>(blk + so.q);         // [s][a]
+  double* Mr = reinterpret_cast<double*>(blk + so.mr);       // [s][a]
+  double* gain = reinterpret_cast<double*>(blk + so.gain);   // [a*S+s] one-step gains
+  double* need = reinterpret_cast<double*>(blk + so.need);   // [s] need of the current replay call
+  int32_t* seq = reinterpret_cast<int32_t*>(blk + so.seq);   // candidate n-step sequence (flat indices)
+  int32_t* perf = reinterpret_cast<int32_t*>(blk + so.perf); // performed updates of this replay call
+  uint16_t* Pk = reinterpret_cast<uint16_t*>(blk + so.pk);   // [s][a] M.states | M.terminals << 15
+  uint16_t* list = reinterpret_cast<uint16_t*>(blk + so.list); // compacted indices of stale gains
+  uint8_t* umask = blk + so.umask;                           // [a*S+s] M.update_mask
+  uint8_t* mbits = blk + so.mbits;                           // [s] valid-action bits (all ones if unmasked)
+  uint8_t* dirty = blk + so.dirty;                           // [s] Q row changed since the gains were computed
 
   const size_t g0 = (size_t)n * N;
   double* Tg = p.T + (size_t)n * S * S;
-  double* SRg = p.SR + (size_t)n * S * S;
+  const double* SRg = p.SR + (size_t)n * S * S;
   const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
-  for (int e = tid; e < N; e += T) {
+  for (int e = lane; e < N; e += 32) {
     Q[e] = p.Q[g0 + e];
     Mr[e] = p.Mr[g0 + e];
     Pk[e] = (uint16_t)(p.Ms[g0 + e] | ((p.Mt[g0 + e] ? 1 : 0) << 15));
     umask[e] = p.update_mask[g0 + e];
   }
-  for (int e = tid; e < S * S; e += T) Mat[e] = SRg[e];
-  for (int e = tid; e < S; e += T) {
+  for (int e = lane; e < S; e += 32) {
     uint32_t mb = (1u << A) - 1u;
     if (amask) {
       mb = 0;
@@ -359,21 +391,24 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_kernel(const 
     }
     mbits[e] = (uint8_t)mb;
   }
-  for (int e = tid; e < kMaxSeq + 2; e += T) {
-    powsr[e] = p.pow_gamma_sr[n * p.pow_stride + e];
-    powq[e] = p.pow_gamma_q[n * p.pow_stride + e];
-  }
+  const double* powsr = p.pow_gamma_sr + n * p.pow_stride;     // float(M.gamma) ** k
+  const double* powq = p.pow_gamma_q + n * p.pow_stride;       // float(M.gamma_q) ** k
   const int mkind = p.mem_policy.kind;
   const double mpar = p.mem_policy.param[n];
-  if (tid < A) {
-    qpar[tid] = xdiv(mpar, (double)(tid + 1));
-    qom[tid] = xdiv(xsub(1.0, mpar), (double)(tid + 1));
-  }
-  __syncthreads();
+  // cached quotients par/n and (1-par)/n of the memory policy (n = 1..A), every lane holds all of them
+  double qpar[A], qom[A];
+#pragma unroll
+  for (int a = 0; a < A; ++a) { qpar[a] = xdiv(mpar, (double)(a + 1)); qom[a] = xdiv(xsub(1.0, mpar), (double)(a + 1)); }
+  __syncwarp();
 
-  DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);      // used by warp 0 only
+  int64_t* carry = p.carry + n * 4;           // [0] last state (-1: timed out)  [1] steps  [2] replayed  [3] replay calls
+  int64_t c_last = ph.init_carry ? -1 : carry[0];
+  int64_t nsteps = ph.init_carry ? 0 : carry[1], nrep = ph.init_carry ? 0 : carry[2], ncalls = ph.init_carry ? 0 : carry[3];
+  const int64_t nsteps0 = nsteps, nrep0 = nrep;
+
+  DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
   const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
-  const double lrq = p.lr_q[n], gq = p.gamma_q[n], gsr = p.gamma_sr[n];
+  const double lrq = p.lr_q[n], gq = p.gamma_q[n];
   const double min_gain = p.min_gain;
   const bool original = p.min_gain_original != 0;
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
@@ -381,7 +416,6 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_kernel(const 
   const bool learn = p.learn != 0;
   const bool do_replay = learn && !p.no_replay;
   const CobelTrace& tr = p.trace;
-  int64_t nsteps = 0, nrep = 0, ncalls = 0;
   int flags = 0;
   double min_gap = __longlong_as_double(0x7FF0000000000000ll);
 
@@ -395,13 +429,11 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_kernel(const 
     double tr_[A];
     load_row<A>(Q + ms * A, tr_);
     const double boot = xmul(xmul(gq, row_max<A>(tr_)), mt ? 1.0 : 0.0);
-#pragma unroll
-    for (int c = 0; c < A; ++c) qn[c] = q[c];
     {
-      double qa = q[0], ra = Mr[s * A];
+      double qa = q[0];
 #pragma unroll
-      for (int c = 1; c < A; ++c) { qa = c == a ? q[c] : qa; ra = c == a ? Mr[s * A + c] : ra; }
-      const double upd = xadd(qa, xmul(lrq, xsub(xadd(ra, boot), qa)));
+      for (int c = 1; c < A; ++c) qa = c == a ? q[c] : qa;
+      const double upd = xadd(qa, xmul(lrq, xsub(xadd(Mr[s * A + a], boot), qa)));
 #pragma unroll
       for (int c = 0; c < A; ++c) qn[c] = c == a ? upd : q[c];
     }
@@ -409,72 +441,74 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_kernel(const 
     probs_row<A>(q, mb, mkind, mpar, qpar, qom, po);
     probs_row<A>(qn, mb, mkind, mpar, qpar, qom, pn);
     const double so_ = sum_seq<A>(po), sn_ = sum_seq<A>(pn);
+    // p / sum(p): x / 1.0 == x, so the (frequent) exactly-normalised case skips the divisions
+    if (sn_ != 1.0) {
 #pragma unroll
-    for (int c = 0; c < A; ++c) t[c] = xmul(xdiv(pn[c], sn_), qn[c]);
+      for (int c = 0; c < A; ++c) pn[c] = xdiv(pn[c], sn_);
+    }
+    if (so_ != 1.0) {
+#pragma unroll
+      for (int c = 0; c < A; ++c) po[c] = xdiv(po[c], so_);
+    }
+#pragma unroll
+    for (int c = 0; c < A; ++c) t[c] = xmul(pn[c], qn[c]);
     const double gnew = sum_seq<A>(t);
 #pragma unroll
-    for (int c = 0; c < A; ++c) t[c] = xmul(xdiv(po[c], so_), qn[c]);
+    for (int c = 0; c < A; ++c) t[c] = xmul(po[c], qn[c]);
     const double gold = sum_seq<A>(t);
     const double g = xsub(gnew, gold);
     return g > min_gain ? g : min_gain;
   };
 
-  // SR = inv(I - gamma T): PMAMemory.update_sr, memory/pma.py:413-415
-  auto update_sr = [&]() { gauss_jordan_inverse<TILE>(Tg, gsr, Mat, SRg, S, elim, tid, flags); };
-
-  // |left Perron vector| of T with unit 2-norm (memory/pma.py:401-408); uses (and destroys) the
-  // matrix buffer, SR is restored from HBM afterwards.
-  auto stationary = [&]() {
-    gth_stationary<TILE>(Tg, Mat, needv, S, elim, tid, flags);
-    for (int e = tid; e < S * S; e += T) Mat[e] = SRg[e];
-    __syncthreads();
-  };
-
-  // PMAMemory.replay, memory/pma.py:168-267
+  // PMAMemory.replay, memory/pma.py:168-267.  cur >= 0: need = SR[cur]; cur < 0: stationary need.
   auto replay = [&](int cur) {
-    const double* need = cur >= 0 ? Mat + (size_t)cur * S : needv;
-    if (cur < 0) stationary();
-    for (int e = tid; e < S; e += T) dirty[e] = 1;                     // first iteration: evaluate every backup
-    if (tid == 0) { sh.count = 0; sh.last_seq = 0; }
-    __syncthreads();
+    const double* nsrc = cur >= 0 ? SRg + (size_t)cur * S : p.need_scratch + (size_t)n * S;
+    for (int e = lane; e < S; e += 32) { need[e] = nsrc[e]; dirty[e] = 1; }   // first iteration: every backup is stale
+    int count = 0, last_seq = 0;
+    __syncwarp();
     for (int it = 0; it < B; ++it) {
-      // ---- (1) extension of the current sequence (memory/pma.py:219-235); warp 0 -------------
-      if (warp == 0) {
-        int ext = -1, clen = 0;
-        const int count = sh.count, last_seq = sh.last_seq;
-        if (count > 0) {
-          const int lp = perf[count - 1];
-          ext = Pk[(lp % S) * A + lp / S] & 0x7FFF;                    // next_state of the last update
-          bool loop = false;
-          for (int j = last_seq + lane; j < count; j += 32) loop |= (perf[j] % S) == ext;
-          loop = __any_sync(kFull, loop);
-          if (!loop) {
-            win.ensure(2, lane);
-            double row[A];
-            load_row<A>(Q + ext * A, row);
-            const int ea = select_action_warp<A>(row, mbits[ext], mpt, win.next(), lane);
-            ext += ea * S;
-            clen = count - last_seq + 1;
-            for (int j = lane; j < clen - 1; j += 32) seq[j] = perf[last_seq + j];
-            if (lane == 0) seq[clen - 1] = ext;
-          } else if (lane == 0) {
-            seq[0] = ext;                                              // failed extension: one-step(ext, action 0)
-          }
+      // ---- (1) extension of the current sequence (memory/pma.py:219-235) -------------------------
+      int ext = -1, clen = 0;
+      if (count > 0) {
+        const int lp = perf[count - 1];
+        ext = Pk[(lp % S) * A + lp / S] & 0x7FFF;                       // next_state of the last update
+        bool loop = false;
+        for (int j = last_seq + lane; j < count; j += 32) loop |= (perf[j] % S) == ext;
+        loop = __any_sync(kFull, loop);
+        if (!loop) {
+          win.ensure(2, lane);
+          double row[A];
+          load_row<A>(Q + ext * A, row);
+          const int ea = select_action_warp<A>(row, mbits[ext], mpt, win.next(), lane);
+          ext += ea * S;
+          clen = count - last_seq + 1;
+          for (int j = lane; j < clen - 1; j += 32) seq[j] = perf[last_seq + j];
+          if (lane == 0) seq[clen - 1] = ext;
+        } else if (lane == 0) {
+          seq[0] = ext;                                                 // failed extension: one-step(ext, action 0)
         }
-        if (lane == 0) { sh.ext = ext; sh.cand_len = clen; }
       }
-      __syncthreads();
-      const int ext = sh.ext, clen = sh.cand_len;
-      if (clen > kMaxSeq) flags |= COBEL_FLAG_TRACE_OVERFLOW;
-      // ---- (2) one-step gains, re-evaluated only where a Q row they read has changed ----------
-      for (int i = tid; i < N; i += T) {
-        const int a = i / S, s = i - a * S;
-        if (dirty[s] || dirty[Pk[s * A + a] & 0x7FFF]) gain[i] = gain_one(i);
+      // ---- (2) one-step gains: compact the stale ones, then one lane-parallel pass ---------------
+      int nd = 0;
+      for (int e0 = 0; e0 < N; e0 += 32) {
+        const int i = e0 + lane;
+        bool stale = false;
+        if (i < N) {
+          const int a = i / S, s = i - a * S;
+          stale = dirty[s] || dirty[Pk[s * A + a] & 0x7FFF];
+        }
+        const unsigned b = __ballot_sync(kFull, stale);
+        if (stale) list[nd + __popc(b & ((1u << lane) - 1u))] = (uint16_t)i;
+        nd += __popc(b);
       }
-      __syncthreads();
-      for (int e = tid; e < S; e += T) dirty[e] = 0;
-      // ---- (3) n-step gain of the candidate (memory/pma.py:269-331), lane j = element j ----------
-      if (warp == 0 && ext >= 0) {
+      __syncwarp();
+      for (int j0 = 0; j0 < nd; j0 += 32)
+        if (j0 + lane < nd) { const int i = list[j0 + lane]; gain[i] = gain_one(i); }
+      for (int e = lane; e < S; e += 32) dirty[e] = 0;
+      __syncwarp();
+      // ---- (3) n-step gain of the candidate (memory/pma.py:269-331), lane j = element j -----------
+      double gext = 0.0;
+      if (ext >= 0) {
         const int nseq = clen > 0 ? clen : 1;
         const int lastI = seq[nseq - 1];
         const uint16_t lpk = Pk[(lastI % S) * A + lastI / S];
@@ -515,61 +549,54 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_kernel(const 
           const int m = nseq - j0 < 32 ? nseq - j0 : 32;
           for (int l = 0; l < m; ++l) total = xadd(total, shfl_f64(sg, l));       // gain += step_gain, in order
         }
-        if (lane == 0) sh.val = total > min_gain ? total : min_gain;
+        gext = total > min_gain ? total : min_gain;
       }
-      __syncthreads();
       // ---- (4) utility = gain * need * update_mask; arg-max with exact ties (memory/pma.py:247-254)
-      const double gext = sh.val;
-      double lmax = -__longlong_as_double(0x7FF0000000000000ll);
-      for (int i = tid; i < N; i += T) {
+      auto utility = [&](int i) -> double {
         const int s = i % S;
         const double g = (i == ext) ? gext : gain[i];
-        const double u_ = xmul(xmul(g, need[s]), umask[i] ? 1.0 : 0.0);
-        util[i] = u_;
-        lmax = u_ > lmax ? u_ : lmax;
+        return xmul(xmul(g, need[s]), umask[i] ? 1.0 : 0.0);
+      };
+      const double ninf = -__longlong_as_double(0x7FF0000000000000ll);
+      double lmax = ninf;
+      for (int i = lane; i < N; i += 32) { const double u_ = utility(i); lmax = u_ > lmax ? u_ : lmax; }
+      const double umax = warp_max_f64(lmax);
+      // ties (flat-index order) and the certificate: gap to the largest utility below the maximum
+      double l2 = ninf;
+      int ktot = 0;
+      for (int e0 = 0; e0 < N; e0 += 32) {
+        const int i = e0 + lane;
+        bool tie = false;
+        if (i < N) { const double v = utility(i); tie = v == umax; if (v < umax && v > l2) l2 = v; }
+        ktot += __popc(__ballot_sync(kFull, tie));
       }
-      const double umax = block_max(lmax, part, tid, T);
-      // certificate: relative gap to the largest utility below the maximum
-      double l2 = -__longlong_as_double(0x7FF0000000000000ll);
-      for (int i = tid; i < N; i += T) { const double v = util[i]; if (v < umax && v > l2) l2 = v; }
-      const double u2 = block_max(l2, part, tid, T);
+      const double u2 = warp_max_f64(l2);
       if (umax != 0.0 && u2 > -1e300) { const double gp = (umax - u2) / fabs(umax); min_gap = gp < min_gap ? gp : min_gap; }
-      // ties in flat-index order: contiguous chunks per thread + integer scan
-      const int chunk = (N + T - 1) / T;
-      const int lo = tid * chunk < N ? tid * chunk : N, hi = lo + chunk < N ? lo + chunk : N;
-      int cnt = 0;
-      for (int i = lo; i < hi; ++i) cnt += util[i] == umax ? 1 : 0;
-      int ktot;
-      const int before = block_exclusive_scan_int(cnt, reinterpret_cast<int*>(part), tid, T, ktot);
-      if (warp == 0) {
-        win.ensure(1, lane);
-        const double u = win.next();
-        if (lane == 0) {
-          // Generator.choice(p = ties / k): cdf_m = m-fold sequential sum of fl(1/k), normalised by cdf_k
-          const double pk_ = xdiv(1.0, (double)ktot);
-          double ck = 0.0;
-          for (int m = 0; m < ktot; ++m) ck = xadd(ck, pk_);
-          double c = 0.0;
-          int pick = ktot - 1;
-          for (int m = 0; m < ktot; ++m) {
-            c = xadd(c, pk_);
-            if (xdiv(c, ck) > u) { pick = m; break; }
-          }
-          sh.idx = pick;
+      win.ensure(1, lane);
+      const double u = win.next();
+      // Generator.choice(p = ties / k): cdf_m = m-fold sequential sum of fl(1/k), normalised by cdf_k
+      int pick = ktot - 1;
+      {
+        const double pk_ = xdiv(1.0, (double)ktot);
+        double ck = 0.0;
+        for (int m = 0; m < ktot; ++m) ck = xadd(ck, pk_);
+        double c = 0.0;
+        for (int m = 0; m < ktot; ++m) {
+          c = xadd(c, pk_);
+          if (xdiv(c, ck) > u) { pick = m; break; }
         }
       }
-      __syncthreads();
-      const int pick = sh.idx;
-      __syncthreads();
-      if (pick >= before && pick < before + cnt) {
-        int r = pick - before;
-        for (int i = lo; i < hi; ++i)
-          if (util[i] == umax && r-- == 0) { sh.a = i; break; }
+      int chosen = 0;
+      for (int e0 = 0; e0 < N; e0 += 32) {
+        const int i = e0 + lane;
+        const bool tie = i < N && utility(i) == umax;
+        const unsigned b = __ballot_sync(kFull, tie);
+        const int c = __popc(b);
+        if (pick < c) { chosen = e0 + __fns(b, 0, pick + 1); break; }
+        pick -= c;
       }
-      __syncthreads();
-      const int chosen = sh.a;
-      // ---- (5) apply the chosen (n-step) update: PMAMemory.update_q, memory/pma.py:452-496 ----------
-      if (warp == 0) {
+      // ---- (5) apply the chosen (n-step) update: PMAMemory.update_q, memory/pma.py:452-496 --------
+      {
         const bool use_seq = clen > 0 && chosen == ext;
         const int nseq = use_seq ? clen : 1;
         if (!use_seq && lane == 0) seq[0] = chosen;
@@ -579,7 +606,7 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_kernel(const 
         double lrow[A];
         load_row<A>(Q + (lpk & 0x7FFF) * A, lrow);
         const double fv = xmul(row_max<A>(lrow), (lpk >> 15) ? 1.0 : 0.0);
-        bool ok = true;                                 // n >= 2: every transition must be non-terminal & experienced
+        bool ok = true;                               // n >= 2: every transition must be non-terminal & experienced
         if (nseq >= 2) {
           bool bad = false;
           for (int j = lane; j < nseq; j += 32) { const int k = seq[j]; bad |= (Pk[(k % S) * A + k / S] >> 15) == 0; }
@@ -598,145 +625,144 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_kernel(const 
             double td = xadd(r, xmul(fv, powq[nseq - j]));
             const double q = Q[s * A + a];
             td = xsub(td, q);
-            Q[s * A + a] = xadd(q, xmul(lrq, td));       // states of a sequence are distinct (no loops)
+            Q[s * A + a] = xadd(q, xmul(lrq, td));     // states of a sequence are distinct (no loops)
             dirty[s] = 1;
           }
         }
-        if (lane == 0) {
-          const int count = sh.count;
-          perf[count] = chosen;
-          sh.count = count + 1;
-          if (ext != chosen) sh.last_seq = it;
-        }
+        if (lane == 0) perf[count] = chosen;
+        ++count;
+        if (ext != chosen) last_seq = it;
+        __syncwarp();
       }
-      __syncthreads();
     }
-    const int count = sh.count;
     if (tr.replay_idx)
-      for (int j = tid; j < count; j += T) {
+      for (int j = lane; j < count; j += 32) {
         if (nrep + j < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + j] = perf[j];
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
-    if (tr.replay_len && tid == 0) {
+    if (tr.replay_len && lane == 0) {
       if (ncalls < tr.replay_calls_cap) tr.replay_len[n * tr.replay_calls_cap + ncalls] = count;
       else flags |= COBEL_FLAG_TRACE_OVERFLOW;
     }
     nrep += count;
     ++ncalls;
-    __syncthreads();
+    __syncwarp();
   };
 
-  for (int trial = 0; trial < p.trials; ++trial) {
-    if (warp == 0) {
-      win.ensure(2, lane);
-      const int s0 = __ldg(p.world.starts + draw_integer(win.next(), K));
-      if (lane == 0) sh.last = s0;
-    }
-    __syncthreads();
-    int s = sh.last;
-    __syncthreads();
-    if (do_replay) replay(s);                                       // awake replay, need = SR[start] (agent/pma.py:206-213)
-    if (warp == 0) {
-      double treward = 0.0;
-      int step = 0, last = -1;
-      for (;; ++step) {
-        win.ensure(1, lane);
-        double row[A];
-        load_row<A>(Q + s * A, row);
-        const int a = select_action_warp<A>(row, mbits[s], pt, win.next(), lane);
-        const int s2 = __ldg(p.world.succ + s * A + a);
-        const double r = __ldg(p.world.reward + s2);
-        const int end = __ldg(p.world.terminal + s2);
-        const int nt = 1 - end;
-        if (tr.step_sa && lane == 0) {
-          if (nsteps < tr.step_cap) tr.step_sa[n * tr.step_cap + nsteps] = s * A + a;
-          else flags |= COBEL_FLAG_TRACE_OVERFLOW;
-        }
-        ++nsteps;
-        if (learn) {
-          // PMA.update_q([experience]) (agent/pma.py:319-353), then M.store (memory/pma.py:148-166)
-          double row2[A];
-          load_row<A>(Q + s2 * A, row2);
-          const double fv = xmul(row_max<A>(row2), nt ? 1.0 : 0.0);
-          const double rr = xadd(0.0, xmul(r, 1.0));
-          double td = xadd(rr, xmul(fv, gamma));
-          const double q = Q[s * A + a];
-          td = xsub(td, q);
-          const double qn = xadd(q, xmul(lr, td));
-          const double m0 = Mr[s * A + a];
-          const double m1 = xadd(m0, xmul(mlr, xsub(r, m0)));
-          for (int j = lane; j < S; j += 32) {           // T[s] += 0.9 * (onehot(s') - T[s])
-            const double t0 = Tg[(size_t)s * S + j];
-            Tg[(size_t)s * S + j] = xadd(t0, xmul(p.lr_T, xsub(j == s2 ? 1.0 : 0.0, t0)));
-          }
-          __syncwarp();
-          if (lane == 0) {
-            Q[s * A + a] = qn;
-            Mr[s * A + a] = m1;
-            Pk[s * A + a] = (uint16_t)(s2 | (nt << 15));
-          }
-          __syncwarp();
-        }
-        s = s2;
-        treward = xadd(treward, r);
-        if (end) last = s2;
-        if (end || step + 1 == p.steps) break;
+  if (ph.end_replay) replay((int)c_last);            // need from the terminal state, or stationary (agent/pma.py:248-256)
+
+  for (int trial = ph.trial_first; trial < ph.trial_first + ph.n_trials; ++trial) {
+    win.ensure(2, lane);
+    int s = __ldg(p.world.starts + draw_integer(win.next(), K));
+    if (do_replay) replay(s);                         // awake replay, need = SR[start] (agent/pma.py:206-213)
+    double treward = 0.0;
+    int step = 0, last = -1;
+    for (;; ++step) {
+      win.ensure(1, lane);
+      double row[A];
+      load_row<A>(Q + s * A, row);
+      const int a = select_action_warp<A>(row, mbits[s], pt, win.next(), lane);
+      const int s2 = __ldg(p.world.succ + s * A + a);
+      const double r = __ldg(p.world.reward + s2);
+      const int end = __ldg(p.world.terminal + s2);
+      const int nt = 1 - end;
+      if (tr.step_sa && lane == 0) {
+        if (nsteps < tr.step_cap) tr.step_sa[n * tr.step_cap + nsteps] = s * A + a;
+        else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
-      if (lane == 0) {
-        tr.trial_steps[n * p.trials + trial] = step;
-        tr.trial_reward[n * p.trials + trial] = treward;
-        sh.last = last;
+      ++nsteps;
+      if (learn) {
+        // PMA.update_q([experience]) (agent/pma.py:319-353), then M.store (memory/pma.py:148-166)
+        double row2[A];
+        load_row<A>(Q + s2 * A, row2);
+        const double fv = xmul(row_max<A>(row2), nt ? 1.0 : 0.0);
+        const double rr = xadd(0.0, xmul(r, 1.0));
+        double td = xadd(rr, xmul(fv, gamma));
+        const double q = Q[s * A + a];
+        td = xsub(td, q);
+        const double qn = xadd(q, xmul(lr, td));
+        const double m0 = Mr[s * A + a];
+        const double m1 = xadd(m0, xmul(mlr, xsub(r, m0)));
+        for (int j = lane; j < S; j += 32) {           // T[s] += 0.9 * (onehot(s') - T[s])
+          const double t0 = Tg[(size_t)s * S + j];
+          Tg[(size_t)s * S + j] = xadd(t0, xmul(p.lr_T, xsub(j == s2 ? 1.0 : 0.0, t0)));
+        }
+        __syncwarp();
+        if (lane == 0) {
+          Q[s * A + a] = qn;
+          Mr[s * A + a] = m1;
+          Pk[s * A + a] = (uint16_t)(s2 | (nt << 15));
+        }
+        __syncwarp();
       }
+      s = s2;
+      treward = xadd(treward, r);
+      if (end) last = s2;
+      if (end || step + 1 == p.steps) break;
     }
-    __syncthreads();
-    if (do_replay) {
-      const int last = sh.last;
-      __syncthreads();
-      update_sr();
-      replay(last);                                                  // need from the terminal state, or stationary
+    if (lane == 0) {
+      tr.trial_steps[n * p.trials + trial] = step;
+      tr.trial_reward[n * p.trials + trial] = treward;
     }
+    c_last = last;
   }
 
-  __syncthreads();
+  __syncwarp();
   if (learn) {
-    for (int e = tid; e < N; e += T) {
+    for (int e = lane; e < N; e += 32) {
       p.Q[g0 + e] = Q[e];
       p.Mr[g0 + e] = Mr[e];
       p.Ms[g0 + e] = Pk[e] & 0x7FFF;
       p.Mt[g0 + e] = Pk[e] >> 15;
     }
   }
-  flags = __syncthreads_or(flags);
-  min_gap = block_max(-min_gap, part, tid, T);
-  if (tid == 0) {
+  flags = __reduce_or_sync(kFull, flags);
+  if (lane == 0) {
     p.stream.draw_count[n] = (int64_t)win.position();
-    tr.n_steps[n] += nsteps;
-    tr.n_replay[n] += nrep;
+    carry[0] = c_last; carry[1] = nsteps; carry[2] = nrep; carry[3] = ncalls;
+    tr.n_steps[n] += nsteps - nsteps0;
+    tr.n_replay[n] += nrep - nrep0;
     if (tr.flags && flags) tr.flags[n] |= flags;
-    if (p.min_gap) p.min_gap[n] = fmin(p.min_gap[n], -min_gap);
+    if (p.min_gap) p.min_gap[n] = fmin(p.min_gap[n], min_gap);
   }
 }
 
-template <int A, int TILE>
-int launch_tile(const CobelPMAParams& p, cudaStream_t st) {
+template <int A>
+int run(const CobelPMAParams& p, cudaStream_t st) {
   const int S = p.world.n_states;
-  const PmaSmem so(S, A, p.batch, TILE);
-  COBEL_REQUIRE(so.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
-                "PMA: %d states need %d bytes of shared memory (the S x S successor representation must fit)", S, so.bytes);
-  COBEL_CUDA_OK(cudaFuncSetAttribute(pma_kernel<A, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, so.bytes));
-  pma_kernel<A, TILE><<<(unsigned)p.n_agents, kThreads, so.bytes, st>>>(p);
-  cobel_count_launch();
+  COBEL_REQUIRE(S <= 160, COBEL_EUNSUPPORTED,
+                "PMA kernels support at most 160 states (register-tiled S x S eliminations), got %d", S);
+  const MainSmem so(S, A);
+  const size_t sm_main = (size_t)kMainWarps * so.bytes;
+  COBEL_REQUIRE(sm_main <= 227 * 1024, COBEL_EUNSUPPORTED, "PMA: %d states x %d actions do not fit in shared memory", S, A);
+  COBEL_CUDA_OK(cudaFuncSetAttribute(pma_main_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_main));
+  const int tile = S <= 7 * 16 ? 7 : 10;
+  const size_t sm_sr = (size_t)(4 * tile * 16 + ((S + 1) & ~1) + S * S) * 8;
+  if (tile == 7) COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
+  else COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
+  const unsigned grid_main = (unsigned)((p.n_agents + kMainWarps - 1) / kMainWarps);
+  auto main_launch = [&](MainPhase ph) {
+    pma_main_kernel<A><<<grid_main, kMainWarps * 32, sm_main, st>>>(p, ph);
+    cobel_count_launch();
+  };
+  auto sr_launch = [&]() {
+    if (tile == 7) pma_sr_kernel<7><<<(unsigned)p.n_agents, kThreads, sm_sr, st>>>(p);
+    else pma_sr_kernel<10><<<(unsigned)p.n_agents, kThreads, sm_sr, st>>>(p);
+    cobel_count_launch();
+  };
+  const bool do_replay = p.learn && !p.no_replay;
+  if (!do_replay) {
+    main_launch(MainPhase{1, 0, 0, p.trials});                 // no replay: all trials in one launch
+  } else {
+    // trial t: main(reset, start replay, steps) -> sr(update_sr [+ stationary]) -> main(end replay, then trial t+1)
+    main_launch(MainPhase{1, 0, 0, 1});
+    for (int t = 0; t < p.trials; ++t) {
+      sr_launch();
+      main_launch(MainPhase{0, 1, t + 1, t + 1 < p.trials ? 1 : 0});
+    }
+  }
   COBEL_CUDA_OK(cudaGetLastError());
   return COBEL_OK;
-}
-
-template <int A>
-int launch(const CobelPMAParams& p, cudaStream_t st) {
-  const int S = p.world.n_states;
-  if (S <= 7 * 16) return launch_tile<A, 7>(p, st);
-  if (S <= 10 * 16) return launch_tile<A, 10>(p, st);
-  cobel_set_error("PMA kernel supports at most 160 states (S x S successor representation in shared memory), got %d", S);
-  return COBEL_EUNSUPPORTED;
 }
 
 }  // namespace
@@ -750,18 +776,18 @@ extern "C" int cobel_pma_run(const CobelPMAParams* pp, void* stream) {
   int rc = cobel_validate_common(p.n_agents, p.world, p.stream, p.policy, p.trace, p.trials, p.steps);
   if (rc) return rc;
   COBEL_REQUIRE(p.Q && p.Mr && p.Ms && p.Mt && p.T && p.SR && p.update_mask && p.lr && p.gamma && p.mem_lr && p.lr_q &&
-                p.gamma_q && p.gamma_sr && p.pow_gamma_sr && p.pow_gamma_q && p.mem_policy.param, COBEL_EINVAL,
-                "agent tables missing");
+                p.gamma_q && p.gamma_sr && p.pow_gamma_sr && p.pow_gamma_q && p.mem_policy.param && p.carry &&
+                p.need_scratch, COBEL_EINVAL, "agent tables missing");
   COBEL_REQUIRE(p.mem_policy.kind >= 0 && p.mem_policy.kind <= 2, COBEL_EINVAL, "bad memory policy");
   COBEL_REQUIRE(p.batch >= 0 && p.batch <= kMaxSeq, COBEL_EUNSUPPORTED, "PMA replay batch must be in 0..%d", kMaxSeq);
   if (p.trials == 0) return COBEL_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (p.world.n_actions) {
-    case 2: return launch<2>(p, st);
-    case 3: return launch<3>(p, st);
-    case 4: return launch<4>(p, st);
-    case 6: return launch<6>(p, st);
-    case 8: return launch<8>(p, st);
+    case 2: return run<2>(p, st);
+    case 3: return run<3>(p, st);
+    case 4: return run<4>(p, st);
+    case 6: return run<6>(p, st);
+    case 8: return run<8>(p, st);
     default:
       cobel_set_error("unsupported number of actions %d (built for 2,3,4,6,8)", p.world.n_actions);
       return COBEL_EUNSUPPORTED;

@@ -53,6 +53,8 @@ class PMAMemory(TableMemory):
         self._SR = torch.as_tensor(SR).to(dev).contiguous()
         self._update_mask = torch.zeros((n, S * self.nb_actions), dtype=torch.uint8, device=dev)
         self._min_gap = torch.full((n,), float('inf'), dtype=torch.float64, device=dev)
+        self._carry = torch.zeros((n, 4), dtype=torch.int64, device=dev)            # kernel scratch
+        self._need_scratch = torch.zeros((n, S), dtype=torch.float64, device=dev)   # kernel scratch
         self.compute_update_mask()
 
     T = property(lambda self: self._view(self._T))

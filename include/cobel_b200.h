@@ -237,6 +237,8 @@ typedef struct CobelPMAParams {
   const double* pow_gamma_q; /* same for M.gamma_q (the reference uses Python's float pow) */
   int64_t  pow_stride;       /* 0 = one table for all agents, COBEL_PMA_MAX_SEQ+2 = one per agent */
   double*  min_gap;          /* optional [N] in/out: smallest relative gap between the two largest distinct utilities */
+  int64_t* carry;            /* scratch [N,4]: per-agent state carried between the launches of one call */
+  double*  need_scratch;     /* scratch [N,S]: stationary `need` of agents whose trial timed out */
   double   lr_T;             /* M.learning_rate_T (0.9) */
   double   min_gain;         /* M.min_gain (1e-6) */
   int32_t  min_gain_original;/* M.min_gain_mode == 'original' */
