@@ -139,14 +139,17 @@ struct Tile {
 };
 
 // SR = inv(I - gamma T) by in-place Gauss-Jordan without pivoting (I - gamma T is strictly
-// diagonally dominant).  The pivot row / column need no special-casing: with f_k := piv - 1 and
-// rowk_k := 1 + 1/piv the generic update m -= f_i * rowk_j / piv also produces the scaled pivot
-// row, -f_i/piv in the pivot column and 1/piv on the pivot.
+// diagonally dominant, so any pivot order is stable; pivots are taken in the order
+// k = ty0 + 16 r0 with r0 as the unrolled outer loop, which makes the pivot row / column of a
+// thread's tile a compile-time register index).  The pivot row / column need no special-casing
+// in the update: the owner of the pivot publishes piv + 1 in the row slot and piv - 1 in the
+// column slot, so that the generic m -= f_i * (rowk_j / piv) also yields the scaled pivot row,
+// -f_i / piv in the pivot column and 1 / piv on the pivot (cancellation error ~ eps * piv).
 template <int TILE>
 __device__ __forceinline__ void gauss_jordan_inverse(const double* __restrict__ Tg, double gsr, double* SRg, int S,
                                                      double* buf, int tid, int& flags) {
   const int ty = tid >> 4, tx = tid & 15;
-  const int SP = TILE * 16;
+  constexpr int SP = TILE * 16 + 2;                 // row / column slots + {piv, 1/piv}
   Tile<TILE> t;
 #pragma unroll
   for (int r = 0; r < TILE; ++r)
@@ -157,42 +160,39 @@ __device__ __forceinline__ void gauss_jordan_inverse(const double* __restrict__ 
       if (i < S && j < S) v -= gsr * Tg[(size_t)i * S + j];
       t.m[r][c] = v;
     }
-  for (int k = 0; k < S; ++k) {
-    double* rowk = buf + (k & 1) * 2 * SP;
-    double* colk = rowk + SP;
-    const int r0 = k >> 4, c0 = k >> 4;
-    if (ty == (k & 15)) {
 #pragma unroll
-      for (int r = 0; r < TILE; ++r)
-        if (r == r0) {
+  for (int r0 = 0; r0 < TILE; ++r0) {
+    for (int ty0 = 0; ty0 < 16; ++ty0) {
+      const int k = ty0 + 16 * r0;
+      if (k >= S) break;
+      double* rowk = buf + (k & 1) * 2 * SP;
+      double* colk = rowk + SP;
+      if (ty == ty0) {
 #pragma unroll
-          for (int c = 0; c < TILE; ++c) rowk[tx + 16 * c] = t.m[r][c];
+        for (int c = 0; c < TILE; ++c) rowk[tx + 16 * c] = t.m[r0][c];
+      }
+      if (tx == ty0) {
+#pragma unroll
+        for (int r = 0; r < TILE; ++r) colk[ty + 16 * r] = t.m[r][r0];
+        if (ty == ty0) {                              // owner of the pivot
+          const double piv = t.m[r0][r0];
+          if (!(fabs(piv) > 1e-300)) flags |= COBEL_FLAG_SINGULAR;
+          rowk[k] = piv + 1.0;
+          colk[k] = piv - 1.0;
+          rowk[SP - 1] = 1.0 / piv;
         }
-    }
-    if (tx == (k & 15)) {
+      }
+      __syncthreads();
+      const double ipiv = rowk[SP - 1];
+      double rk[TILE];
 #pragma unroll
-      for (int c = 0; c < TILE; ++c)
-        if (c == c0) {
+      for (int c = 0; c < TILE; ++c) rk[c] = rowk[tx + 16 * c] * ipiv;
 #pragma unroll
-          for (int r = 0; r < TILE; ++r) colk[ty + 16 * r] = t.m[r][c];
-        }
-    }
-    __syncthreads();
-    const double piv = rowk[k];
-    if (!(fabs(piv) > 1e-300)) flags |= COBEL_FLAG_SINGULAR;
-    const double ipiv = 1.0 / piv;
-    double rk[TILE];
+      for (int r = 0; r < TILE; ++r) {
+        const double f = colk[ty + 16 * r];
 #pragma unroll
-    for (int c = 0; c < TILE; ++c) {
-      const int j = tx + 16 * c;
-      rk[c] = j == k ? 1.0 + ipiv : rowk[j] * ipiv;
-    }
-#pragma unroll
-    for (int r = 0; r < TILE; ++r) {
-      const int i = ty + 16 * r;
-      const double f = i == k ? piv - 1.0 : colk[i];
-#pragma unroll
-      for (int c = 0; c < TILE; ++c) t.m[r][c] = fma(-f, rk[c], t.m[r][c]);
+        for (int c = 0; c < TILE; ++c) t.m[r][c] = fma(-f, rk[c], t.m[r][c]);
+      }
     }
   }
   __syncthreads();
@@ -208,11 +208,12 @@ __device__ __forceinline__ void gauss_jordan_inverse(const double* __restrict__ 
 
 // Stationary distribution of the row-stochastic T by GTH (Grassmann-Taksar-Heyman) elimination,
 // returned in x[0..S) scaled to unit 2-norm.  Mat receives the eliminated matrix (scratch).
+// States are eliminated in descending order k = S-1 .. 1 (r0 unrolled as above).
 template <int TILE>
 __device__ __forceinline__ void gth_stationary(const double* __restrict__ Tg, double* Mat, double* x, int S, double* buf,
                                                int tid, int& flags) {
   const int ty = tid >> 4, tx = tid & 15, lane = tid & 31;
-  const int SP = TILE * 16;
+  constexpr int SP = TILE * 16 + 2;
   Tile<TILE> t;
 #pragma unroll
   for (int r = 0; r < TILE; ++r)
@@ -221,47 +222,42 @@ __device__ __forceinline__ void gth_stationary(const double* __restrict__ Tg, do
       const int i = ty + 16 * r, j = tx + 16 * c;
       t.m[r][c] = (i < S && j < S) ? Tg[(size_t)i * S + j] : 0.0;
     }
-  for (int k = S - 1; k >= 1; --k) {
-    double* rowk = buf + (k & 1) * 2 * SP;
-    double* colk = rowk + SP;
-    const int r0 = k >> 4, c0 = k >> 4;
-    if (ty == (k & 15)) {
 #pragma unroll
-      for (int r = 0; r < TILE; ++r)
-        if (r == r0) {
+  for (int r0 = TILE - 1; r0 >= 0; --r0) {
+    for (int ty0 = 15; ty0 >= 0; --ty0) {
+      const int k = ty0 + 16 * r0;
+      if (k >= S || k < 1) continue;
+      double* rowk = buf + (k & 1) * 2 * SP;
+      double* colk = rowk + SP;
+      if (ty == ty0) {
 #pragma unroll
-          for (int c = 0; c < TILE; ++c) rowk[tx + 16 * c] = t.m[r][c];
-        }
-    }
-    if (tx == (k & 15)) {
+        for (int c = 0; c < TILE; ++c) rowk[tx + 16 * c] = t.m[r0][c];
+      }
+      if (tx == ty0) {
 #pragma unroll
-      for (int c = 0; c < TILE; ++c)
-        if (c == c0) {
-#pragma unroll
-          for (int r = 0; r < TILE; ++r) colk[ty + 16 * r] = t.m[r][c];
-        }
-    }
-    __syncthreads();
-    // every warp forms s = sum_{j<k} P[k][j] with the same reduction tree
-    double ssum = 0.0;
-    for (int j = lane; j < k; j += 32) ssum += rowk[j];
-    for (int d = 16; d > 0; d >>= 1) ssum += shfl_f64_xor(ssum, d);
-    if (!(ssum > 0.0)) { flags |= COBEL_FLAG_SINGULAR; ssum = 1.0; }
-    const double inv = 1.0 / ssum;
-    double rk[TILE];
-#pragma unroll
-    for (int c = 0; c < TILE; ++c) {
-      const int j = tx + 16 * c;
-      rk[c] = j < k ? rowk[j] : 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < TILE; ++r) {
-      const int i = ty + 16 * r;
-      const double f = i < k ? colk[i] * inv : 0.0;
+        for (int r = 0; r < TILE; ++r) colk[ty + 16 * r] = t.m[r][r0];
+      }
+      __syncthreads();
+      // every warp forms s = sum_{j<k} P[k][j] with the same reduction tree
+      double ssum = 0.0;
+      for (int j = lane; j < k; j += 32) ssum += rowk[j];
+      for (int d = 16; d > 0; d >>= 1) ssum += shfl_f64_xor(ssum, d);
+      if (!(ssum > 0.0)) { flags |= COBEL_FLAG_SINGULAR; ssum = 1.0; }
+      const double inv = 1.0 / ssum;
+      double rk[TILE];
 #pragma unroll
       for (int c = 0; c < TILE; ++c) {
         const int j = tx + 16 * c;
-        t.m[r][c] = j == k ? (i < k ? f : t.m[r][c]) : fma(f, rk[c], t.m[r][c]);
+        rk[c] = j < k ? rowk[j] : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < TILE; ++r) {
+        const int i = ty + 16 * r;
+        const double f = i < k ? colk[i] * inv : 0.0;
+#pragma unroll
+        for (int c = 0; c < TILE; ++c) t.m[r][c] = fma(f, rk[c], t.m[r][c]);
+        // column k keeps the scaled entries P[i][k] / s for the back-substitution
+        if (tx == ty0 && i < k) t.m[r][r0] = f;
       }
     }
   }
@@ -303,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_sr_kernel(con
   const int S = p.world.n_states, tid = threadIdx.x;
   const int64_t n = blockIdx.x;
   double* elim = reinterpret_cast<double*>(smem);                 // 2 x (pivot row + pivot column)
-  double* xv = elim + 4 * TILE * 16;                              // [S] stationary vector
+  double* xv = elim + 4 * (TILE * 16 + 2);                        // [S] stationary vector
   double* Mat = xv + ((S + 1) & ~1);                              // [S*S] GTH scratch
   int flags = 0;
   const double* Tg = p.T + (size_t)n * S * S;
@@ -490,17 +486,14 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       }
       // ---- (2) one-step gains: compact the stale ones, then one lane-parallel pass ---------------
       int nd = 0;
-      for (int e0 = 0; e0 < N; e0 += 32) {
-        const int i = e0 + lane;
-        bool stale = false;
-        if (i < N) {
-          const int a = i / S, s = i - a * S;
-          stale = dirty[s] || dirty[Pk[s * A + a] & 0x7FFF];
+      for (int a = 0; a < A; ++a)
+        for (int s0 = 0; s0 < S; s0 += 32) {          // flat index i = a*S + s without integer division
+          const int s = s0 + lane;
+          const bool stale = s < S && (dirty[s] || dirty[Pk[s * A + a] & 0x7FFF]);
+          const unsigned b = __ballot_sync(kFull, stale);
+          if (stale) list[nd + __popc(b & ((1u << lane) - 1u))] = (uint16_t)(a * S + s);
+          nd += __popc(b);
         }
-        const unsigned b = __ballot_sync(kFull, stale);
-        if (stale) list[nd + __popc(b & ((1u << lane) - 1u))] = (uint16_t)i;
-        nd += __popc(b);
-      }
       __syncwarp();
       for (int j0 = 0; j0 < nd; j0 += 32)
         if (j0 + lane < nd) { const int i = list[j0 + lane]; gain[i] = gain_one(i); }
@@ -552,24 +545,26 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         gext = total > min_gain ? total : min_gain;
       }
       // ---- (4) utility = gain * need * update_mask; arg-max with exact ties (memory/pma.py:247-254)
-      auto utility = [&](int i) -> double {
-        const int s = i % S;
+      auto utility = [&](int a, int s) -> double {        // element i = a*S + s
+        const int i = a * S + s;
         const double g = (i == ext) ? gext : gain[i];
         return xmul(xmul(g, need[s]), umask[i] ? 1.0 : 0.0);
       };
       const double ninf = -__longlong_as_double(0x7FF0000000000000ll);
       double lmax = ninf;
-      for (int i = lane; i < N; i += 32) { const double u_ = utility(i); lmax = u_ > lmax ? u_ : lmax; }
+      for (int a = 0; a < A; ++a)
+        for (int s = lane; s < S; s += 32) { const double u_ = utility(a, s); lmax = u_ > lmax ? u_ : lmax; }
       const double umax = warp_max_f64(lmax);
       // ties (flat-index order) and the certificate: gap to the largest utility below the maximum
       double l2 = ninf;
       int ktot = 0;
-      for (int e0 = 0; e0 < N; e0 += 32) {
-        const int i = e0 + lane;
-        bool tie = false;
-        if (i < N) { const double v = utility(i); tie = v == umax; if (v < umax && v > l2) l2 = v; }
-        ktot += __popc(__ballot_sync(kFull, tie));
-      }
+      for (int a = 0; a < A; ++a)
+        for (int s0 = 0; s0 < S; s0 += 32) {
+          const int s = s0 + lane;
+          bool tie = false;
+          if (s < S) { const double v = utility(a, s); tie = v == umax; if (v < umax && v > l2) l2 = v; }
+          ktot += __popc(__ballot_sync(kFull, tie));
+        }
       const double u2 = warp_max_f64(l2);
       if (umax != 0.0 && u2 > -1e300) { const double gp = (umax - u2) / fabs(umax); min_gap = gp < min_gap ? gp : min_gap; }
       win.ensure(1, lane);
@@ -577,7 +572,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       // Generator.choice(p = ties / k): cdf_m = m-fold sequential sum of fl(1/k), normalised by cdf_k
       int pick = ktot - 1;
       {
-        const double pk_ = xdiv(1.0, (double)ktot);
+        const double pk_ = xdiv(1.0, int_to_f64(ktot));
         double ck = 0.0;
         for (int m = 0; m < ktot; ++m) ck = xadd(ck, pk_);
         double c = 0.0;
@@ -586,15 +581,16 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
           if (xdiv(c, ck) > u) { pick = m; break; }
         }
       }
-      int chosen = 0;
-      for (int e0 = 0; e0 < N; e0 += 32) {
-        const int i = e0 + lane;
-        const bool tie = i < N && utility(i) == umax;
-        const unsigned b = __ballot_sync(kFull, tie);
-        const int c = __popc(b);
-        if (pick < c) { chosen = e0 + __fns(b, 0, pick + 1); break; }
-        pick -= c;
-      }
+      int chosen = -1;
+      for (int a = 0; a < A && chosen < 0; ++a)
+        for (int s0 = 0; s0 < S; s0 += 32) {
+          const int s = s0 + lane;
+          const bool tie = s < S && utility(a, s) == umax;
+          const unsigned b = __ballot_sync(kFull, tie);
+          const int c = __popc(b);
+          if (pick < c) { chosen = a * S + s0 + __fns(b, 0, pick + 1); break; }
+          pick -= c;
+        }
       // ---- (5) apply the chosen (n-step) update: PMAMemory.update_q, memory/pma.py:452-496 --------
       {
         const bool use_seq = clen > 0 && chosen == ext;
@@ -649,12 +645,21 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     __syncwarp();
   };
 
-  if (ph.end_replay) replay((int)c_last);            // need from the terminal state, or stationary (agent/pma.py:248-256)
-
-  for (int trial = ph.trial_first; trial < ph.trial_first + ph.n_trials; ++trial) {
-    win.ensure(2, lane);
-    int s = __ldg(p.world.starts + draw_integer(win.next(), K));
-    if (do_replay) replay(s);                         // awake replay, need = SR[start] (agent/pma.py:206-213)
+  // Launch phases with a single (inlined) replay site: stage 0 = end-of-trial replay of the previous
+  // trial (agent/pma.py:248-256), stage 1 = reset + start-of-trial replay (206-213) + online steps.
+  int trial = ph.trial_first, ntr = ph.n_trials;
+  for (int stage = ph.end_replay ? 0 : 1;; stage = 1) {
+    int cur = -2, s = 0;
+    if (stage == 0) {
+      cur = (int)c_last;                                // terminal state, or -1: stationary need
+    } else {
+      if (ntr == 0) break;
+      win.ensure(2, lane);
+      s = __ldg(p.world.starts + draw_integer(win.next(), K));
+      if (do_replay) cur = s;                           // awake replay, need = SR[start]
+    }
+    if (cur != -2) replay(cur);
+    if (stage == 0) continue;
     double treward = 0.0;
     int step = 0, last = -1;
     for (;; ++step) {
@@ -705,6 +710,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       tr.trial_reward[n * p.trials + trial] = treward;
     }
     c_last = last;
+    ++trial; --ntr;
   }
 
   __syncwarp();
@@ -737,7 +743,7 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
   COBEL_REQUIRE(sm_main <= 227 * 1024, COBEL_EUNSUPPORTED, "PMA: %d states x %d actions do not fit in shared memory", S, A);
   COBEL_CUDA_OK(cudaFuncSetAttribute(pma_main_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_main));
   const int tile = S <= 7 * 16 ? 7 : 10;
-  const size_t sm_sr = (size_t)(4 * tile * 16 + ((S + 1) & ~1) + S * S) * 8;
+  const size_t sm_sr = (size_t)(4 * (tile * 16 + 2) + ((S + 1) & ~1) + S * S) * 8;
   if (tile == 7) COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
   else COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
   const unsigned grid_main = (unsigned)((p.n_agents + kMainWarps - 1) / kMainWarps);
