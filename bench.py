@@ -59,6 +59,12 @@ WORKLOADS = {
         metric='agent-steps/sec', unit='agent-steps/s', kernel='sr_kernel<4>',
         agents_per_gpu=4096, trials=4, steps=64, batch=0, world='open20', bytes_per_unit=8 * 400 * 8 + 24,
         unit_key='n_steps', cpu_trials=4),
+    'sr100': dict(
+        desc='C5: SR agents with visited-set compaction, 100x100 open field, 1048576 agents in total (strong scaling: '
+             'sharded over the GPUs), 2 trials x <=48 steps, max_visited 100',
+        metric='agent-steps/sec', unit='agent-steps/s', kernel='sr_compact_kernel<4>',
+        agents_total=1048576, trials=2, steps=48, batch=0, world='open100', bytes_per_unit=8 * 50 * 8 + 24,
+        unit_key='n_steps', cpu_trials=2, scaling='strong', max_visited=100),
     'q': dict(
         desc='QAgent on the linear_track(10,2) topology graph, 4096 agents/GPU, 500 trials x <=50 steps, batch 32',
         metric='agent-steps/sec incl. replay', unit='agent-steps/s', kernel='q_warp_kernel<4>',
@@ -68,7 +74,7 @@ WORKLOADS = {
 
 
 # agents per host core in the cpu_baseline leg: sized for roughly 10-20 s of CPU work per workload
-CPU_AGENTS_PER_CORE = {'dynaq': 16, 'pma': 12, 'q': 16, 'sr': 8, 'sfma': 4}
+CPU_AGENTS_PER_CORE = {'dynaq': 16, 'pma': 12, 'q': 16, 'sr': 8, 'sfma': 4, 'sr100': 1}
 
 
 def peaks():
@@ -84,6 +90,8 @@ def make_world(name):
     from oracle.cases import world_args
     if name == 'open20':
         return make_open_field(20, 20, 0, 1)
+    if name == 'open100':
+        return make_open_field(100, 100, 0, 1, dense_sas=False)
     h, w, kw = world_args(name)
     return make_gridworld(h, w, **kw)
 
@@ -153,7 +161,11 @@ def _cpu_worker(args):
         W = tb.compile_topology(*linear_track(10, 2, 1.0, 20.0, 'right'))
     else:
         world = make_world(wl['world'])
-        W = tb.compile_gridworld(world)
+        if world['sas'] is None:
+            W = {'S': world['states'], 'A': 4, 'succ': world['succ'], 'reward': world['rewards'].astype(np.float64),
+                 'terminal': world['terminals'].astype(np.uint8), 'starts': world['starting_states'].astype(np.int32)}
+        else:
+            W = tb.compile_gridworld(world)
     S, A = W['S'], W['A']
     units = 0
     for g in agent_ids:
@@ -164,7 +176,7 @@ def _cpu_worker(args):
         elif name == 'q':
             rec = tb.q_train(W, tb.q_init(S, A), rng, trials, steps, batch)
             units += len(rec.s)
-        elif name == 'sr':
+        elif name in ('sr', 'sr100'):
             rec = tb.sr_train(W, tb.sr_init(S, A), rng, trials, steps)
             units += len(rec.s)
         elif name == 'sfma':
@@ -271,6 +283,11 @@ class Job:
         elif name == 'sr':
             self.agent = AG.SR(env.observation_space, env.action_space, pol, None, 0.1, 0.99)
             self.state = {'SR': self.agent._SR, 'rew': self.agent._rewards, 'model': self.agent._model}
+        elif name == 'sr100':
+            self.agent = AG.SR(env.observation_space, env.action_space, pol, None, 0.1, 0.99, compact=True,
+                               max_visited=wl['max_visited'])
+            # a fresh compact agent is just "nothing visited yet": rows are initialised on first visit
+            self.state = {'n_visited': self.agent._n_visited}
         elif name == 'sfma':
             from cobel_rl_b200.memory.utils.metrics import DR
             w = self.world
@@ -295,13 +312,13 @@ class Job:
         tr = wl['trials']
         self.host_out = {'trial_steps': torch.empty((n_local, tr), dtype=torch.int32).pin_memory(),
                          'trial_reward': torch.empty((n_local, tr), dtype=torch.float64).pin_memory()}
-        key = 'Q' if 'Q' in self.state else 'rew'
+        key = 'Q' if 'Q' in self.state else ('rew' if 'rew' in self.state else 'n_visited')
         self.out_key = key
         self.host_out[key] = torch.empty(self.state[key].shape, dtype=self.state[key].dtype).pin_memory()
 
     def _train(self):
         wl, a = self.wl, self.agent
-        if self.name == 'sr':
+        if self.name in ('sr', 'sr100'):
             return a.train(self.env, wl['trials'], wl['steps'])
         return a.train(self.env, wl['trials'], wl['steps'], wl['batch'])
 
@@ -414,8 +431,14 @@ def run_ours(args):
     blocks, clocks = {}, None
     for name in names:
         wl = WORKLOADS[name]
-        n_local = wl['agents_per_gpu']
-        lo, hi = cdist.shard_range(n_local * world, rank, world)
+        if wl.get('scaling') == 'strong':
+            lo, hi = cdist.shard_range(wl['agents_total'], rank, world)
+            n_local = hi - lo
+            wl['agents_per_gpu'] = wl['agents_total'] // world
+        else:
+            n_local = wl['agents_per_gpu']
+            lo, hi = cdist.shard_range(n_local * world, rank, world)
+        n_total = int(cdist.sum_over_ranks(n_local, dev))
         job = Job(name, dev, lo, n_local)
         sampler = ClockSampler(local)
         if rank == 0 and name == names[0]:
@@ -427,10 +450,10 @@ def run_ours(args):
         # the only collective of the path: final all-gather of per-agent statistics
         torch.cuda.synchronize(dev)
         g0 = time.perf_counter()
-        gathered = cdist.gather_results(m['res'], n_local * world)
+        gathered = cdist.gather_results(m['res'], n_total)
         torch.cuda.synchronize(dev)
         gather_ms = 1e3 * (time.perf_counter() - g0)
-        assert gathered['n_steps'].shape[0] == n_local * world
+        assert gathered['n_steps'].shape[0] == n_total
         t_step = cdist.max_over_ranks(m['ms'], dev)
         t_e2e = cdist.max_over_ranks(m['ms_e2e'], dev)
         units_total = cdist.sum_over_ranks(m['units'], dev)
@@ -449,8 +472,8 @@ def run_ours(args):
     out = {
         'metric': head['metric'], 'value': head['value'], 'unit': head['unit'], 'n_gpus': world,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': head['ms_per_step'],
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': head['config'], 'roofline': head['roofline'], 'e2e': head['e2e'],
+        'higher_is_better': True, 'scaling': WORKLOADS[names[0]].get('scaling', 'weak'), 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic', 'config': head['config'], 'roofline': head['roofline'], 'e2e': head['e2e'],
         'gpu_launches': head['gpu_launches'], 'clocks': clocks,
     }
     if world == 1 and not args.no_cpu:
@@ -479,6 +502,8 @@ def main():
     if args.agents:
         for w in WORKLOADS.values():
             w['agents_per_gpu'] = args.agents
+            if 'agents_total' in w:
+                w['agents_total'] = args.agents * args.gpus
             w['desc'] += ' [agents per GPU overridden to %d]' % args.agents
     if args.impl == 'reference':
         run_reference(args)

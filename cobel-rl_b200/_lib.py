@@ -57,6 +57,13 @@ class SRParams(C.Structure):
                 ('steps', C.c_int32), ('learn', C.c_int32), ('reserved', C.c_int32)]
 
 
+class SRCompactParams(C.Structure):
+    _fields_ = [('n_agents', C.c_int64), ('world', World), ('stream', Stream), ('policy', Policy),
+                ('trace', Trace), ('SRc', c_ptr), ('rewards', c_ptr), ('model', c_ptr), ('visited', c_ptr),
+                ('n_visited', c_ptr), ('action_mask', c_ptr), ('lr', c_ptr), ('gamma', c_ptr),
+                ('max_visited', C.c_int32), ('trials', C.c_int32), ('steps', C.c_int32), ('learn', C.c_int32)]
+
+
 class SFMAParams(C.Structure):
     _fields_ = [('n_agents', C.c_int64), ('world', World), ('stream', Stream), ('policy', Policy),
                 ('trace', Trace), ('Q', c_ptr), ('Mr', c_ptr), ('Ms', c_ptr), ('Mt', c_ptr), ('C', c_ptr),
@@ -85,7 +92,7 @@ class PMAParams(C.Structure):
 
 
 STRUCTS = {'CobelWorld': World, 'CobelStream': Stream, 'CobelPolicy': Policy, 'CobelTrace': Trace,
-           'CobelDynaQParams': DynaQParams, 'CobelQParams': QParams, 'CobelSRParams': SRParams, 'CobelSFMAParams': SFMAParams, 'CobelPMAParams': PMAParams}
+           'CobelDynaQParams': DynaQParams, 'CobelQParams': QParams, 'CobelSRParams': SRParams, 'CobelSRCompactParams': SRCompactParams, 'CobelSFMAParams': SFMAParams, 'CobelPMAParams': PMAParams}
 
 _SIGNATURES = {
     'cobel_sizeof': (C.c_size_t, [C.c_char_p]),
@@ -97,6 +104,7 @@ _SIGNATURES = {
     'cobel_dynaq_run': (C.c_int, [C.POINTER(DynaQParams), c_ptr]),
     'cobel_q_run': (C.c_int, [C.POINTER(QParams), c_ptr]),
     'cobel_sr_run': (C.c_int, [C.POINTER(SRParams), c_ptr]),
+    'cobel_sr_compact_run': (C.c_int, [C.POINTER(SRCompactParams), c_ptr]),
     'cobel_sfma_run': (C.c_int, [C.POINTER(SFMAParams), c_ptr]),
     'cobel_pma_run': (C.c_int, [C.POINTER(PMAParams), c_ptr]),
 }

@@ -4,6 +4,11 @@
 vector, action selection, environment step, reward / transition-model / SR row update) for all
 N agents in one launch of ``cobel_sr_run`` (csrc/sr.cu).  The reference's dense one-hot
 transition model ``transitions[S,A,S]`` is held as its arg-max ``model[S,A]``.
+
+``SR(..., compact=True, max_visited=V)`` selects the visited-set compaction for very large
+state spaces (100x100 and beyond, csrc/sr_compact.cu): per agent only the V x V block of the
+SR over the states it has touched is stored, everything else is implied (identity rows,
+self-loop model, zero reward); results are bit-identical to the dense agent.
 """
 import numpy as np
 import torch
@@ -15,7 +20,7 @@ from .agent import Agent, launch_stream
 
 class SR(Agent):
     def __init__(self, observation_space, action_space, policy, policy_test=None, learning_rate=0.1,
-                 gamma=0.99, custom_callbacks=None):
+                 gamma=0.99, custom_callbacks=None, compact=False, max_visited=128):
         assert type(observation_space) is Discrete, 'SR requires a discrete observation space!'
         assert type(action_space) is Discrete, 'SR requires a discrete action space!'
         super().__init__(observation_space, action_space, custom_callbacks)
@@ -24,20 +29,55 @@ class SR(Agent):
         self.learning_rate = learning_rate
         self.gamma = gamma
         self.mask_actions = False
+        self.compact = bool(compact)
+        self.max_visited = int(max_visited)
         stream = self._find_stream(self.policy, self.policy_test)
         if stream is not None:
             self._bind(stream)
 
     def _allocate(self, stream):
         S, A, n, dev = int(self.observation_space.n), int(self.action_space.n), stream.n_agents, stream.device
+        self._action_mask = torch.ones((S, A), dtype=torch.bool, device=dev)
+        if self.compact:
+            V = self.max_visited
+            self._SRc = torch.zeros((n, V, V), dtype=torch.float64, device=dev)
+            self._visited = torch.full((n, V), -1, dtype=torch.int32, device=dev)
+            self._n_visited = torch.zeros(n, dtype=torch.int32, device=dev)
+            self._rewards = torch.zeros((n, V), dtype=torch.float64, device=dev)
+            self._model = torch.zeros((n, V, A), dtype=torch.int32, device=dev)
+            return
         self._SR = torch.eye(S, dtype=torch.float64, device=dev).repeat(n, 1, 1).contiguous()     # sr.py:130
         self._model = torch.arange(S, dtype=torch.int32, device=dev).reshape(1, S, 1).repeat(n, 1, A).contiguous()
         self._rewards = torch.zeros((n, S), dtype=torch.float64, device=dev)                       # sr.py:136
         self._action_mask = torch.ones((S, A), dtype=torch.bool, device=dev)
 
-    SR = property(lambda self: self._view(self._SR))
+    @property
+    def SR(self):
+        if self.compact:
+            raise AttributeError('compact SR agent: use SR_compact / visited / n_visited, or dense_sr(agent)')
+        return self._view(self._SR)
+
     rewards = property(lambda self: self._view(self._rewards))
     model = property(lambda self: self._view(self._model))
+    SR_compact = property(lambda self: self._view(self._SRc))
+    visited = property(lambda self: self._view(self._visited))
+    n_visited = property(lambda self: self._view(self._n_visited))
+
+    def dense_sr(self, agent=0):
+        """Materialise the dense ``[S,S]`` SR of one agent of a compact run (checking / analysis)."""
+        S = int(self.observation_space.n)
+        v = int(self._n_visited[agent])
+        idx = self._visited[agent, :v].long()
+        out = torch.eye(S, dtype=torch.float64, device=self._SRc.device)
+        out[idx.unsqueeze(1), idx.unsqueeze(0)] = self._SRc[agent, :v, :v]
+        return out
+
+    def dense_rewards(self, agent=0):
+        S = int(self.observation_space.n)
+        v = int(self._n_visited[agent])
+        out = torch.zeros(S, dtype=torch.float64, device=self._SRc.device)
+        out[self._visited[agent, :v].long()] = self._rewards[agent, :v]
+        return out
 
     @property
     def transitions(self):
@@ -58,7 +98,7 @@ class SR(Agent):
             self._bind(interface.rng)
         st = self._stream
         assert interface.rng is st, 'environment and agent must share one BatchStream'
-        assert interface.n_states == self._SR.shape[1] and interface.n_actions == self._model.shape[2]
+        assert interface.n_states == int(self.observation_space.n) and interface.n_actions == self._model.shape[2]
         pol = self.policy if learn else self.policy_test
         results = []
         for _, n_tr in self._chunks(trials):
@@ -66,10 +106,21 @@ class SR(Agent):
             tr, res = self._make_trace(n_tr, steps, 0, 0, 0, keep)
             lr, gm = st.param(self.learning_rate, 'learning_rate'), st.param(self.gamma, 'gamma')
             mptr, mstride = self._mask_args(keep)
-            p = _lib.SRParams(st.n_agents, interface.c_world(), st.c_struct(), pol.c_struct(st, keep), tr,
-                              self._SR.data_ptr(), self._rewards.data_ptr(), self._model.data_ptr(), mptr, mstride,
-                              lr.data_ptr(), gm.data_ptr(), n_tr, steps, 1 if learn else 0, 0)
-            _lib.check(_lib.lib().cobel_sr_run(p, launch_stream(st)))
+            if self.compact:
+                assert mstride == 0, 'compact SR supports one action mask shared by all agents'
+                p = _lib.SRCompactParams(st.n_agents, interface.c_world(), st.c_struct(), pol.c_struct(st, keep), tr,
+                                         self._SRc.data_ptr(), self._rewards.data_ptr(), self._model.data_ptr(),
+                                         self._visited.data_ptr(), self._n_visited.data_ptr(), mptr, lr.data_ptr(),
+                                         gm.data_ptr(), self.max_visited, n_tr, steps, 1 if learn else 0)
+                _lib.check(_lib.lib().cobel_sr_compact_run(p, launch_stream(st)))
+                if bool((res['flags'] & 16).any()):
+                    raise _lib.CobelError('an agent visited more than max_visited=%d distinct states; raise max_visited '
+                                          'or shorten the horizon' % self.max_visited)
+            else:
+                p = _lib.SRParams(st.n_agents, interface.c_world(), st.c_struct(), pol.c_struct(st, keep), tr,
+                                  self._SR.data_ptr(), self._rewards.data_ptr(), self._model.data_ptr(), mptr, mstride,
+                                  lr.data_ptr(), gm.data_ptr(), n_tr, steps, 1 if learn else 0, 0)
+                _lib.check(_lib.lib().cobel_sr_run(p, launch_stream(st)))
             self._check_flags(res)
             self._fire_trial_callbacks(res, self.current_trial)
             self.current_trial += n_tr
@@ -98,5 +149,5 @@ class SR(Agent):
 
     def predict_on_batch(self, batch):
         idx = np.array(batch).astype(int).reshape(-1)
-        out = torch.stack([self._stream.single and self.retrieve_q(int(s)) or self.retrieve_q(int(s)) for s in idx], dim=-2)
+        out = torch.stack([self.retrieve_q(int(s)) for s in idx], dim=-2)
         return out.cpu().numpy() if self._stream.single else out

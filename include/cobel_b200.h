@@ -95,7 +95,8 @@ enum {
   COBEL_FLAG_TRACE_OVERFLOW = 1,  /* a step_sa / replay_idx / replay_len buffer was too small */
   COBEL_FLAG_CDF_NEAR_TIE   = 2,  /* an inverse-CDF draw fell within rounding distance of a bin edge */
   COBEL_FLAG_LOG_OVERFLOW   = 4,  /* QAgent experience log full */
-  COBEL_FLAG_SINGULAR       = 8   /* PMA: (I - gamma T) pivot underflow */
+  COBEL_FLAG_SINGULAR       = 8,  /* PMA: (I - gamma T) pivot underflow */
+  COBEL_FLAG_VISITED_OVERFLOW = 16 /* compact SR: an agent visited more than max_visited distinct states */
 };
 
 /* ---- Dyna-Q: agent/dyna_q.py:140-330 + memory/dyna_q.py:62-157 ------------- */
@@ -165,6 +166,29 @@ typedef struct CobelSRParams {
 } CobelSRParams;
 
 int cobel_sr_run(const CobelSRParams* p, void* stream);
+
+/* ---- SR agent with visited-set compaction (very large state spaces, config C5) --------------- */
+typedef struct CobelSRCompactParams {
+  int64_t n_agents;
+  CobelWorld world;
+  CobelStream stream;
+  CobelPolicy policy;
+  CobelTrace trace;
+  double*  SRc;              /* [N,Vmax,Vmax] SRc[i,j] = agent.SR[visited[i], visited[j]]; rows/columns beyond
+                                n_visited are undefined; every other entry of the dense SR is the identity */
+  double*  rewards;          /* [N,Vmax] agent.rewards at the visited states (0 elsewhere) */
+  int32_t* model;            /* [N,Vmax,A] LOCAL index of the modelled successor of (visited[i], a) (self elsewhere) */
+  int32_t* visited;          /* [N,Vmax] global state of local index i, in order of first visit */
+  int32_t* n_visited;        /* [N] in/out: V */
+  const uint8_t* action_mask;/* [S,A] shared by all agents; NULL = mask_actions False */
+  const double* lr;          /* [N] */
+  const double* gamma;       /* [N] */
+  int32_t max_visited;       /* Vmax */
+  int32_t trials, steps;
+  int32_t learn;
+} CobelSRCompactParams;
+
+int cobel_sr_compact_run(const CobelSRCompactParams* p, void* stream);
 
 /* ---- SFMA: agent/sfma.py:189-474 + memory/sfma.py:21-416 --------------------------------- */
 enum { COBEL_SFMA_DEFAULT = 0, COBEL_SFMA_FORWARD = 1, COBEL_SFMA_REVERSE = 2, COBEL_SFMA_BLEND_FORWARD = 3,
