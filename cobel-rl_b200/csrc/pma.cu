@@ -316,21 +316,23 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_sr_kernel(con
 // pma_main_kernel: one warp per agent.
 // ---------------------------------------------------------------------------
 struct MainSmem {      // byte offsets inside one agent's shared-memory block
-  int q, mr, gain, need, pk, list, seq, perf, umask, mbits, dirty, bytes;
+  int q, mr, util, need, poff, pk, pitems, list, seq, perf, dst, mbits, bytes;
+  static constexpr int kListCap = 256;     // stale-gain list; larger sets fall back to a full pass
   __host__ __device__ MainSmem(int S, int A) {
     const int N = S * A;
     q = 0;
     mr = q + N * 8;
-    gain = mr + N * 8;
-    need = gain + N * 8;
-    seq = need + ((S + 1) & ~1) * 8;
-    perf = seq + (kMaxSeq + 2) * 4;
-    pk = perf + (kMaxSeq + 2) * 4;
-    list = pk + N * 2;
-    umask = list + N * 2;
-    mbits = umask + N;
-    dirty = mbits + S;
-    bytes = (dirty + S + 15) & ~15;
+    util = mr + N * 8;
+    need = util + N * 8;
+    poff = need + ((S + 1) & ~1) * 8;
+    pk = poff + ((S + 2) & ~1) * 4;
+    pitems = pk + N * 2;
+    list = pitems + N * 2;
+    seq = list + kListCap * 2;
+    perf = seq + (kMaxSeq + 2) * 2;
+    dst = perf + (kMaxSeq + 2) * 2;
+    mbits = dst + (kMaxSeq + 2) * 2;
+    bytes = (mbits + S + 15) & ~15;
   }
 };
 
@@ -359,15 +361,17 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   unsigned char* blk = smem + (size_t)warp * so.bytes;
   double* Q = reinterpret_cast<double*>(blk + so.q);         // [s][a]
   double* Mr = reinterpret_cast<double*>(blk + so.mr);       // [s][a]
-  double* gain = reinterpret_cast<double*>(blk + so.gain);   // [a*S+s] one-step gains
+  double* util = reinterpret_cast<double*>(blk + so.util);   // [a*S+s] gain * need * update_mask of the one-step backups
   double* need = reinterpret_cast<double*>(blk + so.need);   // [s] need of the current replay call
-  int32_t* seq = reinterpret_cast<int32_t*>(blk + so.seq);   // candidate n-step sequence (flat indices)
-  int32_t* perf = reinterpret_cast<int32_t*>(blk + so.perf); // performed updates of this replay call
-  uint16_t* Pk = reinterpret_cast<uint16_t*>(blk + so.pk);   // [s][a] M.states | M.terminals << 15
-  uint16_t* list = reinterpret_cast<uint16_t*>(blk + so.list); // compacted indices of stale gains
-  uint8_t* umask = blk + so.umask;                           // [a*S+s] M.update_mask
-  uint8_t* mbits = blk + so.mbits;                           // [s] valid-action bits (all ones if unmasked)
-  uint8_t* dirty = blk + so.dirty;                           // [s] Q row changed since the gains were computed
+  int32_t* poff = reinterpret_cast<int32_t*>(blk + so.poff); // [S+1] CSR offsets: backups whose next state is t
+  uint16_t* Pk = reinterpret_cast<uint16_t*>(blk + so.pk);   // [s][a] M.states | update_mask << 13 | M.terminals << 15
+  uint16_t* pitems = reinterpret_cast<uint16_t*>(blk + so.pitems); // [N] CSR items (flat indices a*S+s)
+  uint16_t* list = reinterpret_cast<uint16_t*>(blk + so.list);     // flat indices of the stale gains
+  uint16_t* seq = reinterpret_cast<uint16_t*>(blk + so.seq);   // candidate n-step sequence (flat indices)
+  uint16_t* perf = reinterpret_cast<uint16_t*>(blk + so.perf); // performed updates of this replay call
+  uint16_t* dst = reinterpret_cast<uint16_t*>(blk + so.dst);   // states whose Q row changed in the last update
+  uint8_t* mbits = blk + so.mbits;                             // [s] valid-action bits (all ones if unmasked)
+  constexpr int kSt = 0x1FFF, kUm = 0x2000;
 
   const size_t g0 = (size_t)n * N;
   double* Tg = p.T + (size_t)n * S * S;
@@ -376,8 +380,8 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   for (int e = lane; e < N; e += 32) {
     Q[e] = p.Q[g0 + e];
     Mr[e] = p.Mr[g0 + e];
-    Pk[e] = (uint16_t)(p.Ms[g0 + e] | ((p.Mt[g0 + e] ? 1 : 0) << 15));
-    umask[e] = p.update_mask[g0 + e];
+    const int s_ = e / A, a_ = e - s_ * A;
+    Pk[e] = (uint16_t)(p.Ms[g0 + e] | (p.update_mask[g0 + a_ * S + s_] ? kUm : 0) | ((p.Mt[g0 + e] ? 1 : 0) << 15));
   }
   for (int e = lane; e < S; e += 32) {
     uint32_t mb = (1u << A) - 1u;
@@ -421,7 +425,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     double q[A], qn[A], po[A], pn[A], t[A];
     load_row<A>(Q + s * A, q);
     const uint16_t pk = Pk[s * A + a];
-    const int ms = pk & 0x7FFF, mt = pk >> 15;
+    const int ms = pk & kSt, mt = pk >> 15;
     double tr_[A];
     load_row<A>(Q + ms * A, tr_);
     const double boot = xmul(xmul(gq, row_max<A>(tr_)), mt ? 1.0 : 0.0);
@@ -456,18 +460,48 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     return g > min_gain ? g : min_gain;
   };
 
+  // utility of the one-step backup i: gain * need * update_mask (memory/pma.py:247-249)
+  auto util_one = [&](int i) -> double {
+    const int a = i / S, s = i - a * S;
+    return xmul(xmul(gain_one(i), need[s]), (Pk[s * A + a] & kUm) ? 1.0 : 0.0);
+  };
+
   // PMAMemory.replay, memory/pma.py:168-267.  cur >= 0: need = SR[cur]; cur < 0: stationary need.
   auto replay = [&](int cur) {
     const double* nsrc = cur >= 0 ? SRg + (size_t)cur * S : p.need_scratch + (size_t)n * S;
-    for (int e = lane; e < S; e += 32) { need[e] = nsrc[e]; dirty[e] = 1; }   // first iteration: every backup is stale
-    int count = 0, last_seq = 0;
+    for (int e = lane; e < S; e += 32) need[e] = nsrc[e];
+    // CSR of the backups grouped by their next state (M.states does not change during a replay):
+    // the backups that read Q row t are row t itself and pitems[poff[t] .. poff[t+1])
+    for (int e = lane; e <= S; e += 32) poff[e] = 0;
+    __syncwarp();
+    for (int e = lane; e < N; e += 32) atomicAdd(&poff[(Pk[e] & kSt) + 1], 1);
+    __syncwarp();
+    if (lane == 0) for (int t = 0; t < S; ++t) poff[t + 1] += poff[t];
+    __syncwarp();
+    for (int e = lane; e < N; e += 32) {            // fill from the back of each group, then the offsets are the starts again
+      const int s_ = e / A, a_ = e - s_ * A;
+      const int t = Pk[e] & kSt;
+      pitems[atomicSub(&poff[t + 1], 1) - 1] = (uint16_t)(a_ * S + s_);
+    }
+    __syncwarp();
+    // poff[t+1] now holds the start of group t; shift so that poff[t] = start, poff[S] = N
+    int nxt[6];
+    const int per = (S + 32) / 32;                  // entries handled per lane (S <= 160 -> per <= 6)
+    for (int x = 0; x < per; ++x) { const int t = lane * per + x; nxt[x] = t < S ? poff[t + 1] : 0; }
+    __syncwarp();
+    for (int x = 0; x < per; ++x) { const int t = lane * per + x; if (t < S) poff[t] = nxt[x]; }
+    if (lane == 0) poff[S] = N;
+    __syncwarp();
+    // first iteration: every backup is stale
+    for (int i = lane; i < N; i += 32) util[i] = util_one(i);
+    int count = 0, last_seq = 0, ndst = 0;
     __syncwarp();
     for (int it = 0; it < B; ++it) {
       // ---- (1) extension of the current sequence (memory/pma.py:219-235) -------------------------
       int ext = -1, clen = 0;
       if (count > 0) {
         const int lp = perf[count - 1];
-        ext = Pk[(lp % S) * A + lp / S] & 0x7FFF;                       // next_state of the last update
+        ext = Pk[(lp % S) * A + lp / S] & kSt;                          // next_state of the last update
         bool loop = false;
         for (int j = last_seq + lane; j < count; j += 32) loop |= (perf[j] % S) == ext;
         loop = __any_sync(kFull, loop);
@@ -479,26 +513,30 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
           ext += ea * S;
           clen = count - last_seq + 1;
           for (int j = lane; j < clen - 1; j += 32) seq[j] = perf[last_seq + j];
-          if (lane == 0) seq[clen - 1] = ext;
+          if (lane == 0) seq[clen - 1] = (uint16_t)ext;
         } else if (lane == 0) {
-          seq[0] = ext;                                                 // failed extension: one-step(ext, action 0)
+          seq[0] = (uint16_t)ext;                                       // failed extension: one-step(ext, action 0)
         }
       }
-      // ---- (2) one-step gains: compact the stale ones, then one lane-parallel pass ---------------
-      int nd = 0;
-      for (int a = 0; a < A; ++a)
-        for (int s0 = 0; s0 < S; s0 += 32) {          // flat index i = a*S + s without integer division
-          const int s = s0 + lane;
-          const bool stale = s < S && (dirty[s] || dirty[Pk[s * A + a] & 0x7FFF]);
-          const unsigned b = __ballot_sync(kFull, stale);
-          if (stale) list[nd + __popc(b & ((1u << lane) - 1u))] = (uint16_t)(a * S + s);
-          nd += __popc(b);
+      // ---- (2) re-evaluate the backups that read a Q row changed by the previous update ----------
+      if (ndst > 0) {
+        int nd = 0;
+        for (int d = 0; d < ndst && nd <= MainSmem::kListCap; ++d) {
+          const int t = dst[d];
+          const int p0 = poff[t], np = poff[t + 1] - p0;
+          if (nd + A + np <= MainSmem::kListCap)
+            for (int x = lane; x < A + np; x += 32) list[nd + x] = x < A ? (uint16_t)(x * S + t) : pitems[p0 + x - A];
+          nd += A + np;
         }
-      __syncwarp();
-      for (int j0 = 0; j0 < nd; j0 += 32)
-        if (j0 + lane < nd) { const int i = list[j0 + lane]; gain[i] = gain_one(i); }
-      for (int e = lane; e < S; e += 32) dirty[e] = 0;
-      __syncwarp();
+        __syncwarp();
+        if (nd <= MainSmem::kListCap) {
+          for (int j0 = 0; j0 < nd; j0 += 32)
+            if (j0 + lane < nd) { const int i = list[j0 + lane]; util[i] = util_one(i); }
+        } else {
+          for (int i = lane; i < N; i += 32) util[i] = util_one(i);
+        }
+        __syncwarp();
+      }
       // ---- (3) n-step gain of the candidate (memory/pma.py:269-331), lane j = element j -----------
       double gext = 0.0;
       if (ext >= 0) {
@@ -506,7 +544,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         const int lastI = seq[nseq - 1];
         const uint16_t lpk = Pk[(lastI % S) * A + lastI / S];
         double lrow[A];
-        load_row<A>(Q + (lpk & 0x7FFF) * A, lrow);
+        load_row<A>(Q + (lpk & kSt) * A, lrow);
         const double fv = xmul(row_max<A>(lrow), (lpk >> 15) ? 1.0 : 0.0);
         double total = 0.0;
         for (int j0 = 0; j0 < nseq; j0 += 32) {
@@ -544,27 +582,29 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         }
         gext = total > min_gain ? total : min_gain;
       }
-      // ---- (4) utility = gain * need * update_mask; arg-max with exact ties (memory/pma.py:247-254)
-      auto utility = [&](int a, int s) -> double {        // element i = a*S + s
-        const int i = a * S + s;
-        const double g = (i == ext) ? gext : gain[i];
-        return xmul(xmul(g, need[s]), umask[i] ? 1.0 : 0.0);
-      };
+      // ---- (4) arg-max of the utilities with exact ties (memory/pma.py:247-254); the candidate's
+      // n-step gain overrides the one-step entry `ext` for this iteration only
+      double saved = 0.0;
+      if (ext >= 0) {
+        const int ea = ext / S, es = ext - ea * S;
+        saved = util[ext];
+        __syncwarp();
+        if (lane == 0) util[ext] = xmul(xmul(gext, need[es]), (Pk[es * A + ea] & kUm) ? 1.0 : 0.0);
+        __syncwarp();
+      }
       const double ninf = -__longlong_as_double(0x7FF0000000000000ll);
       double lmax = ninf;
-      for (int a = 0; a < A; ++a)
-        for (int s = lane; s < S; s += 32) { const double u_ = utility(a, s); lmax = u_ > lmax ? u_ : lmax; }
+      for (int i = lane; i < N; i += 32) { const double v = util[i]; lmax = v > lmax ? v : lmax; }
       const double umax = warp_max_f64(lmax);
       // ties (flat-index order) and the certificate: gap to the largest utility below the maximum
       double l2 = ninf;
       int ktot = 0;
-      for (int a = 0; a < A; ++a)
-        for (int s0 = 0; s0 < S; s0 += 32) {
-          const int s = s0 + lane;
-          bool tie = false;
-          if (s < S) { const double v = utility(a, s); tie = v == umax; if (v < umax && v > l2) l2 = v; }
-          ktot += __popc(__ballot_sync(kFull, tie));
-        }
+      for (int i0 = 0; i0 < N; i0 += 32) {
+        const int i = i0 + lane;
+        bool tie = false;
+        if (i < N) { const double v = util[i]; tie = v == umax; if (v < umax && v > l2) l2 = v; }
+        ktot += __popc(__ballot_sync(kFull, tie));
+      }
       const double u2 = warp_max_f64(l2);
       if (umax != 0.0 && u2 > -1e300) { const double gp = (umax - u2) / fabs(umax); min_gap = gp < min_gap ? gp : min_gap; }
       win.ensure(1, lane);
@@ -582,25 +622,28 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         }
       }
       int chosen = -1;
-      for (int a = 0; a < A && chosen < 0; ++a)
-        for (int s0 = 0; s0 < S; s0 += 32) {
-          const int s = s0 + lane;
-          const bool tie = s < S && utility(a, s) == umax;
-          const unsigned b = __ballot_sync(kFull, tie);
-          const int c = __popc(b);
-          if (pick < c) { chosen = a * S + s0 + __fns(b, 0, pick + 1); break; }
-          pick -= c;
-        }
+      for (int i0 = 0; i0 < N; i0 += 32) {
+        const int i = i0 + lane;
+        const bool tie = i < N && util[i] == umax;
+        const unsigned b = __ballot_sync(kFull, tie);
+        const int c = __popc(b);
+        if (pick < c) { chosen = i0 + __fns(b, 0, pick + 1); break; }
+        pick -= c;
+      }
+      if (ext >= 0) {
+        __syncwarp();
+        if (lane == 0) util[ext] = saved;
+      }
       // ---- (5) apply the chosen (n-step) update: PMAMemory.update_q, memory/pma.py:452-496 --------
       {
         const bool use_seq = clen > 0 && chosen == ext;
         const int nseq = use_seq ? clen : 1;
-        if (!use_seq && lane == 0) seq[0] = chosen;
+        if (!use_seq && lane == 0) seq[0] = (uint16_t)chosen;
         __syncwarp();
         const int lastI = seq[nseq - 1];
         const uint16_t lpk = Pk[(lastI % S) * A + lastI / S];
         double lrow[A];
-        load_row<A>(Q + (lpk & 0x7FFF) * A, lrow);
+        load_row<A>(Q + (lpk & kSt) * A, lrow);
         const double fv = xmul(row_max<A>(lrow), (lpk >> 15) ? 1.0 : 0.0);
         bool ok = true;                               // n >= 2: every transition must be non-terminal & experienced
         if (nseq >= 2) {
@@ -609,6 +652,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
           ok = !__any_sync(kFull, bad);
         }
         __syncwarp();
+        ndst = 0;
         if (ok) {
           for (int j = lane; j < nseq; j += 32) {
             const int i = seq[j];
@@ -622,10 +666,11 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
             const double q = Q[s * A + a];
             td = xsub(td, q);
             Q[s * A + a] = xadd(q, xmul(lrq, td));     // states of a sequence are distinct (no loops)
-            dirty[s] = 1;
+            dst[j] = (uint16_t)s;
           }
+          ndst = nseq;
         }
-        if (lane == 0) perf[count] = chosen;
+        if (lane == 0) perf[count] = (uint16_t)chosen;
         ++count;
         if (ext != chosen) last_seq = it;
         __syncwarp();
@@ -696,7 +741,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         if (lane == 0) {
           Q[s * A + a] = qn;
           Mr[s * A + a] = m1;
-          Pk[s * A + a] = (uint16_t)(s2 | (nt << 15));
+          Pk[s * A + a] = (uint16_t)((Pk[s * A + a] & kUm) | s2 | (nt << 15));
         }
         __syncwarp();
       }
@@ -718,7 +763,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     for (int e = lane; e < N; e += 32) {
       p.Q[g0 + e] = Q[e];
       p.Mr[g0 + e] = Mr[e];
-      p.Ms[g0 + e] = Pk[e] & 0x7FFF;
+      p.Ms[g0 + e] = Pk[e] & kSt;
       p.Mt[g0 + e] = Pk[e] >> 15;
     }
   }
@@ -736,7 +781,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
 template <int A>
 int run(const CobelPMAParams& p, cudaStream_t st) {
   const int S = p.world.n_states;
-  COBEL_REQUIRE(S <= 160, COBEL_EUNSUPPORTED,
+  COBEL_REQUIRE(S <= 160 && S * A <= 65535, COBEL_EUNSUPPORTED,
                 "PMA kernels support at most 160 states (register-tiled S x S eliminations), got %d", S);
   const MainSmem so(S, A);
   const size_t sm_main = (size_t)kMainWarps * so.bytes;
