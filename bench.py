@@ -85,6 +85,18 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_traffic(name, agents_per_gpu):
+    """DRAM bytes per launch of the workload's dominant kernel from the committed ncu capture
+    (profiles/traffic.json), or None if no capture exists for this configuration."""
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(name)
+    except (OSError, ValueError):
+        return None
+    if not t or t.get('agents_per_gpu') != agents_per_gpu:
+        return None
+    return t['bytes_per_launch']
+
+
 def make_world(name):
     from cobel_rl_b200.misc.gridworld_tools import make_gridworld, make_open_field
     from oracle.cases import world_args
@@ -404,7 +416,8 @@ def result_block(name, m, world, peak, peak_src, job, t_step, t_e2e, units_total
                    'timing': 'CUDA events on the launching stream per step (table reset outside), mean of K, max over ranks',
                    'seed': SEED},
         'roofline': {'bound': 'hbm', 'kernel': wl['kernel'], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                     'frac': achieved / peak, 'traffic': measured_traffic(name, wl['agents_per_gpu']),
+                     'peak_source': peak_src,
                      'algorithmic_bytes_per_unit': wl['bytes_per_unit'],
                      'note': 'per-agent tables stay in shared memory for the whole launch, so DRAM traffic is far '
                              'below the algorithmic bytes; the kernels are issue / dependency-latency bound '

@@ -172,12 +172,22 @@ COBEL_DEV int select_action(const double (&v)[A], uint32_t mask, int kind, doubl
   return draw_categorical<A>(p, u);
 }
 
+// max of a row as a balanced tree (max is exact, so the association is free): two dependent
+// compare+select levels for A = 4 instead of three on the serial TD-update chain
 template <int A>
 COBEL_DEV double row_max(const double (&v)[A]) {
-  double m = v[0];
+  if constexpr (A == 4) {
+    return xmax(xmax(v[0], v[1]), xmax(v[2], v[3]));
+  } else if constexpr (A == 6) {
+    return xmax(xmax(xmax(v[0], v[1]), xmax(v[2], v[3])), xmax(v[4], v[5]));
+  } else if constexpr (A == 8) {
+    return xmax(xmax(xmax(v[0], v[1]), xmax(v[2], v[3])), xmax(xmax(v[4], v[5]), xmax(v[6], v[7])));
+  } else {
+    double m = v[0];
 #pragma unroll
-  for (int a = 1; a < A; ++a) m = xmax(m, v[a]);
-  return m;
+    for (int a = 1; a < A; ++a) m = xmax(m, v[a]);
+    return m;
+  }
 }
 
 // ---------------------------------------------------------------------------

@@ -267,7 +267,7 @@ __device__ __forceinline__ void gth_stationary(const double* __restrict__ Tg, do
 #pragma unroll
     for (int c = 0; c < TILE; ++c) {
       const int i = ty + 16 * r, j = tx + 16 * c;
-      if (i < S && j < S) Mat[i * S + j] = t.m[r][c];
+      if (i < S && j < S) Mat[j * S + i] = t.m[r][c];      // transposed: column k becomes a contiguous row
     }
   __syncthreads();
   if (tid < 32) {                                   // x_0 = 1, x_k = sum_{i<k} x_i P[i][k]: one warp, no block barriers
@@ -275,7 +275,7 @@ __device__ __forceinline__ void gth_stationary(const double* __restrict__ Tg, do
     __syncwarp();
     for (int k = 1; k < S; ++k) {
       double acc = 0.0;
-      for (int i = lane; i < k; i += 32) acc = fma(x[i], Mat[i * S + k], acc);
+      for (int i = lane; i < k; i += 32) acc = fma(x[i], Mat[k * S + i], acc);
       for (int d = 16; d > 0; d >>= 1) acc += shfl_f64_xor(acc, d);
       if (lane == 0) x[k] = acc;
       __syncwarp();

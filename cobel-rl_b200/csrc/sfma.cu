@@ -23,7 +23,7 @@ namespace {
 enum { MODE_DEFAULT = 0, MODE_FORWARD, MODE_REVERSE, MODE_BLEND_FORWARD, MODE_BLEND_REVERSE, MODE_INTERPOLATE, MODE_SWEEPING };
 
 struct SfmaSmem {
-  int q, mr, c, t, r, inh, part, mx, mbits, rep, bytes;
+  int q, mr, c, t, r, inh, part, mx, mbits, rep, lst, bytes;
   __host__ __device__ SfmaSmem(int S, int A, int T, int B, bool recency) {
     const int N = S * A;
     q = 0;
@@ -36,7 +36,8 @@ struct SfmaSmem {
     rep = part + (T + 32) * 8;
     mx = rep + ((B + 1) & ~1) * 4;
     mbits = mx + N * 2;
-    bytes = (mbits + S + 15) & ~15;
+    lst = (mbits + S + 3) & ~3;
+    bytes = (lst + N * 4 + 15) & ~15;
   }
 };
 
@@ -72,6 +73,25 @@ COBEL_DEV double block_exclusive_scan(double v, double* part, int tid, int T, do
   const double res = part[warp] + (inc - v);
   __syncthreads();                                  // part[] may be reused by the caller
   return res;
+}
+
+// integer exclusive block scan (T <= 1024)
+COBEL_DEV int block_exclusive_scan_int(int v, double* part, int tid, int T, int& total) {
+  int* ip = reinterpret_cast<int*>(part);
+  const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(kFull, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) ip[warp] = inc;
+  __syncthreads();
+  int off = 0, tot = 0;
+  for (int w = 0; w < nw; ++w) { if (w < warp) off += ip[w]; tot += ip[w]; }
+  total = tot;
+  __syncthreads();
+  return off + inc - v;
 }
 
 // Inverse-CDF draw over non-negative weights w[0..N): the first i whose running sum / total
@@ -138,6 +158,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
   int32_t* rep = reinterpret_cast<int32_t*>(smem + so.rep);  // reactivated flat indices of one replay
   uint16_t* Mx = reinterpret_cast<uint16_t*>(smem + so.mx);  // [s][a] next state | non-terminal << 15
   uint8_t* mbits = smem + so.mbits;                          // [s] valid-action bits
+  uint32_t* L = reinterpret_cast<uint32_t*>(smem + so.lst);  // experienced experiences (C > 0): action << 16 | state, ascending flat index
   // dependency scratch of the level-parallel batch aliases the (then idle) priority scratch
   uint32_t* wm = reinterpret_cast<uint32_t*>(R);
   uint32_t* rm = wm + S;
@@ -176,9 +197,8 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
 
   // similarity of experience i = (a, s') to the current experience, by replay mode
   // (memory/sfma.py:283-306)
-  auto dvec = [&](int i, int cur, int nxt) -> double {
-    const int a = i / S, sp = i - a * S;
-    const int ms = Mx[sp * A + a] & 0x7FFF;                 // states.flatten('F')[i]
+  auto dvec = [&](int a, int sp, int cur, int nxt) -> double {
+    const int ms = Mx[sp * A + a] & 0x7FFF;                 // states.flatten('F')[a*S + sp]
     const double* Dc = D + (size_t)cur * S;
     const double* Dn = D + (size_t)nxt * S;
     switch (p.mode) {
@@ -203,11 +223,25 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     }
     __syncthreads();
     int cur = last, action = sh.action;
+    // Experiences that were never stored have strength 0, hence priority 0 and weight exp(0) - 1 = 0:
+    // they can never be drawn and add exact zeros to every sum.  All passes below therefore run
+    // over the compact, index-ordered list L of experiences with C > 0 (C is constant during a replay).
+    int nnz;
+    {
+      const int chunk = (N + T - 1) / T;
+      const int lo = tid * chunk < N ? tid * chunk : N, hi = lo + chunk < N ? lo + chunk : N;
+      int cnt = 0;
+      for (int i = lo; i < hi; ++i) cnt += C[i] > 0.0 ? 1 : 0;
+      int off = block_exclusive_scan_int(cnt, part, tid, T, nnz);
+      for (int i = lo; i < hi; ++i)
+        if (C[i] > 0.0) { const int a = i / S; L[off++] = ((uint32_t)a << 16) | (uint32_t)(i - a * S); }
+    }
+    __syncthreads();
     if (cur < 0) {                                                         // start ~ clip(C, 0) / sum
-      for (int e = tid; e < N; e += T) R[e] = C[e] > 0.0 ? C[e] : 0.0;
+      for (int j = tid; j < nnz; j += T) { const uint32_t l = L[j]; R[j] = C[(l >> 16) * S + (l & 0xFFFF)]; }
       __syncthreads();
-      const int e = block_sample(R, N, sh.u, part, &sh, tid, T, flags);
-      cur = e % S; action = e / S;
+      const uint32_t l = L[block_sample(R, nnz, sh.u, part, &sh, tid, T, flags)];
+      cur = l & 0xFFFF; action = l >> 16;
     }
     int nxt = Mx[cur * A + action] & 0x7FFF;
     for (int e = tid; e < S; e += T) I[e] = 0.0;                           // sfma.py:277
@@ -215,12 +249,13 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     int count = 0;
     for (int it = 0; it < B; ++it) {
       double lmax = 0.0;
-      for (int i = tid; i < N; i += T) {
-        const int a = i / S, sp = i - a * S;
-        double r = xmul(xmul(C[i], dvec(i, cur, nxt)), xsub(1.0, I[sp]));  // C * D * (1 - I)
+      for (int j = tid; j < nnz; j += T) {
+        const uint32_t l = L[j];
+        const int a = l >> 16, sp = l & 0xFFFF, i = a * S + sp;
+        double r = xmul(xmul(C[i], dvec(a, sp, cur, nxt)), xsub(1.0, I[sp]));  // C * D * (1 - I)
         if (recency) r = xmul(r, Tr[i]);
         if (r < thr) r = 0.0;
-        R[i] = r;
+        R[j] = r;
         lmax = r > lmax ? r : lmax;
       }
       // block max (R >= 0): all-zero <=> np.sum(R) == 0 (sfma.py:316)
@@ -231,27 +266,29 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
       for (int w = 1; w < (T >> 5); ++w) m = part[w] > m ? part[w] : m;
       __syncthreads();
       if (!(m > 0.0)) break;
-      int e;
+      int jsel;
       if (p.deterministic) {                                               // argmax(R): first maximum
         if (tid == 0) sh.idx = 0x7fffffff;
         __syncthreads();
-        for (int i = tid; i < N; i += T) if (R[i] == m) { atomicMin(&sh.idx, i); break; }
+        for (int j = tid; j < nnz; j += T) if (R[j] == m) { atomicMin(&sh.idx, j); break; }
         __syncthreads();
-        e = sh.idx;
+        jsel = sh.idx;
         __syncthreads();
       } else {
-        // probs ~ exp(beta * R / max) - 1  (softmax(R, -1, beta), sfma.py:349-373)
-        for (int i = tid; i < N; i += T) R[i] = xadd(exp(xmul(xdiv(R[i], m), beta)), -1.0);
+        // probs ~ exp(beta * R / max) - 1  (softmax(R, -1, beta), sfma.py:349-373); exp(0) - 1 == 0 exactly
+        for (int j = tid; j < nnz; j += T) { const double r = R[j]; R[j] = r > 0.0 ? xadd(exp(xmul(xdiv(r, m), beta)), -1.0) : 0.0; }
         if (warp == 0) {
           win.ensure(1, lane);
           const double u = win.next();
           if (lane == 0) sh.u = u;
         }
         __syncthreads();
-        e = block_sample(R, N, sh.u, part, &sh, tid, T, flags);
+        jsel = block_sample(R, nnz, sh.u, part, &sh, tid, T, flags);
       }
-      action = e / S;
-      cur = e - action * S;
+      const uint32_t l = L[jsel];
+      action = l >> 16;
+      cur = l & 0xFFFF;
+      const int e = action * S + cur;
       nxt = Mx[cur * A + action] & 0x7FFF;
       for (int s = tid; s < S; s += T) {                                   // sfma.py:333-335
         double v = xmul(I[s], dinh);

@@ -186,15 +186,24 @@ COBEL_DEV void td_batch_level_parallel(double* Q, uint32_t* wm, uint32_t* rm, in
   const unsigned act = __ballot_sync(kFull, active);
   const unsigned below = (1u << lane) - 1u;
   // writers / readers per state (wm / rm are all-zero on entry and are re-zeroed on exit)
+  unsigned same_s = 0;
   if (active) {
     // all lanes with the same key store the same mask: a benign same-value race
-    wm[s] = __match_any_sync(act, s);
+    same_s = __match_any_sync(act, s);
+    wm[s] = same_s;
     rm[s2] = __match_any_sync(act, s2);
+  }
+  // lanes with my action, from A cheap ballots instead of a third MATCH
+  unsigned same_a = 0;
+#pragma unroll
+  for (int x = 0; x < A; ++x) {
+    const unsigned bx = __ballot_sync(kFull, active && a == x);
+    same_a = a == x ? bx : same_a;
   }
   __syncwarp();
   unsigned strict = 0, weak = 0;
   if (active) {
-    const unsigned same_sa = __match_any_sync(act, s * A + a);      // i writes the entry j reads+writes
+    const unsigned same_sa = same_s & same_a;                       // i writes the entry j reads+writes
     strict = (wm[s2] | same_sa) & below;                            // i writes into the row j reads
     weak = rm[s] & below;                                           // j writes into the row i reads
   }
