@@ -144,6 +144,9 @@ class Agent(abc.ABC):
 
     def _chunks(self, trials):
         c = trials if not self.trials_per_launch else int(self.trials_per_launch)
+        if trials <= 0:          # a zero-trial session is a no-op that still returns empty statistics
+            yield 0, 0
+            return
         t = 0
         while t < trials:
             yield t, min(c, trials - t)

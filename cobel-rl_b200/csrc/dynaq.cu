@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
   const int B = p.batch;
   const bool learn = p.learn != 0;
-  const bool step_replay = learn && !p.no_replay && !p.episodic_replay && B > 0;
-  const bool trial_replay = learn && !p.no_replay && p.episodic_replay && B > 0;
+  const bool step_replay = learn && !p.no_replay && !p.episodic_replay;     // a batch of 0 is still a (draw-free) call
+  const bool trial_replay = learn && !p.no_replay && p.episodic_replay;
   const CobelTrace& tr = p.trace;
   int64_t nsteps = 0, nrep = 0, ncalls = 0;
   int flags = 0;
@@ -227,7 +227,7 @@ int cobel_validate_common(int64_t n_agents, const CobelWorld& w, const CobelStre
   COBEL_REQUIRE(s.draw_count, COBEL_EINVAL, "stream.draw_count missing");
   COBEL_REQUIRE(pol.param && pol.kind >= 0 && pol.kind <= 2, COBEL_EINVAL, "bad policy");
   COBEL_REQUIRE(trials >= 0 && steps > 0, COBEL_EINVAL, "trials must be >= 0 and steps > 0");
-  COBEL_REQUIRE(tr.trial_steps && tr.trial_reward && tr.n_steps && tr.n_replay, COBEL_EINVAL,
+  COBEL_REQUIRE(tr.n_steps && tr.n_replay && (trials == 0 || (tr.trial_steps && tr.trial_reward)), COBEL_EINVAL,
                 "trace.trial_steps/trial_reward/n_steps/n_replay are mandatory");
   return COBEL_OK;
 }

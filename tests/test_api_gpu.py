@@ -1,0 +1,142 @@
+"""GPU: host-side class API behaviour (reference-shaped single-agent mode, callbacks, chunked
+launches, interactive env/policy/memory calls) and edge cases (ragged agent counts, replay
+batches larger / smaller than a warp, zero trials)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tabular as tb
+from oracle.philox import LazyStream
+from helpers import assert_equal_records, make_world, unpack_run
+
+pytestmark = pytest.mark.gpu
+
+
+def _dynaq(n, seed=21, world='open5', **kw):
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.policy import EpsilonGreedy
+    stream = cb.BatchStream(n, seed=seed, device='cuda:0')
+    env = Gridworld(make_world(world), rng=stream)
+    ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), **kw)
+    return stream, env, ag
+
+
+def test_single_agent_mode_has_reference_shapes():
+    stream, env, ag = _dynaq(None)
+    assert isinstance(env.current_state, int)
+    s, info = env.reset()
+    assert isinstance(s, int) and info == {}
+    s2, r, end, trunc, info = env.step(0)
+    assert isinstance(s2, int) and isinstance(r, float) and isinstance(end, bool) and trunc is False
+    assert env.get_position().shape == (2,)
+    ag.train(env, 5, 20, 32)
+    assert tuple(ag.Q.shape) == (25, 4) and tuple(ag.M.rewards.shape) == (25, 4)
+    assert ag.predict_on_batch([0, 3, 7]).shape == (3, 4)
+    assert ag.current_trial == 5
+
+
+@pytest.mark.parametrize('n,batch', [(1, 32), (5, 7), (9, 64), (3, 0), (4, 33)])
+def test_ragged_agent_counts_and_batch_sizes(n, batch):
+    stream, env, ag = _dynaq(n, seed=5)
+    ag.record = True
+    res = ag.train(env, 6, 25, batch)
+    torch.cuda.synchronize()
+    W = tb.compile_gridworld(make_world('open5'))
+    for i in range(n):
+        rng = tb.Draws(LazyStream(5, i), 1)
+        st = tb.dynaq_init(25, 4)
+        rec = tb.dynaq_train(W, st, rng, 6, 25, batch).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got['Q'] = ag.Q[i].cpu().numpy(); rec['Q'] = st['Q']
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q'], what='agent %d' % i)
+        assert int(stream.draw_count[i]) == rng.k
+
+
+def test_zero_trials_is_a_noop():
+    stream, env, ag = _dynaq(3)
+    before = stream.draw_count.clone()
+    res = ag.train(env, 0, 10, 32)
+    assert res['trial_steps'].shape == (3, 0) and torch.equal(stream.draw_count, before)
+    assert float(ag.Q.abs().sum()) == 0.0
+
+
+def test_callbacks_chunked_launches_and_stop():
+    seen = []
+
+    def on_trial_end(logs):
+        seen.append((logs['trial'], logs['trial_session'], logs['steps'].clone(), logs['trial_reward'].clone()))
+        if logs['trial'] == 5:
+            logs['agent'].stop = True
+
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.policy import EpsilonGreedy
+    stream = cb.BatchStream(4, seed=3, device='cuda:0')
+    env = Gridworld(make_world('open5'), rng=stream)
+    ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream),
+               custom_callbacks={'on_trial_end': [on_trial_end]})
+    ag.trials_per_launch = 3
+    res = ag.train(env, 12, 20, 8)
+    # stop was raised while processing trial 5 -> the session ends after the launch that contains it (trials 3..5)
+    assert [t for t, _, _, _ in seen] == list(range(6)) and ag.current_trial == 6
+    assert res['trial_steps'].shape == (4, 6)
+    assert torch.equal(torch.stack([s for _, _, s, _ in seen], dim=1), res['trial_steps'])
+    # chunked launches give the same result as one launch
+    stream2 = cb.BatchStream(4, seed=3, device='cuda:0')
+    env2 = Gridworld(make_world('open5'), rng=stream2)
+    ag2 = DynaQ(env2.observation_space, env2.action_space, EpsilonGreedy(0.1, rng=stream2))
+    res2 = ag2.train(env2, 6, 20, 8)
+    assert torch.equal(res2['trial_steps'], res['trial_steps']) and torch.equal(ag2.Q, ag.Q)
+
+
+def test_interactive_policy_and_memory_calls():
+    """Policy.get_action_probs / select_action and DynaQMemory.store / retrieve_batch outside train()."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.memory import DynaQMemory
+    from cobel_rl_b200.policy import EpsilonGreedy, ExclusiveEpsilonGreedy, Softmax
+    stream = cb.BatchStream(3, seed=8, device='cuda:0')
+    v = torch.tensor([[0.0, 1.0, 1.0, -2.0], [0.5, 0.5, 0.5, 0.5], [3.0, 0.0, 1.0, 2.0]], dtype=torch.float64, device='cuda:0')
+    mask = torch.tensor([[1, 1, 1, 1], [1, 0, 1, 1], [0, 1, 1, 1]], dtype=torch.bool, device='cuda:0')
+    for pol, spec in ((EpsilonGreedy(0.2, rng=stream), ('eps', 0.2)), (ExclusiveEpsilonGreedy(0.2, rng=stream), ('xeps', 0.2)),
+                      (Softmax(1.5, rng=stream), ('softmax', 1.5))):
+        p = pol.get_action_probs(v, mask).cpu().numpy()
+        for i in range(3):
+            np.testing.assert_allclose(p[i], tb.action_probs(spec, v[i].cpu().numpy(), mask[i].cpu().numpy()), rtol=1e-15, atol=0)
+        k0 = stream.draw_count.clone()
+        a = pol.select_action(v, mask)
+        assert a.shape == (3,) and torch.equal(stream.draw_count, k0 + 1)
+        assert bool(mask[torch.arange(3), a.cpu()].all())
+    mem = DynaQMemory(25, 4, 0.9, rng=stream)
+    mem.store({'state': torch.tensor([1, 2, 3]), 'action': 1, 'reward': 2.0, 'next_state': torch.tensor([6, 7, 8]), 'terminal': 1})
+    got = mem.retrieve(torch.tensor([1, 2, 3]), 1)
+    assert got['reward'].tolist() == [1.8, 1.8, 1.8] and got['next_state'].tolist() == [6, 7, 8]
+    b = mem.retrieve_batch(5)
+    assert b['state'].shape == (3, 5) and int(b['state'].max()) < 25
+
+
+def test_topology_discrete_mode_runs_tabular_agents():
+    """Topology(discrete=True) exposes node indices so that DynaQ can run on a graph
+    (10x2 linear track of config C4); equals the same structure as a gridworld."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Topology
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.policy import EpsilonGreedy
+    from cobel_rl_b200.misc.topology_tools import linear_track
+    nodes, starts = linear_track(10, 2, 1.0, 1.0, 'right')
+    stream = cb.BatchStream(2, seed=12, device='cuda:0')
+    env = Topology(nodes, starts, rng=stream, discrete=True)
+    ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream))
+    ag.record = True
+    res = ag.train(env, 8, 40, 16)
+    torch.cuda.synchronize()
+    W = tb.compile_topology(nodes, starts)
+    for i in range(2):
+        rng = tb.Draws(LazyStream(12, i), 1)
+        st = tb.dynaq_init(20, 4)
+        rec = tb.dynaq_train(W, st, rng, 8, 40, 16).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got['Q'] = ag.Q[i].cpu().numpy(); rec['Q'] = st['Q']
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'Q'], what='agent %d' % i)
