@@ -13,4 +13,4 @@ __version__ = '0.1.0'
 
 from .stream import BatchStream  # noqa: F401
 from . import spaces  # noqa: F401
-from . import interface, policy, memory, agent, misc  # noqa: F401
+from . import interface, policy, memory, agent, misc, monitor, optimizer  # noqa: F401

@@ -140,3 +140,37 @@ def test_topology_discrete_mode_runs_tabular_agents():
         got = unpack_run(res, i, 4, W['succ'], W['reward'])
         got['Q'] = ag.Q[i].cpu().numpy(); rec['Q'] = st['Q']
         assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'Q'], what='agent %d' % i)
+
+
+def test_grid_search_over_batched_dynaq_and_monitors(tmp_path):
+    """SURVEY.md 8f-1/2: every combination x run of a grid search is one agent of a single launch;
+    monitors are fed from the batched per-trial logs."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.policy import EpsilonGreedy
+    from cobel_rl_b200.monitor import EscapeLatencyMonitor
+    from cobel_rl_b200.optimizer import GridSearchOptimizer
+    world = make_world('open5')
+    launches = []
+
+    def simulation(task, params):
+        n = len(params['_run'])
+        stream = cb.BatchStream(n, seed=task['seed'], device='cuda:0')
+        env = Gridworld(world, rng=stream)
+        mon = EscapeLatencyMonitor(task['trials'], 50, n_agents=n)
+        ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(params['epsilon'], rng=stream), None,
+                   params['lr'], 0.99, custom_callbacks={'on_trial_end': [mon.update]})
+        res = ag.train(env, task['trials'], 50, 32)
+        launches.append(n)
+        assert np.array_equal(mon.get_trace(), res['trial_steps'].cpu().numpy())
+        return mon.get_trace()                              # [n, trials] escape latencies
+
+    def loss(sim, data):                                     # mean latency over the last trials vs a target
+        return float(sum((np.mean([run[-5:] for run in sim[t]]) - data[t]) ** 2 for t in sim))
+
+    opt = GridSearchOptimizer(str(tmp_path) + '/', {'epsilon': [0.05, 0.3, 0.8], 'lr': [0.2, 0.99]}, nb_runs=16)
+    fit = opt.fit(simulation, {'a': {'seed': 1, 'trials': 30}}, {'a': 3.0}, loss)
+    assert launches == [6 * 16] and len(fit) == 6
+    # strongly exploring agents (epsilon 0.8) are the worst fit to a short-latency target
+    assert max(fit, key=fit.get)[0] == 0.8
