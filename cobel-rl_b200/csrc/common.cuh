@@ -1,5 +1,5 @@
-// common.cuh -- shared device helpers: exact fp64 arithmetic, the Philox stream,
-// action selection and NumPy-order reductions.  sm_100a only.
+// common.cuh -- shared device helpers: exact fp64 arithmetic, the Philox stream and
+// conversion-free uniform / integer draws.  sm_100a only.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -101,75 +101,6 @@ COBEL_DEV int draw_integer(double u, int n) {
   const double x = xmul(u, int_to_f64(n));
   const int i = __double2loint(__dadd_rd(x, 4503599627370496.0));
   return i < n - 1 ? i : n - 1;
-}
-
-// ---------------------------------------------------------------------------
-// Action selection for A actions held in registers.
-//   probabilities: policy/greedy.py:60-88, 117-147; policy/softmax.py:60-88
-//   draw: Generator.choice(p=probs) == searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right')
-// mask bit a set = action a valid.
-// ---------------------------------------------------------------------------
-template <int A>
-COBEL_DEV void action_probs(const double (&v)[A], uint32_t mask, int kind, double par, double (&p)[A]) {
-  int nv = 0;
-  double m = 0.0;
-  bool first = true;
-#pragma unroll
-  for (int a = 0; a < A; ++a)
-    if (mask >> a & 1u) { ++nv; m = first ? v[a] : xmax(m, v[a]); first = false; }
-  if (kind == COBEL_POLICY_SOFTMAX) {
-    double sum = 0.0;
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-      p[a] = 0.0;
-      if (mask >> a & 1u) { p[a] = exp(xmul(xsub(v[a], m), par)); sum = xadd(sum, p[a]); }
-    }
-#pragma unroll
-    for (int a = 0; a < A; ++a)
-      if (mask >> a & 1u) p[a] = xdiv(p[a], sum);
-    return;
-  }
-  int k = 0;
-#pragma unroll
-  for (int a = 0; a < A; ++a) k += ((mask >> a & 1u) && v[a] == m) ? 1 : 0;
-  const double om = xsub(1.0, par);
-  if (kind == COBEL_POLICY_EPS_GREEDY) {
-    const double base = xdiv(par, (double)nv);
-    const double tie = xdiv(om, (double)k);
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-      const bool valid = mask >> a & 1u;
-      p[a] = valid ? xadd(base, v[a] == m ? tie : 0.0) : 0.0;
-    }
-  } else {  // exclusive epsilon-greedy
-    const int d = nv - k > 1 ? nv - k : 1;
-    const double tie = xdiv(om, (double)k);
-    const double expl = xdiv(par, (double)d);
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-      const bool valid = mask >> a & 1u;
-      p[a] = valid ? (v[a] == m ? xadd(tie, 0.0) : xadd(0.0, expl)) : 0.0;
-    }
-  }
-}
-
-template <int A>
-COBEL_DEV int draw_categorical(const double (&p)[A], double u) {
-  double c[A];
-  c[0] = p[0];
-#pragma unroll
-  for (int a = 1; a < A; ++a) c[a] = xadd(c[a - 1], p[a]);
-  int idx = 0;
-#pragma unroll
-  for (int a = 0; a < A - 1; ++a) idx += (xdiv(c[a], c[A - 1]) <= u) ? 1 : 0;
-  return idx;    // c[A-1]/c[A-1] == 1 > u always
-}
-
-template <int A>
-COBEL_DEV int select_action(const double (&v)[A], uint32_t mask, int kind, double par, double u) {
-  double p[A];
-  action_probs<A>(v, mask, kind, par, p);
-  return draw_categorical<A>(p, u);
 }
 
 // max of a row as a balanced tree (max is exact, so the association is free): two dependent

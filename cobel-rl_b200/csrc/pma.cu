@@ -86,44 +86,6 @@ COBEL_DEV double sum_seq(const double (&x)[A]) {     // np.sum over < 8 elements
   return s;
 }
 
-// integer exclusive scan over the block (contiguous chunks per thread are summed by the caller)
-COBEL_DEV int block_exclusive_scan_int(int v, int* part, int tid, int T, int& total) {
-  const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
-  int inc = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int o = __shfl_up_sync(kFull, inc, d);
-    if (lane >= d) inc += o;
-  }
-  if (lane == 31) part[warp] = inc;
-  __syncthreads();
-  int off = 0, tot = 0;
-  for (int w = 0; w < nw; ++w) { if (w < warp) off += part[w]; tot += part[w]; }
-  total = tot;
-  __syncthreads();
-  return off + inc - v;
-}
-
-COBEL_DEV double block_max(double v, double* part, int tid, int T) {
-  for (int d = 16; d > 0; d >>= 1) { const double o = shfl_f64_xor(v, d); v = o > v ? o : v; }
-  if ((tid & 31) == 0) part[tid >> 5] = v;
-  __syncthreads();
-  double m = part[0];
-  for (int w = 1; w < (T >> 5); ++w) m = part[w] > m ? part[w] : m;
-  __syncthreads();
-  return m;
-}
-
-COBEL_DEV double block_sum(double v, double* part, int tid, int T) {
-  for (int d = 16; d > 0; d >>= 1) v += shfl_f64_xor(v, d);
-  if ((tid & 31) == 0) part[tid >> 5] = v;
-  __syncthreads();
-  double m = 0.0;
-  for (int w = 0; w < (T >> 5); ++w) m += part[w];
-  __syncthreads();
-  return m;
-}
-
 // ---------------------------------------------------------------------------
 // Register-tiled dense eliminations on an S x S matrix distributed over the 16 x 16 thread
 // grid of the CTA: thread (ty, tx) owns elements (ty + 16 r, tx + 16 c), r, c < TILE.  Each
