@@ -105,6 +105,8 @@ def make_world(name):
     if name == 'open100':
         return make_open_field(100, 100, 0, 1, dense_sas=False)
     h, w, kw = world_args(name)
+    kw = dict(kw)
+    kw.pop('slippery', None)
     return make_gridworld(h, w, **kw)
 
 

@@ -17,7 +17,7 @@ c_ptr = C.c_void_p
 class World(C.Structure):
     _fields_ = [('n_states', C.c_int32), ('n_actions', C.c_int32), ('n_starts', C.c_int32),
                 ('reserved', C.c_int32), ('succ', c_ptr), ('reward', c_ptr), ('terminal', c_ptr),
-                ('starts', c_ptr)]
+                ('starts', c_ptr), ('tp_off', c_ptr), ('tp_next', c_ptr), ('tp_prob', c_ptr)]
 
 
 class Stream(C.Structure):
@@ -32,7 +32,7 @@ class Policy(C.Structure):
 class Trace(C.Structure):
     _fields_ = [('trial_steps', c_ptr), ('trial_reward', c_ptr), ('n_steps', c_ptr), ('n_replay', c_ptr),
                 ('step_sa', c_ptr), ('step_cap', C.c_int64), ('replay_idx', c_ptr), ('replay_cap', C.c_int64),
-                ('replay_len', c_ptr), ('replay_calls_cap', C.c_int64), ('flags', c_ptr)]
+                ('replay_len', c_ptr), ('replay_calls_cap', C.c_int64), ('flags', c_ptr), ('step_next', c_ptr)]
 
 
 class DynaQParams(C.Structure):

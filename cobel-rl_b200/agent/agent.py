@@ -108,13 +108,14 @@ class Agent(abc.ABC):
             calls_cap = trials * (steps * replay_per_step + replay_calls_per_trial)
             replay_cap = calls_cap * replay_len_max
             res['step_sa'] = torch.full((n, max(step_cap, 1)), -1, dtype=torch.int32, device=dev)
+            res['step_next'] = torch.full((n, max(step_cap, 1)), -1, dtype=torch.int32, device=dev)
             res['replay_idx'] = torch.full((n, max(replay_cap, 1)), -1, dtype=torch.int32, device=dev)
             res['replay_len'] = torch.full((n, max(calls_cap, 1)), -1, dtype=torch.int32, device=dev)
         keep.append(res)
         tr = _lib.Trace(res['trial_steps'].data_ptr(), res['trial_reward'].data_ptr(), res['n_steps'].data_ptr(),
                         res['n_replay'].data_ptr(), _lib.ptr(res.get('step_sa')), step_cap,
                         _lib.ptr(res.get('replay_idx')), replay_cap, _lib.ptr(res.get('replay_len')), calls_cap,
-                        res['flags'].data_ptr())
+                        res['flags'].data_ptr(), _lib.ptr(res.get('step_next')))
         return tr, res
 
     def _mask_args(self, keep):

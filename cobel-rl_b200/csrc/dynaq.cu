@@ -126,12 +126,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
 
   for (int trial = 0; trial < p.trials; ++trial) {
     // interface/gridworld.py:142: one uniform draw over the starting states
-    win.ensure(2 + (step_replay && B <= 32 ? B : 0), lane);
+    win.ensure(3 + (step_replay && B <= 32 ? B : 0), lane);
     int s = starts_s[draw_integer(win.next(), K)];
     double treward = 0.0;
     int step = 0;
     for (;; ++step) {
-      win.ensure(1 + (step_replay && B <= 32 ? B : 0), lane);
+      win.ensure(2 + (step_replay && B <= 32 ? B : 0), lane);
       double row[A];
       load_row<A>(Q + s * A, row);
       uint32_t mask = (1u << A) - 1u;
@@ -141,12 +141,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
         for (int a = 0; a < A; ++a) mask |= (amask[s * A + a] ? 1u : 0u) << a;
       }
       const int a = select_action_warp<A>(row, mask, pt, win.next(), lane);
-      const int s2 = succ_s[s * A + a];
+      const int s2 = p.world.tp_off ? stochastic_successor(p.world, s * A + a, win.next()) : succ_s[s * A + a];
       const double r = rew_s[s2];
       const int end = term_s[s2];
       const int nt = 1 - end;
       if (tr.step_sa && lane == 0) {
-        if (nsteps < tr.step_cap) tr.step_sa[n * tr.step_cap + nsteps] = s * A + a;
+        if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
       ++nsteps;

@@ -670,16 +670,16 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     double treward = 0.0;
     int step = 0, last = -1;
     for (;; ++step) {
-      win.ensure(1, lane);
+      win.ensure(2, lane);
       double row[A];
       load_row<A>(Q + s * A, row);
       const int a = select_action_warp<A>(row, mbits[s], pt, win.next(), lane);
-      const int s2 = __ldg(p.world.succ + s * A + a);
+      const int s2 = p.world.tp_off ? stochastic_successor(p.world, s * A + a, win.next()) : __ldg(p.world.succ + s * A + a);
       const double r = __ldg(p.world.reward + s2);
       const int end = __ldg(p.world.terminal + s2);
       const int nt = 1 - end;
       if (tr.step_sa && lane == 0) {
-        if (nsteps < tr.step_cap) tr.step_sa[n * tr.step_cap + nsteps] = s * A + a;
+        if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
       ++nsteps;

@@ -81,23 +81,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __gr
   int flags = 0;
 
   for (int trial = 0; trial < p.trials; ++trial) {
-    win.ensure(2 + (learn && B <= 32 ? B : 0), lane);
+    win.ensure(3 + (learn && B <= 32 ? B : 0), lane);
     int s = starts_s[draw_integer(win.next(), K)];                // interface reset: one draw
     double treward = 0.0;
     int step = 0;
     for (;; ++step) {
-      win.ensure(1 + (learn && B <= 32 ? B : 0), lane);
+      win.ensure(2 + (learn && B <= 32 ? B : 0), lane);
       const int ks = key_s[s];
       double row[A];
       load_row<A>(Q + ks * A, row);
       const int a = select_action_warp<A>(row, (1u << A) - 1u, pt, win.next(), lane);
-      const int s2 = succ_s[s * A + a];
+      const int s2 = p.world.tp_off ? stochastic_successor(p.world, s * A + a, win.next()) : succ_s[s * A + a];
       const double r = rew_s[s2];
       const int end = term_s[s2];
       const int nt = 1 - end;
       const int ks2 = key_s[s2];
       if (tr.step_sa && lane == 0) {
-        if (nsteps < tr.step_cap) tr.step_sa[n * tr.step_cap + nsteps] = s * A + a;
+        if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
       ++nsteps;

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) sr_kernel(const __grid_constant__ CobelSR
       __syncthreads();
       // ---- action selection and environment step: every warp computes the same (warp-uniform)
       // result, which keeps all warps' stream windows in lock-step without a broadcast ---------
-      win.ensure(1, lane);
+      win.ensure(2, lane);
       double row[A];
 #pragma unroll
       for (int x = 0; x < A; ++x) row[x] = qv[x];
@@ -152,11 +152,11 @@ __global__ void __launch_bounds__(256) sr_kernel(const __grid_constant__ CobelSR
         for (int x = 0; x < A; ++x) mask |= (amask[s * A + x] ? 1u : 0u) << x;
       }
       const int a = select_action_warp<A>(row, mask, pt, win.next(), lane);
-      const int s2 = __ldg(p.world.succ + s * A + a);
+      const int s2 = p.world.tp_off ? stochastic_successor(p.world, s * A + a, win.next()) : __ldg(p.world.succ + s * A + a);
       const double r = __ldg(p.world.reward + s2);
       const int end = __ldg(p.world.terminal + s2);
       if (tr.step_sa && tid == 0) {
-        if (nsteps < tr.step_cap) tr.step_sa[n * tr.step_cap + nsteps] = s * A + a;
+        if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
       ++nsteps;

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sr_compact_kernel(const __g
 #pragma unroll
       for (int a = 0; a < A; ++a) row[a] = shfl_f64(qa, a);
       // ---- action selection, environment step ----------------------------------------------------
-      win.ensure(1, lane);
+      win.ensure(2, lane);
       uint32_t mask = (1u << A) - 1u;
       if (p.action_mask) {
         mask = 0;
@@ -183,11 +183,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sr_compact_kernel(const __g
         for (int a = 0; a < A; ++a) mask |= (p.action_mask[(size_t)s * A + a] ? 1u : 0u) << a;
       }
       const int a = select_action_warp<A>(row, mask, pt, win.next(), lane);
-      const int s2 = __ldg(p.world.succ + (size_t)s * A + a);
+      const int s2 = p.world.tp_off ? stochastic_successor(p.world, s * A + a, win.next()) : __ldg(p.world.succ + (size_t)s * A + a);
       const double r = __ldg(p.world.reward + s2);
       const int end = __ldg(p.world.terminal + s2);
       if (tr.step_sa && lane == 0) {
-        if (nsteps < tr.step_cap) tr.step_sa[n * tr.step_cap + nsteps] = s * A + a;
+        if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
       ++nsteps;

@@ -43,6 +43,21 @@ COBEL_DEV void load_row(const double* r, double (&v)[A]) {
   }
 }
 
+// Next state of a non-deterministic gridworld: Generator.choice(arange(S), p=sas[s,a,:])
+// (interface/gridworld.py:118-123) = first index whose sequential cumsum / total exceeds u; the
+// zero entries of the row add exact zeros, so the cumsum runs over the non-zeros only.
+COBEL_DEV int stochastic_successor(const CobelWorld& w, int sa, double u) {
+  const int lo = __ldg(w.tp_off + sa), hi = __ldg(w.tp_off + sa + 1);
+  double tot = 0.0;
+  for (int j = lo; j < hi; ++j) tot = xadd(tot, __ldg(w.tp_prob + j));
+  double c = 0.0;
+  for (int j = lo; j < hi; ++j) {
+    c = xadd(c, __ldg(w.tp_prob + j));
+    if (xdiv(c, tot) > u) return __ldg(w.tp_next + j);
+  }
+  return __ldg(w.tp_next + hi - 1);
+}
+
 // ---------------------------------------------------------------------------
 // DrawWindow: lane l holds draws 2*(b0+l) and 2*(b0+l)+1 of the agent's stream, i.e. the warp
 // holds the 64 consecutive draws starting at 2*b0.  One Philox block per lane per refill

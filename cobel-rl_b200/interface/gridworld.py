@@ -42,12 +42,14 @@ def successor_table(world):
 class Gridworld(Interface):
     def __init__(self, world, widget=None, rng=None):
         super().__init__(widget, rng)
-        assert world.get('deterministic', True), \
-            'non-deterministic gridworlds are not supported by the B200 path yet'
         self.world = world
+        self.deterministic = bool(world.get('deterministic', True))
+        assert self.deterministic or world.get('sas') is not None, 'non-deterministic worlds need the dense sas'
+
         self.observation_space = Discrete(world['states'])
         self.action_space = Discrete(4)
-        self._set_tables(successor_table(world), world['rewards'], world['terminals'], world['starting_states'])
+        self._set_tables(successor_table(world), world['rewards'], world['terminals'], world['starting_states'],
+                         None if self.deterministic else world['sas'])
         self._coordinates = torch.as_tensor(np.asarray(world['coordinates']), dtype=torch.float64).to(self.rng.device)
         self._current = torch.zeros(self.rng.n_agents, dtype=torch.int64, device=self.rng.device)
         self.reset()      # gridworld.py:89 -- consumes one draw per agent, like the reference
@@ -63,7 +65,13 @@ class Gridworld(Interface):
     def step(self, action):
         """gridworld.py:92-129 for all agents: (state, reward, end_trial, False, {})."""
         a = torch.as_tensor(action, device=self.rng.device).reshape(-1).to(torch.int64)
-        self._current = self._succ[self._current, a].to(torch.int64)
+        if self.deterministic:
+            self._current = self._succ[self._current, a].to(torch.int64)
+        else:   # gridworld.py:118-123: one categorical draw over the sas row per agent
+            rows = torch.as_tensor(np.asarray(self.world['sas']), device=self.rng.device)[self._current, a]
+            cdf = torch.cumsum(rows, dim=1)
+            cdf = cdf / cdf[:, -1:]
+            self._current = (cdf <= self.rng.next(1)).sum(dim=1)
         reward = self._reward[self._current]
         end = self._terminal[self._current].bool()
         return self._out(self._current), self._out(reward), self._out(end), False, {}

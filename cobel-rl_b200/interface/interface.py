@@ -6,6 +6,7 @@ reference's scalar types.
 """
 import abc
 
+import numpy as np
 import torch
 
 from .. import _lib
@@ -32,8 +33,19 @@ class Interface(abc.ABC):
         ...
 
     # -- table view consumed by the fused kernels (include/cobel_b200.h: CobelWorld)
-    def _set_tables(self, succ, reward, terminal, starts):
+    def _set_tables(self, succ, reward, terminal, starts, sas=None):
         dev = self.rng.device
+        self._tp = None
+        if sas is not None:
+            # non-deterministic world: CSR of the non-zero entries of sas[s,a,:], ascending next state
+            sas = np.asarray(sas, dtype=np.float64)
+            S, A, _ = sas.shape
+            flat = sas.reshape(S * A, S)
+            nz_row, nz_col = np.nonzero(flat)
+            off = np.zeros(S * A + 1, dtype=np.int32)
+            np.cumsum(np.bincount(nz_row, minlength=S * A), out=off[1:])
+            self._tp = (torch.as_tensor(off).to(dev), torch.as_tensor(nz_col.astype(np.int32)).to(dev),
+                        torch.as_tensor(flat[nz_row, nz_col]).contiguous().to(dev))
         self._succ = torch.as_tensor(succ, dtype=torch.int32).contiguous().to(dev)
         self._reward = torch.as_tensor(reward, dtype=torch.float64).contiguous().to(dev)
         self._terminal = torch.as_tensor(terminal).to(torch.uint8).contiguous().to(dev)
@@ -49,8 +61,10 @@ class Interface(abc.ABC):
         return self._succ.shape[1]
 
     def c_world(self):
+        tp = self._tp if self._tp is not None else (None, None, None)
         return _lib.World(self.n_states, self.n_actions, self._starts.numel(), 0, self._succ.data_ptr(),
-                          self._reward.data_ptr(), self._terminal.data_ptr(), self._starts.data_ptr())
+                          self._reward.data_ptr(), self._terminal.data_ptr(), self._starts.data_ptr(),
+                          _lib.ptr(tp[0]), _lib.ptr(tp[1]), _lib.ptr(tp[2]))
 
     def _out(self, t):
         """Squeeze the agent axis for single-agent streams (reference return types)."""

@@ -54,6 +54,12 @@ typedef struct CobelWorld {
   const double*  reward;    /* [S]    reward on arrival */
   const uint8_t* terminal;  /* [S]    1 = trial ends on arrival */
   const int32_t* starts;    /* [K]    starting states, reset draws uniformly */
+  /* Non-deterministic gridworlds (interface/gridworld.py:118-123): CSR of the non-zero entries of
+   * sas[s,a,:] in ascending next-state order; the step then consumes one more uniform and draws
+   * s' ~ categorical(sas[s,a,:]) exactly like Generator.choice(p=...).  NULL = deterministic (succ). */
+  const int32_t* tp_off;    /* [S*A+1] */
+  const int32_t* tp_next;   /* [nnz]   */
+  const double*  tp_prob;   /* [nnz]   */
 } CobelWorld;
 
 /* Random-stream contract (one uniform stream per agent, consumed in program
@@ -89,6 +95,8 @@ typedef struct CobelTrace {
   int32_t* replay_len;       /* optional [N, replay_calls_cap]: length of every replay call */
   int64_t  replay_calls_cap;
   int32_t* flags;            /* optional [N] in/out: COBEL_FLAG_* bits raised by the agent */
+  int32_t* step_next;        /* optional [N, step_cap]: arrival state of every step (needed to reconstruct
+                                trajectories in non-deterministic worlds) */
 } CobelTrace;
 
 enum {

@@ -30,9 +30,20 @@ def world_args(name):
     if name == 'track10x2':  # config C4's linear track as a gridworld
         return 2, 10, dict(terminals=[9, 19], rewards=np.array([[9, 1], [19, 1]]), goals=[9, 19],
                            starting_states=[0, 10])
+    if name == 'slip5':      # non-deterministic transitions (interface/gridworld.py:118-123)
+        return 5, 5, dict(terminals=[0], rewards=np.array([[0, 1]]), goals=[0], slippery=0.25)
     if name == 'open8':
         return 8, 8, dict(terminals=[0], rewards=np.array([[0, 1]]), goals=[0])
     raise KeyError(name)
+
+
+def make_slippery(world, slip=0.2):
+    """Turn a deterministic WorldDict into a non-deterministic one (in place): with probability
+    ``slip`` the move of a uniformly random action is executed instead of the chosen one."""
+    sas = np.asarray(world['sas'])
+    world['sas'] = (1.0 - slip) * sas + slip * np.mean(sas, axis=1, keepdims=True)
+    world['deterministic'] = False
+    return world
 
 
 # name -> (kind, world, agent index in the stream, run arguments)
@@ -48,6 +59,7 @@ CASES = {
                                                        episodic_replay=True)),
     'dynaq_open5_noreplay': ('dynaq', 'open5', 5, dict(trials=25, steps=20, batch=32, policy=('eps', 0.1),
                                                        no_replay=True)),
+    'dynaq_slip5':          ('dynaq', 'slip5', 23, dict(trials=25, steps=40, batch=32, policy=('eps', 0.1))),
     # QAgent (unit_tests/test_q.py:46-77; demo/topology/demo.py:40-103)
     'q_open5':              ('q_grid', 'open5', 6, dict(trials=25, steps=50, batch=32, policy=('eps', 0.1))),
     'q_track':              ('q_topo', ('linear_track', (10, 2, 1.0, 20.0, 'right')), 7,
@@ -59,6 +71,7 @@ CASES = {
     'sr_open13':            ('sr', 'open13', 11, dict(trials=10, steps=120, policy=('eps', 0.1))),
     'sr_walls5_mask':       ('sr', 'walls5', 12, dict(trials=20, steps=40, policy=('eps', 0.2), mask_actions=True,
                                                       valid_mask=True, lr=0.3, gamma=0.9)),
+    'sr_slip5':             ('sr', 'slip5', 24, dict(trials=20, steps=40, policy=('eps', 0.1))),
     # SFMA (demo/gridworld/demo_sfma.py:36-80; unit_tests/test_sfma.py:20-97)
     'sfma_walls5_default':  ('sfma', 'walls5', 13, dict(trials=25, steps=50, batch=32, mode='default', mask_actions=True,
                                                         valid_mask=True)),
@@ -69,12 +82,14 @@ CASES = {
     'sfma_open8_forward':   ('sfma', 'open8', 17, dict(trials=12, steps=80, batch=32, mode='forward', mask_actions=False)),
     'sfma_walls5_sweeping_recency': ('sfma', 'walls5', 18, dict(trials=20, steps=50, batch=32, mode='sweeping',
                                                                mask_actions=True, recency=True)),
+    'sfma_slip5':           ('sfma', 'slip5', 25, dict(trials=15, steps=40, batch=16, mode='default', mask_actions=False)),
     # PMA (demo/gridworld/demo_pma.py:29-72; unit_tests/test_pma.py:15-78)
     'pma_walls5':           ('pma', 'walls5', 19, dict(trials=6, steps=50, batch=16, gamma_q=0.99, mask_actions=True,
                                                        valid_mask=True)),
     'pma_walls5_timeout':   ('pma', 'walls5', 20, dict(trials=6, steps=6, batch=16, gamma_q=0.99, mask_actions=True)),
     'pma_walls5_prefill':   ('pma', 'walls5', 21, dict(trials=6, steps=30, batch=16, gamma_q=0.99, mask_actions=True,
                                                        prefill=True)),
+    'pma_slip5':            ('pma', 'slip5', 26, dict(trials=5, steps=30, batch=16, gamma_q=0.99, mask_actions=False)),
     'pma_walls10':          ('pma', 'walls10', 22, dict(trials=3, steps=100, batch=32, gamma_q=0.99, mask_actions=True,
                                                         valid_mask=True)),
 }

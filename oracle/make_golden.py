@@ -20,7 +20,10 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 
 def build_world(cobel, name):
     h, w, kw = cases.world_args(name)
-    return cobel.misc.gridworld_tools.make_gridworld(h, w, **kw)
+    kw = dict(kw)
+    slip = kw.pop('slippery', None)
+    world = cobel.misc.gridworld_tools.make_gridworld(h, w, **kw)
+    return cases.make_slippery(world, slip) if slip else world
 
 
 def main(only=None):

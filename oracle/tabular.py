@@ -65,10 +65,10 @@ def compile_gridworld(world):
     Deterministic worlds only: ``s' = argmax(sas[s, a, :])`` (first maximum).
     Reward and terminal flag are looked up at the arrival state (125-126).
     """
-    assert world['deterministic'], 'oracle covers deterministic gridworlds'
     sas = np.asarray(world['sas'])
     succ = np.argmax(sas, axis=2).astype(np.int32)
     return {
+        'sas': None if world['deterministic'] else sas,
         'S': int(world['states']), 'A': 4, 'succ': succ,
         'reward': np.asarray(world['rewards'], dtype=np.float64).copy(),
         'terminal': np.asarray(world['terminals']).astype(np.uint8),
@@ -111,9 +111,13 @@ def env_reset(W, rng):
     return int(W['starts'][draw_integer(rng.next(), len(W['starts']))])
 
 
-def env_step(W, s, a):
-    """interface/gridworld.py:115-129 / interface/topology.py:149-157."""
-    s2 = int(W['succ'][s, a])
+def env_step(W, s, a, rng=None):
+    """interface/gridworld.py:115-129 / interface/topology.py:149-157.  Non-deterministic worlds
+    (gridworld.py:118-123) draw the next state with one uniform: ``choice(arange(S), p=sas[s,a])``."""
+    if W.get('sas') is not None:
+        s2 = draw_categorical(W['sas'][s, a], rng.next())
+    else:
+        s2 = int(W['succ'][s, a])
     return s2, float(W['reward'][s2]), int(W['terminal'][s2])
 
 
@@ -237,7 +241,7 @@ def dynaq_train(W, st, rng, trials, steps, batch, *, policy=('eps', 0.1), lr=0.9
         treward, step = 0.0, 0
         for step in range(steps):
             a = select_action(policy, Q[s], st['action_mask'][s] if mask_actions else None, rng)
-            s2, r, end = env_step(W, s, a)
+            s2, r, end = env_step(W, s, a, rng)
             nt = 1 - end
             # memory/dyna_q.py:92-96 (store before update)
             Mr[s, a] += mem_lr * (r - Mr[s, a]); Ms[s, a] = s2; Mt[s, a] = nt
@@ -264,7 +268,7 @@ def tabular_test(W, Q, rng, trials, steps, *, policy=('eps', 0.0), action_mask=N
         treward, step = 0.0, 0
         for step in range(steps):
             a = select_action(policy, Q[s], None if action_mask is None else action_mask[s], rng)
-            s2, r, end = env_step(W, s, a)
+            s2, r, end = env_step(W, s, a, rng)
             rec.step(s, a, s2, r)
             s = s2
             treward += r
@@ -296,7 +300,7 @@ def q_train(W, st, rng, trials, steps, batch, *, policy=('eps', 0.1), lr=0.9, ga
         treward, step = 0.0, 0
         for step in range(steps):
             a = select_action(policy, Q[s], None, rng)
-            s2, r, end = env_step(W, s, a)
+            s2, r, end = env_step(W, s, a, rng)
             nt = 1 - end
             log.append((s, a, r, s2, nt))
             _td_update(Q, s, a, r, s2, nt, lr, gamma)
@@ -362,7 +366,7 @@ def sr_train(W, st, rng, trials, steps, *, policy=('eps', 0.1), lr=0.1, gamma=0.
         for step in range(steps):
             mask = st['action_mask'][s] if mask_actions else None
             a = select_action(policy, sr_retrieve_q(st, s), mask, rng)
-            s2, r, end = env_step(W, s, a)
+            s2, r, end = env_step(W, s, a, rng)
             if learn:
                 sr_update(st, s, a, r, s2, 1 - end, lr, gamma)
             rec.step(s, a, s2, r)
@@ -482,7 +486,7 @@ def sfma_train(W, st, D, rng, trials, steps, batch, *, policy=('eps', 0.1), lr=0
         treward, step = 0.0, 0
         for step in range(steps):
             a = select_action(policy, Q[s], st['action_mask'][s] if mask_actions else None, rng)
-            s2, r, end = env_step(W, s, a)
+            s2, r, end = env_step(W, s, a, rng)
             nt = 1 - end
             # SFMAMemory.store, memory/sfma.py:206-215
             Mr[s, a] += mem_lr * (r - Mr[s, a]); Ms[s, a] = s2; Mt[s, a] = nt
@@ -738,7 +742,7 @@ def pma_train(W, st, rng, trials, steps, batch, *, policy=('eps', 0.1), mem_poli
         for step in range(steps):
             Q = st['Q']
             a = select_action(policy, Q[s], st['action_mask'][s] if mask_actions else None, rng)
-            s2, r, end = env_step(W, s, a)
+            s2, r, end = env_step(W, s, a, rng)
             nt = 1 - end
             # PMA.update_q([experience]), agent/pma.py:319-353 with a one-element list
             fv = np.amax(Q[s2]) * nt

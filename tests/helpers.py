@@ -30,7 +30,10 @@ def make_world(name, tools=None):
     if tools is None:
         from cobel_rl_b200.misc import gridworld_tools as tools
     h, w, kw = cases.world_args(name)
-    return tools.make_gridworld(h, w, **kw)
+    kw = dict(kw)
+    slip = kw.pop('slippery', None)
+    world = tools.make_gridworld(h, w, **kw)
+    return cases.make_slippery(world, slip) if slip else world
 
 
 def make_topology(spec, tools=None):
@@ -129,7 +132,7 @@ def unpack_run(res, i, A, succ, reward):
     ns = int(res['n_steps'][i])
     sa = res['step_sa'][i, :ns].cpu().numpy()
     s, a = sa // A, sa % A
-    s2 = np.asarray(succ)[s, a]
+    s2 = res['step_next'][i, :ns].cpu().numpy() if 'step_next' in res else np.asarray(succ)[s, a]
     nrep = int(res['n_replay'][i])
     rl = res['replay_len'][i].cpu().numpy()
     rl = rl[rl >= 0]
