@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
   };
 
   // SFMAMemory.replay (memory/sfma.py:238-347) + the Q updates of SFMA.replay (agent/sfma.py:416-419)
-  auto replay = [&](int last) {
+  auto replay = [&](int last, bool apply_updates) {
     if (warp == 0) {
       win.ensure(2, lane);
       const int act0 = draw_integer(win.next(), A);                        // sfma.py:264 (always drawn)
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
       }
     for (int e = tid; e < 2 * S; e += T) wm[e] = 0;                        // wm, rm alias R
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 0 && apply_updates) {
       for (int b0 = 0; b0 < count; b0 += 32) {
         const bool active = b0 + lane < count;
         int es = 0, ea = 0, es2 = 0, ent = 0;
@@ -342,7 +342,9 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     __syncthreads();
     int s = sh.last;
     __syncthreads();
-    if (do_replay && p.start_replay) replay(s);
+    // the replay at trial start only generates a trace (memory call, agent/sfma.py:272-275): no Q updates
+    // (it runs whenever agent.start_replay is set, also with no_replay=True, like the reference)
+    if (learn && p.start_replay) replay(s, false);
     // ---- the online steps of the trial: warp 0, warp-uniform ---------------------------------
     if (warp == 0) {
       double treward = 0.0;
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     __syncthreads();
     if (do_replay) {
       const int last = sh.last;
-      for (int rpl = 0; rpl < p.nb_replays; ++rpl) replay(last);
+      for (int rpl = 0; rpl < p.nb_replays; ++rpl) replay(last, true);
       if (recency) for (int e = tid; e < N; e += T) Tr[e] = 0.0;           // M.T.fill(0), agent/sfma.py:324
       __syncthreads();
     }

@@ -76,3 +76,64 @@ def t_maze(nb_nodes_stem, nb_nodes_arm, nb_nodes_width, spacing=1.0, reward=1.0,
         nodes[str(span * i + (span - 1) * int(location == 'right'))].update({'terminal': True, 'reward': reward})
     starting_nodes = list(nodes.keys())[-nb_nodes_width:]
     return nodes, starting_nodes
+
+
+def hexagonal(nb_nodes, limits=(0.0, 1.0), reward=1.0, location=None):
+    """topology_tools.py:175-272: hexagonal lattice (odd rows shifted by half a spacing, nodes beyond
+    the upper x limit dropped) with 6 neighbour slots.  A neighbour is any node closer than 1.5
+    spacings; it is put into the slot whose nominal direction (in the reference's slot order
+    240, 300, 0, 60, 120, 180 degrees, first minimum of the absolute angular difference without
+    wrap-around) is closest to its bearing, empty slots point to the node itself, and the slot
+    list is finally reversed -- all as in the reference, including its float behaviour."""
+    assert nb_nodes > 1, 'Invalid number of nodes!'
+    assert limits[1] > limits[0], 'Invalid coordinate range!'
+    spacing = (limits[1] - limits[0]) / (nb_nodes - 1)
+    ticks = np.linspace(limits[0], limits[1], nb_nodes)
+    xy = np.array([[x, y] for y in ticks for x in ticks])
+    odd = np.repeat(np.arange(nb_nodes) % 2 == 1, nb_nodes)
+    xy[odd, 0] += spacing / 2
+    xy = xy[xy[:, 0] <= limits[1]]
+    pose_xy = [(x, limits[1] - (y - limits[0])) for x, y in xy]
+    n = len(pose_xy)
+    P = np.array(pose_xy)
+    dist = np.sqrt(((P[:, None, :] - P[None, :, :]) ** 2).sum(axis=2))
+    slots = np.array([(i * 60 - 120) % 360 for i in range(6)])
+    nodes = {}
+    for a in range(n):
+        nid = str(a)
+        assigned = [nid] * 6
+        # the reference also runs its own id (six times) through the slot search: bearing 0 -> slot of 0 degrees
+        candidates = [a] * 6 + [b for b in range(n) if b != a and dist[a, b] < spacing * 1.5]
+        for b in candidates:
+            bearing = np.angle(complex(P[b, 0] - P[a, 0], P[b, 1] - P[a, 1]), deg=True) % 360
+            assigned[int(np.argmin(np.abs(slots - bearing)))] = str(b)
+        nodes[nid] = {'id': nid, 'pose': (pose_xy[a][0], pose_xy[a][1], 0.0, 0.0, 0.0, 0.0), 'terminal': False,
+                      'reward': 0.0, 'neighbors': assigned[::-1]}
+    if location is None or location not in nodes:
+        location = str(nb_nodes - 1)
+    nodes[location].update({'terminal': True, 'reward': reward})
+    starting_nodes = [k for k in nodes if k != location]
+    return nodes, starting_nodes
+
+
+def cross(nb_nodes_arm, nb_nodes_width, spacing=1.0, rotation=0.0):
+    """topology_tools.py:376-469: plus-shaped maze (top arm, middle band, bottom arm), no goal; every
+    node is a starting node; poses are centred, scaled by ``spacing`` and rotated by ``rotation`` degrees."""
+    assert nb_nodes_arm > 0, 'The arm must be at least 1 node long!'
+    assert nb_nodes_width > 0, 'The corridors must be at least 1 node wide!'
+    assert spacing > 0, 'Node spacing must be positive!'
+    arm, wid = nb_nodes_arm, nb_nodes_width
+    D = 2 * arm + wid
+    cells = [(arm + j, D - 1 - i) for i in range(arm) for j in range(wid)]
+    cells += [(i, D - 1 - arm - j) for j in range(wid) for i in range(D)]
+    cells += [(arm + j, D - 1 - (i + arm + wid)) for i in range(arm) for j in range(wid)]
+    nodes = _lattice_nodes(cells, 1.0)
+    ticks = np.linspace(0, 1.0, D)
+    scale = (D - 1) * spacing
+    offset = spacing * (D - 1) / 2
+    theta = np.deg2rad(rotation)
+    R = np.array([[np.cos(theta), -np.sin(theta)], [np.sin(theta), np.cos(theta)]])
+    for (ix, iy), node in zip(cells, nodes.values()):
+        x, y = R @ (np.array((ticks[ix], ticks[iy])) * scale - offset)
+        node['pose'] = (float(x), float(y), 0.0, 0.0, 0.0, 0.0)
+    return nodes, list(nodes.keys())

@@ -467,10 +467,12 @@ def sfma_train(W, st, D, rng, trials, steps, batch, *, policy=('eps', 0.1), lr=0
     rec = rec if rec is not None else Record()
     kw = dict(replay_kwargs or {})
 
-    def replay(state):
-        # agent/sfma.py:392-421: the batch is sampled first, then applied in order
+    def replay(state, apply=True):
+        # agent/sfma.py:392-421: the batch is sampled first, then applied in order.  The replay at
+        # trial start calls the memory only (agent/sfma.py:272-275): a trace is generated and the
+        # inhibition changes, but Q is not updated.
         idx = sfma_memory_replay(st, D, rng, batch, state, mode=mode, **kw)
-        for i in idx:
+        for i in (idx if apply else []):
             ea, es = divmod(i, S)
             es2 = int(Ms[es, ea])
             td = _td_update(Q, es, ea, Mr[es, ea], es2, int(Mt[es, ea]), lr, gamma,
@@ -482,7 +484,7 @@ def sfma_train(W, st, D, rng, trials, steps, batch, *, policy=('eps', 0.1), lr=0
         last = None
         s = env_reset(W, rng)
         if start_replay:
-            replay(s)
+            replay(s, apply=False)
         treward, step = 0.0, 0
         for step in range(steps):
             a = select_action(policy, Q[s], st['action_mask'][s] if mask_actions else None, rng)

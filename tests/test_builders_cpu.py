@@ -1,0 +1,56 @@
+"""CPU (build container only: needs /root/reference): the product's world / graph builders produce
+exactly the reference's WorldDicts and node dictionaries (keys, dtypes, values, neighbour order)."""
+import numpy as np
+import pytest
+
+from cobel_rl_b200.misc import gridworld_tools as mg, topology_tools as mt
+from cobel_rl_b200.memory.utils import metrics as mm
+
+WALLS = [(1, 2), (2, 1), (6, 7), (7, 6), (11, 12), (12, 11), (13, 8), (8, 13)]
+
+
+def same_world(a, b):
+    for k in b:
+        x, y = a[k], b[k]
+        if isinstance(y, np.ndarray):
+            assert x.dtype == y.dtype and np.array_equal(x, y), k
+        else:
+            assert x == y, (k, x, y)
+
+
+def test_gridworld_builders(reference):
+    from cobel.misc import gridworld_tools as rg
+    kw = dict(terminals=[4], rewards=np.array([[4, 10]]), goals=[4], starting_states=[12], invalid_transitions=WALLS)
+    same_world(mg.make_gridworld(5, 5, **kw), rg.make_gridworld(5, 5, **kw))
+    same_world(mg.make_open_field(7, 4, 3, 2.5), rg.make_open_field(7, 4, 3, 2.5))
+    same_world(mg.make_empty_field(3, 6), rg.make_empty_field(3, 6))
+    cols = np.array([0, 0, 0, 1, 1, 1, 2, 2, 1, 0])
+    same_world(mg.make_windy_gridworld(7, 10, cols, 37, 1., 'up'), rg.make_windy_gridworld(7, 10, cols, 37, 1., 'up'))
+    same_world(mg.make_windy_gridworld(7, 10, cols, 37, 1., 'down'), rg.make_windy_gridworld(7, 10, cols, 37, 1., 'down'))
+    same_world(mg.make_gridworld(6, 6, invalid_states=[7, 8, 20]), rg.make_gridworld(6, 6, invalid_states=[7, 8, 20]))
+    big = mg.make_open_field(100, 100, 0, 1, dense_sas=False)
+    assert big['sas'] is None and big['succ'].shape == (10000, 4)
+
+
+def test_topology_builders(reference):
+    from cobel.misc import topology_tools as rt
+    for args in [(10, 2, 1.0, 20., 'right'), (5, 1, 0.5, 1., 'left'), (4, 3)]:
+        assert mt.linear_track(*args) == rt.linear_track(*args), args
+    for args in [(5,), ((3, 4),), (4, (0., 2.), 3., '5'), ((2, 5), ((0., 1.), (1., 3.)))]:
+        assert mt.grid(*args) == rt.grid(*args), args
+    for args in [(4, 3, 1), (6, 3, 2), (2, 2, 3, 0.5, 2., 'left')]:
+        assert mt.t_maze(*args) == rt.t_maze(*args), args
+    for args in [(10,), (6,), (5, (0., 2.), 3., '7'), (2,), (9, (1.0, 4.0))]:
+        assert mt.hexagonal(*args) == rt.hexagonal(*args), args
+    for args in [(3, 1), (2, 2, 0.5, 30.0), (4, 3, 2.0, 90.0), (1, 1)]:
+        assert mt.cross(*args) == rt.cross(*args), args
+
+
+def test_metrics(reference):
+    from cobel.memory.utils import metrics as rm
+    from cobel.misc import gridworld_tools as rg
+    world = rg.make_gridworld(5, 5, terminals=[4], invalid_transitions=WALLS)
+    np.testing.assert_array_equal(mm.DR(5, 5, world['sas'], 0.9, WALLS).D, rm.DR(5, 5, world['sas'], 0.9, WALLS).D)
+    np.testing.assert_array_equal(mm.DR(5, 5, world['sas'], 0.9, []).D, rm.DR(5, 5, world['sas'], 0.9, []).D)
+    np.testing.assert_array_equal(mm.SR(world['sas'], 0.8).D, rm.SR(world['sas'], 0.8).D)
+    np.testing.assert_allclose(mm.Euclidean(4, 3).D, rm.Euclidean(4, 3).D, rtol=1e-15)

@@ -1,0 +1,72 @@
+"""CPU (build container only: needs /root/reference): the oracle restatement against the LIVE,
+unmodified reference on fresh seeds / configurations that have no committed golden fixture.
+Everything must be bit-equal (same NumPy / LAPACK on both sides)."""
+import numpy as np
+import pytest
+
+from oracle import cases, ref_runs, tabular as tb
+from oracle.philox import LazyStream
+from helpers import KEYS, assert_equal_records
+
+
+def _world(reference, name):
+    h, w, kw = cases.world_args(name)
+    kw = dict(kw)
+    slip = kw.pop('slippery', None)
+    world = reference.misc.gridworld_tools.make_gridworld(h, w, **kw)
+    return cases.make_slippery(world, slip) if slip else world
+
+
+@pytest.mark.parametrize('seed_agent', [(11, 0), (12, 5)])
+def test_dynaq_live(reference, seed_agent):
+    seed, agent = seed_agent
+    world = _world(reference, 'walls5')
+    u = LazyStream(seed, agent)
+    ref = ref_runs.run_dynaq(world, u, 15, 30, 16, policy=('xeps', 0.3), lr=0.8, gamma=0.9, mem_lr=0.7)
+    W = tb.compile_gridworld(world)
+    rng = tb.Draws(LazyStream(seed, agent), 1)
+    st = tb.dynaq_init(25, 4)
+    got = tb.dynaq_train(W, st, rng, 15, 30, 16, policy=('xeps', 0.3), lr=0.8, gamma=0.9, mem_lr=0.7).arrays()
+    got.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], draws=rng.k)
+    assert_equal_records(got, ref, KEYS['dynaq'])
+
+
+def test_sr_and_q_live(reference):
+    world = _world(reference, 'open8')
+    W = tb.compile_gridworld(world)
+    u = LazyStream(99, 3)
+    ref = ref_runs.run_sr(world, u, 8, 60, policy=('softmax', 4.0), lr=0.4, gamma=0.9)
+    rng = tb.Draws(LazyStream(99, 3), 1)
+    st = tb.sr_init(64, 4)
+    got = tb.sr_train(W, st, rng, 8, 60, policy=('softmax', 4.0), lr=0.4, gamma=0.9).arrays()
+    got.update(SR=st['SR'], rew=st['rew'], model=st['model'], draws=rng.k)
+    assert_equal_records(got, ref, [k for k in KEYS['sr']])
+    ref = ref_runs.run_q_gridworld(world, u, 8, 40, 12, policy=('eps', 0.25), lr=0.5, gamma=0.95)
+    rng = tb.Draws(LazyStream(99, 3), 1)
+    st = tb.q_init(64, 4)
+    got = tb.q_train(W, st, rng, 8, 40, 12, policy=('eps', 0.25), lr=0.5, gamma=0.95).arrays()
+    got.update(Q=st['Q'], draws=rng.k)
+    assert_equal_records(got, ref, KEYS['q_grid'])
+
+
+def test_sfma_and_pma_live(reference):
+    world = _world(reference, 'walls5')
+    W = tb.compile_gridworld(world)
+    D = reference.memory.utils.metrics.DR(5, 5, world['sas'], 0.9, world['invalid_transitions']).D
+    u = LazyStream(7, 9)
+    ref = ref_runs.run_sfma(world, D, u, 10, 25, 16, mode='blend_reverse', mask_actions=True, start_replay=True, nb_replays=2)
+    rng = tb.Draws(LazyStream(7, 9), 1)
+    st = tb.sfma_init(25, 4)
+    got = tb.sfma_train(W, st, D, rng, 10, 25, 16, mode='blend_reverse', mask_actions=True, start_replay=True,
+                        nb_replays=2).arrays()
+    got.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], C=st['C'], T=st['T'], I=st['I'], draws=rng.k)
+    assert_equal_records(got, ref, KEYS['sfma'])
+    ref = ref_runs.run_pma(world, u, 4, 12, 12, policy=('eps', 0.2), mem_policy=('eps', 0.05), lr_q=0.7, gamma_q=0.95,
+                           mask_actions=True, min_gain_mode='')
+    rng = tb.Draws(LazyStream(7, 9), 1)
+    st = tb.pma_init(tb.t0_from_succ(W['succ']), 25, 4)
+    got = tb.pma_train(W, st, rng, 4, 12, 12, policy=('eps', 0.2), mem_policy=('eps', 0.05), lr_q=0.7, gamma_q=0.95,
+                       mask_actions=True, replay_kwargs={'original': False}).arrays()
+    got.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], T=st['T'], SR=st['SR'], update_mask=st['update_mask'],
+               draws=rng.k)
+    assert_equal_records(got, ref, KEYS['pma'])
