@@ -147,7 +147,10 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n = blockIdx.x;
   const bool recency = p.recency != 0;
-  const SfmaSmem so(S, A, T, B, recency);
+  // M.T is only read by the replay when `recency` is set, and it is zeroed after every trial with
+  // replay (agent/sfma.py:324); it has to be tracked only if it is read or survives the trial
+  const bool track_t = recency || p.no_replay != 0;
+  const SfmaSmem so(S, A, T, B, track_t);
   double* Q = reinterpret_cast<double*>(smem + so.q);        // [s][a]
   double* Mr = reinterpret_cast<double*>(smem + so.mr);      // [s][a]
   double* C = reinterpret_cast<double*>(smem + so.c);        // [a*S + s]
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     Mr[e] = p.Mr[g0 + e];
     Mx[e] = (uint16_t)(p.Ms[g0 + e] | ((p.Mt[g0 + e] ? 1 : 0) << 15));
     C[e] = p.C[g0 + e];
-    if (recency) Tr[e] = p.T[g0 + e];
+    if (track_t) Tr[e] = p.T[g0 + e];
   }
   for (int e = tid; e < S; e += T) {
     I[e] = p.I[(size_t)n * S + e];
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
         if (learn) {
           // SFMAMemory.store (memory/sfma.py:206-215): EMA reward, next state, flag, strengths, recency
           if (dstr != 1.0) for (int e = lane; e < N; e += 32) C[e] = xmul(C[e], dstr);
-          if (recency) for (int e = lane; e < N; e += 32) Tr[e] = xmul(Tr[e], drec);
+          if (track_t) for (int e = lane; e < N; e += 32) Tr[e] = xmul(Tr[e], drec);
           const double m0 = Mr[s * A + a];
           const double m1 = xadd(m0, xmul(mlr, xsub(r, m0)));
           // SFMA.update_q (agent/sfma.py:423-458): max over the unmasked actions of s'
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
             Mr[s * A + a] = m1;
             Mx[s * A + a] = (uint16_t)(s2 | (nt << 15));
             C[a * S + s] = xadd(C[a * S + s], p.c_step);
-            if (recency) Tr[a * S + s] = 1.0;
+            if (track_t) Tr[a * S + s] = 1.0;
             Q[s * A + a] = qn;
           }
           __syncwarp();
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     if (do_replay) {
       const int last = sh.last;
       for (int rpl = 0; rpl < p.nb_replays; ++rpl) replay(last, true);
-      if (recency) for (int e = tid; e < N; e += T) Tr[e] = 0.0;           // M.T.fill(0), agent/sfma.py:324
+      if (track_t) for (int e = tid; e < N; e += T) Tr[e] = 0.0;           // M.T.fill(0), agent/sfma.py:324
       __syncthreads();
     }
   }
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
       p.Mt[g0 + e] = Mx[e] >> 15;
       p.C[g0 + e] = C[e];
       // without the recency option T is never read; it is zero after every trial with replay
-      if (recency) p.T[g0 + e] = Tr[e];
+      if (track_t) p.T[g0 + e] = Tr[e];
       else if (do_replay && p.trials > 0) p.T[g0 + e] = 0.0;
     }
     for (int e = tid; e < S; e += T) p.I[(size_t)n * S + e] = I[e];
@@ -438,7 +441,7 @@ int launch(const CobelSFMAParams& p, cudaStream_t st) {
   const int S = p.world.n_states, N = S * A;
   COBEL_REQUIRE(S <= 0x7FFF, COBEL_EUNSUPPORTED, "SFMA kernel supports at most 32767 states");
   const int T = N <= 128 ? 64 : N <= 512 ? 128 : 256;
-  const SfmaSmem so(S, A, T, p.batch, p.recency != 0);
+  const SfmaSmem so(S, A, T, p.batch, p.recency != 0 || p.no_replay != 0);
   COBEL_REQUIRE(so.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
                 "SFMA tables of %d states x %d actions need %d bytes of shared memory", S, A, so.bytes);
   COBEL_CUDA_OK(cudaFuncSetAttribute(sfma_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, so.bytes));

@@ -62,3 +62,50 @@ def test_pma_batch_sweep_vs_oracle():
         assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q', 'T', 'SR', 'draws'],
                              rtol=RTOL, what='agent %d' % i)
     assert float(mem.min_gap.min()) > 1e-9
+
+
+def test_pma_no_replay_test_mode_and_softmax_memory_policy():
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import PMA
+    from cobel_rl_b200.memory import PMAMemory
+    from cobel_rl_b200.policy import EpsilonGreedy, ExclusiveEpsilonGreedy
+    world = make_world('walls5')
+    W = tb.compile_gridworld(world)
+    # (a) no_replay + test()
+    stream = cb.BatchStream(2, seed=66, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = PMAMemory(world['sas'], EpsilonGreedy(0.1, rng=stream), rng=stream)
+    ag = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.3, rng=stream), mem)
+    ag.record = True
+    res = ag.train(env, 5, 12, 16, no_replay=True)
+    rt = ag.test(env, 2, 12)
+    torch.cuda.synchronize()
+    for i in range(2):
+        rng = tb.Draws(LazyStream(66, i), 1)
+        st = tb.pma_init(tb.t0_from_succ(W['succ']), 25, 4)
+        rec = tb.pma_train(W, st, rng, 5, 12, 16, policy=('eps', 0.3), no_replay=True).arrays()
+        rec2 = tb.tabular_test(W, st['Q'], rng, 2, 12, policy=('eps', 0.3)).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got.update(Q=ag.Q[i].cpu().numpy(), T=mem.T[i].cpu().numpy(), SR=mem.SR[i].cpu().numpy())
+        rec.update(Q=st['Q'], T=st['T'], SR=st['SR'])
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'Q', 'T', 'SR'], what='agent %d' % i)
+        assert_equal_records(unpack_run(rt, i, 4, W['succ'], W['reward']), rec2, ['states', 'actions', 'trial_steps'])
+        assert int(stream.draw_count[i]) == rng.k
+    # (b) exclusive epsilon-greedy as memory policy, min_gain_mode != 'original'
+    stream = cb.BatchStream(2, seed=67, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = PMAMemory(world['sas'], ExclusiveEpsilonGreedy(0.2, rng=stream), gamma_q=0.95, rng=stream)
+    mem.min_gain_mode = ''
+    ag = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem)
+    ag.record = True
+    res = ag.train(env, 4, 20, 12)
+    torch.cuda.synchronize()
+    for i in range(2):
+        rng = tb.Draws(LazyStream(67, i), 1)
+        st = tb.pma_init(tb.t0_from_succ(W['succ']), 25, 4)
+        rec = tb.pma_train(W, st, rng, 4, 20, 12, mem_policy=('xeps', 0.2), gamma_q=0.95,
+                           replay_kwargs={'original': False}).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got['Q'] = ag.Q[i].cpu().numpy(); rec['Q'] = st['Q']
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q'], what='xeps agent %d' % i)

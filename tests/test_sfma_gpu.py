@@ -71,3 +71,38 @@ def test_metrics_match_reference_fixture():
     world = make_world('walls5')
     D = DR(5, 5, world['sas'], 0.9, world['invalid_transitions']).D
     np.testing.assert_allclose(D, load_golden('sfma_walls5_default')['D'], rtol=1e-12, atol=1e-15)
+
+
+def test_sfma_no_replay_and_test_mode():
+    """no_replay=True: strengths / recency keep evolving but nothing is replayed (M.T is then never
+    zeroed); test(): acts with `policy`, learns nothing."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import SFMA
+    from cobel_rl_b200.memory import SFMAMemory
+    from cobel_rl_b200.memory.utils.metrics import DR
+    from cobel_rl_b200.policy import EpsilonGreedy
+    world = make_world('walls5')
+    metric = DR(5, 5, world['sas'], 0.9, world['invalid_transitions'])
+    stream = cb.BatchStream(3, seed=55, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = SFMAMemory(metric, 25, 4, rng=stream)
+    ag = SFMA(env.observation_space, env.action_space, EpsilonGreedy(0.2, rng=stream), mem, rng=stream)
+    ag.record = True
+    res = ag.train(env, 6, 15, 8, no_replay=True)
+    rt = ag.test(env, 3, 15)
+    torch.cuda.synchronize()
+    W = tb.compile_gridworld(world)
+    for i in range(3):
+        rng = tb.Draws(LazyStream(55, i), 1)
+        st = tb.sfma_init(25, 4)
+        rec = tb.sfma_train(W, st, metric.D, rng, 6, 15, 8, policy=('eps', 0.2), no_replay=True).arrays()
+        rec2 = tb.tabular_test(W, st['Q'], rng, 3, 15, policy=('eps', 0.2)).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got.update(Q=ag.Q[i].cpu().numpy(), C=mem.C[i].cpu().numpy(), T=mem.T[i].cpu().numpy())
+        rec.update(Q=st['Q'], C=st['C'], T=st['T'])
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'Q', 'C', 'T'], what='agent %d' % i)
+        assert float(np.abs(st['T']).sum()) > 0
+        got2 = unpack_run(rt, i, 4, W['succ'], W['reward'])
+        assert_equal_records(got2, rec2, ['states', 'actions', 'trial_steps'], what='test agent %d' % i)
+        assert int(stream.draw_count[i]) == rng.k
