@@ -73,7 +73,8 @@ class SFMAParams(C.Structure):
                 ('c_step', C.c_double), ('i_step', C.c_double), ('blend', C.c_double), ('interp_fwd', C.c_double),
                 ('interp_rev', C.c_double), ('mode', C.c_int32), ('recency', C.c_int32), ('deterministic', C.c_int32),
                 ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32), ('nb_replays', C.c_int32),
-                ('start_replay', C.c_int32), ('no_replay', C.c_int32), ('learn', C.c_int32)]
+                ('start_replay', C.c_int32), ('random_replay', C.c_int32), ('reserved', C.c_int32),
+                ('no_replay', C.c_int32), ('learn', C.c_int32)]
 
 
 PMA_MAX_SEQ = 64

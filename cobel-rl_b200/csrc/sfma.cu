@@ -23,8 +23,8 @@ namespace {
 enum { MODE_DEFAULT = 0, MODE_FORWARD, MODE_REVERSE, MODE_BLEND_FORWARD, MODE_BLEND_REVERSE, MODE_INTERPOLATE, MODE_SWEEPING };
 
 struct SfmaSmem {
-  int q, mr, c, t, r, inh, part, mx, mbits, rep, lst, bytes;
-  __host__ __device__ SfmaSmem(int S, int A, int T, int B, bool recency) {
+  int q, mr, c, t, r, inh, part, mx, mbits, rep, lst, cdf, bytes;
+  __host__ __device__ SfmaSmem(int S, int A, int T, int B, bool recency, bool random_replay) {
     const int N = S * A;
     q = 0;
     mr = q + N * 8;
@@ -37,7 +37,8 @@ struct SfmaSmem {
     mx = rep + ((B + 1) & ~1) * 4;
     mbits = mx + N * 2;
     lst = (mbits + S + 3) & ~3;
-    bytes = (lst + N * 4 + 15) & ~15;
+    cdf = (lst + N * 4 + 7) & ~7;
+    bytes = (cdf + (random_replay ? N * 8 : 0) + 15) & ~15;
   }
 };
 
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
   // M.T is only read by the replay when `recency` is set, and it is zeroed after every trial with
   // replay (agent/sfma.py:324); it has to be tracked only if it is read or survives the trial
   const bool track_t = recency || p.no_replay != 0;
-  const SfmaSmem so(S, A, T, B, track_t);
+  const SfmaSmem so(S, A, T, B, track_t, p.random_replay != 0);
   double* Q = reinterpret_cast<double*>(smem + so.q);        // [s][a]
   double* Mr = reinterpret_cast<double*>(smem + so.mr);      // [s][a]
   double* C = reinterpret_cast<double*>(smem + so.c);        // [a*S + s]
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
   int32_t* rep = reinterpret_cast<int32_t*>(smem + so.rep);  // reactivated flat indices of one replay
   uint16_t* Mx = reinterpret_cast<uint16_t*>(smem + so.mx);  // [s][a] next state | non-terminal << 15
   uint8_t* mbits = smem + so.mbits;                          // [s] valid-action bits
+  double* cdft = reinterpret_cast<double*>(smem + so.cdf);   // random replay: m-fold sums of fl(1/n_valid)
   uint32_t* L = reinterpret_cast<uint32_t*>(smem + so.lst);  // experienced experiences (C > 0): action << 16 | state, ascending flat index
   // dependency scratch of the level-parallel batch aliases the (then idle) priority scratch
   uint32_t* wm = reinterpret_cast<uint32_t*>(R);
@@ -185,6 +187,26 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     mbits[e] = (uint8_t)mb;
   }
   __syncthreads();
+
+  // agent.random: batches are drawn uniformly over the unmasked experiences (retrieve_random_batch,
+  // memory/sfma.py:375-416): probs = mask / sum(mask); NumPy's choice() searches u in
+  // cumsum(probs) / cumsum(probs)[-1], i.e. in the m-fold sequential sums of fl(1 / n_valid)
+  int nvalid = 0;
+  if (p.random_replay) {
+    if (tid == 0) {
+      int m = 0;
+      for (int a = 0; a < A; ++a)
+        for (int sp = 0; sp < S; ++sp)
+          if (mbits[sp] >> a & 1) ++m;
+      const double pv = xdiv(1.0, int_to_f64(m));
+      double c = 0.0;
+      for (int j = 0; j < m; ++j) { c = xadd(c, pv); cdft[j] = c; }
+      sh.idx = m;
+    }
+    __syncthreads();
+    nvalid = sh.idx;
+    __syncthreads();
+  }
 
   DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);      // used by warp 0 only
   const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
@@ -217,6 +239,63 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
 
   // SFMAMemory.replay (memory/sfma.py:238-347) + the Q updates of SFMA.replay (agent/sfma.py:416-419)
   auto replay = [&](int last, bool apply_updates) {
+    if (p.random_replay && apply_updates) {
+      // lane b of warp 0 resolves draw b: smallest m with cdf_m / cdf_last > u, then the m-th valid (a, s)
+      if (warp == 0) {
+        const double tot = cdft[nvalid - 1];
+        for (int b0 = 0; b0 < B; b0 += 32) {
+          const int nb = B - b0 < 32 ? B - b0 : 32;
+          win.ensure(nb, lane);
+          const double u = win.peek(lane < nb ? lane : 0);
+          win.advance(nb);
+          if (lane < nb) {
+            int lo = 0, hi = nvalid - 1;                       // invariant: answer in [lo, hi]
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (xdiv(cdft[mid], tot) > u) hi = mid; else lo = mid + 1;
+            }
+            int m = lo, e = -1;                                // m-th valid experience in F order
+            for (int a = 0; a < A && e < 0; ++a)
+              for (int sp = 0; sp < S; ++sp)
+                if ((mbits[sp] >> a & 1) && m-- == 0) { e = a * S + sp; break; }
+            rep[b0 + lane] = e;
+          }
+        }
+      }
+      __syncthreads();
+      const int count = B;
+      if (tr.replay_idx)
+        for (int j = tid; j < count; j += T) {
+          if (nrep + j < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + j] = rep[j];
+          else flags |= COBEL_FLAG_TRACE_OVERFLOW;
+        }
+      for (int e = tid; e < 2 * S; e += T) wm[e] = 0;
+      __syncthreads();
+      if (warp == 0) {
+        for (int b0 = 0; b0 < count; b0 += 32) {
+          const bool active = b0 + lane < count;
+          int es = 0, ea = 0, es2 = 0, ent = 0;
+          double er = 0.0;
+          if (active) {
+            const int e = rep[b0 + lane];
+            ea = e / S; es = e - ea * S;
+            er = Mr[es * A + ea];
+            const uint16_t v = Mx[es * A + ea];
+            es2 = v & 0x7FFF; ent = v >> 15;
+          }
+          td_batch_level_parallel<A>(Q, wm, rm, S, lane, active, es, ea, er, es2, ent, lr, gamma,
+                                     masked ? mbits : nullptr);
+        }
+      }
+      if (tr.replay_len && tid == 0) {
+        if (ncalls < tr.replay_calls_cap) tr.replay_len[n * tr.replay_calls_cap + ncalls] = count;
+        else flags |= COBEL_FLAG_TRACE_OVERFLOW;
+      }
+      nrep += count;
+      ++ncalls;
+      __syncthreads();
+      return;
+    }
     if (warp == 0) {
       win.ensure(2, lane);
       const int act0 = draw_integer(win.next(), A);                        // sfma.py:264 (always drawn)
@@ -441,7 +520,7 @@ int launch(const CobelSFMAParams& p, cudaStream_t st) {
   const int S = p.world.n_states, N = S * A;
   COBEL_REQUIRE(S <= 0x7FFF, COBEL_EUNSUPPORTED, "SFMA kernel supports at most 32767 states");
   const int T = N <= 128 ? 64 : N <= 512 ? 128 : 256;
-  const SfmaSmem so(S, A, T, p.batch, p.recency != 0 || p.no_replay != 0);
+  const SfmaSmem so(S, A, T, p.batch, p.recency != 0 || p.no_replay != 0, p.random_replay != 0);
   COBEL_REQUIRE(so.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
                 "SFMA tables of %d states x %d actions need %d bytes of shared memory", S, A, so.bytes);
   COBEL_CUDA_OK(cudaFuncSetAttribute(sfma_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, so.bytes));

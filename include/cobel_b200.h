@@ -234,6 +234,8 @@ typedef struct CobelSFMAParams {
   int32_t trials, steps, batch;
   int32_t nb_replays;        /* agent.nb_replays */
   int32_t start_replay;      /* agent.start_replay */
+  int32_t random_replay;     /* agent.random: uniform batches over the unmasked experiences (memory/sfma.py:375-416) */
+  int32_t reserved;
   int32_t no_replay;
   int32_t learn;             /* 1 = train(), 0 = test() */
 } CobelSFMAParams;

@@ -82,6 +82,8 @@ CASES = {
     'sfma_open8_forward':   ('sfma', 'open8', 17, dict(trials=12, steps=80, batch=32, mode='forward', mask_actions=False)),
     'sfma_walls5_sweeping_recency': ('sfma', 'walls5', 18, dict(trials=20, steps=50, batch=32, mode='sweeping',
                                                                mask_actions=True, recency=True)),
+    'sfma_walls5_random':   ('sfma', 'walls5', 27, dict(trials=15, steps=30, batch=32, mode='default', mask_actions=True,
+                                                       valid_mask=True, random_replay=True)),
     'sfma_slip5':           ('sfma', 'slip5', 25, dict(trials=15, steps=40, batch=16, mode='default', mask_actions=False)),
     # PMA (demo/gridworld/demo_pma.py:29-72; unit_tests/test_pma.py:15-78)
     'pma_walls5':           ('pma', 'walls5', 19, dict(trials=6, steps=50, batch=16, gamma_q=0.99, mask_actions=True,

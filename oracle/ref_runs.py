@@ -165,7 +165,7 @@ def run_sr(world, u, trials, steps, *, policy=('eps', 0.1), lr=0.1, gamma=0.99, 
 
 def run_sfma(world, D, u, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99, gamma=0.99,
              mem_lr=0.9, mask_actions=False, mode='default', recency=False, start_replay=False,
-             nb_replays=1, metric=None, action_mask=None):
+             nb_replays=1, metric=None, action_mask=None, random_replay=False):
     cobel = ref_loader.load()
     rng = StreamRNG(u)
     env = _gridworld(cobel, world, rng)
@@ -192,6 +192,7 @@ def run_sfma(world, D, u, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99,
     if action_mask is not None:
         agent.action_mask = np.array(action_mask, dtype=bool)
     agent.start_replay = start_replay
+    agent.random = random_replay
     agent.nb_replays = nb_replays
     agent.train(env, trials, steps, batch)
     out = cap.arrays()

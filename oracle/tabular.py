@@ -457,11 +457,11 @@ def sfma_memory_replay(st, D, rng, length, current_state, *, mode='default', bet
 def sfma_train(W, st, D, rng, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99, gamma=0.99,
                mem_lr=0.9, mask_actions=False, mode='default', decay_strength=1.0,
                decay_recency=0.9, no_replay=False, nb_replays=1, start_replay=False,
-               replay_kwargs=None, rec=None):
+               random_replay=False, replay_kwargs=None, rec=None):
     """SFMA.train, agent/sfma.py:233-328 (store before update_q; replay at trial end
     from the terminal state, or from a strength-sampled experience when the trial
-    timed out; ``M.T`` zeroed after every trial, 324).  ``random`` / ``dynamic``
-    replay selection are not restated."""
+    timed out; ``M.T`` zeroed after every trial, 324).  ``random_replay`` restates ``agent.random``;
+    ``dynamic`` mode selection is not restated."""
     S, A = W['S'], W['A']
     Q, Mr, Ms, Mt, C, T = st['Q'], st['Mr'], st['Ms'], st['Mt'], st['C'], st['T']
     rec = rec if rec is not None else Record()
@@ -471,7 +471,17 @@ def sfma_train(W, st, D, rng, trials, steps, batch, *, policy=('eps', 0.1), lr=0
         # agent/sfma.py:392-421: the batch is sampled first, then applied in order.  The replay at
         # trial start calls the memory only (agent/sfma.py:272-275): a trace is generated and the
         # inhibition changes, but Q is not updated.
-        idx = sfma_memory_replay(st, D, rng, batch, state, mode=mode, **kw)
+        if random_replay and apply:
+            # agent/sfma.py:408-414 + SFMAMemory.retrieve_random_batch (memory/sfma.py:375-416): `batch`
+            # draws in ONE Generator.choice call over the (masked) experiences, F-order unravel
+            mask = st['action_mask'].flatten(order='F') if mask_actions else np.ones(S * A)
+            probs = np.ones(S * A) * mask.astype(int)
+            probs /= np.sum(probs)
+            cdf = np.cumsum(probs)
+            cdf /= cdf[-1]
+            idx = [int(cdf.searchsorted(rng.next(), side='right')) for _ in range(batch)]
+        else:
+            idx = sfma_memory_replay(st, D, rng, batch, state, mode=mode, **kw)
         for i in (idx if apply else []):
             ea, es = divmod(i, S)
             es2 = int(Ms[es, ea])

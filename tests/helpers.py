@@ -98,6 +98,7 @@ def oracle_case(name, agent=None, golden=None):
             st['action_mask'] = tb.valid_move_mask(W['succ'])
         D = (golden if golden is not None else load_golden(name))['D']
         rk = {'recency': a.pop('recency')} if 'recency' in a else {}
+        a['random_replay'] = a.pop('random_replay', False)
         out = tb.sfma_train(W, st, D, rng, trials, steps, a.pop('batch'), replay_kwargs=rk, **a).arrays()
         out.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], C=st['C'], T=st['T'], I=st['I'], draws=rng.k)
     elif kind == 'pma':
@@ -220,6 +221,7 @@ def cuda_case(name, n_extra=2, device='cuda:0'):
         ag = AG.SFMA(env.observation_space, env.action_space, pol, mem, None, a.pop('lr', 0.99), a.pop('gamma', 0.99),
                      rng=stream)
         ag.mask_actions = a.pop('mask_actions', False)
+        ag.random = a.pop('random_replay', False)
         if valid_mask:
             ag.action_mask = tb.valid_move_mask(succ)
         ag.record = True
