@@ -127,20 +127,51 @@ class Agent(abc.ABC):
         S, A = m.shape[-2], m.shape[-1]
         return m.data_ptr(), (S * A if m.dim() == 3 else 0)
 
-    def _fire_trial_callbacks(self, res, first_trial, extra=None):
+    def _fire_trial_callbacks(self, res, first_trial, replay_calls=(0, 0), flat_order='F'):
+        """Fire the per-trial hooks after a launch, once per trial in order, with batched values.
+        ``replay_calls = (calls at trial start, calls at trial end)`` additionally fires
+        ``on_replay_begin`` / ``on_replay_end`` (agent/pma.py:112-135, agent/sfma.py:139-187) with
+        ``logs['replay']`` = dict of padded ``[N, L]`` tensors (flat index, state, action; -1 = no
+        experience) when the run was recorded (``agent.record``), else ``None``."""
         cbs = self.callbacks.custom_callbacks
-        if not any(k in cbs for k in ('on_trial_begin', 'on_trial_end', 'on_replay_end')):
+        if not any(k in cbs for k in Callbacks.HOOKS):
             return
         single = self._stream.single
         trials = res['trial_steps'].shape[1]
+        per_trial = replay_calls[0] + replay_calls[1]
+        offsets = None
+        if per_trial and 'replay_len' in res and ('on_replay_end' in cbs or 'on_replay_begin' in cbs):
+            lens = res['replay_len'][:, :trials * per_trial].clamp(min=0).long()
+            offsets = torch.cumsum(lens, dim=1) - lens
+        S = int(self.observation_space.n) if hasattr(self.observation_space, 'n') else 0
+
+        def replay_logs(call):
+            if offsets is None:
+                return None
+            ln, off = lens[:, call], offsets[:, call]
+            L = int(ln.max()) if ln.numel() else 0
+            pos = torch.arange(L, device=ln.device).unsqueeze(0)
+            valid = pos < ln.unsqueeze(1)
+            idx = torch.gather(res['replay_idx'].long(), 1, (off.unsqueeze(1) + pos).clamp(max=res['replay_idx'].shape[1] - 1))
+            idx = torch.where(valid, idx, torch.full_like(idx, -1))
+            A = int(self.action_space.n)
+            state = torch.where(valid, idx % S if flat_order == 'F' else idx // A, idx)
+            action = torch.where(valid, idx // S if flat_order == 'F' else idx % A, idx)
+            return {'index': idx, 'state': state, 'action': action, 'length': ln}
+
         for t in range(trials):
             steps_t, rew_t = res['trial_steps'][:, t], res['trial_reward'][:, t]
             logs = {'trial_reward': 0.0, 'trial': first_trial + t, 'trial_session': t}
             logs = self.callbacks.on_trial_begin(logs)
+            for c in range(per_trial):
+                if c == replay_calls[0]:      # the online steps lie between the start and the end replays
+                    logs['steps'] = int(steps_t[0]) if single else steps_t
+                    logs['trial_reward'] = float(rew_t[0]) if single else rew_t
+                logs = self.callbacks.on_replay_begin(logs)
+                logs['replay'] = replay_logs(t * per_trial + c)
+                logs = self.callbacks.on_replay_end(logs)
             logs['steps'] = int(steps_t[0]) if single else steps_t
             logs['trial_reward'] = float(rew_t[0]) if single else rew_t
-            if extra:
-                logs.update(extra(t))
             logs = self.callbacks.on_trial_end(logs)
 
     def _chunks(self, trials):

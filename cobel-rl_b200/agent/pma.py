@@ -81,7 +81,7 @@ class PMA(Agent):
             keep.append(par)
             _lib.check(_lib.lib().cobel_pma_run(p, launch_stream(st)))
             self._check_flags(res)
-            self._fire_trial_callbacks(res, self.current_trial)
+            self._fire_trial_callbacks(res, self.current_trial, (1, 1) if (learn and not no_replay) else (0, 0))
             self.current_trial += n_tr
             results.append(res)
         self.last_run = self._merge(results)

@@ -174,3 +174,39 @@ def test_grid_search_over_batched_dynaq_and_monitors(tmp_path):
     assert launches == [6 * 16] and len(fit) == 6
     # strongly exploring agents (epsilon 0.8) are the worst fit to a short-latency target
     assert max(fit, key=fit.get)[0] == 0.8
+
+
+def test_replay_callbacks_pma_and_sfma():
+    """on_replay_end receives the performed / reactivated experiences of every replay call
+    (agent/pma.py:112-135, agent/sfma.py:139-187) as padded batched tensors."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import PMA, SFMA
+    from cobel_rl_b200.memory import PMAMemory, SFMAMemory
+    from cobel_rl_b200.memory.utils.metrics import DR
+    from cobel_rl_b200.policy import EpsilonGreedy
+    world = make_world('walls5')
+    for kind in ('pma', 'sfma'):
+        got = []
+        stream = cb.BatchStream(3, seed=91, device='cuda:0')
+        env = Gridworld(world, rng=stream)
+        cbs = {'on_replay_end': [lambda logs: got.append((logs['trial'], logs['replay']))]}
+        if kind == 'pma':
+            mem = PMAMemory(world['sas'], EpsilonGreedy(0.1, rng=stream), rng=stream)
+            ag = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem, custom_callbacks=cbs)
+            per_trial = 2
+        else:
+            mem = SFMAMemory(DR(5, 5, world['sas'], 0.9, world['invalid_transitions']), 25, 4, rng=stream)
+            ag = SFMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem, custom_callbacks=cbs,
+                      rng=stream)
+            ag.start_replay = True
+            per_trial = 2
+        ag.record = True
+        res = ag.train(env, 4, 20, 8)
+        assert [t for t, _ in got] == [t for t in range(4) for _ in range(per_trial)]
+        flat = torch.cat([r['index'][0][r['index'][0] >= 0] for _, r in got])
+        n0 = int(res['n_replay'][0])
+        assert torch.equal(flat.int(), res['replay_idx'][0, :n0])
+        r = got[-1][1]
+        ok = r['index'] >= 0
+        assert torch.equal((r['action'] * 25 + r['state'])[ok], r['index'][ok])
