@@ -50,3 +50,16 @@ def test_no_fallback_without_library(monkeypatch):
     monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libcobel_b200.so')
     with pytest.raises(_lib.CobelError):
         _lib.lib()
+
+
+def test_integration_md_stub_matches_library(built, monkeypatch):
+    """The ctypes stub shown in INTEGRATION.md must mirror the header: execute its struct definitions
+    against the built library (its own cobel_sizeof assertion runs)."""
+    import __graft_entry__ as g
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    block = text.split('```python')[2].split('```')[0]
+    defs = block.split('def dynaq_train_b200')[0]
+    monkeypatch.setenv('COBEL_B200_LIB', g.LIB)
+    ns = {}
+    exec(compile(defs, 'INTEGRATION.md', 'exec'), ns)
+    assert ctypes.sizeof(ns['DynaQParams']) == built.cobel_sizeof(b'CobelDynaQParams')
