@@ -46,7 +46,7 @@ WORKLOADS = {
     'pma': dict(
         desc='C3: 16384 PMA agents/GPU, 10x10 gridworld with walls, 4 trials x <=100 steps, replay batch 32 at '
              'trial start and end',
-        metric='PMA replay updates/sec', unit='replay-updates/s', kernel='pma_kernel<4>',
+        metric='PMA replay updates/sec', unit='replay-updates/s', kernel='pma_main_kernel<4> + pma_sr_kernel<7>',
         agents_per_gpu=16384, trials=4, steps=100, batch=32, world='walls10', bytes_per_unit=23 * 400 + 8 * 100,
         unit_key='n_replay', cpu_trials=4),
     'sfma': dict(

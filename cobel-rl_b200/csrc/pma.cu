@@ -454,9 +454,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     for (int x = 0; x < per; ++x) { const int t = lane * per + x; if (t < S) poff[t] = nxt[x]; }
     if (lane == 0) poff[S] = N;
     __syncwarp();
-    // first iteration: every backup is stale
-    for (int i = lane; i < N; i += 32) util[i] = util_one(i);
-    int count = 0, last_seq = 0, ndst = 0;
+    int count = 0, last_seq = 0, ndst = -1;          // ndst < 0: first iteration, every backup is stale
     __syncwarp();
     for (int it = 0; it < B; ++it) {
       // ---- (1) extension of the current sequence (memory/pma.py:219-235) -------------------------
@@ -481,21 +479,26 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         }
       }
       // ---- (2) re-evaluate the backups that read a Q row changed by the previous update ----------
-      if (ndst > 0) {
+      // (one code site for the compact list and for the full pass keeps the loop body small:
+      //  the kernel was instruction-cache bound with three inlined copies of the gain evaluation)
+      if (ndst != 0) {
         int nd = 0;
-        for (int d = 0; d < ndst && nd <= MainSmem::kListCap; ++d) {
+        bool full = ndst < 0;
+        for (int d = 0; d < ndst && !full; ++d) {
           const int t = dst[d];
           const int p0 = poff[t], np = poff[t + 1] - p0;
-          if (nd + A + np <= MainSmem::kListCap)
+          if (nd + A + np <= MainSmem::kListCap) {
             for (int x = lane; x < A + np; x += 32) list[nd + x] = x < A ? (uint16_t)(x * S + t) : pitems[p0 + x - A];
-          nd += A + np;
+            nd += A + np;
+          } else {
+            full = true;
+          }
         }
         __syncwarp();
-        if (nd <= MainSmem::kListCap) {
-          for (int j0 = 0; j0 < nd; j0 += 32)
-            if (j0 + lane < nd) { const int i = list[j0 + lane]; util[i] = util_one(i); }
-        } else {
-          for (int i = lane; i < N; i += 32) util[i] = util_one(i);
+        const int total = full ? N : nd;
+        for (int j0 = 0; j0 < total; j0 += 32) {
+          const int j = j0 + lane;
+          if (j < total) { const int i = full ? j : list[j]; util[i] = util_one(i); }
         }
         __syncwarp();
       }
@@ -558,22 +561,29 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       double lmax = ninf;
       for (int i = lane; i < N; i += 32) { const double v = util[i]; lmax = v > lmax ? v : lmax; }
       const double umax = warp_max_f64(lmax);
-      // ties (flat-index order) and the certificate: gap to the largest utility below the maximum
+      // ties (flat-index order) and the certificate: gap to the largest utility below the maximum;
+      // lane c keeps the tie ballot of chunk c (N <= 1024), so the chosen tie is located without a third pass
       double l2 = ninf;
-      int ktot = 0;
-      for (int i0 = 0; i0 < N; i0 += 32) {
+      unsigned mytb = 0;
+      for (int i0 = 0, c = 0; i0 < N; i0 += 32, ++c) {
         const int i = i0 + lane;
         bool tie = false;
         if (i < N) { const double v = util[i]; tie = v == umax; if (v < umax && v > l2) l2 = v; }
-        ktot += __popc(__ballot_sync(kFull, tie));
+        const unsigned b = __ballot_sync(kFull, tie);
+        mytb = lane == c ? b : mytb;
       }
+      const int mycnt = __popc(mytb);
+      int incl = mycnt;                                  // inclusive scan of the per-chunk tie counts
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
+      const int ktot = __shfl_sync(kFull, incl, 31);
       const double u2 = warp_max_f64(l2);
       if (umax != 0.0 && u2 > -1e300) { const double gp = (umax - u2) / fabs(umax); min_gap = gp < min_gap ? gp : min_gap; }
       win.ensure(1, lane);
       const double u = win.next();
       // Generator.choice(p = ties / k): cdf_m = m-fold sequential sum of fl(1/k), normalised by cdf_k
       int pick = ktot - 1;
-      {
+      if (ktot > 1) {
         const double pk_ = xdiv(1.0, int_to_f64(ktot));
         double ck = 0.0;
         for (int m = 0; m < ktot; ++m) ck = xadd(ck, pk_);
@@ -583,15 +593,10 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
           if (xdiv(c, ck) > u) { pick = m; break; }
         }
       }
-      int chosen = -1;
-      for (int i0 = 0; i0 < N; i0 += 32) {
-        const int i = i0 + lane;
-        const bool tie = i < N && util[i] == umax;
-        const unsigned b = __ballot_sync(kFull, tie);
-        const int c = __popc(b);
-        if (pick < c) { chosen = i0 + __fns(b, 0, pick + 1); break; }
-        pick -= c;
-      }
+      // the chunk whose [incl - cnt, incl) range contains `pick`, then the pick-th set bit of its ballot
+      const unsigned owner = __ballot_sync(kFull, pick >= incl - mycnt && pick < incl);
+      const int oc = __ffs(owner) - 1;
+      const int chosen = oc * 32 + __shfl_sync(kFull, (int)__fns(mytb, 0, pick - (incl - mycnt) + 1), oc);
       if (ext >= 0) {
         __syncwarp();
         if (lane == 0) util[ext] = saved;
@@ -743,7 +748,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
 template <int A>
 int run(const CobelPMAParams& p, cudaStream_t st) {
   const int S = p.world.n_states;
-  COBEL_REQUIRE(S <= 160 && S * A <= 65535, COBEL_EUNSUPPORTED,
+  COBEL_REQUIRE(S <= 160 && S * A <= 1024, COBEL_EUNSUPPORTED,
                 "PMA kernels support at most 160 states (register-tiled S x S eliminations), got %d", S);
   const MainSmem so(S, A);
   const size_t sm_main = (size_t)kMainWarps * so.bytes;
