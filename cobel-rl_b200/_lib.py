@@ -153,6 +153,14 @@ def check(rc):
     raise CobelError(msg)
 
 
+def call(name, device, *args):
+    """Invoke an entry point with `device` as the current CUDA device (the library launches on the
+    current device; the stream passed in `args` must belong to it) and raise on a non-zero status."""
+    import torch
+    with torch.cuda.device(device):
+        check(getattr(lib(), name)(*args))
+
+
 def ptr(t):
     """Device address of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()

@@ -79,7 +79,7 @@ class DynaQ(Agent):
                                  self.M._terminals.data_ptr(), mptr, mstride, lr.data_ptr(), gm.data_ptr(),
                                  mlr.data_ptr(), n_tr, steps, batch_size, 1 if learn else 0,
                                  1 if no_replay else 0, 1 if self.episodic_replay else 0)
-            _lib.check(_lib.lib().cobel_dynaq_run(p, launch_stream(st)))
+            _lib.call('cobel_dynaq_run', st.device, p, launch_stream(st))
             self._check_flags(res)
             self._fire_trial_callbacks(res, self.current_trial)
             self.current_trial += n_tr

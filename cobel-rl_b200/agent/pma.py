@@ -79,7 +79,7 @@ class PMA(Agent):
                 1 if M.min_gain_mode == 'original' else 0, n_tr, steps, batch_size, 1 if no_replay else 0,
                 1 if learn else 0)
             keep.append(par)
-            _lib.check(_lib.lib().cobel_pma_run(p, launch_stream(st)))
+            _lib.call('cobel_pma_run', st.device, p, launch_stream(st))
             self._check_flags(res)
             self._fire_trial_callbacks(res, self.current_trial, (1, 1) if (learn and not no_replay) else (0, 0))
             self.current_trial += n_tr

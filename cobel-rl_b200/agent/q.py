@@ -99,7 +99,7 @@ class QAgent(Agent):
                              _lib.ptr(self._log) if learn else None, self._log.shape[1] if learn else 0,
                              self._log_len.data_ptr(), lr.data_ptr(), gm.data_ptr(), n_tr, steps,
                              batch_size if learn else 0, 1 if learn else 0)
-            _lib.check(_lib.lib().cobel_q_run(p, launch_stream(st)))
+            _lib.call('cobel_q_run', st.device, p, launch_stream(st))
             self._check_flags(res)
             self._fire_trial_callbacks(res, self.current_trial)
             self.current_trial += n_tr

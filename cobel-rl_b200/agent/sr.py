@@ -112,7 +112,7 @@ class SR(Agent):
                                          self._SRc.data_ptr(), self._rewards.data_ptr(), self._model.data_ptr(),
                                          self._visited.data_ptr(), self._n_visited.data_ptr(), mptr, lr.data_ptr(),
                                          gm.data_ptr(), self.max_visited, n_tr, steps, 1 if learn else 0)
-                _lib.check(_lib.lib().cobel_sr_compact_run(p, launch_stream(st)))
+                _lib.call('cobel_sr_compact_run', st.device, p, launch_stream(st))
                 if bool((res['flags'] & 16).any()):
                     raise _lib.CobelError('an agent visited more than max_visited=%d distinct states; raise max_visited '
                                           'or shorten the horizon' % self.max_visited)
@@ -120,7 +120,7 @@ class SR(Agent):
                 p = _lib.SRParams(st.n_agents, interface.c_world(), st.c_struct(), pol.c_struct(st, keep), tr,
                                   self._SR.data_ptr(), self._rewards.data_ptr(), self._model.data_ptr(), mptr, mstride,
                                   lr.data_ptr(), gm.data_ptr(), n_tr, steps, 1 if learn else 0, 0)
-                _lib.check(_lib.lib().cobel_sr_run(p, launch_stream(st)))
+                _lib.call('cobel_sr_run', st.device, p, launch_stream(st))
             self._check_flags(res)
             self._fire_trial_callbacks(res, self.current_trial)
             self.current_trial += n_tr

@@ -55,7 +55,7 @@ class BatchStream:
         """Consume the next ``n_draws`` uniforms of every agent -> ``[N, n_draws]`` tensor."""
         out = torch.empty((self.n_agents, n_draws), dtype=torch.float64, device=self.device)
         s = self.c_struct()
-        _lib.check(_lib.lib().cobel_stream_next(s, self.n_agents, n_draws, out.data_ptr(), cuda_stream(self.device)))
+        _lib.call('cobel_stream_next', self.device, s, self.n_agents, n_draws, out.data_ptr(), cuda_stream(self.device))
         return out
 
     def integers(self, n):

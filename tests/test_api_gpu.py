@@ -210,3 +210,24 @@ def test_replay_callbacks_pma_and_sfma():
         r = got[-1][1]
         ok = r['index'] >= 0
         assert torch.equal((r['action'] * 25 + r['state'])[ok], r['index'][ok])
+
+
+def test_non_current_device():
+    """Agents bound to a BatchStream on cuda:1 run there even while cuda:0 is torch's current device,
+    and give the same results as on cuda:0 (needs 2 GPUs)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.policy import EpsilonGreedy
+    out = []
+    for dev in ('cuda:0', 'cuda:1'):
+        stream = cb.BatchStream(8, seed=2, device=dev)
+        env = Gridworld(make_world('open5'), rng=stream)
+        ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream))
+        res = ag.train(env, 10, 30, 32)
+        torch.cuda.synchronize(dev)
+        assert ag.Q.device == torch.device(dev)
+        out.append((ag.Q.cpu(), res['trial_steps'].cpu()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
