@@ -231,3 +231,56 @@ def test_non_current_device():
         assert ag.Q.device == torch.device(dev)
         out.append((ag.Q.cpu(), res['trial_steps'].cpu()))
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+
+
+def test_unsupported_shapes_and_options_fail_loudly():
+    """Nothing silently diverges from the reference: unsupported shapes / options raise."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld, Topology
+    from cobel_rl_b200.agent import DynaQ, PMA, SFMA
+    from cobel_rl_b200.memory import PMAMemory, SFMAMemory
+    from cobel_rl_b200.memory.utils.metrics import Euclidean
+    from cobel_rl_b200.policy import EpsilonGreedy
+    from cobel_rl_b200.misc.gridworld_tools import make_open_field
+    stream = cb.BatchStream(2, seed=1, device='cuda:0')
+    # 5 neighbours per node: no kernel instantiation for A = 5
+    nodes = {str(i): {'id': str(i), 'pose': (float(i), 0., 0., 0., 0., 0.), 'terminal': i == 3, 'reward': float(i == 3),
+                      'neighbors': [str((i + d) % 4) for d in range(5)]} for i in range(4)}
+    env5 = Topology(nodes, rng=stream, discrete=True)
+    ag = DynaQ(env5.observation_space, env5.action_space, EpsilonGreedy(0.1, rng=stream))
+    with pytest.raises(NotImplementedError):
+        ag.train(env5, 2, 5, 4)
+    # PMA: the S x S successor representation must fit the register-tiled kernels (S <= 160)
+    world = make_open_field(13, 13, 0, 1)
+    stream = cb.BatchStream(2, seed=1, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = PMAMemory(world['sas'], EpsilonGreedy(0.1, rng=stream), rng=stream)
+    pma = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem)
+    with pytest.raises(NotImplementedError):
+        pma.train(env, 1, 5, 4)
+    mem.allow_loops = True
+    with pytest.raises(NotImplementedError):
+        pma.train(env, 1, 5, 4)
+    # SFMA: options of the reference that are not implemented
+    world = make_world('open5')
+    stream = cb.BatchStream(2, seed=1, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    smem = SFMAMemory(Euclidean(5, 5), 25, 4, rng=stream)
+    sfma = SFMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), smem, rng=stream)
+    sfma.dynamic = True
+    with pytest.raises(NotImplementedError):
+        sfma.train(env, 1, 5, 4)
+    sfma.dynamic = False
+    smem.reward_mod = True
+    with pytest.raises(NotImplementedError):
+        sfma.train(env, 1, 5, 4)
+    smem.reward_mod = False
+    sfma.train(env, 2, 10, 4)              # and the supported configuration runs (Euclidean metric)
+    # environment / agent mismatch and a CPU device are rejected
+    other = Gridworld(make_open_field(4, 4, 0, 1), rng=cb.BatchStream(2, seed=1, device='cuda:0'))
+    with pytest.raises(AssertionError):
+        sfma.train(other, 1, 5, 4)
+    from cobel_rl_b200 import _lib
+    cpu_stream = cb.BatchStream(2, device='cpu')
+    with pytest.raises(_lib.CobelError):
+        cpu_stream.next(1)
