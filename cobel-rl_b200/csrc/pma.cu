@@ -206,20 +206,24 @@ __device__ __forceinline__ void gth_stationary(const double* __restrict__ Tg, do
       for (int d = 16; d > 0; d >>= 1) ssum += shfl_f64_xor(ssum, d);
       if (!(ssum > 0.0)) { flags |= COBEL_FLAG_SINGULAR; ssum = 1.0; }
       const double inv = 1.0 / ssum;
+      // only rows / columns below k take part: with k = ty0 + 16 r0 these are the tile rows and
+      // columns 0..r0, a compile-time bound -- the work shrinks with k (S^3/3 instead of S^3)
       double rk[TILE];
 #pragma unroll
       for (int c = 0; c < TILE; ++c) {
-        const int j = tx + 16 * c;
-        rk[c] = j < k ? rowk[j] : 0.0;
+        if (c <= r0) { const int j = tx + 16 * c; rk[c] = j < k ? rowk[j] : 0.0; }
       }
 #pragma unroll
       for (int r = 0; r < TILE; ++r) {
-        const int i = ty + 16 * r;
-        const double f = i < k ? colk[i] * inv : 0.0;
+        if (r <= r0) {
+          const int i = ty + 16 * r;
+          const double f = i < k ? colk[i] * inv : 0.0;
 #pragma unroll
-        for (int c = 0; c < TILE; ++c) t.m[r][c] = fma(f, rk[c], t.m[r][c]);
-        // column k keeps the scaled entries P[i][k] / s for the back-substitution
-        if (tx == ty0 && i < k) t.m[r][r0] = f;
+          for (int c = 0; c < TILE; ++c)
+            if (c <= r0) t.m[r][c] = fma(f, rk[c], t.m[r][c]);
+          // column k keeps the scaled entries P[i][k] / s for the back-substitution
+          if (tx == ty0 && i < k) t.m[r][r0] = f;
+        }
       }
     }
   }
