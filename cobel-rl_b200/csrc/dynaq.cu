@@ -44,7 +44,9 @@ struct WorldSmem {      // byte offsets of the CTA-shared environment tables
   }
 };
 
-template <int A>
+// PLAIN = no optional trace buffers, no action mask, deterministic world: the common production case gets a
+// kernel without those per-step checks (the instruction count per step is what bounds this kernel).
+template <int A, bool PLAIN>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const __grid_constant__ CobelDynaQParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int S = p.world.n_states, K = p.world.n_starts, SA = S * A;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
   const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
-  const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
+  const uint8_t* amask = (!PLAIN && p.action_mask) ? p.action_mask + n * p.mask_agent_stride : nullptr;
   const int B = p.batch;
   const bool learn = p.learn != 0;
   const bool step_replay = learn && !p.no_replay && !p.episodic_replay;     // a batch of 0 is still a (draw-free) call
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
         rr = Mr[i];
         const uint16_t v = Mx[i];
         rs2 = v & 0x7FFF; rnt = v >> 15;
-        if (tr.replay_idx) {
+        if (!PLAIN && tr.replay_idx) {
           if (nrep + lane < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + lane] = i;
           else flags |= COBEL_FLAG_TRACE_OVERFLOW;
         }
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
       td_batch_level_parallel<A>(Q, wm, rm, S, lane, active, rs, ra, rr, rs2, rnt, lr, gamma);
       nrep += nb;
     }
-    if (tr.replay_len && lane == 0) {
+    if (!PLAIN && tr.replay_len && lane == 0) {
       if (ncalls < tr.replay_calls_cap) tr.replay_len[n * tr.replay_calls_cap + ncalls] = B;
       else flags |= COBEL_FLAG_TRACE_OVERFLOW;
     }
@@ -135,17 +137,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
       double row[A];
       load_row<A>(Q + s * A, row);
       uint32_t mask = (1u << A) - 1u;
-      if (amask) {
+      if (!PLAIN && amask) {
         mask = 0;
 #pragma unroll
         for (int a = 0; a < A; ++a) mask |= (amask[s * A + a] ? 1u : 0u) << a;
       }
       const int a = select_action_warp<A>(row, mask, pt, win.next(), lane);
-      const int s2 = p.world.tp_off ? stochastic_successor(p.world, s * A + a, win.next()) : succ_s[s * A + a];
+      const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : succ_s[s * A + a];
       const double r = rew_s[s2];
       const int end = term_s[s2];
       const int nt = 1 - end;
-      if (tr.step_sa && lane == 0) {
+      if (!PLAIN && tr.step_sa && lane == 0) {
         if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
@@ -209,9 +211,15 @@ int launch(const CobelDynaQParams& p, cudaStream_t st) {
   const size_t sm = (size_t)wo.bytes + (size_t)kWarpsPerCta * ao.bytes;
   COBEL_REQUIRE(sm <= 227 * 1024, COBEL_EUNSUPPORTED,
                 "Dyna-Q tables of %d states x %d actions do not fit in shared memory (%zu bytes per CTA)", S, A, sm);
-  COBEL_CUDA_OK(cudaFuncSetAttribute(dynaq_warp_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   const unsigned grid = (unsigned)((p.n_agents + kWarpsPerCta - 1) / kWarpsPerCta);
-  dynaq_warp_kernel<A><<<grid, kWarpsPerCta * 32, sm, st>>>(p);
+  const bool plain = !p.action_mask && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx && !p.trace.replay_len;
+  if (plain) {
+    COBEL_CUDA_OK(cudaFuncSetAttribute(dynaq_warp_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dynaq_warp_kernel<A, true><<<grid, kWarpsPerCta * 32, sm, st>>>(p);
+  } else {
+    COBEL_CUDA_OK(cudaFuncSetAttribute(dynaq_warp_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dynaq_warp_kernel<A, false><<<grid, kWarpsPerCta * 32, sm, st>>>(p);
+  }
   cobel_count_launch();
   COBEL_CUDA_OK(cudaGetLastError());
   return COBEL_OK;
