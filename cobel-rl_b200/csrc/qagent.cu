@@ -38,7 +38,8 @@ struct QWorldSmem {
   }
 };
 
-template <int A>
+// PLAIN = no optional trace buffers, deterministic world (see dynaq.cu)
+template <int A, bool PLAIN>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __grid_constant__ CobelQParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int S = p.world.n_states, K = p.world.n_starts, NK = p.n_keys;
@@ -91,12 +92,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __gr
       double row[A];
       load_row<A>(Q + ks * A, row);
       const int a = select_action_warp<A>(row, (1u << A) - 1u, pt, win.next(), lane);
-      const int s2 = p.world.tp_off ? stochastic_successor(p.world, s * A + a, win.next()) : succ_s[s * A + a];
+      const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : succ_s[s * A + a];
       const double r = rew_s[s2];
       const int end = term_s[s2];
       const int nt = 1 - end;
       const int ks2 = key_s[s2];
-      if (tr.step_sa && lane == 0) {
+      if (!PLAIN && tr.step_sa && lane == 0) {
         if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __gr
             const int i = draw_integer(u, (int)len);
             const LogRecord rec = log[i];
             es = rec.state; ea = rec.action; es2 = rec.next_state; ent = rec.nonterminal; er = rec.reward;
-            if (tr.replay_idx) {
+            if (!PLAIN && tr.replay_idx) {
               if (nrep + lane < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + lane] = i;
               else flags |= COBEL_FLAG_TRACE_OVERFLOW;
             }
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __gr
           td_batch_level_parallel<A>(Q, wm, rm, NK, lane, active, es, ea, er, es2, ent, lr, gamma);
           nrep += nb;
         }
-        if (tr.replay_len && lane == 0) {            // one replay call per step, also for batch 0 (q.py:216)
+        if (!PLAIN && tr.replay_len && lane == 0) {  // one replay call per step, also for batch 0 (q.py:216)
           if (ncalls < tr.replay_calls_cap) tr.replay_len[n * tr.replay_calls_cap + ncalls] = B;
           else flags |= COBEL_FLAG_TRACE_OVERFLOW;
         }
@@ -178,9 +179,15 @@ int launch(const CobelQParams& p, cudaStream_t st) {
   const size_t sm = (size_t)wo.bytes + (size_t)kWarpsPerCta * ao.bytes;
   COBEL_REQUIRE(sm <= 227 * 1024, COBEL_EUNSUPPORTED,
                 "QAgent tables (%d states, %d keys, %d actions) do not fit in shared memory", p.world.n_states, p.n_keys, A);
-  COBEL_CUDA_OK(cudaFuncSetAttribute(q_warp_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   const unsigned grid = (unsigned)((p.n_agents + kWarpsPerCta - 1) / kWarpsPerCta);
-  q_warp_kernel<A><<<grid, kWarpsPerCta * 32, sm, st>>>(p);
+  const bool plain = !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx && !p.trace.replay_len;
+  if (plain) {
+    COBEL_CUDA_OK(cudaFuncSetAttribute(q_warp_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    q_warp_kernel<A, true><<<grid, kWarpsPerCta * 32, sm, st>>>(p);
+  } else {
+    COBEL_CUDA_OK(cudaFuncSetAttribute(q_warp_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    q_warp_kernel<A, false><<<grid, kWarpsPerCta * 32, sm, st>>>(p);
+  }
   cobel_count_launch();
   COBEL_CUDA_OK(cudaGetLastError());
   return COBEL_OK;

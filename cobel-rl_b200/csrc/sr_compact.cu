@@ -84,7 +84,8 @@ struct CompactSmem {
   }
 };
 
-template <int A>
+// PLAIN = no optional trace buffers, no action mask, deterministic world (see dynaq.cu)
+template <int A, bool PLAIN>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) sr_compact_kernel(const __grid_constant__ CobelSRCompactParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int S = p.world.n_states, K = p.world.n_starts, Vmax = p.max_visited;
@@ -177,16 +178,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sr_compact_kernel(const __g
       // ---- action selection, environment step ----------------------------------------------------
       win.ensure(2, lane);
       uint32_t mask = (1u << A) - 1u;
-      if (p.action_mask) {
+      if (!PLAIN && p.action_mask) {
         mask = 0;
 #pragma unroll
         for (int a = 0; a < A; ++a) mask |= (p.action_mask[(size_t)s * A + a] ? 1u : 0u) << a;
       }
       const int a = select_action_warp<A>(row, mask, pt, win.next(), lane);
-      const int s2 = p.world.tp_off ? stochastic_successor(p.world, s * A + a, win.next()) : __ldg(p.world.succ + (size_t)s * A + a);
+      const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : __ldg(p.world.succ + (size_t)s * A + a);
       const double r = __ldg(p.world.reward + s2);
       const int end = __ldg(p.world.terminal + s2);
-      if (tr.step_sa && lane == 0) {
+      if (!PLAIN && tr.step_sa && lane == 0) {
         if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
@@ -241,9 +242,14 @@ int launch(const CobelSRCompactParams& p, cudaStream_t st) {
   const CompactSmem so(p.max_visited, A);
   const size_t sm = (size_t)kWarpsPerCta * so.bytes;
   COBEL_REQUIRE(sm <= 227 * 1024, COBEL_EUNSUPPORTED, "max_visited %d does not fit in shared memory", p.max_visited);
-  COBEL_CUDA_OK(cudaFuncSetAttribute(sr_compact_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   const unsigned grid = (unsigned)((p.n_agents + kWarpsPerCta - 1) / kWarpsPerCta);
-  sr_compact_kernel<A><<<grid, kWarpsPerCta * 32, sm, st>>>(p);
+  if (!p.action_mask && !p.world.tp_off && !p.trace.step_sa) {
+    COBEL_CUDA_OK(cudaFuncSetAttribute(sr_compact_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    sr_compact_kernel<A, true><<<grid, kWarpsPerCta * 32, sm, st>>>(p);
+  } else {
+    COBEL_CUDA_OK(cudaFuncSetAttribute(sr_compact_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    sr_compact_kernel<A, false><<<grid, kWarpsPerCta * 32, sm, st>>>(p);
+  }
   cobel_count_launch();
   COBEL_CUDA_OK(cudaGetLastError());
   return COBEL_OK;
