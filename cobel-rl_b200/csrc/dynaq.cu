@@ -44,8 +44,9 @@ struct WorldSmem {      // byte offsets of the CTA-shared environment tables
   }
 };
 
-// PLAIN = no optional trace buffers, no action mask, deterministic world: the common production case gets a
-// kernel without those per-step checks (the instruction count per step is what bounds this kernel).
+// PLAIN = the common production case (epsilon-greedy training with per-step replay, no optional trace buffers,
+// no action mask, deterministic world): a kernel without the per-step checks and the other policies' code
+// (the instruction count per step is what bounds this kernel).
 template <int A, bool PLAIN>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const __grid_constant__ CobelDynaQParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -87,9 +88,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
   const uint8_t* amask = (!PLAIN && p.action_mask) ? p.action_mask + n * p.mask_agent_stride : nullptr;
   const int B = p.batch;
-  const bool learn = p.learn != 0;
-  const bool step_replay = learn && !p.no_replay && !p.episodic_replay;     // a batch of 0 is still a (draw-free) call
-  const bool trial_replay = learn && !p.no_replay && p.episodic_replay;
+  const bool learn = PLAIN || p.learn != 0;
+  const bool step_replay = PLAIN || (learn && !p.no_replay && !p.episodic_replay);   // a batch of 0 is still a (draw-free) call
+  const bool trial_replay = !PLAIN && learn && !p.no_replay && p.episodic_replay;
   const CobelTrace& tr = p.trace;
   int64_t nsteps = 0, nrep = 0, ncalls = 0;
   int flags = 0;
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
 #pragma unroll
         for (int a = 0; a < A; ++a) mask |= (amask[s * A + a] ? 1u : 0u) << a;
       }
-      const int a = select_action_warp<A>(row, mask, pt, win.next(), lane);
+      const int a = select_action_warp<A, PLAIN ? COBEL_POLICY_EPS_GREEDY : -1>(row, mask, pt, win.next(), lane);
       const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : succ_s[s * A + a];
       const double r = rew_s[s2];
       const int end = term_s[s2];
@@ -212,7 +213,8 @@ int launch(const CobelDynaQParams& p, cudaStream_t st) {
   COBEL_REQUIRE(sm <= 227 * 1024, COBEL_EUNSUPPORTED,
                 "Dyna-Q tables of %d states x %d actions do not fit in shared memory (%zu bytes per CTA)", S, A, sm);
   const unsigned grid = (unsigned)((p.n_agents + kWarpsPerCta - 1) / kWarpsPerCta);
-  const bool plain = !p.action_mask && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx && !p.trace.replay_len;
+  const bool plain = !p.action_mask && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx && !p.trace.replay_len &&
+                     p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn && !p.no_replay && !p.episodic_replay;
   if (plain) {
     COBEL_CUDA_OK(cudaFuncSetAttribute(dynaq_warp_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dynaq_warp_kernel<A, true><<<grid, kWarpsPerCta * 32, sm, st>>>(p);

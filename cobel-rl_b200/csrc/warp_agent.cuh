@@ -124,8 +124,10 @@ struct PolicyTab {
   }
 };
 
-template <int A>
+// KIND >= 0 fixes the policy kind at compile time (drops the other kinds' code from the kernel)
+template <int A, int KIND = -1>
 COBEL_DEV int select_action_warp(const double (&v)[A], uint32_t mask, const PolicyTab& pt, double u, int lane) {
+  const int kind = KIND >= 0 ? KIND : pt.kind;
   constexpr uint32_t kAll = (1u << A) - 1u;
   double m;
   int nv = A;
@@ -138,7 +140,7 @@ COBEL_DEV int select_action_warp(const double (&v)[A], uint32_t mask, const Poli
     for (int a = 0; a < A; ++a) m = (mask >> a & 1u) ? xmax(m, v[a]) : m;
   }
   double p[A];
-  if (pt.kind == COBEL_POLICY_SOFTMAX) {
+  if (kind == COBEL_POLICY_SOFTMAX) {
     double sum = 0.0;
 #pragma unroll
     for (int a = 0; a < A; ++a) {
@@ -155,7 +157,7 @@ COBEL_DEV int select_action_warp(const double (&v)[A], uint32_t mask, const Poli
     ties &= mask;
     const int k = __popc(ties);
     const double tie = shfl_f64(pt.q_om, k - 1);                      // (1-eps)/k
-    if (pt.kind == COBEL_POLICY_EPS_GREEDY) {
+    if (kind == COBEL_POLICY_EPS_GREEDY) {
       const double base = shfl_f64(pt.q_par, nv - 1);                 // eps/n_valid
       const double top = xadd(base, tie), low = xadd(base, 0.0);
 #pragma unroll
