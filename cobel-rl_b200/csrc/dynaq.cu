@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   __syncwarp();
 
   for (int e = lane; e < S; e += 32) { wm[e] = 0; rm[e] = 0; }
-  DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
+  DrawWindowT<!PLAIN> win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
   const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
   const uint8_t* amask = (!PLAIN && p.action_mask) ? p.action_mask + n * p.mask_agent_stride : nullptr;
@@ -215,7 +215,7 @@ int launch(const CobelDynaQParams& p, cudaStream_t st) {
   const unsigned grid = (unsigned)((p.n_agents + kWarpsPerCta - 1) / kWarpsPerCta);
   const bool plain = !p.action_mask && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx && !p.trace.replay_len &&
                      p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn && !p.no_replay && !p.episodic_replay &&
-                     p.batch == 32;
+                     p.batch == 32 && !p.stream.user_stream;
   if (plain) {
     COBEL_CUDA_OK(cudaFuncSetAttribute(dynaq_warp_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dynaq_warp_kernel<A, true><<<grid, kWarpsPerCta * 32, sm, st>>>(p);

@@ -70,11 +70,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __gr
   for (int e = lane; e < NK; e += 32) { wm[e] = 0; rm[e] = 0; }
   __syncwarp();
 
-  DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
+  DrawWindowT<!PLAIN> win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
   const double lr = p.lr[n], gamma = p.gamma[n];
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
-  const int B = p.batch;
-  const bool learn = p.learn != 0;
+  const int B = PLAIN ? 32 : p.batch;
+  const bool learn = PLAIN || p.learn != 0;
   LogRecord* log = reinterpret_cast<LogRecord*>(p.log) + (size_t)n * p.log_cap;
   int64_t len = learn ? p.log_len[n] : 0;
   const CobelTrace& tr = p.trace;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __gr
       const int ks = key_s[s];
       double row[A];
       load_row<A>(Q + ks * A, row);
-      const int a = select_action_warp<A>(row, (1u << A) - 1u, pt, win.next(), lane);
+      const int a = select_action_warp<A, PLAIN ? COBEL_POLICY_EPS_GREEDY : -1>(row, (1u << A) - 1u, pt, win.next(), lane);
       const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : succ_s[s * A + a];
       const double r = rew_s[s2];
       const int end = term_s[s2];
@@ -180,7 +180,8 @@ int launch(const CobelQParams& p, cudaStream_t st) {
   COBEL_REQUIRE(sm <= 227 * 1024, COBEL_EUNSUPPORTED,
                 "QAgent tables (%d states, %d keys, %d actions) do not fit in shared memory", p.world.n_states, p.n_keys, A);
   const unsigned grid = (unsigned)((p.n_agents + kWarpsPerCta - 1) / kWarpsPerCta);
-  const bool plain = !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx && !p.trace.replay_len;
+  const bool plain = !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx && !p.trace.replay_len &&
+                     p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn && p.batch == 32 && !p.stream.user_stream;
   if (plain) {
     COBEL_CUDA_OK(cudaFuncSetAttribute(q_warp_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     q_warp_kernel<A, true><<<grid, kWarpsPerCta * 32, sm, st>>>(p);

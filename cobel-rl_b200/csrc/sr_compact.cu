@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sr_compact_kernel(const __g
   for (int e = lane; e < V * A; e += 32) model[e] = (uint16_t)p.model[(size_t)n * Vmax * A + e];
   __syncwarp();
 
-  DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
+  DrawWindowT<!PLAIN> win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
   const double lr = p.lr[n], gamma = p.gamma[n];
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
   const bool learn = p.learn != 0;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sr_compact_kernel(const __g
 #pragma unroll
         for (int a = 0; a < A; ++a) mask |= (p.action_mask[(size_t)s * A + a] ? 1u : 0u) << a;
       }
-      const int a = select_action_warp<A>(row, mask, pt, win.next(), lane);
+      const int a = select_action_warp<A, PLAIN ? COBEL_POLICY_EPS_GREEDY : -1>(row, mask, pt, win.next(), lane);
       const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : __ldg(p.world.succ + (size_t)s * A + a);
       const double r = __ldg(p.world.reward + s2);
       const int end = __ldg(p.world.terminal + s2);
@@ -243,7 +243,8 @@ int launch(const CobelSRCompactParams& p, cudaStream_t st) {
   const size_t sm = (size_t)kWarpsPerCta * so.bytes;
   COBEL_REQUIRE(sm <= 227 * 1024, COBEL_EUNSUPPORTED, "max_visited %d does not fit in shared memory", p.max_visited);
   const unsigned grid = (unsigned)((p.n_agents + kWarpsPerCta - 1) / kWarpsPerCta);
-  if (!p.action_mask && !p.world.tp_off && !p.trace.step_sa) {
+  if (!p.action_mask && !p.world.tp_off && !p.trace.step_sa && p.policy.kind == COBEL_POLICY_EPS_GREEDY &&
+      !p.stream.user_stream) {
     COBEL_CUDA_OK(cudaFuncSetAttribute(sr_compact_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     sr_compact_kernel<A, true><<<grid, kWarpsPerCta * 32, sm, st>>>(p);
   } else {

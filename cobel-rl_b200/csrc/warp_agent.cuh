@@ -63,7 +63,9 @@ COBEL_DEV int stochastic_successor(const CobelWorld& w, int sa, double u) {
 // holds the 64 consecutive draws starting at 2*b0.  One Philox block per lane per refill
 // instead of one per draw per agent.
 // ---------------------------------------------------------------------------
-struct DrawWindow {
+// MAYBE_USER = false compiles the user-stream ("stream from HBM") branches out.
+template <bool MAYBE_USER>
+struct DrawWindowT {
   uint64_t agent;
   uint32_t key0, key1;
   uint64_t base;          // stream index of window slot 0 (even)
@@ -76,7 +78,7 @@ struct DrawWindow {
   COBEL_DEV void init(const CobelStream& s, int64_t local_agent, uint64_t k) {
     agent = (uint64_t)(s.agent_id_base + local_agent);
     key0 = (uint32_t)s.seed; key1 = (uint32_t)(s.seed >> 32);
-    user = s.user_stream ? s.user_stream + local_agent * s.user_stream_len : nullptr;
+    user = (MAYBE_USER && s.user_stream) ? s.user_stream + local_agent * s.user_stream_len : nullptr;
     user_len = s.user_stream_len;
     base = k; off = 0; cap = 0;     // empty: the first ensure() refills
     ua = ub = 0.0;
@@ -84,7 +86,7 @@ struct DrawWindow {
   COBEL_DEV uint64_t position() const { return base + (uint64_t)off; }
   // make the next `need` draws available (need <= 63); warp-uniform
   COBEL_DEV void ensure(int need, int lane) {
-    if (user || off + need <= cap) return;
+    if ((MAYBE_USER && user) || off + need <= cap) return;
     const uint64_t k = base + (uint64_t)off;
     base = k & ~1ull; off = (int)(k & 1ull); cap = 64;
     const uint64_t b = (base >> 1) + lane;
@@ -94,7 +96,7 @@ struct DrawWindow {
   }
   // draw number (next + ahead), `ahead` may differ per lane; all 32 lanes must call
   COBEL_DEV double peek(int ahead) const {
-    if (user) {
+    if (MAYBE_USER && user) {
       const uint64_t kk = base + (uint64_t)(off + ahead);
       return kk < (uint64_t)user_len ? user[kk] : 0.0;
     }
@@ -105,6 +107,7 @@ struct DrawWindow {
   COBEL_DEV void advance(int n) { off += n; }
   COBEL_DEV double next() { const double u = peek(0); ++off; return u; }
 };
+using DrawWindow = DrawWindowT<true>;
 
 // ---------------------------------------------------------------------------
 // Warp-uniform action selection (all lanes hold the same v[], mask, u and get the same action).
