@@ -21,15 +21,16 @@ namespace {
 constexpr int kWarpsPerCta = 4;
 
 struct AgentSmem {      // byte offsets inside one agent's shared-memory block
-  int q, mr, mx, wm, rm, bytes;
-  __host__ __device__ AgentSmem(int S, int A) {
+  int q, mr, mx, wm, rm, ptab, bytes;
+  __host__ __device__ AgentSmem(int S, int A, bool eps_tab) {
     const int SA = S * A;
     q = 0;
     mr = q + SA * 8;
     wm = mr + SA * 8;
     rm = wm + S * 4;
     mx = rm + S * 4;
-    bytes = (mx + SA * 2 + 15) & ~15;
+    ptab = (mx + SA * 2 + 15) & ~15;
+    bytes = ptab + (eps_tab ? kEpsTabDoubles * 8 : 0);
   }
 };
 
@@ -53,7 +54,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   const int S = p.world.n_states, K = p.world.n_starts, SA = S * A;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const WorldSmem wo(S, A, K);
-  const AgentSmem ao(S, A);
+  constexpr bool kEpsTab = PLAIN && A <= 4;      // tie-pattern CDF table instead of per-step probabilities
+  const AgentSmem ao(S, A, kEpsTab);
 
   double* rew_s = reinterpret_cast<double*>(smem + wo.rew);
   int32_t* succ_s = reinterpret_cast<int32_t*>(smem + wo.succ);
@@ -86,6 +88,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   DrawWindowT<!PLAIN> win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
   const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
+  double* ptab = reinterpret_cast<double*>(blk + ao.ptab);
+  if constexpr (kEpsTab) eps_cdf_table_init<A>(ptab, pt, lane);
   const uint8_t* amask = (!PLAIN && p.action_mask) ? p.action_mask + n * p.mask_agent_stride : nullptr;
   const int B = PLAIN ? 32 : p.batch;           // the PLAIN kernel is built for the reference's default batch of 32
   const bool learn = PLAIN || p.learn != 0;
@@ -143,7 +147,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
 #pragma unroll
         for (int a = 0; a < A; ++a) mask |= (amask[s * A + a] ? 1u : 0u) << a;
       }
-      const int a = select_action_warp<A, PLAIN ? COBEL_POLICY_EPS_GREEDY : -1>(row, mask, pt, win.next(), lane);
+      int a;
+      if constexpr (kEpsTab) a = select_action_eps_tab<A>(row, ptab, win.next(), lane);
+      else a = select_action_warp<A, PLAIN ? COBEL_POLICY_EPS_GREEDY : -1>(row, mask, pt, win.next(), lane);
       const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : succ_s[s * A + a];
       const double r = rew_s[s2];
       const int end = term_s[s2];
@@ -208,14 +214,14 @@ int launch(const CobelDynaQParams& p, cudaStream_t st) {
   const int S = p.world.n_states, K = p.world.n_starts;
   COBEL_REQUIRE(S <= 0x7FFF, COBEL_EUNSUPPORTED, "Dyna-Q kernel supports at most 32767 states");
   const WorldSmem wo(S, A, K);
-  const AgentSmem ao(S, A);
+  const bool plain = !p.action_mask && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx && !p.trace.replay_len &&
+                     p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn && !p.no_replay && !p.episodic_replay &&
+                     p.batch == 32 && !p.stream.user_stream;
+  const AgentSmem ao(S, A, plain && A <= 4);
   const size_t sm = (size_t)wo.bytes + (size_t)kWarpsPerCta * ao.bytes;
   COBEL_REQUIRE(sm <= 227 * 1024, COBEL_EUNSUPPORTED,
                 "Dyna-Q tables of %d states x %d actions do not fit in shared memory (%zu bytes per CTA)", S, A, sm);
   const unsigned grid = (unsigned)((p.n_agents + kWarpsPerCta - 1) / kWarpsPerCta);
-  const bool plain = !p.action_mask && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx && !p.trace.replay_len &&
-                     p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn && !p.no_replay && !p.episodic_replay &&
-                     p.batch == 32 && !p.stream.user_stream;
   if (plain) {
     COBEL_CUDA_OK(cudaFuncSetAttribute(dynaq_warp_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dynaq_warp_kernel<A, true><<<grid, kWarpsPerCta * 32, sm, st>>>(p);

@@ -186,6 +186,47 @@ COBEL_DEV int select_action_warp(const double (&v)[A], uint32_t mask, const Poli
 }
 
 // ---------------------------------------------------------------------------
+// Epsilon-greedy over an unmasked row of A <= 4 actions: p[] (policy/greedy.py:60-88) depends only on
+// the tie pattern (which entries equal the row maximum), so the 2^A - 1 possible normalised CDFs
+// (policy/greedy.py:58) are tabulated once per agent -- with exactly the operations
+// select_action_warp performs per step -- and a step is a row max, A compares and one lookup.
+// `tab` is kEpsTabDoubles doubles of shared memory per agent: entry [pattern * 4 + a].
+// ---------------------------------------------------------------------------
+constexpr int kEpsTabDoubles = 64;
+template <int A>
+COBEL_DEV void eps_cdf_table_init(double* tab, const PolicyTab& pt, int lane) {
+  static_assert(A <= 4, "tie-pattern table is built for at most 4 actions");
+  const int pat = lane & ((1 << A) - 1);
+  const int k = __popc(pat);
+  const double base = shfl_f64(pt.q_par, A - 1);                    // eps/A
+  const double tie = shfl_f64(pt.q_om, k > 0 ? k - 1 : 0);          // (1-eps)/k
+  const double top = xadd(base, tie), low = xadd(base, 0.0);
+  double cdf[A];
+  double c = (pat & 1) ? top : low;
+  cdf[0] = c;
+#pragma unroll
+  for (int a = 1; a < A; ++a) { c = xadd(c, (pat >> a & 1) ? top : low); cdf[a] = c; }
+  if (c != 1.0) {
+#pragma unroll
+    for (int a = 0; a < A; ++a) cdf[a] = xdiv(cdf[a], c);
+  }
+  if (lane > 0 && lane < (1 << A)) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) tab[pat * 4 + a] = a < A ? cdf[a] : 2.0;
+  }
+  __syncwarp();
+}
+template <int A>
+COBEL_DEV int select_action_eps_tab(const double (&v)[A], const double* tab, double u, int lane) {
+  const double m = row_max<A>(v);
+  uint32_t ties = 0;
+#pragma unroll
+  for (int a = 0; a < A; ++a) ties |= (v[a] == m ? 1u : 0u) << a;
+  const double mine = tab[ties * 4 + (lane & 3)];
+  return __popc(__ballot_sync(kFull, lane < A - 1 && mine <= u));
+}
+
+// ---------------------------------------------------------------------------
 // Level-parallel execution of a batch of one-step TD updates that the reference applies
 // strictly in order (agent/dyna_q.py:329-330, agent/q.py:353-354).
 //
