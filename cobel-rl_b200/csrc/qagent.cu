@@ -25,9 +25,10 @@ struct __align__(16) LogRecord {
 static_assert(sizeof(LogRecord) == 16, "log record must be 16 bytes");
 
 struct QSmem {
-  int q, wm, rm, bytes;
+  int q, wm, rm, ptab, bytes;
   __host__ __device__ QSmem(int NK, int A) {
-    q = 0; wm = q + NK * A * 8; rm = wm + NK * 4; bytes = (rm + NK * 4 + 15) & ~15;
+    q = 0; wm = q + NK * A * 8; rm = wm + NK * 4; ptab = (rm + NK * 4 + 15) & ~15;
+    bytes = ptab + kEpsTabDoubles * 8;   // tie-pattern CDF table of the PLAIN kernel (warp_agent.cuh)
   }
 };
 struct QWorldSmem {
@@ -73,6 +74,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __gr
   DrawWindowT<!PLAIN> win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
   const double lr = p.lr[n], gamma = p.gamma[n];
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
+  constexpr bool kEpsTab = PLAIN && A <= 4;
+  double* ptab = reinterpret_cast<double*>(blk + ao.ptab);
+  if constexpr (kEpsTab) eps_cdf_table_init<A>(ptab, pt, lane);
   const int B = PLAIN ? 32 : p.batch;
   const bool learn = PLAIN || p.learn != 0;
   LogRecord* log = reinterpret_cast<LogRecord*>(p.log) + (size_t)n * p.log_cap;
@@ -91,7 +95,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __gr
       const int ks = key_s[s];
       double row[A];
       load_row<A>(Q + ks * A, row);
-      const int a = select_action_warp<A, PLAIN ? COBEL_POLICY_EPS_GREEDY : -1>(row, (1u << A) - 1u, pt, win.next(), lane);
+      int a;
+      if constexpr (kEpsTab) a = select_action_eps_tab<A>(row, ptab, win.next(), lane);
+      else a = select_action_warp<A, PLAIN ? COBEL_POLICY_EPS_GREEDY : -1>(row, (1u << A) - 1u, pt, win.next(), lane);
       const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : succ_s[s * A + a];
       const double r = rew_s[s2];
       const int end = term_s[s2];

@@ -71,7 +71,7 @@ __device__ __noinline__ double pairwise_sparse(const int* pos, const double* val
 }
 
 struct CompactSmem {
-  int rew, pos, val, vis, model, lidx, sidx, bytes;
+  int rew, pos, val, vis, model, lidx, sidx, ptab, bytes;
   __host__ __device__ CompactSmem(int Vmax, int A) {
     rew = 0;
     val = rew + Vmax * 8;              // products of one row, A rows
@@ -80,7 +80,8 @@ struct CompactSmem {
     sidx = lidx + Vmax * 4;
     vis = sidx + Vmax * 4;
     model = vis + Vmax * 4;
-    bytes = (model + Vmax * A * 2 + 15) & ~15;
+    ptab = (model + Vmax * A * 2 + 15) & ~15;
+    bytes = ptab + kEpsTabDoubles * 8;   // tie-pattern CDF table of the PLAIN kernel (warp_agent.cuh)
   }
 };
 
@@ -111,6 +112,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sr_compact_kernel(const __g
   DrawWindowT<!PLAIN> win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
   const double lr = p.lr[n], gamma = p.gamma[n];
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
+  constexpr bool kEpsTab = PLAIN && A <= 4;
+  double* ptab = reinterpret_cast<double*>(blk + so.ptab);
+  if constexpr (kEpsTab) eps_cdf_table_init<A>(ptab, pt, lane);
   const bool learn = p.learn != 0;
   const CobelTrace& tr = p.trace;
   int64_t nsteps = 0;
@@ -183,7 +187,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sr_compact_kernel(const __g
 #pragma unroll
         for (int a = 0; a < A; ++a) mask |= (p.action_mask[(size_t)s * A + a] ? 1u : 0u) << a;
       }
-      const int a = select_action_warp<A, PLAIN ? COBEL_POLICY_EPS_GREEDY : -1>(row, mask, pt, win.next(), lane);
+      int a;
+      if constexpr (kEpsTab) a = select_action_eps_tab<A>(row, ptab, win.next(), lane);
+      else a = select_action_warp<A, PLAIN ? COBEL_POLICY_EPS_GREEDY : -1>(row, mask, pt, win.next(), lane);
       const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : __ldg(p.world.succ + (size_t)s * A + a);
       const double r = __ldg(p.world.reward + s2);
       const int end = __ldg(p.world.terminal + s2);
