@@ -21,8 +21,9 @@ namespace {
 constexpr int kWarpsPerCta = 4;
 
 struct AgentSmem {      // byte offsets inside one agent's shared-memory block
-  int q, mr, mx, wm, rm, ptab, bytes;
-  __host__ __device__ AgentSmem(int S, int A, bool eps_tab) {
+  int q, mr, mx, wm, rm, ptab, draws, bytes;
+  __host__ __device__ AgentSmem(int S, int A, bool plain) {
+    const bool eps_tab = plain && A <= 4;
     const int SA = S * A;
     q = 0;
     mr = q + SA * 8;
@@ -30,7 +31,8 @@ struct AgentSmem {      // byte offsets inside one agent's shared-memory block
     rm = wm + S * 4;
     mx = rm + S * 4;
     ptab = (mx + SA * 2 + 15) & ~15;
-    bytes = ptab + (eps_tab ? kEpsTabDoubles * 8 : 0);
+    draws = ptab + (eps_tab ? kEpsTabDoubles * 8 : 0);
+    bytes = draws + (plain ? kSmemDraws * 8 : 0);
   }
 };
 
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const WorldSmem wo(S, A, K);
   constexpr bool kEpsTab = PLAIN && A <= 4;      // tie-pattern CDF table instead of per-step probabilities
-  const AgentSmem ao(S, A, kEpsTab);
+  const AgentSmem ao(S, A, PLAIN);
 
   double* rew_s = reinterpret_cast<double*>(smem + wo.rew);
   int32_t* succ_s = reinterpret_cast<int32_t*>(smem + wo.succ);
@@ -85,7 +87,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   __syncwarp();
 
   for (int e = lane; e < S; e += 32) { wm[e] = 0; rm[e] = 0; }
-  DrawWindowT<!PLAIN> win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
+  typename WindowFor<PLAIN>::type win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
+  win.attach(reinterpret_cast<double*>(blk + ao.draws));
   const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
   double* ptab = reinterpret_cast<double*>(blk + ao.ptab);
@@ -217,7 +220,7 @@ int launch(const CobelDynaQParams& p, cudaStream_t st) {
   const bool plain = !p.action_mask && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx && !p.trace.replay_len &&
                      p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn && !p.no_replay && !p.episodic_replay &&
                      p.batch == 32 && !p.stream.user_stream;
-  const AgentSmem ao(S, A, plain && A <= 4);
+  const AgentSmem ao(S, A, plain);
   const size_t sm = (size_t)wo.bytes + (size_t)kWarpsPerCta * ao.bytes;
   COBEL_REQUIRE(sm <= 227 * 1024, COBEL_EUNSUPPORTED,
                 "Dyna-Q tables of %d states x %d actions do not fit in shared memory (%zu bytes per CTA)", S, A, sm);

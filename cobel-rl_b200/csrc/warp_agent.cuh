@@ -106,8 +106,52 @@ struct DrawWindowT {
   }
   COBEL_DEV void advance(int n) { off += n; }
   COBEL_DEV double next() { const double u = peek(0); ++off; return u; }
+  COBEL_DEV void attach(double*) {}
 };
 using DrawWindow = DrawWindowT<true>;
+
+// ---------------------------------------------------------------------------
+// SmemDrawWindow: the same interface over a window of kSmemDraws draws in shared memory (the PLAIN
+// kernels).  A refill costs one Philox block per lane per 64 draws whatever is consumed, and a Dyna-Q
+// step consumes 34: a 64-draw window serves one step per refill (53 % of the generated draws used), a
+// 256-draw window seven (93 %); reading a draw is one LDS.64 instead of four shuffles.
+// ---------------------------------------------------------------------------
+constexpr int kSmemDraws = 256;
+struct SmemDrawWindow {
+  uint64_t agent;
+  uint32_t key0, key1;
+  uint64_t base;          // stream index of buf[0] (even)
+  int off;                // buf slot of the next draw: k = base + off
+  int cap;                // slots filled (0 = empty)
+  double* buf;            // [kSmemDraws], 16-byte aligned, this agent's
+
+  COBEL_DEV void attach(double* b) { buf = b; }
+  COBEL_DEV void init(const CobelStream& s, int64_t local_agent, uint64_t k) {
+    agent = (uint64_t)(s.agent_id_base + local_agent);
+    key0 = (uint32_t)s.seed; key1 = (uint32_t)(s.seed >> 32);
+    base = k; off = 0; cap = 0;
+  }
+  COBEL_DEV uint64_t position() const { return base + (uint64_t)off; }
+  COBEL_DEV void ensure(int need, int lane) {
+    if (off + need <= cap) return;
+    const uint64_t k = base + (uint64_t)off;
+    base = k & ~1ull; off = (int)(k & 1ull); cap = kSmemDraws;
+    __syncwarp();                                   // every lane has read what it needed of the old window
+#pragma unroll
+    for (int j = 0; j < kSmemDraws / 64; ++j) {
+      const uint64_t b = (base >> 1) + (uint64_t)(j * 32 + lane);
+      uint32_t o[4];
+      philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)agent, (uint32_t)(agent >> 32), key0, key1, o);
+      reinterpret_cast<double2*>(buf)[j * 32 + lane] = make_double2(u53(o[0], o[1]), u53(o[2], o[3]));
+    }
+    __syncwarp();
+  }
+  COBEL_DEV double peek(int ahead) const { return buf[off + ahead]; }
+  COBEL_DEV void advance(int n) { off += n; }
+  COBEL_DEV double next() { return buf[off++]; }
+};
+template <bool PLAIN> struct WindowFor { using type = DrawWindowT<true>; };
+template <> struct WindowFor<true> { using type = SmemDrawWindow; };
 
 // ---------------------------------------------------------------------------
 // Warp-uniform action selection (all lanes hold the same v[], mask, u and get the same action).
