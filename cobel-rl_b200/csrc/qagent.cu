@@ -25,10 +25,11 @@ struct __align__(16) LogRecord {
 static_assert(sizeof(LogRecord) == 16, "log record must be 16 bytes");
 
 struct QSmem {
-  int q, wm, rm, ptab, bytes;
+  int q, wm, rm, ptab, draws, bytes;
   __host__ __device__ QSmem(int NK, int A) {
     q = 0; wm = q + NK * A * 8; rm = wm + NK * 4; ptab = (rm + NK * 4 + 15) & ~15;
-    bytes = ptab + kEpsTabDoubles * 8;   // tie-pattern CDF table of the PLAIN kernel (warp_agent.cuh)
+    draws = ptab + kEpsTabDoubles * 8;   // tie-pattern CDF table and stream window of the PLAIN kernel (warp_agent.cuh)
+    bytes = draws + kSmemDraws * 8;
   }
 };
 struct QWorldSmem {
@@ -71,7 +72,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __gr
   for (int e = lane; e < NK; e += 32) { wm[e] = 0; rm[e] = 0; }
   __syncwarp();
 
-  DrawWindowT<!PLAIN> win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
+  typename WindowFor<PLAIN>::type win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
+  win.attach(reinterpret_cast<double*>(blk + ao.draws));
   const double lr = p.lr[n], gamma = p.gamma[n];
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
   constexpr bool kEpsTab = PLAIN && A <= 4;

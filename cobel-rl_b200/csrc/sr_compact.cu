@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sr_compact_kernel(const __g
   for (int e = lane; e < V * A; e += 32) model[e] = (uint16_t)p.model[(size_t)n * Vmax * A + e];
   __syncwarp();
 
+  // two draws per step: the 64-draw register window wastes nothing here (a shared-memory window measured 10 % slower)
   DrawWindowT<!PLAIN> win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
   const double lr = p.lr[n], gamma = p.gamma[n];
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);

@@ -117,13 +117,14 @@ using DrawWindow = DrawWindowT<true>;
 // 256-draw window seven (93 %); reading a draw is one LDS.64 instead of four shuffles.
 // ---------------------------------------------------------------------------
 constexpr int kSmemDraws = 256;
-struct SmemDrawWindow {
+template <int NDRAWS>
+struct SmemDrawWindowT {
   uint64_t agent;
   uint32_t key0, key1;
   uint64_t base;          // stream index of buf[0] (even)
   int off;                // buf slot of the next draw: k = base + off
   int cap;                // slots filled (0 = empty)
-  double* buf;            // [kSmemDraws], 16-byte aligned, this agent's
+  double* buf;            // [NDRAWS], 16-byte aligned, this agent's
 
   COBEL_DEV void attach(double* b) { buf = b; }
   COBEL_DEV void init(const CobelStream& s, int64_t local_agent, uint64_t k) {
@@ -135,10 +136,10 @@ struct SmemDrawWindow {
   COBEL_DEV void ensure(int need, int lane) {
     if (off + need <= cap) return;
     const uint64_t k = base + (uint64_t)off;
-    base = k & ~1ull; off = (int)(k & 1ull); cap = kSmemDraws;
+    base = k & ~1ull; off = (int)(k & 1ull); cap = NDRAWS;
     __syncwarp();                                   // every lane has read what it needed of the old window
 #pragma unroll
-    for (int j = 0; j < kSmemDraws / 64; ++j) {
+    for (int j = 0; j < NDRAWS / 64; ++j) {
       const uint64_t b = (base >> 1) + (uint64_t)(j * 32 + lane);
       uint32_t o[4];
       philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)agent, (uint32_t)(agent >> 32), key0, key1, o);
@@ -150,8 +151,9 @@ struct SmemDrawWindow {
   COBEL_DEV void advance(int n) { off += n; }
   COBEL_DEV double next() { return buf[off++]; }
 };
-template <bool PLAIN> struct WindowFor { using type = DrawWindowT<true>; };
-template <> struct WindowFor<true> { using type = SmemDrawWindow; };
+using SmemDrawWindow = SmemDrawWindowT<kSmemDraws>;
+template <bool PLAIN, int NDRAWS = kSmemDraws> struct WindowFor { using type = DrawWindowT<true>; };
+template <int NDRAWS> struct WindowFor<true, NDRAWS> { using type = SmemDrawWindowT<NDRAWS>; };
 
 // ---------------------------------------------------------------------------
 // Warp-uniform action selection (all lanes hold the same v[], mask, u and get the same action).
