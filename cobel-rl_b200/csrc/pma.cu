@@ -41,8 +41,17 @@ constexpr int kMaxSeq = 64;          // longest n-step sequence (replay batch) s
 
 // Policy probabilities for one Q row (thread-local): policy/greedy.py:60-88,117-147, policy/softmax.py:60-88.
 // qpar[n-1] = par/n and qom[n-1] = (1-par)/n are the cached quotients.
+// t[idx] by a select chain: a dynamically indexed register array would live in local memory
 template <int A>
-COBEL_DEV void probs_row(const double (&v)[A], uint32_t mask, int kind, double par, const double* qpar, const double* qom,
+COBEL_DEV double pick(const double (&t)[A], int idx) {
+  double v = t[0];
+#pragma unroll
+  for (int a = 1; a < A; ++a) v = idx == a ? t[a] : v;
+  return v;
+}
+
+template <int A>
+COBEL_DEV void probs_row(const double (&v)[A], uint32_t mask, int kind, double par, const double (&qpar)[A], const double (&qom)[A],
                          double (&p)[A]) {
   double m = -__longlong_as_double(0x7FF0000000000000ll);
 #pragma unroll
@@ -65,14 +74,14 @@ COBEL_DEV void probs_row(const double (&v)[A], uint32_t mask, int kind, double p
   for (int a = 0; a < A; ++a) ties |= (v[a] == m ? 1u : 0u) << a;
   ties &= mask;
   const int k = __popc(ties);
-  const double tie = qom[k - 1];
+  const double tie = pick<A>(qom, k - 1);
   double top, low;
   if (kind == COBEL_POLICY_EPS_GREEDY) {
-    const double base = qpar[nv - 1];
+    const double base = pick<A>(qpar, nv - 1);
     top = xadd(base, tie); low = xadd(base, 0.0);
   } else {
     const int d = nv - k > 1 ? nv - k : 1;
-    top = xadd(tie, 0.0); low = xadd(0.0, qpar[d - 1]);
+    top = xadd(tie, 0.0); low = xadd(0.0, pick<A>(qpar, d - 1));
   }
 #pragma unroll
   for (int a = 0; a < A; ++a) p[a] = (mask >> a & 1u) ? ((ties >> a & 1u) ? top : low) : 0.0;
@@ -315,7 +324,10 @@ struct MainPhase {
   int n_trials;         // trials run by this launch (0 or 1 when replays are enabled)
 };
 
-template <int A>
+// PLAIN = epsilon-greedy agent and memory policies, training with replay, deterministic world, no optional
+// trace buffers, generated stream: the other policies' code (fp64 exp) and the per-step checks are compiled out
+// (the kernel is instruction-fetch bound: profiles/r1_pma_v3.txt).
+template <int A, bool PLAIN>
 __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __grid_constant__ CobelPMAParams p,
                                                                       const __grid_constant__ MainPhase ph) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -338,6 +350,12 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   uint16_t* dst = reinterpret_cast<uint16_t*>(blk + so.dst);   // states whose Q row changed in the last update
   uint8_t* mbits = blk + so.mbits;                             // [s] valid-action bits (all ones if unmasked)
   constexpr int kSt = 0x1FFF, kUm = 0x2000;
+  // flat backup index i = a*S + s (the reference's order, memory/pma.py:205) -> a, s, s*A + a without integer
+  // division: i < 1024 and S <= 160, so (i * ceil(2^20 / S)) >> 20 == i / S exactly
+  const uint32_t magicS = ((1u << 20) + (uint32_t)S - 1u) / (uint32_t)S;
+  auto act_of = [&](int i) -> int { return (int)(((uint32_t)i * magicS) >> 20); };
+  auto st_of = [&](int i) -> int { return i - act_of(i) * S; };
+  auto sa_of = [&](int i) -> int { const int a_ = act_of(i); return (i - a_ * S) * A + a_; };
 
   const size_t g0 = (size_t)n * N;
   double* Tg = p.T + (size_t)n * S * S;
@@ -359,7 +377,8 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   }
   const double* powsr = p.pow_gamma_sr + n * p.pow_stride;     // float(M.gamma) ** k
   const double* powq = p.pow_gamma_q + n * p.pow_stride;       // float(M.gamma_q) ** k
-  const int mkind = p.mem_policy.kind;
+  constexpr int kPol = PLAIN ? COBEL_POLICY_EPS_GREEDY : -1;
+  const int mkind = PLAIN ? COBEL_POLICY_EPS_GREEDY : p.mem_policy.kind;
   const double mpar = p.mem_policy.param[n];
   // cached quotients par/n and (1-par)/n of the memory policy (n = 1..A), every lane holds all of them
   double qpar[A], qom[A];
@@ -372,22 +391,22 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   int64_t nsteps = ph.init_carry ? 0 : carry[1], nrep = ph.init_carry ? 0 : carry[2], ncalls = ph.init_carry ? 0 : carry[3];
   const int64_t nsteps0 = nsteps, nrep0 = nrep;
 
-  DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
+  DrawWindowT<!PLAIN> win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
   const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
   const double lrq = p.lr_q[n], gq = p.gamma_q[n];
   const double min_gain = p.min_gain;
-  const bool original = p.min_gain_original != 0;
+  const bool original = !PLAIN && p.min_gain_original != 0;
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
   PolicyTab mpt; mpt.init(mkind, mpar, lane);
-  const bool learn = p.learn != 0;
-  const bool do_replay = learn && !p.no_replay;
+  const bool learn = PLAIN || p.learn != 0;
+  const bool do_replay = PLAIN || (learn && !p.no_replay);
   const CobelTrace& tr = p.trace;
   int flags = 0;
   double min_gap = __longlong_as_double(0x7FF0000000000000ll);
 
   // gain of the one-step backup i = (a, s): PMAMemory.compute_gain_batch, memory/pma.py:333-386
   auto gain_one = [&](int i) -> double {
-    const int a = i / S, s = i - a * S;
+    const int a = act_of(i), s = i - a * S;
     double q[A], qn[A], po[A], pn[A], t[A];
     load_row<A>(Q + s * A, q);
     const uint16_t pk = Pk[s * A + a];
@@ -428,7 +447,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
 
   // utility of the one-step backup i: gain * need * update_mask (memory/pma.py:247-249)
   auto util_one = [&](int i) -> double {
-    const int a = i / S, s = i - a * S;
+    const int a = act_of(i), s = i - a * S;
     return xmul(xmul(gain_one(i), need[s]), (Pk[s * A + a] & kUm) ? 1.0 : 0.0);
   };
 
@@ -451,11 +470,12 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     }
     __syncwarp();
     // poff[t+1] now holds the start of group t; shift so that poff[t] = start, poff[S] = N
-    int nxt[6];
-    const int per = (S + 32) / 32;                  // entries handled per lane (S <= 160 -> per <= 6)
-    for (int x = 0; x < per; ++x) { const int t = lane * per + x; nxt[x] = t < S ? poff[t + 1] : 0; }
+    int nxt[6];                                     // S <= 160: at most 6 entries per lane
+#pragma unroll
+    for (int x = 0; x < 6; ++x) { const int t = lane + 32 * x; nxt[x] = t < S ? poff[t + 1] : 0; }
     __syncwarp();
-    for (int x = 0; x < per; ++x) { const int t = lane * per + x; if (t < S) poff[t] = nxt[x]; }
+#pragma unroll
+    for (int x = 0; x < 6; ++x) { const int t = lane + 32 * x; if (t < S) poff[t] = nxt[x]; }
     if (lane == 0) poff[S] = N;
     __syncwarp();
     int count = 0, last_seq = 0, ndst = -1;          // ndst < 0: first iteration, every backup is stale
@@ -465,15 +485,15 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       int ext = -1, clen = 0;
       if (count > 0) {
         const int lp = perf[count - 1];
-        ext = Pk[(lp % S) * A + lp / S] & kSt;                          // next_state of the last update
+        ext = Pk[sa_of(lp)] & kSt;                          // next_state of the last update
         bool loop = false;
-        for (int j = last_seq + lane; j < count; j += 32) loop |= (perf[j] % S) == ext;
+        for (int j = last_seq + lane; j < count; j += 32) loop |= st_of(perf[j]) == ext;
         loop = __any_sync(kFull, loop);
         if (!loop) {
           win.ensure(2, lane);
           double row[A];
           load_row<A>(Q + ext * A, row);
-          const int ea = select_action_warp<A>(row, mbits[ext], mpt, win.next(), lane);
+          const int ea = select_action_warp<A, kPol>(row, mbits[ext], mpt, win.next(), lane);
           ext += ea * S;
           clen = count - last_seq + 1;
           for (int j = lane; j < clen - 1; j += 32) seq[j] = perf[last_seq + j];
@@ -511,7 +531,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       if (ext >= 0) {
         const int nseq = clen > 0 ? clen : 1;
         const int lastI = seq[nseq - 1];
-        const uint16_t lpk = Pk[(lastI % S) * A + lastI / S];
+        const uint16_t lpk = Pk[sa_of(lastI)];
         double lrow[A];
         load_row<A>(Q + (lpk & kSt) * A, lrow);
         const double fv = xmul(row_max<A>(lrow), (lpk >> 15) ? 1.0 : 0.0);
@@ -521,7 +541,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
           double sg = 0.0;
           if (j < nseq) {
             const int i = seq[j];
-            const int a = i / S, s = i - a * S;
+            const int a = act_of(i), s = i - a * S;
             double q[A], qn[A], pb[A], pa[A], t[A];
             load_row<A>(Q + s * A, q);
             const uint32_t mb = mbits[s];
@@ -529,7 +549,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
             double r = 0.0;
             for (int f = 0; f < nseq - j; ++f) {
               const int k = seq[j + f];
-              r = xadd(r, xmul(Mr[(k % S) * A + k / S], powsr[f]));
+              r = xadd(r, xmul(Mr[sa_of(k)], powsr[f]));
             }
             const double target = xadd(r, xmul(fv, powq[nseq - j]));
 #pragma unroll
@@ -555,25 +575,30 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       // n-step gain overrides the one-step entry `ext` for this iteration only
       double saved = 0.0;
       if (ext >= 0) {
-        const int ea = ext / S, es = ext - ea * S;
+        const int ea = act_of(ext), es = ext - ea * S;
         saved = util[ext];
         __syncwarp();
         if (lane == 0) util[ext] = xmul(xmul(gext, need[es]), (Pk[es * A + ea] & kUm) ? 1.0 : 0.0);
         __syncwarp();
       }
       const double ninf = -__longlong_as_double(0x7FF0000000000000ll);
-      double lmax = ninf;
-      for (int i = lane; i < N; i += 32) { const double v = util[i]; lmax = v > lmax ? v : lmax; }
+      // one pass: per-lane maximum, its tie mask over the lane's entries (bit c = entry lane + 32 c) and the lane's
+      // second-largest distinct value; then the warp maximum decides which lanes' masks count
+      double lmax = ninf, l2 = ninf;
+      unsigned tm = 0;
+      for (int i = lane, c = 0; i < N; i += 32, ++c) {
+        const double v = util[i];
+        if (v > lmax) { l2 = lmax; lmax = v; tm = 1u << c; }
+        else if (v == lmax) tm |= 1u << c;
+        else if (v > l2) l2 = v;
+      }
       const double umax = warp_max_f64(lmax);
-      // ties (flat-index order) and the certificate: gap to the largest utility below the maximum;
-      // lane c keeps the tie ballot of chunk c (N <= 1024), so the chosen tie is located without a third pass
-      double l2 = ninf;
+      if (lmax != umax) { tm = 0; l2 = lmax; }
+      // ties in flat-index order: lane c keeps the tie ballot of chunk c (N <= 1024); the certificate is the gap
+      // to the largest utility below the maximum
       unsigned mytb = 0;
-      for (int i0 = 0, c = 0; i0 < N; i0 += 32, ++c) {
-        const int i = i0 + lane;
-        bool tie = false;
-        if (i < N) { const double v = util[i]; tie = v == umax; if (v < umax && v > l2) l2 = v; }
-        const unsigned b = __ballot_sync(kFull, tie);
+      for (int c = 0; c * 32 < N; ++c) {
+        const unsigned b = __ballot_sync(kFull, (tm >> c & 1u) != 0);
         mytb = lane == c ? b : mytb;
       }
       const int mycnt = __popc(mytb);
@@ -612,14 +637,14 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         if (!use_seq && lane == 0) seq[0] = (uint16_t)chosen;
         __syncwarp();
         const int lastI = seq[nseq - 1];
-        const uint16_t lpk = Pk[(lastI % S) * A + lastI / S];
+        const uint16_t lpk = Pk[sa_of(lastI)];
         double lrow[A];
         load_row<A>(Q + (lpk & kSt) * A, lrow);
         const double fv = xmul(row_max<A>(lrow), (lpk >> 15) ? 1.0 : 0.0);
         bool ok = true;                               // n >= 2: every transition must be non-terminal & experienced
         if (nseq >= 2) {
           bool bad = false;
-          for (int j = lane; j < nseq; j += 32) { const int k = seq[j]; bad |= (Pk[(k % S) * A + k / S] >> 15) == 0; }
+          for (int j = lane; j < nseq; j += 32) { const int k = seq[j]; bad |= (Pk[sa_of(k)] >> 15) == 0; }
           ok = !__any_sync(kFull, bad);
         }
         __syncwarp();
@@ -627,11 +652,11 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         if (ok) {
           for (int j = lane; j < nseq; j += 32) {
             const int i = seq[j];
-            const int a = i / S, s = i - a * S;
+            const int a = act_of(i), s = i - a * S;
             double r = 0.0;
             for (int f = 0; f < nseq - j; ++f) {
               const int k = seq[j + f];
-              r = xadd(r, xmul(Mr[(k % S) * A + k / S], powq[f]));
+              r = xadd(r, xmul(Mr[sa_of(k)], powq[f]));
             }
             double td = xadd(r, xmul(fv, powq[nseq - j]));
             const double q = Q[s * A + a];
@@ -647,12 +672,12 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         __syncwarp();
       }
     }
-    if (tr.replay_idx)
+    if (!PLAIN && tr.replay_idx)
       for (int j = lane; j < count; j += 32) {
         if (nrep + j < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + j] = perf[j];
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
-    if (tr.replay_len && lane == 0) {
+    if (!PLAIN && tr.replay_len && lane == 0) {
       if (ncalls < tr.replay_calls_cap) tr.replay_len[n * tr.replay_calls_cap + ncalls] = count;
       else flags |= COBEL_FLAG_TRACE_OVERFLOW;
     }
@@ -680,14 +705,18 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     int step = 0, last = -1;
     for (;; ++step) {
       win.ensure(2, lane);
+      // T[s] is updated at the end of the step (M.store): issue its HBM loads now, behind the action selection
+      double trow[5];                                  // S <= 160: at most 5 entries per lane
+#pragma unroll
+      for (int x = 0; x < 5; ++x) { const int j = lane + 32 * x; trow[x] = (learn && j < S) ? Tg[(size_t)s * S + j] : 0.0; }
       double row[A];
       load_row<A>(Q + s * A, row);
-      const int a = select_action_warp<A>(row, mbits[s], pt, win.next(), lane);
-      const int s2 = p.world.tp_off ? stochastic_successor(p.world, s * A + a, win.next()) : __ldg(p.world.succ + s * A + a);
+      const int a = select_action_warp<A, kPol>(row, mbits[s], pt, win.next(), lane);
+      const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : __ldg(p.world.succ + s * A + a);
       const double r = __ldg(p.world.reward + s2);
       const int end = __ldg(p.world.terminal + s2);
       const int nt = 1 - end;
-      if (tr.step_sa && lane == 0) {
+      if (!PLAIN && tr.step_sa && lane == 0) {
         if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
@@ -704,9 +733,10 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         const double qn = xadd(q, xmul(lr, td));
         const double m0 = Mr[s * A + a];
         const double m1 = xadd(m0, xmul(mlr, xsub(r, m0)));
-        for (int j = lane; j < S; j += 32) {           // T[s] += 0.9 * (onehot(s') - T[s])
-          const double t0 = Tg[(size_t)s * S + j];
-          Tg[(size_t)s * S + j] = xadd(t0, xmul(p.lr_T, xsub(j == s2 ? 1.0 : 0.0, t0)));
+#pragma unroll
+        for (int x = 0; x < 5; ++x) {                  // T[s] += lr_T * (onehot(s') - T[s]), memory/pma.py:162-165
+          const int j = lane + 32 * x;
+          if (j < S) Tg[(size_t)s * S + j] = xadd(trow[x], xmul(p.lr_T, xsub(j == s2 ? 1.0 : 0.0, trow[x])));
         }
         __syncwarp();
         if (lane == 0) {
@@ -757,14 +787,19 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
   const MainSmem so(S, A);
   const size_t sm_main = (size_t)kMainWarps * so.bytes;
   COBEL_REQUIRE(sm_main <= 227 * 1024, COBEL_EUNSUPPORTED, "PMA: %d states x %d actions do not fit in shared memory", S, A);
-  COBEL_CUDA_OK(cudaFuncSetAttribute(pma_main_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_main));
+  const bool plain = p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.mem_policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn &&
+                     !p.no_replay && !p.min_gain_original && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx &&
+                     !p.trace.replay_len && !p.stream.user_stream;
+  COBEL_CUDA_OK(cudaFuncSetAttribute(pma_main_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_main));
+  COBEL_CUDA_OK(cudaFuncSetAttribute(pma_main_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_main));
   const int tile = S <= 7 * 16 ? 7 : 10;
   const size_t sm_sr = (size_t)(4 * (tile * 16 + 2) + ((S + 1) & ~1) + S * S) * 8;
   if (tile == 7) COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
   else COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
   const unsigned grid_main = (unsigned)((p.n_agents + kMainWarps - 1) / kMainWarps);
   auto main_launch = [&](MainPhase ph) {
-    pma_main_kernel<A><<<grid_main, kMainWarps * 32, sm_main, st>>>(p, ph);
+    if (plain) pma_main_kernel<A, true><<<grid_main, kMainWarps * 32, sm_main, st>>>(p, ph);
+    else pma_main_kernel<A, false><<<grid_main, kMainWarps * 32, sm_main, st>>>(p, ph);
     cobel_count_launch();
   };
   auto sr_launch = [&]() {
