@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcobel_b200.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_f64p = C.c_void_p   # device pointers travel as raw addresses
 c_ptr = C.c_void_p
@@ -89,7 +89,8 @@ class PMAParams(C.Structure):
                 ('pow_stride', C.c_int64), ('min_gap', c_ptr), ('carry', c_ptr), ('need_scratch', c_ptr),
                 ('lr_T', C.c_double), ('min_gain', C.c_double),
                 ('min_gain_original', C.c_int32), ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32),
-                ('no_replay', C.c_int32), ('learn', C.c_int32)]
+                ('no_replay', C.c_int32), ('learn', C.c_int32), ('sr_band', C.c_int32), ('reserved', C.c_int32),
+                ('band_scratch', c_ptr)]
 
 
 STRUCTS = {'CobelWorld': World, 'CobelStream': Stream, 'CobelPolicy': Policy, 'CobelTrace': Trace,

@@ -68,6 +68,7 @@ class PMA(Agent):
                                                       lr_q=M.learning_rate_q, gamma_q=M.gamma_q, gamma_sr=M.gamma).items()}
             psr, pq, pstride = M.power_tables(st, keep)
             mptr, mstride = self._mask_args(keep)
+            band, bscratch = M.sr_band(interface.transition_band) if (learn and not no_replay) else (-1, None)
             p = _lib.PMAParams(
                 st.n_agents, interface.c_world(), st.c_struct(), pol.c_struct(st, keep), M.policy.c_struct(st, keep), tr,
                 self._Q.data_ptr(), M._rewards.data_ptr(), M._states.data_ptr(), M._terminals.data_ptr(),
@@ -77,10 +78,12 @@ class PMA(Agent):
                 M._min_gap.data_ptr(), M._carry.data_ptr(), M._need_scratch.data_ptr(),
                 float(M.learning_rate_T), float(M.min_gain),
                 1 if M.min_gain_mode == 'original' else 0, n_tr, steps, batch_size, 1 if no_replay else 0,
-                1 if learn else 0)
+                1 if learn else 0, band, 0, _lib.ptr(bscratch))
             keep.append(par)
             _lib.call('cobel_pma_run', st.device, p, launch_stream(st))
             self._check_flags(res)
+            if band >= 0 and bool((res['flags'] & 32).any()):      # COBEL_FLAG_BAND_VIOLATION
+                raise _lib.CobelError('PMA: T or a transition left the band of %d assumed by the banded update_sr' % band)
             self._fire_trial_callbacks(res, self.current_trial, (1, 1) if (learn and not no_replay) else (0, 0))
             self.current_trial += n_tr
             results.append(res)

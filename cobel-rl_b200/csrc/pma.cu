@@ -269,7 +269,8 @@ __device__ __forceinline__ void gth_stationary(const double* __restrict__ Tg, do
 // out (carry[.,0] < 0) also the stationary `need` vector into need_scratch[n].
 // ---------------------------------------------------------------------------
 template <int TILE>
-__global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_sr_kernel(const __grid_constant__ CobelPMAParams p) {
+__global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_sr_kernel(const __grid_constant__ CobelPMAParams p,
+                                                                            const int final_only) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int S = p.world.n_states, tid = threadIdx.x;
   const int64_t n = blockIdx.x;
@@ -279,12 +280,123 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_sr_kernel(con
   int flags = 0;
   const double* Tg = p.T + (size_t)n * S * S;
   gauss_jordan_inverse<TILE>(Tg, p.gamma_sr[n], p.SR + (size_t)n * S * S, S, elim, tid, flags);
-  if (p.carry[n * 4 + 0] < 0) {
+  if (final_only) {
+    // end of a banded call (sr_band >= 0): SR is refreshed once, and the caller's band guarantee is verified
+    const int bw = p.sr_band;
+    for (int e = tid; e < S * S; e += kThreads) {
+      const int i = e / S, j = e - i * S;
+      if (abs(i - j) > bw && Tg[e] != 0.0) flags |= COBEL_FLAG_BAND_VIOLATION;
+    }
+  } else if (p.carry[n * 4 + 0] < 0) {
     gth_stationary<TILE>(Tg, Mat, xv, S, elim, tid, flags);
     for (int e = tid; e < S; e += kThreads) p.need_scratch[(size_t)n * S + e] = xv[e];
   }
   flags = __syncthreads_or(flags);
   if (tid == 0 && flags && p.trace.flags) p.trace.flags[n] |= flags;
+}
+
+// ---------------------------------------------------------------------------
+// Banded update_sr for one agent by one warp (CobelPMAParams.sr_band): replay reads ONE row of
+// SR = inv(M), M = I - gamma T (memory/pma.py:401-411), and T of a W-wide gridworld has half bandwidth
+// bw = W, so instead of the S^3 dense inverse the warp factorises the band (S * bw^2 operations, no
+// pivoting: M is strictly diagonally dominant, the factors stay inside the band) and solves
+// x^T M = e_c^T for the row (2 * S * bw).  The result is what the dense elimination gives with the
+// multiplications by the exact zeros outside the band left out.
+// Band storage in global scratch (L1/L2 resident): b[i * W + (j - i + bw)] = M[i][j], W = 2 bw + 1.
+// ---------------------------------------------------------------------------
+COBEL_DEV void band_load(const double* __restrict__ Tg, double g, double* b, int S, int bw, int lane, bool identity_minus) {
+  const int W = 2 * bw + 1;
+  for (int i = 0; i < S; ++i)
+    for (int d = lane; d < W; d += 32) {
+      const int j = i - bw + d;
+      double v = 0.0;
+      if (j >= 0 && j < S) {
+        const double t = Tg[(size_t)i * S + j];
+        v = identity_minus ? ((i == j ? 1.0 : 0.0) - g * t) : t;
+      }
+      b[i * W + d] = v;
+    }
+  __syncwarp();
+}
+
+// In-place LU without pivoting; the diagonal receives 1 / pivot, the sub-diagonal part the multipliers.
+COBEL_DEV void band_lu(double* b, int S, int bw, int lane, int& flags) {
+  const int W = 2 * bw + 1;
+  for (int k = 0; k < S; ++k) {
+    const int nb = min(bw, S - 1 - k);
+    const double piv = b[k * W + bw];
+    if (!(fabs(piv) > 1e-300)) flags |= COBEL_FLAG_SINGULAR;
+    const double ipiv = 1.0 / piv;
+    for (int e = lane; e < nb * nb; e += 32) {
+      const int ii = e / nb + 1, jj = e - (ii - 1) * nb + 1;
+      const double l = b[(k + ii) * W + bw - ii] * ipiv;
+      const double u = b[k * W + bw + jj];
+      b[(k + ii) * W + bw - ii + jj] = fma(-l, u, b[(k + ii) * W + bw - ii + jj]);
+    }
+    __syncwarp();
+    if (lane < nb) b[(k + 1 + lane) * W + bw - 1 - lane] *= ipiv;
+    if (lane == 0) b[k * W + bw] = ipiv;
+    __syncwarp();
+  }
+}
+
+// x = row c of inv(M) from the factors: U^T y = e_c (forward, column sweeps), then L^T x = y (backward).
+// x lives in shared memory.
+COBEL_DEV void band_solve_row(const double* b, int S, int bw, int c, double* x, int lane) {
+  const int W = 2 * bw + 1;
+  for (int e = lane; e < S; e += 32) x[e] = e == c ? 1.0 : 0.0;
+  __syncwarp();
+  for (int j = c; j < S; ++j) {                       // y_j = rhs_j / U[j][j]; rhs_i -= U[j][i] y_j, i in (j, j+bw]
+    const double yj = x[j] * b[j * W + bw];
+    const int nb = min(bw, S - 1 - j);
+    __syncwarp();
+    if (lane == 0) x[j] = yj;
+    if (lane < nb) x[j + 1 + lane] = fma(-b[j * W + bw + 1 + lane], yj, x[j + 1 + lane]);
+    __syncwarp();
+  }
+  for (int j = S - 1; j > 0; --j) {                   // x_j final; x_i -= L[j][i] x_j, i in [j-bw, j)
+    const double xj = x[j];
+    const int nb = min(bw, j);
+    if (lane < nb) x[j - 1 - lane] = fma(-b[j * W + bw - 1 - lane], xj, x[j - 1 - lane]);
+    __syncwarp();
+  }
+}
+
+// Stationary distribution of the banded row-stochastic T by GTH elimination (see gth_stationary), scaled to
+// unit 2-norm, into x (shared memory).  b holds the band of T and is destroyed.
+COBEL_DEV void band_gth(double* b, int S, int bw, double* x, int lane, int& flags) {
+  const int W = 2 * bw + 1;
+  for (int k = S - 1; k >= 1; --k) {
+    const int nb = min(bw, k);                        // states k-nb .. k-1 take part
+    double ssum = lane < nb ? b[k * W + bw - 1 - lane] : 0.0;
+    for (int d = 16; d > 0; d >>= 1) ssum += shfl_f64_xor(ssum, d);
+    if (!(ssum > 0.0)) { flags |= COBEL_FLAG_SINGULAR; ssum = 1.0; }
+    const double inv = 1.0 / ssum;
+    for (int e = lane; e < nb * nb; e += 32) {
+      const int ii = e / nb + 1, jj = e - (ii - 1) * nb + 1;        // i = k - ii, j = k - jj
+      const double f = b[(k - ii) * W + bw + ii] * inv;            // P[i][k] / s
+      const double r = b[k * W + bw - jj];                         // P[k][j]
+      b[(k - ii) * W + bw + ii - jj] = fma(f, r, b[(k - ii) * W + bw + ii - jj]);
+    }
+    __syncwarp();
+    if (lane < nb) b[(k - 1 - lane) * W + bw + 1 + lane] *= inv;   // column k keeps P[i][k] / s
+    __syncwarp();
+  }
+  if (lane == 0) x[0] = 1.0;
+  __syncwarp();
+  for (int k = 1; k < S; ++k) {                       // x_k = sum_{i<k} x_i P[i][k]
+    const int nb = min(bw, k);
+    double acc = lane < nb ? x[k - 1 - lane] * b[(k - 1 - lane) * W + bw + 1 + lane] : 0.0;
+    for (int d = 16; d > 0; d >>= 1) acc += shfl_f64_xor(acc, d);
+    if (lane == 0) x[k] = acc;
+    __syncwarp();
+  }
+  double sq = 0.0;
+  for (int i = lane; i < S; i += 32) sq = fma(x[i], x[i], sq);
+  for (int d = 16; d > 0; d >>= 1) sq += shfl_f64_xor(sq, d);
+  const double nrm = sqrt(sq);
+  for (int i = lane; i < S; i += 32) x[i] = fabs(x[i]) / nrm;
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------
@@ -327,7 +439,8 @@ struct MainPhase {
 // PLAIN = epsilon-greedy agent and memory policies, training with replay, deterministic world, no optional
 // trace buffers, generated stream: the other policies' code (fp64 exp) and the per-step checks are compiled out
 // (the kernel is instruction-fetch bound: profiles/r1_pma_v3.txt).
-template <int A, bool PLAIN>
+// BAND = banded update_sr inside this kernel (all trials in one launch), see band_lu above.
+template <int A, bool PLAIN, bool BAND>
 __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __grid_constant__ CobelPMAParams p,
                                                                       const __grid_constant__ MainPhase ph) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -395,7 +508,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
   const double lrq = p.lr_q[n], gq = p.gamma_q[n];
   const double min_gain = p.min_gain;
-  const bool original = !PLAIN && p.min_gain_original != 0;
+  const bool original = p.min_gain_original != 0;
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
   PolicyTab mpt; mpt.init(mkind, mpar, lane);
   const bool learn = PLAIN || p.learn != 0;
@@ -451,10 +564,10 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     return xmul(xmul(gain_one(i), need[s]), (Pk[s * A + a] & kUm) ? 1.0 : 0.0);
   };
 
-  // PMAMemory.replay, memory/pma.py:168-267.  cur >= 0: need = SR[cur]; cur < 0: stationary need.
-  auto replay = [&](int cur) {
-    const double* nsrc = cur >= 0 ? SRg + (size_t)cur * S : p.need_scratch + (size_t)n * S;
-    for (int e = lane; e < S; e += 32) need[e] = nsrc[e];
+  // PMAMemory.replay, memory/pma.py:168-267.  nsrc = the need vector in HBM (an SR row or the stationary
+  // need); nullptr: need[] has been filled in place by the banded solver.
+  auto replay = [&](const double* nsrc) {
+    if (nsrc) for (int e = lane; e < S; e += 32) need[e] = nsrc[e];
     // CSR of the backups grouped by their next state (M.states does not change during a replay):
     // the backups that read Q row t are row t itself and pitems[poff[t] .. poff[t+1])
     for (int e = lane; e <= S; e += 32) poff[e] = 0;
@@ -688,19 +801,52 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
 
   // Launch phases with a single (inlined) replay site: stage 0 = end-of-trial replay of the previous
   // trial (agent/pma.py:248-256), stage 1 = reset + start-of-trial replay (206-213) + online steps.
+  // Dense mode: one trial per launch, pma_sr_kernel in between.  BAND: stage 1, stage 0, stage 1, ... in one launch.
+  const int bw = p.sr_band;
+  double* bscr = BAND ? p.band_scratch + (size_t)n * S * (2 * bw + 1) : nullptr;
+  const double gsr = p.gamma_sr[n];
+  bool have_lu = false;        // bscr holds the factors of I - gamma T for the current T
+  bool sr_given = true;        // no update_sr yet in this call: the start replay reads the caller's SR
   int trial = ph.trial_first, ntr = ph.n_trials;
-  for (int stage = ph.end_replay ? 0 : 1;; stage = 1) {
-    int cur = -2, s = 0;
+  for (int stage = ph.end_replay ? 0 : 1;;) {
+    const double* nsrc = nullptr;
+    bool rep = true;
+    int s = 0;
     if (stage == 0) {
-      cur = (int)c_last;                                // terminal state, or -1: stationary need
+      if (BAND) {                                        // M.update_sr() + compute_need(last)
+        if (c_last < 0) {
+          band_load(Tg, 0.0, bscr, S, bw, lane, false);
+          band_gth(bscr, S, bw, need, lane, flags);
+        } else {
+          band_load(Tg, gsr, bscr, S, bw, lane, true);
+          band_lu(bscr, S, bw, lane, flags);
+          have_lu = true;
+          band_solve_row(bscr, S, bw, (int)c_last, need, lane);
+        }
+        sr_given = false;
+      } else {
+        nsrc = c_last >= 0 ? SRg + (size_t)c_last * S : p.need_scratch + (size_t)n * S;   // terminal state / stationary need
+      }
     } else {
       if (ntr == 0) break;
       win.ensure(2, lane);
       s = __ldg(p.world.starts + draw_integer(win.next(), K));
-      if (do_replay) cur = s;                           // awake replay, need = SR[start]
+      rep = do_replay;                                   // awake replay, need = SR[start]
+      if (rep) {
+        if (BAND && !sr_given) {
+          if (!have_lu) {
+            band_load(Tg, gsr, bscr, S, bw, lane, true);
+            band_lu(bscr, S, bw, lane, flags);
+            have_lu = true;
+          }
+          band_solve_row(bscr, S, bw, s, need, lane);
+        } else {
+          nsrc = SRg + (size_t)s * S;
+        }
+      }
     }
-    if (cur != -2) replay(cur);
-    if (stage == 0) continue;
+    if (rep) replay(nsrc);
+    if (stage == 0) { stage = 1; continue; }
     double treward = 0.0;
     int step = 0, last = -1;
     for (;; ++step) {
@@ -716,6 +862,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       const double r = __ldg(p.world.reward + s2);
       const int end = __ldg(p.world.terminal + s2);
       const int nt = 1 - end;
+      if (BAND && abs(s2 - s) > bw) flags |= COBEL_FLAG_BAND_VIOLATION;
       if (!PLAIN && tr.step_sa && lane == 0) {
         if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
@@ -757,6 +904,8 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     }
     c_last = last;
     ++trial; --ntr;
+    have_lu = false;                                     // T changed
+    if (BAND && do_replay) stage = 0;
   }
 
   __syncwarp();
@@ -788,36 +937,47 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
   const size_t sm_main = (size_t)kMainWarps * so.bytes;
   COBEL_REQUIRE(sm_main <= 227 * 1024, COBEL_EUNSUPPORTED, "PMA: %d states x %d actions do not fit in shared memory", S, A);
   const bool plain = p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.mem_policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn &&
-                     !p.no_replay && !p.min_gain_original && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx &&
+                     !p.no_replay && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx &&
                      !p.trace.replay_len && !p.stream.user_stream;
-  COBEL_CUDA_OK(cudaFuncSetAttribute(pma_main_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_main));
-  COBEL_CUDA_OK(cudaFuncSetAttribute(pma_main_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_main));
+  const bool do_replay = p.learn && !p.no_replay;
+  const bool band = do_replay && p.sr_band >= 0;
   const int tile = S <= 7 * 16 ? 7 : 10;
   const size_t sm_sr = (size_t)(4 * (tile * 16 + 2) + ((S + 1) & ~1) + S * S) * 8;
   if (tile == 7) COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
   else COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
   const unsigned grid_main = (unsigned)((p.n_agents + kMainWarps - 1) / kMainWarps);
-  auto main_launch = [&](MainPhase ph) {
-    if (plain) pma_main_kernel<A, true><<<grid_main, kMainWarps * 32, sm_main, st>>>(p, ph);
-    else pma_main_kernel<A, false><<<grid_main, kMainWarps * 32, sm_main, st>>>(p, ph);
+  auto main_launch = [&](MainPhase ph) -> int {
+    auto go = [&](auto kernel) -> int {
+      COBEL_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_main));
+      kernel<<<grid_main, kMainWarps * 32, sm_main, st>>>(p, ph);
+      cobel_count_launch();
+      return COBEL_OK;
+    };
+    if (band) return plain ? go(pma_main_kernel<A, true, true>) : go(pma_main_kernel<A, false, true>);
+    return plain ? go(pma_main_kernel<A, true, false>) : go(pma_main_kernel<A, false, false>);
+  };
+  auto sr_launch = [&](int final_only) {
+    if (tile == 7) pma_sr_kernel<7><<<(unsigned)p.n_agents, kThreads, sm_sr, st>>>(p, final_only);
+    else pma_sr_kernel<10><<<(unsigned)p.n_agents, kThreads, sm_sr, st>>>(p, final_only);
     cobel_count_launch();
   };
-  auto sr_launch = [&]() {
-    if (tile == 7) pma_sr_kernel<7><<<(unsigned)p.n_agents, kThreads, sm_sr, st>>>(p);
-    else pma_sr_kernel<10><<<(unsigned)p.n_agents, kThreads, sm_sr, st>>>(p);
-    cobel_count_launch();
-  };
-  const bool do_replay = p.learn && !p.no_replay;
+  int rc = COBEL_OK;
   if (!do_replay) {
-    main_launch(MainPhase{1, 0, 0, p.trials});                 // no replay: all trials in one launch
+    rc = main_launch(MainPhase{1, 0, 0, p.trials});            // no replay: all trials in one launch
+  } else if (band) {
+    // banded update_sr inside the main kernel: all trials in one launch, then SR = inv(I - gamma T) once
+    rc = main_launch(MainPhase{1, 0, 0, p.trials});
+    if (rc) return rc;
+    sr_launch(1);
   } else {
     // trial t: main(reset, start replay, steps) -> sr(update_sr [+ stationary]) -> main(end replay, then trial t+1)
-    main_launch(MainPhase{1, 0, 0, 1});
-    for (int t = 0; t < p.trials; ++t) {
-      sr_launch();
-      main_launch(MainPhase{0, 1, t + 1, t + 1 < p.trials ? 1 : 0});
+    rc = main_launch(MainPhase{1, 0, 0, 1});
+    for (int t = 0; t < p.trials && !rc; ++t) {
+      sr_launch(0);
+      rc = main_launch(MainPhase{0, 1, t + 1, t + 1 < p.trials ? 1 : 0});
     }
   }
+  if (rc) return rc;
   COBEL_CUDA_OK(cudaGetLastError());
   return COBEL_OK;
 }
@@ -837,6 +997,8 @@ extern "C" int cobel_pma_run(const CobelPMAParams* pp, void* stream) {
                 p.need_scratch, COBEL_EINVAL, "agent tables missing");
   COBEL_REQUIRE(p.mem_policy.kind >= 0 && p.mem_policy.kind <= 2, COBEL_EINVAL, "bad memory policy");
   COBEL_REQUIRE(p.batch >= 0 && p.batch <= kMaxSeq, COBEL_EUNSUPPORTED, "PMA replay batch must be in 0..%d", kMaxSeq);
+  COBEL_REQUIRE(p.sr_band < 0 || (p.sr_band <= 31 && p.band_scratch), COBEL_EINVAL,
+                "sr_band must be < 0 (dense update_sr) or 0..31 with band_scratch[N, S*(2*sr_band+1)]");
   if (p.trials == 0) return COBEL_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (p.world.n_actions) {

@@ -46,6 +46,11 @@ class Interface(abc.ABC):
             np.cumsum(np.bincount(nz_row, minlength=S * A), out=off[1:])
             self._tp = (torch.as_tensor(off).to(dev), torch.as_tensor(nz_col.astype(np.int32)).to(dev),
                         torch.as_tensor(flat[nz_row, nz_col]).contiguous().to(dev))
+        # largest |s' - s| over all possible transitions (PMA's banded update_sr, include/cobel_b200.h sr_band)
+        succ_np = np.asarray(succ, dtype=np.int64)
+        self.transition_band = int(np.abs(succ_np - np.arange(succ_np.shape[0])[:, None]).max()) if succ_np.size else 0
+        if sas is not None:
+            self.transition_band = max(self.transition_band, int(np.abs(nz_col - nz_row // A).max()))
         self._succ = torch.as_tensor(succ, dtype=torch.int32).contiguous().to(dev)
         self._reward = torch.as_tensor(reward, dtype=torch.float64).contiguous().to(dev)
         self._terminal = torch.as_tensor(terminal).to(torch.uint8).contiguous().to(dev)

@@ -55,9 +55,37 @@ class PMAMemory(TableMemory):
         self._min_gap = torch.full((n,), float('inf'), dtype=torch.float64, device=dev)
         self._carry = torch.zeros((n, 4), dtype=torch.int64, device=dev)            # kernel scratch
         self._need_scratch = torch.zeros((n, S), dtype=torch.float64, device=dev)   # kernel scratch
+        self._band_T = self._matrix_band(self._T0)     # half bandwidth of T; None = must be re-measured
+        self._band_scratch = None
+        self.sr_band_max = 24                          # wider T: dense update_sr every trial (csrc/pma.cu)
         self.compute_update_mask()
 
-    T = property(lambda self: self._view(self._T))
+    @staticmethod
+    def _matrix_band(T):
+        i, j = np.nonzero(np.asarray(T))
+        return int(np.abs(i - j).max()) if i.size else 0
+
+    @property
+    def T(self):
+        self._band_T = None                            # the caller may write through the view
+        return self._view(self._T)
+
+    def sr_band(self, world_band):
+        """Half bandwidth that T keeps during a run (its own and the world's transitions), or -1 for the dense
+        update_sr; allocates the factorisation scratch."""
+        if self._band_T is None:
+            nz = (self._T != 0).any(dim=0).nonzero()
+            self._band_T = int((nz[:, 0] - nz[:, 1]).abs().max().item()) if nz.numel() else 0
+        bw = max(self._band_T, int(world_band))
+        S = self.nb_states
+        if bw > self.sr_band_max or 2 * bw + 1 >= S:
+            return -1, None
+        self._band_T = bw                              # experienced transitions stay inside the world's band
+        n = self._T.shape[0] * S * (2 * bw + 1)
+        if self._band_scratch is None or self._band_scratch.numel() < n:
+            self._band_scratch = torch.empty(n, dtype=torch.float64, device=self._T.device)
+        return bw, self._band_scratch
+
     SR = property(lambda self: self._view(self._SR))
     update_mask = property(lambda self: self._view(self._update_mask).bool())
     min_gap = property(lambda self: self._view(self._min_gap))

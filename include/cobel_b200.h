@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define COBEL_ABI_VERSION 1
+#define COBEL_ABI_VERSION 2
 
 enum {
   COBEL_OK = 0,
@@ -104,7 +104,8 @@ enum {
   COBEL_FLAG_CDF_NEAR_TIE   = 2,  /* an inverse-CDF draw fell within rounding distance of a bin edge */
   COBEL_FLAG_LOG_OVERFLOW   = 4,  /* QAgent experience log full */
   COBEL_FLAG_SINGULAR       = 8,  /* PMA: (I - gamma T) pivot underflow */
-  COBEL_FLAG_VISITED_OVERFLOW = 16 /* compact SR: an agent visited more than max_visited distinct states */
+  COBEL_FLAG_VISITED_OVERFLOW = 16,/* compact SR: an agent visited more than max_visited distinct states */
+  COBEL_FLAG_BAND_VIOLATION = 32  /* PMA: T or a transition outside the band promised by sr_band */
 };
 
 /* ---- Dyna-Q: agent/dyna_q.py:140-330 + memory/dyna_q.py:62-157 ------------- */
@@ -279,6 +280,15 @@ typedef struct CobelPMAParams {
   int32_t trials, steps, batch;
   int32_t no_replay;
   int32_t learn;             /* 1 = train(), 0 = test() */
+  /* Banded update_sr (memory/pma.py:413-415 needs only the SR rows that replay reads, :401-411).  sr_band >= 0 is
+   * the caller's guarantee that T[i][j] == 0 for |i - j| > sr_band and that every world transition satisfies
+   * |s' - s| <= sr_band (a W-wide gridworld: sr_band = W): all trials then run in ONE launch, each agent
+   * factorising its banded I - gamma T and solving for the one SR row a replay call needs, and SR is
+   * refreshed once, densely, at the end of the call.  A violated guarantee raises COBEL_FLAG_BAND_VIOLATION.
+   * sr_band < 0: dense update_sr after every trial (any T). */
+  int32_t sr_band;
+  int32_t reserved;
+  double*  band_scratch;     /* scratch [N, S*(2*sr_band+1)] when sr_band >= 0 */
 } CobelPMAParams;
 
 int cobel_pma_run(const CobelPMAParams* p, void* stream);

@@ -28,9 +28,11 @@ def test_pma_matches_reference_golden(name):
     assert_equal_records(got, want, KEYS['pma'], rtol=RTOL, what=name)
 
 
-def test_pma_batch_sweep_vs_oracle():
+@pytest.mark.parametrize('dense', [False, True])
+def test_pma_batch_sweep_vs_oracle(dense):
     """Several agents with per-agent hyper-parameters on the 10x10 walled world (config C3 shape),
-    including timed-out trials (stationary need)."""
+    including timed-out trials (stationary need).  dense=False: banded update_sr inside the main kernel
+    (one launch for all trials); dense=True: the dense Gauss-Jordan / GTH kernel after every trial."""
     import cobel_rl_b200 as cb
     from cobel_rl_b200.interface import Gridworld
     from cobel_rl_b200.agent import PMA
@@ -48,6 +50,9 @@ def test_pma_batch_sweep_vs_oracle():
     W = tb.compile_gridworld(world)
     ag.action_mask = tb.valid_move_mask(W['succ'])
     ag.record = True
+    if dense:
+        mem.sr_band_max = -1
+    assert mem.sr_band(env.transition_band)[0] == (-1 if dense else 10)
     res = ag.train(env, trials, steps, batch)
     torch.cuda.synchronize()
     assert int(res['flags'].sum()) == 0
@@ -109,3 +114,23 @@ def test_pma_no_replay_test_mode_and_softmax_memory_policy():
         got = unpack_run(res, i, 4, W['succ'], W['reward'])
         got['Q'] = ag.Q[i].cpu().numpy(); rec['Q'] = st['Q']
         assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q'], what='xeps agent %d' % i)
+
+
+def test_pma_band_violation_is_reported():
+    """A caller that promises a narrower band than T has gets COBEL_FLAG_BAND_VIOLATION, not a wrong answer."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200 import _lib
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import PMA
+    from cobel_rl_b200.memory import PMAMemory
+    from cobel_rl_b200.policy import EpsilonGreedy
+    world = make_world('walls10')
+    stream = cb.BatchStream(2, seed=5, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = PMAMemory(world['sas'], EpsilonGreedy(0.1, rng=stream), rng=stream)
+    ag = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem)
+    assert env.transition_band == 10
+    real = mem.sr_band
+    mem.sr_band = lambda wb: (3, real(wb)[1])            # lie: the world's band is 10
+    with pytest.raises(_lib.CobelError, match='band'):
+        ag.train(env, 1, 20, 4)
