@@ -304,92 +304,192 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_sr_kernel(con
 // multiplications by the exact zeros outside the band left out.
 // Band storage in global scratch (L1/L2 resident): b[i * W + (j - i + bw)] = M[i][j], W = 2 bw + 1.
 // ---------------------------------------------------------------------------
-COBEL_DEV void band_load(const double* __restrict__ Tg, double g, double* b, int S, int bw, int lane, bool identity_minus) {
-  const int W = 2 * bw + 1;
-  for (int i = 0; i < S; ++i)
-    for (int d = lane; d < W; d += 32) {
-      const int j = i - bw + d;
-      double v = 0.0;
-      if (j >= 0 && j < S) {
-        const double t = Tg[(size_t)i * S + j];
-        v = identity_minus ? ((i == j ? 1.0 : 0.0) - g * t) : t;
-      }
-      b[i * W + d] = v;
-    }
-  __syncwarp();
+// The factorisation is latency-critical (S dependent steps), so rows are STREAMED through a small
+// shared-memory ring with cp.async kBandAhead rows ahead of the step that needs them: the HBM/L2
+// latency of T (dense source) and of the stored factors is off the dependency chain, and a finished
+// row goes back to global scratch with a fire-and-forget store.
+constexpr int kBandAhead = 4;
+
+COBEL_DEV void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 8 : 0;                       // src-size 0: the 8 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+COBEL_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+COBEL_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// rows of the ring: the bw + 1 active rows, one being replaced and kBandAhead in flight, rounded up to a power of two
+__host__ __device__ inline int band_ring_rows(int bw) {
+  int r = 1;
+  while (r < bw + 2 + kBandAhead) r <<= 1;
+  return r;
 }
 
-// In-place LU without pivoting; the diagonal receives 1 / pivot, the sub-diagonal part the multipliers.
-COBEL_DEV void band_lu(double* b, int S, int bw, int lane, int& flags) {
-  const int W = 2 * bw + 1;
+struct BandRing {
+  double* ring;      // [R][W] shared memory, row i lives in slot i % R (R a power of two)
+  int S, bw, W, R, lane;
+  COBEL_DEV BandRing(double* r, int S_, int bw_, int lane_) : ring(r), S(S_), bw(bw_), W(2 * bw_ + 1), R(band_ring_rows(bw_)), lane(lane_) {}
+  COBEL_DEV double* row(int i) const { return ring + (i & (R - 1)) * W; }
+  // one commit group per call, also for rows outside [0, S) (keeps the group arithmetic uniform)
+  COBEL_DEV void fetch_T(const double* __restrict__ Tg, int i) const {     // band of row i of the dense T
+    if (i >= 0 && i < S)
+      for (int d = lane; d < W; d += 32) {
+        const int j = i - bw + d;
+        const bool ok = j >= 0 && j < S;
+        cp_async8(row(i) + d, Tg + (size_t)i * S + (ok ? j : i), ok);
+      }
+    cp_async_commit();
+  }
+  COBEL_DEV void fetch_band(const double* __restrict__ b, int i) const {   // row i of a stored band
+    if (i >= 0 && i < S)
+      for (int d = lane; d < W; d += 32) cp_async8(row(i) + d, b + (size_t)i * W + d, true);
+    cp_async_commit();
+  }
+  COBEL_DEV void store_band(double* b, int i) const {
+    for (int d = lane; d < W; d += 32) b[(size_t)i * W + d] = row(i)[d];
+  }
+};
+
+// Factors of M = I - g T into fac (band storage): the diagonal receives 1 / pivot, the sub-diagonal part the
+// multipliers.  LU without pivoting.
+__device__ __noinline__ int band_lu(const double* __restrict__ Tg, double g, double* fac, double* ringmem, int S, int bw,
+                                    int lane) {
+  int flags = 0;
+  const BandRing rg(ringmem, S, bw, lane);
+  const int W = rg.W;
+  auto to_M = [&](int i) {                            // T band row -> M band row, in place
+    if (i < S) for (int d = lane; d < W; d += 32) { double* e = rg.row(i) + d; *e = (d == bw ? 1.0 : 0.0) - g * *e; }
+  };
+  // element e = lane + 32 x of the bw x bw update block is (ii, jj) = (e / bw + 1, e % bw + 1): advanced incrementally
+  const int bws = bw > 0 ? bw : 1;
+  const int ii0 = lane / bws + 1, jj0 = lane % bws + 1, di = 32 / bws, dj = 32 % bws;
+  for (int i = 0; i < bw; ++i) rg.fetch_T(Tg, i);
+  cp_async_wait<0>();
+  __syncwarp();
+  for (int i = 0; i < bw; ++i) to_M(i);
+  for (int i = bw; i <= bw + kBandAhead; ++i) rg.fetch_T(Tg, i);
   for (int k = 0; k < S; ++k) {
+    cp_async_wait<kBandAhead>();                      // row k + bw has landed
+    __syncwarp();
+    to_M(k + bw);
+    __syncwarp();
     const int nb = min(bw, S - 1 - k);
-    const double piv = b[k * W + bw];
+    const double* rk = rg.row(k);
+    const double piv = rk[bw];
     if (!(fabs(piv) > 1e-300)) flags |= COBEL_FLAG_SINGULAR;
     const double ipiv = 1.0 / piv;
-    for (int e = lane; e < nb * nb; e += 32) {
-      const int ii = e / nb + 1, jj = e - (ii - 1) * nb + 1;
-      const double l = b[(k + ii) * W + bw - ii] * ipiv;
-      const double u = b[k * W + bw + jj];
-      b[(k + ii) * W + bw - ii + jj] = fma(-l, u, b[(k + ii) * W + bw - ii + jj]);
+    for (int e = lane, ii = ii0, jj = jj0; e < bw * bw; e += 32) {  // (ii, jj) enumerate bw x bw; the last steps guard
+      if (ii <= nb && jj <= nb) {
+        double* ri = rg.row(k + ii);
+        const double l = ri[bw - ii] * ipiv;
+        ri[bw - ii + jj] = fma(-l, rk[bw + jj], ri[bw - ii + jj]);
+      }
+      jj += dj; ii += di;
+      if (jj > bw) { jj -= bw; ++ii; }
     }
     __syncwarp();
-    if (lane < nb) b[(k + 1 + lane) * W + bw - 1 - lane] *= ipiv;
-    if (lane == 0) b[k * W + bw] = ipiv;
+    if (lane < nb) rg.row(k + 1 + lane)[bw - 1 - lane] *= ipiv;
+    if (lane == 0) rg.row(k)[bw] = ipiv;
     __syncwarp();
+    rg.store_band(fac, k);
+    __syncwarp();
+    rg.fetch_T(Tg, k + bw + kBandAhead + 1);          // into the slot row k just left
   }
+  cp_async_wait<0>();
+  __syncwarp();
+  return flags;
 }
 
 // x = row c of inv(M) from the factors: U^T y = e_c (forward, column sweeps), then L^T x = y (backward).
-// x lives in shared memory.
-COBEL_DEV void band_solve_row(const double* b, int S, int bw, int c, double* x, int lane) {
-  const int W = 2 * bw + 1;
+// x lives in shared memory; the factor rows stream through the ring.
+__device__ __noinline__ void band_solve_row(const double* __restrict__ fac, double* ringmem, int S, int bw, int c, double* x,
+                                            int lane) {
+  const BandRing rg(ringmem, S, bw, lane);
   for (int e = lane; e < S; e += 32) x[e] = e == c ? 1.0 : 0.0;
-  __syncwarp();
+  for (int j = c; j <= c + kBandAhead; ++j) rg.fetch_band(fac, j);
   for (int j = c; j < S; ++j) {                       // y_j = rhs_j / U[j][j]; rhs_i -= U[j][i] y_j, i in (j, j+bw]
-    const double yj = x[j] * b[j * W + bw];
+    cp_async_wait<kBandAhead>();
+    __syncwarp();
+    const double* rj = rg.row(j);
+    const double yj = x[j] * rj[bw];
     const int nb = min(bw, S - 1 - j);
     __syncwarp();
     if (lane == 0) x[j] = yj;
-    if (lane < nb) x[j + 1 + lane] = fma(-b[j * W + bw + 1 + lane], yj, x[j + 1 + lane]);
+    if (lane < nb) x[j + 1 + lane] = fma(-rj[bw + 1 + lane], yj, x[j + 1 + lane]);
     __syncwarp();
+    rg.fetch_band(fac, j + kBandAhead + 1);
   }
+  cp_async_wait<0>();
+  __syncwarp();
+  for (int j = S - 1; j >= S - 1 - kBandAhead; --j) rg.fetch_band(fac, j);
   for (int j = S - 1; j > 0; --j) {                   // x_j final; x_i -= L[j][i] x_j, i in [j-bw, j)
+    cp_async_wait<kBandAhead>();
+    __syncwarp();
+    const double* rj = rg.row(j);
     const double xj = x[j];
     const int nb = min(bw, j);
-    if (lane < nb) x[j - 1 - lane] = fma(-b[j * W + bw - 1 - lane], xj, x[j - 1 - lane]);
+    if (lane < nb) x[j - 1 - lane] = fma(-rj[bw - 1 - lane], xj, x[j - 1 - lane]);
     __syncwarp();
+    rg.fetch_band(fac, j - kBandAhead - 1);
   }
+  cp_async_wait<0>();
+  __syncwarp();
 }
 
 // Stationary distribution of the banded row-stochastic T by GTH elimination (see gth_stationary), scaled to
-// unit 2-norm, into x (shared memory).  b holds the band of T and is destroyed.
-COBEL_DEV void band_gth(double* b, int S, int bw, double* x, int lane, int& flags) {
-  const int W = 2 * bw + 1;
+// unit 2-norm, into x (shared memory).  fac receives the eliminated rows (column k holds P[i][k] / s_k).
+__device__ __noinline__ int band_gth(const double* __restrict__ Tg, double* fac, double* ringmem, int S, int bw, double* x,
+                                     int lane) {
+  int flags = 0;
+  const BandRing rg(ringmem, S, bw, lane);
+  // elimination k = S-1 .. 1 works on rows k-bw .. k: stream upwards
+  for (int i = S - 1; i >= S - 1 - bw - kBandAhead; --i) rg.fetch_T(Tg, i);
   for (int k = S - 1; k >= 1; --k) {
+    cp_async_wait<kBandAhead>();                      // row k - bw has landed
+    __syncwarp();
     const int nb = min(bw, k);                        // states k-nb .. k-1 take part
-    double ssum = lane < nb ? b[k * W + bw - 1 - lane] : 0.0;
+    const double* rk = rg.row(k);
+    double ssum = lane < nb ? rk[bw - 1 - lane] : 0.0;
     for (int d = 16; d > 0; d >>= 1) ssum += shfl_f64_xor(ssum, d);
     if (!(ssum > 0.0)) { flags |= COBEL_FLAG_SINGULAR; ssum = 1.0; }
     const double inv = 1.0 / ssum;
     for (int e = lane; e < nb * nb; e += 32) {
       const int ii = e / nb + 1, jj = e - (ii - 1) * nb + 1;        // i = k - ii, j = k - jj
-      const double f = b[(k - ii) * W + bw + ii] * inv;            // P[i][k] / s
-      const double r = b[k * W + bw - jj];                         // P[k][j]
-      b[(k - ii) * W + bw + ii - jj] = fma(f, r, b[(k - ii) * W + bw + ii - jj]);
+      double* ri = rg.row(k - ii);
+      const double f = ri[bw + ii] * inv;                          // P[i][k] / s
+      ri[bw + ii - jj] = fma(f, rk[bw - jj], ri[bw + ii - jj]);
     }
     __syncwarp();
-    if (lane < nb) b[(k - 1 - lane) * W + bw + 1 + lane] *= inv;   // column k keeps P[i][k] / s
+    if (lane < nb) rg.row(k - 1 - lane)[bw + 1 + lane] *= inv;     // column k keeps P[i][k] / s
     __syncwarp();
+    rg.store_band(fac, k);                                         // (only its scaled super-diagonal part is read again)
+    __syncwarp();
+    rg.fetch_T(Tg, k - bw - kBandAhead - 1);
   }
+  rg.store_band(fac, 0);
+  cp_async_wait<0>();
   if (lane == 0) x[0] = 1.0;
   __syncwarp();
-  for (int k = 1; k < S; ++k) {                       // x_k = sum_{i<k} x_i P[i][k]
-    const int nb = min(bw, k);
-    double acc = lane < nb ? x[k - 1 - lane] * b[(k - 1 - lane) * W + bw + 1 + lane] : 0.0;
-    for (int d = 16; d > 0; d >>= 1) acc += shfl_f64_xor(acc, d);
-    if (lane == 0) x[k] = acc;
-    __syncwarp();
+  // x_k = sum_{i<k} x_i P[i][k] / s_k: the scaled column k sits in rows k-bw .. k-1 of fac
+  auto colk = [&](int k) -> double {                  // lane's entry of the scaled column k (0 outside)
+    return (k < S && lane < min(bw, k)) ? fac[(size_t)(k - 1 - lane) * rg.W + bw + 1 + lane] : 0.0;
+  };
+  double c[4];                                        // loads run four steps ahead of the recurrence
+#pragma unroll
+  for (int u = 0; u < 4; ++u) c[u] = colk(1 + u);
+  for (int k0 = 1; k0 < S; k0 += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u;
+      if (k < S) {
+        double acc = lane < min(bw, k) ? x[k - 1 - lane] * c[u] : 0.0;
+        for (int d = 16; d > 0; d >>= 1) acc += shfl_f64_xor(acc, d);
+        if (lane == 0) x[k] = acc;
+        __syncwarp();
+        c[u] = colk(k + 4);
+      }
+    }
   }
   double sq = 0.0;
   for (int i = lane; i < S; i += 32) sq = fma(x[i], x[i], sq);
@@ -397,6 +497,103 @@ COBEL_DEV void band_gth(double* b, int S, int bw, double* x, int lane, int& flag
   const double nrm = sqrt(sq);
   for (int i = lane; i < S; i += 32) x[i] = fabs(x[i]) / nrm;
   __syncwarp();
+  return flags;
+}
+
+// ---------------------------------------------------------------------------
+// pma_sr_band_kernel: the full SR = inv(I - gamma T) of a banded T, once at the end of a banded call.
+// One CTA per agent, from the band factors pma_main_kernel leaves in band_scratch: thread r solves row r of the
+// inverse (x^T M = e_r^T) in its own row of a shared-memory S x S matrix -- no barriers between the S steps,
+// the factor rows are broadcast loads.  2 S^2 bw operations instead of the S^3 of the dense Gauss-Jordan.
+// ---------------------------------------------------------------------------
+template <int BW>      // BW >= sr_band: length of the per-thread register window
+__global__ void __launch_bounds__(160) pma_sr_band_kernel(const __grid_constant__ CobelPMAParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int S = p.world.n_states, bw = p.sr_band, W = 2 * bw + 1, tid = threadIdx.x;
+  const int64_t n = blockIdx.x;
+  const int LD = S | 1;                                            // odd row stride: conflict-free column walks
+  double* X = reinterpret_cast<double*>(smem);                     // [S][LD]
+  constexpr int WP = 2 * BW + 1;                                   // padded factor row: entry [BW + i] = M-factor[j][j + i]
+  double* fac = X + (size_t)S * LD;                                // [S][WP] the factors left by pma_main_kernel, staged
+  {                                                                // once and zero-padded to the window length
+    const double* fg = p.band_scratch + (size_t)n * 2 * S * W;
+    for (int e = tid; e < S * WP; e += blockDim.x) {
+      const int j = e / WP, d = e - j * WP - BW;                   // d = column offset -BW .. BW
+      fac[e] = (d >= -bw && d <= bw) ? fg[(size_t)j * W + bw + d] : 0.0;
+    }
+  }
+  __syncthreads();
+  // Thread r solves x^T M = e_r^T.  The right-hand side entries that a step can still change are kept in a
+  // register window, so a step is BW independent FMAs with broadcast factor loads (issued one step ahead)
+  // and one shared-memory store; the whole warp walks j from its first row (entries before a thread's own row
+  // are zero).
+  const int r = tid, j0 = tid & ~31;
+  if (j0 < S) {
+    double* x = X + (size_t)min(r, S - 1) * LD;
+    double w[BW], fc[BW + 1], fn[BW + 1];
+#pragma unroll
+    for (int i = 0; i < BW; ++i) w[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i <= BW; ++i) fc[i] = fac[(size_t)j0 * WP + BW + i];
+    double cur = 0.0;
+    for (int j = j0; j < S; ++j) {                                 // U^T y = e_r
+      const double* fnext = fac + (size_t)min(j + 1, S - 1) * WP + BW;
+#pragma unroll
+      for (int i = 0; i <= BW; ++i) fn[i] = fnext[i];
+      const double yj = (cur + (j == r ? 1.0 : 0.0)) * fc[0];
+      if (r < S) x[j] = yj;
+#pragma unroll
+      for (int i = 1; i <= BW; ++i) w[i - 1] = fma(-fc[i], yj, w[i - 1]);
+      cur = w[0];
+#pragma unroll
+      for (int i = 1; i < BW; ++i) w[i - 1] = w[i];
+      w[BW - 1] = 0.0;
+#pragma unroll
+      for (int i = 0; i <= BW; ++i) fc[i] = fn[i];
+    }
+#pragma unroll
+    for (int i = 0; i < BW; ++i) w[i] = 0.0;
+#pragma unroll
+    for (int i = 1; i <= BW; ++i) fc[i] = fac[(size_t)(S - 1) * WP + BW - i];
+    cur = 0.0;
+    double yv = (r < S && S - 1 >= j0) ? x[S - 1] : 0.0;
+    for (int j = S - 1; j >= 0; --j) {                             // L^T x = y (unit diagonal)
+      const int jn = max(j - 1, 0);
+      const double* fnext = fac + (size_t)jn * WP + BW;
+#pragma unroll
+      for (int i = 1; i <= BW; ++i) fn[i] = fnext[-i];
+      const double ynext = (r < S && jn >= j0) ? x[jn] : 0.0;     // y_j = 0 before the warp's first row
+      const double xj = yv + cur;
+      if (r < S) x[j] = xj;
+#pragma unroll
+      for (int i = 1; i <= BW; ++i) w[i - 1] = fma(-fc[i], xj, w[i - 1]);
+      cur = w[0];
+#pragma unroll
+      for (int i = 1; i < BW; ++i) w[i - 1] = w[i];
+      w[BW - 1] = 0.0;
+#pragma unroll
+      for (int i = 1; i <= BW; ++i) fc[i] = fn[i];
+      yv = ynext;
+    }
+  }
+  __syncthreads();
+  double* SRg = p.SR + (size_t)n * S * S;
+  for (int e = tid; e < S * S; e += blockDim.x) { const int i = e / S; SRg[e] = X[i * LD + (e - i * S)]; }
+}
+
+// The caller's band guarantee on the initial T (a streaming read of T, once per banded call).
+__global__ void __launch_bounds__(256) pma_band_check_kernel(const __grid_constant__ CobelPMAParams p) {
+  const int S = p.world.n_states, bw = p.sr_band;
+  const int64_t n = blockIdx.x;
+  const double* Tg = p.T + (size_t)n * S * S;
+  int bad = 0;
+#pragma unroll 8
+  for (int e = threadIdx.x; e < S * S; e += 256) {
+    const int i = e / S, j = e - i * S;
+    bad |= (abs(i - j) > bw && Tg[e] != 0.0) ? 1 : 0;
+  }
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0 && bad && p.trace.flags) p.trace.flags[n] |= COBEL_FLAG_BAND_VIOLATION;
 }
 
 // ---------------------------------------------------------------------------
@@ -409,18 +606,21 @@ struct MainSmem {      // byte offsets inside one agent's shared-memory block
     const int N = S * A;
     q = 0;
     mr = q + N * 8;
-    util = mr + N * 8;
-    need = util + N * 8;
-    poff = need + ((S + 1) & ~1) * 8;
-    pk = poff + ((S + 2) & ~1) * 4;
-    pitems = pk + N * 2;
+    need = mr + N * 8;
+    pk = need + ((S + 1) & ~1) * 8;
+    mbits = pk + N * 2;
+    // from here on: buffers that are dead between replay calls -- the banded solver's row ring aliases them
+    util = (mbits + S + 7) & ~7;
+    poff = util + N * 8;
+    pitems = poff + ((S + 2) & ~1) * 4;
     list = pitems + N * 2;
     seq = list + kListCap * 2;
     perf = seq + (kMaxSeq + 2) * 2;
     dst = perf + (kMaxSeq + 2) * 2;
-    mbits = dst + (kMaxSeq + 2) * 2;
-    bytes = (mbits + S + 15) & ~15;
+    bytes = (dst + (kMaxSeq + 2) * 2 + 15) & ~15;
   }
+  // doubles available to the banded solver's ring (from `util` to the end of the block)
+  __host__ __device__ int ring_doubles() const { return (bytes - util) / 8; }
 };
 
 COBEL_DEV double warp_max_f64(double v) {
@@ -803,7 +1003,8 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   // trial (agent/pma.py:248-256), stage 1 = reset + start-of-trial replay (206-213) + online steps.
   // Dense mode: one trial per launch, pma_sr_kernel in between.  BAND: stage 1, stage 0, stage 1, ... in one launch.
   const int bw = p.sr_band;
-  double* bscr = BAND ? p.band_scratch + (size_t)n * S * (2 * bw + 1) : nullptr;
+  double* bscr = BAND ? p.band_scratch + (size_t)n * 2 * S * (2 * bw + 1) : nullptr;   // [0]: LU factors, [1]: GTH rows
+  double* bgth = BAND ? bscr + S * (2 * bw + 1) : nullptr;
   const double gsr = p.gamma_sr[n];
   bool have_lu = false;        // bscr holds the factors of I - gamma T for the current T
   bool sr_given = true;        // no update_sr yet in this call: the start replay reads the caller's SR
@@ -815,13 +1016,11 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     if (stage == 0) {
       if (BAND) {                                        // M.update_sr() + compute_need(last)
         if (c_last < 0) {
-          band_load(Tg, 0.0, bscr, S, bw, lane, false);
-          band_gth(bscr, S, bw, need, lane, flags);
+          flags |= band_gth(Tg, bgth, util, S, bw, need, lane);
         } else {
-          band_load(Tg, gsr, bscr, S, bw, lane, true);
-          band_lu(bscr, S, bw, lane, flags);
+          flags |= band_lu(Tg, gsr, bscr, util, S, bw, lane);
           have_lu = true;
-          band_solve_row(bscr, S, bw, (int)c_last, need, lane);
+          band_solve_row(bscr, util, S, bw, (int)c_last, need, lane);
         }
         sr_given = false;
       } else {
@@ -835,11 +1034,10 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       if (rep) {
         if (BAND && !sr_given) {
           if (!have_lu) {
-            band_load(Tg, gsr, bscr, S, bw, lane, true);
-            band_lu(bscr, S, bw, lane, flags);
+            flags |= band_lu(Tg, gsr, bscr, util, S, bw, lane);
             have_lu = true;
           }
-          band_solve_row(bscr, S, bw, s, need, lane);
+          band_solve_row(bscr, util, S, bw, s, need, lane);
         } else {
           nsrc = SRg + (size_t)s * S;
         }
@@ -908,6 +1106,8 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     if (BAND && do_replay) stage = 0;
   }
 
+  // banded call: leave the factors of the final I - gamma T for pma_sr_band_kernel (SR is refreshed once per call)
+  if (BAND && do_replay && !sr_given && !have_lu) flags |= band_lu(Tg, gsr, bscr, util, S, bw, lane);
   __syncwarp();
   if (learn) {
     for (int e = lane; e < N; e += 32) {
@@ -940,7 +1140,9 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
                      !p.no_replay && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx &&
                      !p.trace.replay_len && !p.stream.user_stream;
   const bool do_replay = p.learn && !p.no_replay;
-  const bool band = do_replay && p.sr_band >= 0;
+  // the banded path needs its row ring to fit into the replay buffers it aliases; otherwise dense update_sr
+  const bool band = do_replay && p.sr_band >= 0 &&
+                    band_ring_rows(p.sr_band) * (2 * p.sr_band + 1) <= so.ring_doubles();
   const int tile = S <= 7 * 16 ? 7 : 10;
   const size_t sm_sr = (size_t)(4 * (tile * 16 + 2) + ((S + 1) & ~1) + S * S) * 8;
   if (tile == 7) COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
@@ -966,9 +1168,27 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
     rc = main_launch(MainPhase{1, 0, 0, p.trials});            // no replay: all trials in one launch
   } else if (band) {
     // banded update_sr inside the main kernel: all trials in one launch, then SR = inv(I - gamma T) once
+    pma_band_check_kernel<<<(unsigned)p.n_agents, 256, 0, st>>>(p);
+    cobel_count_launch();
     rc = main_launch(MainPhase{1, 0, 0, p.trials});
     if (rc) return rc;
-    sr_launch(1);
+    const int LD = S | 1;
+    const int bwp = p.sr_band <= 4 ? 4 : p.sr_band <= 8 ? 8 : p.sr_band <= 12 ? 12 : p.sr_band <= 16 ? 16 : p.sr_band <= 24 ? 24 : 32;
+    const size_t sm_band = ((size_t)S * LD + (size_t)S * (2 * bwp + 1)) * 8;
+    if (sm_band <= 227 * 1024) {
+      auto go = [&](auto kernel) -> int {
+        COBEL_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_band));
+        kernel<<<(unsigned)p.n_agents, (S + 31) & ~31, sm_band, st>>>(p);
+        cobel_count_launch();
+        return COBEL_OK;
+      };
+      rc = p.sr_band <= 4 ? go(pma_sr_band_kernel<4>) : p.sr_band <= 8 ? go(pma_sr_band_kernel<8>) :
+           p.sr_band <= 12 ? go(pma_sr_band_kernel<12>) : p.sr_band <= 16 ? go(pma_sr_band_kernel<16>) :
+           p.sr_band <= 24 ? go(pma_sr_band_kernel<24>) : go(pma_sr_band_kernel<32>);
+      if (rc) return rc;
+    } else {
+      sr_launch(1);
+    }
   } else {
     // trial t: main(reset, start replay, steps) -> sr(update_sr [+ stationary]) -> main(end replay, then trial t+1)
     rc = main_launch(MainPhase{1, 0, 0, 1});

@@ -81,7 +81,7 @@ class PMAMemory(TableMemory):
         if bw > self.sr_band_max or 2 * bw + 1 >= S:
             return -1, None
         self._band_T = bw                              # experienced transitions stay inside the world's band
-        n = self._T.shape[0] * S * (2 * bw + 1)
+        n = self._T.shape[0] * 2 * S * (2 * bw + 1)
         if self._band_scratch is None or self._band_scratch.numel() < n:
             self._band_scratch = torch.empty(n, dtype=torch.float64, device=self._T.device)
         return bw, self._band_scratch

@@ -288,7 +288,7 @@ typedef struct CobelPMAParams {
    * sr_band < 0: dense update_sr after every trial (any T). */
   int32_t sr_band;
   int32_t reserved;
-  double*  band_scratch;     /* scratch [N, S*(2*sr_band+1)] when sr_band >= 0 */
+  double*  band_scratch;     /* scratch [N, 2, S*(2*sr_band+1)] when sr_band >= 0 */
 } CobelPMAParams;
 
 int cobel_pma_run(const CobelPMAParams* p, void* stream);
