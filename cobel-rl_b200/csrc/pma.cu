@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(256) pma_band_check_kernel(const __grid_consta
 // pma_main_kernel: one warp per agent.
 // ---------------------------------------------------------------------------
 struct MainSmem {      // byte offsets inside one agent's shared-memory block
-  int q, mr, util, need, poff, pk, pitems, list, seq, perf, dst, mbits, bytes;
+  int q, mr, util, need, poff, pk, pitems, list, seq, perf, dst, rs, mbits, bytes;
   static constexpr int kListCap = 256;     // stale-gain list; larger sets fall back to a full pass
   __host__ __device__ MainSmem(int S, int A) {
     const int N = S * A;
@@ -617,7 +617,8 @@ struct MainSmem {      // byte offsets inside one agent's shared-memory block
     seq = list + kListCap * 2;
     perf = seq + (kMaxSeq + 2) * 2;
     dst = perf + (kMaxSeq + 2) * 2;
-    bytes = (dst + (kMaxSeq + 2) * 2 + 15) & ~15;
+    rs = (dst + (kMaxSeq + 2) * 2 + 7) & ~7;
+    bytes = (rs + (kMaxSeq + 2) * 8 + 15) & ~15;
   }
   // doubles available to the banded solver's ring (from `util` to the end of the block)
   __host__ __device__ int ring_doubles() const { return (bytes - util) / 8; }
@@ -661,6 +662,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   uint16_t* seq = reinterpret_cast<uint16_t*>(blk + so.seq);   // candidate n-step sequence (flat indices)
   uint16_t* perf = reinterpret_cast<uint16_t*>(blk + so.perf); // performed updates of this replay call
   uint16_t* dst = reinterpret_cast<uint16_t*>(blk + so.dst);   // states whose Q row changed in the last update
+  double* rs = reinterpret_cast<double*>(blk + so.rs);         // M.rewards of the candidate sequence's elements
   uint8_t* mbits = blk + so.mbits;                             // [s] valid-action bits (all ones if unmasked)
   constexpr int kSt = 0x1FFF, kUm = 0x2000;
   // flat backup index i = a*S + s (the reference's order, memory/pma.py:205) -> a, s, s*A + a without integer
@@ -843,6 +845,8 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       double gext = 0.0;
       if (ext >= 0) {
         const int nseq = clen > 0 ? clen : 1;
+        for (int j = lane; j < nseq; j += 32) rs[j] = Mr[sa_of(seq[j])];
+        __syncwarp();
         const int lastI = seq[nseq - 1];
         const uint16_t lpk = Pk[sa_of(lastI)];
         double lrow[A];
@@ -860,10 +864,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
             const uint32_t mb = mbits[s];
             probs_row<A>(q, mb, mkind, mpar, qpar, qom, pb);
             double r = 0.0;
-            for (int f = 0; f < nseq - j; ++f) {
-              const int k = seq[j + f];
-              r = xadd(r, xmul(Mr[sa_of(k)], powsr[f]));
-            }
+            for (int f = 0; f < nseq - j; ++f) r = xadd(r, xmul(rs[j + f], powsr[f]));
             const double target = xadd(r, xmul(fv, powq[nseq - j]));
 #pragma unroll
             for (int c = 0; c < A; ++c) {
@@ -947,7 +948,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       {
         const bool use_seq = clen > 0 && chosen == ext;
         const int nseq = use_seq ? clen : 1;
-        if (!use_seq && lane == 0) seq[0] = (uint16_t)chosen;
+        if (!use_seq && lane == 0) { seq[0] = (uint16_t)chosen; rs[0] = Mr[sa_of(chosen)]; }
         __syncwarp();
         const int lastI = seq[nseq - 1];
         const uint16_t lpk = Pk[sa_of(lastI)];
@@ -967,10 +968,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
             const int i = seq[j];
             const int a = act_of(i), s = i - a * S;
             double r = 0.0;
-            for (int f = 0; f < nseq - j; ++f) {
-              const int k = seq[j + f];
-              r = xadd(r, xmul(Mr[sa_of(k)], powq[f]));
-            }
+            for (int f = 0; f < nseq - j; ++f) r = xadd(r, xmul(rs[j + f], powq[f]));
             double td = xadd(r, xmul(fv, powq[nseq - j]));
             const double q = Q[s * A + a];
             td = xsub(td, q);
