@@ -676,12 +676,14 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   double* Tg = p.T + (size_t)n * S * S;
   const double* SRg = p.SR + (size_t)n * S * S;
   const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
+#pragma unroll 1
   for (int e = lane; e < N; e += 32) {
     Q[e] = p.Q[g0 + e];
     Mr[e] = p.Mr[g0 + e];
     const int s_ = e / A, a_ = e - s_ * A;
     Pk[e] = (uint16_t)(p.Ms[g0 + e] | (p.update_mask[g0 + a_ * S + s_] ? kUm : 0) | ((p.Mt[g0 + e] ? 1 : 0) << 15));
   }
+#pragma unroll 1
   for (int e = lane; e < S; e += 32) {
     uint32_t mb = (1u << A) - 1u;
     if (amask) {
@@ -769,15 +771,24 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   // PMAMemory.replay, memory/pma.py:168-267.  nsrc = the need vector in HBM (an SR row or the stationary
   // need); nullptr: need[] has been filled in place by the banded solver.
   auto replay = [&](const double* nsrc) {
-    if (nsrc) for (int e = lane; e < S; e += 32) need[e] = nsrc[e];
+    if (nsrc) {
+#pragma unroll 1
+      for (int e = lane; e < S; e += 32) need[e] = nsrc[e];
+    }
     // CSR of the backups grouped by their next state (M.states does not change during a replay):
     // the backups that read Q row t are row t itself and pitems[poff[t] .. poff[t+1])
+#pragma unroll 1
     for (int e = lane; e <= S; e += 32) poff[e] = 0;
     __syncwarp();
+#pragma unroll 1
     for (int e = lane; e < N; e += 32) atomicAdd(&poff[(Pk[e] & kSt) + 1], 1);
     __syncwarp();
-    if (lane == 0) for (int t = 0; t < S; ++t) poff[t + 1] += poff[t];
+    if (lane == 0) {
+#pragma unroll 1
+      for (int t = 0; t < S; ++t) poff[t + 1] += poff[t];
+    }
     __syncwarp();
+#pragma unroll 1
     for (int e = lane; e < N; e += 32) {            // fill from the back of each group, then the offsets are the starts again
       const int s_ = e / A, a_ = e - s_ * A;
       const int t = Pk[e] & kSt;
@@ -802,6 +813,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         const int lp = perf[count - 1];
         ext = Pk[sa_of(lp)] & kSt;                          // next_state of the last update
         bool loop = false;
+#pragma unroll 1
         for (int j = last_seq + lane; j < count; j += 32) loop |= st_of(perf[j]) == ext;
         loop = __any_sync(kFull, loop);
         if (!loop) {
@@ -811,6 +823,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
           const int ea = select_action_warp<A, kPol>(row, mbits[ext], mpt, win.next(), lane);
           ext += ea * S;
           clen = count - last_seq + 1;
+#pragma unroll 1
           for (int j = lane; j < clen - 1; j += 32) seq[j] = perf[last_seq + j];
           if (lane == 0) seq[clen - 1] = (uint16_t)ext;
         } else if (lane == 0) {
@@ -823,10 +836,12 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       if (ndst != 0) {
         int nd = 0;
         bool full = ndst < 0;
+#pragma unroll 1
         for (int d = 0; d < ndst && !full; ++d) {
           const int t = dst[d];
           const int p0 = poff[t], np = poff[t + 1] - p0;
           if (nd + A + np <= MainSmem::kListCap) {
+#pragma unroll 1
             for (int x = lane; x < A + np; x += 32) list[nd + x] = x < A ? (uint16_t)(x * S + t) : pitems[p0 + x - A];
             nd += A + np;
           } else {
@@ -835,6 +850,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         }
         __syncwarp();
         const int total = full ? N : nd;
+#pragma unroll 1
         for (int j0 = 0; j0 < total; j0 += 32) {
           const int j = j0 + lane;
           if (j < total) { const int i = full ? j : list[j]; util[i] = util_one(i); }
@@ -845,6 +861,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       double gext = 0.0;
       if (ext >= 0) {
         const int nseq = clen > 0 ? clen : 1;
+#pragma unroll 1
         for (int j = lane; j < nseq; j += 32) rs[j] = Mr[sa_of(seq[j])];
         __syncwarp();
         const int lastI = seq[nseq - 1];
@@ -853,6 +870,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         load_row<A>(Q + (lpk & kSt) * A, lrow);
         const double fv = xmul(row_max<A>(lrow), (lpk >> 15) ? 1.0 : 0.0);
         double total = 0.0;
+#pragma unroll 1
         for (int j0 = 0; j0 < nseq; j0 += 32) {
           const int j = j0 + lane;
           double sg = 0.0;
@@ -864,6 +882,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
             const uint32_t mb = mbits[s];
             probs_row<A>(q, mb, mkind, mpar, qpar, qom, pb);
             double r = 0.0;
+#pragma unroll 1
             for (int f = 0; f < nseq - j; ++f) r = xadd(r, xmul(rs[j + f], powsr[f]));
             const double target = xadd(r, xmul(fv, powq[nseq - j]));
 #pragma unroll
@@ -881,6 +900,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
             if (original) sg = sg > min_gain ? sg : min_gain;
           }
           const int m = nseq - j0 < 32 ? nseq - j0 : 32;
+#pragma unroll 1
           for (int l = 0; l < m; ++l) total = xadd(total, shfl_f64(sg, l));       // gain += step_gain, in order
         }
         gext = total > min_gain ? total : min_gain;
@@ -900,6 +920,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       // second-largest distinct value; then the warp maximum decides which lanes' masks count
       double lmax = ninf, l2 = ninf;
       unsigned tm = 0;
+#pragma unroll 1
       for (int i = lane, c = 0; i < N; i += 32, ++c) {
         const double v = util[i];
         if (v > lmax) { l2 = lmax; lmax = v; tm = 1u << c; }
@@ -911,6 +932,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       // ties in flat-index order: lane c keeps the tie ballot of chunk c (N <= 1024); the certificate is the gap
       // to the largest utility below the maximum
       unsigned mytb = 0;
+#pragma unroll 1
       for (int c = 0; c * 32 < N; ++c) {
         const unsigned b = __ballot_sync(kFull, (tm >> c & 1u) != 0);
         mytb = lane == c ? b : mytb;
@@ -929,8 +951,10 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       if (ktot > 1) {
         const double pk_ = xdiv(1.0, int_to_f64(ktot));
         double ck = 0.0;
+#pragma unroll 1
         for (int m = 0; m < ktot; ++m) ck = xadd(ck, pk_);
         double c = 0.0;
+#pragma unroll 1
         for (int m = 0; m < ktot; ++m) {
           c = xadd(c, pk_);
           if (xdiv(c, ck) > u) { pick = m; break; }
@@ -958,16 +982,19 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         bool ok = true;                               // n >= 2: every transition must be non-terminal & experienced
         if (nseq >= 2) {
           bool bad = false;
+#pragma unroll 1
           for (int j = lane; j < nseq; j += 32) { const int k = seq[j]; bad |= (Pk[sa_of(k)] >> 15) == 0; }
           ok = !__any_sync(kFull, bad);
         }
         __syncwarp();
         ndst = 0;
         if (ok) {
+#pragma unroll 1
           for (int j = lane; j < nseq; j += 32) {
             const int i = seq[j];
             const int a = act_of(i), s = i - a * S;
             double r = 0.0;
+#pragma unroll 1
             for (int f = 0; f < nseq - j; ++f) r = xadd(r, xmul(rs[j + f], powq[f]));
             double td = xadd(r, xmul(fv, powq[nseq - j]));
             const double q = Q[s * A + a];
@@ -984,6 +1011,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       }
     }
     if (!PLAIN && tr.replay_idx)
+#pragma unroll 1
       for (int j = lane; j < count; j += 32) {
         if (nrep + j < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + j] = perf[j];
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
@@ -1108,6 +1136,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   if (BAND && do_replay && !sr_given && !have_lu) flags |= band_lu(Tg, gsr, bscr, util, S, bw, lane);
   __syncwarp();
   if (learn) {
+#pragma unroll 1
     for (int e = lane; e < N; e += 32) {
       p.Q[g0 + e] = Q[e];
       p.Mr[g0 + e] = Mr[e];
