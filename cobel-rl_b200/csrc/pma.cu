@@ -41,6 +41,10 @@ constexpr int kMaxSeq = 64;          // longest n-step sequence (replay batch) s
 
 // Policy probabilities for one Q row (thread-local): policy/greedy.py:60-88,117-147, policy/softmax.py:60-88.
 // qpar[n-1] = par/n and qom[n-1] = (1-par)/n are the cached quotients.
+// The PMA kernels are instruction-fetch bound (their replay loop alone exceeds the 32 KB L1.5 instruction cache):
+// the fp64 division (a ~40-instruction sequence) is one shared copy here.
+__device__ __noinline__ double pdiv(double a, double b) { return __ddiv_rn(a, b); }
+
 // t[idx] by a select chain: a dynamically indexed register array would live in local memory
 template <int A>
 COBEL_DEV double pick(const double (&t)[A], int idx) {
@@ -66,7 +70,7 @@ COBEL_DEV void probs_row(const double (&v)[A], uint32_t mask, int kind, double p
     }
 #pragma unroll
     for (int a = 0; a < A; ++a)
-      if (mask >> a & 1u) p[a] = xdiv(p[a], sum);
+      if (mask >> a & 1u) p[a] = pdiv(p[a], sum);
     return;
   }
   uint32_t ties = 0;
@@ -334,6 +338,7 @@ struct BandRing {
   // one commit group per call, also for rows outside [0, S) (keeps the group arithmetic uniform)
   COBEL_DEV void fetch_T(const double* __restrict__ Tg, int i) const {     // band of row i of the dense T
     if (i >= 0 && i < S)
+#pragma unroll 1
       for (int d = lane; d < W; d += 32) {
         const int j = i - bw + d;
         const bool ok = j >= 0 && j < S;
@@ -343,10 +348,12 @@ struct BandRing {
   }
   COBEL_DEV void fetch_band(const double* __restrict__ b, int i) const {   // row i of a stored band
     if (i >= 0 && i < S)
+#pragma unroll 1
       for (int d = lane; d < W; d += 32) cp_async8(row(i) + d, b + (size_t)i * W + d, true);
     cp_async_commit();
   }
   COBEL_DEV void store_band(double* b, int i) const {
+#pragma unroll 1
     for (int d = lane; d < W; d += 32) b[(size_t)i * W + d] = row(i)[d];
   }
 };
@@ -359,16 +366,23 @@ __device__ __noinline__ int band_lu(const double* __restrict__ Tg, double g, dou
   const BandRing rg(ringmem, S, bw, lane);
   const int W = rg.W;
   auto to_M = [&](int i) {                            // T band row -> M band row, in place
-    if (i < S) for (int d = lane; d < W; d += 32) { double* e = rg.row(i) + d; *e = (d == bw ? 1.0 : 0.0) - g * *e; }
+    if (i < S) {
+#pragma unroll 1
+      for (int d = lane; d < W; d += 32) { double* e = rg.row(i) + d; *e = (d == bw ? 1.0 : 0.0) - g * *e; }
+    }
   };
   // element e = lane + 32 x of the bw x bw update block is (ii, jj) = (e / bw + 1, e % bw + 1): advanced incrementally
   const int bws = bw > 0 ? bw : 1;
   const int ii0 = lane / bws + 1, jj0 = lane % bws + 1, di = 32 / bws, dj = 32 % bws;
+#pragma unroll 1
   for (int i = 0; i < bw; ++i) rg.fetch_T(Tg, i);
   cp_async_wait<0>();
   __syncwarp();
+#pragma unroll 1
   for (int i = 0; i < bw; ++i) to_M(i);
+#pragma unroll 1
   for (int i = bw; i <= bw + kBandAhead; ++i) rg.fetch_T(Tg, i);
+#pragma unroll 1
   for (int k = 0; k < S; ++k) {
     cp_async_wait<kBandAhead>();                      // row k + bw has landed
     __syncwarp();
@@ -379,6 +393,7 @@ __device__ __noinline__ int band_lu(const double* __restrict__ Tg, double g, dou
     const double piv = rk[bw];
     if (!(fabs(piv) > 1e-300)) flags |= COBEL_FLAG_SINGULAR;
     const double ipiv = 1.0 / piv;
+#pragma unroll 1
     for (int e = lane, ii = ii0, jj = jj0; e < bw * bw; e += 32) {  // (ii, jj) enumerate bw x bw; the last steps guard
       if (ii <= nb && jj <= nb) {
         double* ri = rg.row(k + ii);
@@ -406,8 +421,11 @@ __device__ __noinline__ int band_lu(const double* __restrict__ Tg, double g, dou
 __device__ __noinline__ void band_solve_row(const double* __restrict__ fac, double* ringmem, int S, int bw, int c, double* x,
                                             int lane) {
   const BandRing rg(ringmem, S, bw, lane);
+#pragma unroll 1
   for (int e = lane; e < S; e += 32) x[e] = e == c ? 1.0 : 0.0;
+#pragma unroll 1
   for (int j = c; j <= c + kBandAhead; ++j) rg.fetch_band(fac, j);
+#pragma unroll 1
   for (int j = c; j < S; ++j) {                       // y_j = rhs_j / U[j][j]; rhs_i -= U[j][i] y_j, i in (j, j+bw]
     cp_async_wait<kBandAhead>();
     __syncwarp();
@@ -422,7 +440,9 @@ __device__ __noinline__ void band_solve_row(const double* __restrict__ fac, doub
   }
   cp_async_wait<0>();
   __syncwarp();
+#pragma unroll 1
   for (int j = S - 1; j >= S - 1 - kBandAhead; --j) rg.fetch_band(fac, j);
+#pragma unroll 1
   for (int j = S - 1; j > 0; --j) {                   // x_j final; x_i -= L[j][i] x_j, i in [j-bw, j)
     cp_async_wait<kBandAhead>();
     __syncwarp();
@@ -444,7 +464,9 @@ __device__ __noinline__ int band_gth(const double* __restrict__ Tg, double* fac,
   int flags = 0;
   const BandRing rg(ringmem, S, bw, lane);
   // elimination k = S-1 .. 1 works on rows k-bw .. k: stream upwards
+#pragma unroll 1
   for (int i = S - 1; i >= S - 1 - bw - kBandAhead; --i) rg.fetch_T(Tg, i);
+#pragma unroll 1
   for (int k = S - 1; k >= 1; --k) {
     cp_async_wait<kBandAhead>();                      // row k - bw has landed
     __syncwarp();
@@ -454,6 +476,7 @@ __device__ __noinline__ int band_gth(const double* __restrict__ Tg, double* fac,
     for (int d = 16; d > 0; d >>= 1) ssum += shfl_f64_xor(ssum, d);
     if (!(ssum > 0.0)) { flags |= COBEL_FLAG_SINGULAR; ssum = 1.0; }
     const double inv = 1.0 / ssum;
+#pragma unroll 1
     for (int e = lane; e < nb * nb; e += 32) {
       const int ii = e / nb + 1, jj = e - (ii - 1) * nb + 1;        // i = k - ii, j = k - jj
       double* ri = rg.row(k - ii);
@@ -492,9 +515,11 @@ __device__ __noinline__ int band_gth(const double* __restrict__ Tg, double* fac,
     }
   }
   double sq = 0.0;
+#pragma unroll 1
   for (int i = lane; i < S; i += 32) sq = fma(x[i], x[i], sq);
   for (int d = 16; d > 0; d >>= 1) sq += shfl_f64_xor(sq, d);
   const double nrm = sqrt(sq);
+#pragma unroll 1
   for (int i = lane; i < S; i += 32) x[i] = fabs(x[i]) / nrm;
   __syncwarp();
   return flags;
@@ -746,11 +771,11 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     // p / sum(p): x / 1.0 == x, so the (frequent) exactly-normalised case skips the divisions
     if (sn_ != 1.0) {
 #pragma unroll
-      for (int c = 0; c < A; ++c) pn[c] = xdiv(pn[c], sn_);
+      for (int c = 0; c < A; ++c) pn[c] = pdiv(pn[c], sn_);
     }
     if (so_ != 1.0) {
 #pragma unroll
-      for (int c = 0; c < A; ++c) po[c] = xdiv(po[c], so_);
+      for (int c = 0; c < A; ++c) po[c] = pdiv(po[c], so_);
     }
 #pragma unroll
     for (int c = 0; c < A; ++c) t[c] = xmul(pn[c], qn[c]);
@@ -949,7 +974,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       // Generator.choice(p = ties / k): cdf_m = m-fold sequential sum of fl(1/k), normalised by cdf_k
       int pick = ktot - 1;
       if (ktot > 1) {
-        const double pk_ = xdiv(1.0, int_to_f64(ktot));
+        const double pk_ = pdiv(1.0, int_to_f64(ktot));
         double ck = 0.0;
 #pragma unroll 1
         for (int m = 0; m < ktot; ++m) ck = xadd(ck, pk_);
@@ -957,7 +982,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
 #pragma unroll 1
         for (int m = 0; m < ktot; ++m) {
           c = xadd(c, pk_);
-          if (xdiv(c, ck) > u) { pick = m; break; }
+          if (pdiv(c, ck) > u) { pick = m; break; }
         }
       }
       // the chunk whose [incl - cnt, incl) range contains `pick`, then the pick-th set bit of its ballot
