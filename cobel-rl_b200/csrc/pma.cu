@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   int64_t nsteps = ph.init_carry ? 0 : carry[1], nrep = ph.init_carry ? 0 : carry[2], ncalls = ph.init_carry ? 0 : carry[3];
   const int64_t nsteps0 = nsteps, nrep0 = nrep;
 
-  DrawWindowT<!PLAIN> win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
+  DrawWindowT<!PLAIN, true> win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);
   const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
   const double lrq = p.lr_q[n], gq = p.gamma_q[n];
   const double min_gain = p.min_gain;

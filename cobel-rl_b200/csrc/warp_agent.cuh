@@ -63,8 +63,17 @@ COBEL_DEV int stochastic_successor(const CobelWorld& w, int sa, double u) {
 // holds the 64 consecutive draws starting at 2*b0.  One Philox block per lane per refill
 // instead of one per draw per agent.
 // ---------------------------------------------------------------------------
-// MAYBE_USER = false compiles the user-stream ("stream from HBM") branches out.
-template <bool MAYBE_USER>
+// One Philox block -> two uniforms, as ONE shared copy of the ~110-instruction sequence: for kernels that are
+// instruction-fetch bound (PMA) and refill from several sites.
+static __device__ __noinline__ double2 philox_pair_shared(uint64_t b, uint64_t agent, uint32_t key0, uint32_t key1) {
+  uint32_t o[4];
+  philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)agent, (uint32_t)(agent >> 32), key0, key1, o);
+  return make_double2(u53(o[0], o[1]), u53(o[2], o[3]));
+}
+
+// MAYBE_USER = false compiles the user-stream ("stream from HBM") branches out; SMALL_CODE = true refills
+// through the shared (not inlined) Philox routine.
+template <bool MAYBE_USER, bool SMALL_CODE = false>
 struct DrawWindowT {
   uint64_t agent;
   uint32_t key0, key1;
@@ -90,9 +99,14 @@ struct DrawWindowT {
     const uint64_t k = base + (uint64_t)off;
     base = k & ~1ull; off = (int)(k & 1ull); cap = 64;
     const uint64_t b = (base >> 1) + lane;
-    uint32_t o[4];
-    philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)agent, (uint32_t)(agent >> 32), key0, key1, o);
-    ua = u53(o[0], o[1]); ub = u53(o[2], o[3]);
+    if constexpr (SMALL_CODE) {
+      const double2 d = philox_pair_shared(b, agent, key0, key1);
+      ua = d.x; ub = d.y;
+    } else {
+      uint32_t o[4];
+      philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)agent, (uint32_t)(agent >> 32), key0, key1, o);
+      ua = u53(o[0], o[1]); ub = u53(o[2], o[3]);
+    }
   }
   // draw number (next + ahead), `ahead` may differ per lane; all 32 lanes must call
   COBEL_DEV double peek(int ahead) const {
