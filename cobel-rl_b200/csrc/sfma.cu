@@ -101,6 +101,7 @@ COBEL_DEV int block_sample(const double* w, int N, double u, double* part, Block
   const int chunk = (N + T - 1) / T;
   const int lo = tid * chunk < N ? tid * chunk : N, hi = lo + chunk < N ? lo + chunk : N;
   double local = 0.0;
+#pragma unroll 1
   for (int i = lo; i < hi; ++i) local += w[i];
   double total;
   const double excl = block_exclusive_scan(local, part, tid, T, total);
@@ -123,6 +124,7 @@ COBEL_DEV int block_sample(const double* w, int N, double u, double* part, Block
     double acc = excl;
     int found = -1, lastpos = lo;
     bool near = fabs(excl - target) < tol;
+#pragma unroll 1
     for (int i = lo; i < hi; ++i) {
       if (!(w[i] > 0.0)) continue;
       lastpos = i;
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
 
   const size_t g0 = (size_t)n * N;
   const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
+#pragma unroll 1
   for (int e = tid; e < N; e += T) {
     Q[e] = p.Q[g0 + e];
     Mr[e] = p.Mr[g0 + e];
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     C[e] = p.C[g0 + e];
     if (track_t) Tr[e] = p.T[g0 + e];
   }
+#pragma unroll 1
   for (int e = tid; e < S; e += T) {
     I[e] = p.I[(size_t)n * S + e];
     uint32_t mb = (1u << A) - 1u;
@@ -243,6 +247,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
       // lane b of warp 0 resolves draw b: smallest m with cdf_m / cdf_last > u, then the m-th valid (a, s)
       if (warp == 0) {
         const double tot = cdft[nvalid - 1];
+#pragma unroll 1
         for (int b0 = 0; b0 < B; b0 += 32) {
           const int nb = B - b0 < 32 ? B - b0 : 32;
           win.ensure(nb, lane);
@@ -265,13 +270,16 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
       __syncthreads();
       const int count = B;
       if (tr.replay_idx)
+#pragma unroll 1
         for (int j = tid; j < count; j += T) {
           if (nrep + j < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + j] = rep[j];
           else flags |= COBEL_FLAG_TRACE_OVERFLOW;
         }
+#pragma unroll 1
       for (int e = tid; e < 2 * S; e += T) wm[e] = 0;
       __syncthreads();
       if (warp == 0) {
+#pragma unroll 1
         for (int b0 = 0; b0 < count; b0 += 32) {
           const bool active = b0 + lane < count;
           int es = 0, ea = 0, es2 = 0, ent = 0;
@@ -313,24 +321,29 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
       const int chunk = (N + T - 1) / T;
       const int lo = tid * chunk < N ? tid * chunk : N, hi = lo + chunk < N ? lo + chunk : N;
       int cnt = 0;
+#pragma unroll 1
       for (int i = lo; i < hi; ++i) cnt += C[i] > 0.0 ? 1 : 0;
       int off = block_exclusive_scan_int(cnt, part, tid, T, nnz);
+#pragma unroll 1
       for (int i = lo; i < hi; ++i)
         if (C[i] > 0.0) { const int a = i / S; L[off++] = ((uint32_t)a << 16) | (uint32_t)(i - a * S); }
     }
     __syncthreads();
     if (cur < 0) {                                                         // start ~ clip(C, 0) / sum
+#pragma unroll 1
       for (int j = tid; j < nnz; j += T) { const uint32_t l = L[j]; R[j] = C[(l >> 16) * S + (l & 0xFFFF)]; }
       __syncthreads();
       const uint32_t l = L[block_sample(R, nnz, sh.u, part, &sh, tid, T, flags)];
       cur = l & 0xFFFF; action = l >> 16;
     }
     int nxt = Mx[cur * A + action] & 0x7FFF;
+#pragma unroll 1
     for (int e = tid; e < S; e += T) I[e] = 0.0;                           // sfma.py:277
     __syncthreads();
     int count = 0;
     for (int it = 0; it < B; ++it) {
       double lmax = 0.0;
+#pragma unroll 1
       for (int j = tid; j < nnz; j += T) {
         const uint32_t l = L[j];
         const int a = l >> 16, sp = l & 0xFFFF, i = a * S + sp;
@@ -352,12 +365,14 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
       if (p.deterministic) {                                               // argmax(R): first maximum
         if (tid == 0) sh.idx = 0x7fffffff;
         __syncthreads();
+#pragma unroll 1
         for (int j = tid; j < nnz; j += T) if (R[j] == m) { atomicMin(&sh.idx, j); break; }
         __syncthreads();
         jsel = sh.idx;
         __syncthreads();
       } else {
         // probs ~ exp(beta * R / max) - 1  (softmax(R, -1, beta), sfma.py:349-373); exp(0) - 1 == 0 exactly
+#pragma unroll 1
         for (int j = tid; j < nnz; j += T) { const double r = R[j]; R[j] = r > 0.0 ? xadd(exp(xmul(xdiv(r, m), beta)), -1.0) : 0.0; }
         if (warp == 0) {
           win.ensure(1, lane);
@@ -372,6 +387,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
       cur = l & 0xFFFF;
       const int e = action * S + cur;
       nxt = Mx[cur * A + action] & 0x7FFF;
+#pragma unroll 1
       for (int s = tid; s < S; s += T) {                                   // sfma.py:333-335
         double v = xmul(I[s], dinh);
         if (s == cur) { v = xadd(v, p.i_step); v = v < 1.0 ? v : 1.0; }
@@ -383,13 +399,16 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     }
     // apply the reactivated experiences to Q in order (agent/sfma.py:416-419)
     if (tr.replay_idx)
+#pragma unroll 1
       for (int j = tid; j < count; j += T) {
         if (nrep + j < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + j] = rep[j];
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
+#pragma unroll 1
     for (int e = tid; e < 2 * S; e += T) wm[e] = 0;                        // wm, rm alias R
     __syncthreads();
     if (warp == 0 && apply_updates) {
+#pragma unroll 1
       for (int b0 = 0; b0 < count; b0 += 32) {
         const bool active = b0 + lane < count;
         int es = 0, ea = 0, es2 = 0, ent = 0;
@@ -447,8 +466,14 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
         ++nsteps;
         if (learn) {
           // SFMAMemory.store (memory/sfma.py:206-215): EMA reward, next state, flag, strengths, recency
-          if (dstr != 1.0) for (int e = lane; e < N; e += 32) C[e] = xmul(C[e], dstr);
-          if (track_t) for (int e = lane; e < N; e += 32) Tr[e] = xmul(Tr[e], drec);
+          if (dstr != 1.0) {
+#pragma unroll 1
+            for (int e = lane; e < N; e += 32) C[e] = xmul(C[e], dstr);
+          }
+          if (track_t) {
+#pragma unroll 1
+            for (int e = lane; e < N; e += 32) Tr[e] = xmul(Tr[e], drec);
+          }
           const double m0 = Mr[s * A + a];
           const double m1 = xadd(m0, xmul(mlr, xsub(r, m0)));
           // SFMA.update_q (agent/sfma.py:423-458): max over the unmasked actions of s'
@@ -487,13 +512,17 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     if (do_replay) {
       const int last = sh.last;
       for (int rpl = 0; rpl < p.nb_replays; ++rpl) replay(last, true);
-      if (track_t) for (int e = tid; e < N; e += T) Tr[e] = 0.0;           // M.T.fill(0), agent/sfma.py:324
+      if (track_t) {
+#pragma unroll 1
+        for (int e = tid; e < N; e += T) Tr[e] = 0.0;           // M.T.fill(0), agent/sfma.py:324
+      }
       __syncthreads();
     }
   }
 
   __syncthreads();
   if (learn) {
+#pragma unroll 1
     for (int e = tid; e < N; e += T) {
       p.Q[g0 + e] = Q[e];
       p.Mr[g0 + e] = Mr[e];
@@ -504,6 +533,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
       if (track_t) p.T[g0 + e] = Tr[e];
       else if (do_replay && p.trials > 0) p.T[g0 + e] = 0.0;
     }
+#pragma unroll 1
     for (int e = tid; e < S; e += T) p.I[(size_t)n * S + e] = I[e];
   }
   flags = __syncthreads_or(flags);
