@@ -40,13 +40,13 @@ SEED = 0x5EED
 WORKLOADS = {
     'dynaq': dict(
         desc='C2: 4096 Dyna-Q agents/GPU, 5x5 open field, 500 trials x <=50 steps, batch 32',
-        metric='agent-steps/sec incl. replay', unit='agent-steps/s', kernel='dynaq_warp_kernel<4>',
+        metric='agent-steps/sec incl. replay', unit='agent-steps/s', kernel='dynaq_warp_kernel<4,PLAIN>',
         agents_per_gpu=4096, trials=500, steps=50, batch=32, world='open5', bytes_per_unit=2066,
         unit_key='n_steps', cpu_trials=500),
     'pma': dict(
         desc='C3: 16384 PMA agents/GPU, 10x10 gridworld with walls, 4 trials x <=100 steps, replay batch 32 at '
              'trial start and end',
-        metric='PMA replay updates/sec', unit='replay-updates/s', kernel='pma_main_kernel<4> + pma_sr_kernel<7>',
+        metric='PMA replay updates/sec', unit='replay-updates/s', kernel='pma_main_kernel<4,PLAIN,BAND> + pma_band_check_kernel + pma_sr_band_kernel<12>',
         agents_per_gpu=16384, trials=4, steps=100, batch=32, world='walls10', bytes_per_unit=23 * 400 + 8 * 100,
         unit_key='n_replay', cpu_trials=4),
     'sfma': dict(
@@ -62,12 +62,12 @@ WORKLOADS = {
     'sr100': dict(
         desc='C5: SR agents with visited-set compaction, 100x100 open field, 1048576 agents in total (strong scaling: '
              'sharded over the GPUs), 2 trials x <=48 steps, max_visited 100',
-        metric='agent-steps/sec', unit='agent-steps/s', kernel='sr_compact_kernel<4>',
+        metric='agent-steps/sec', unit='agent-steps/s', kernel='sr_compact_kernel<4,PLAIN>',
         agents_total=1048576, trials=2, steps=48, batch=0, world='open100', bytes_per_unit=8 * 50 * 8 + 24,
         unit_key='n_steps', cpu_trials=2, scaling='strong', max_visited=100),
     'q': dict(
         desc='QAgent on the linear_track(10,2) topology graph, 4096 agents/GPU, 500 trials x <=50 steps, batch 32',
-        metric='agent-steps/sec incl. replay', unit='agent-steps/s', kernel='q_warp_kernel<4>',
+        metric='agent-steps/sec incl. replay', unit='agent-steps/s', kernel='q_warp_kernel<4,PLAIN>',
         agents_per_gpu=4096, trials=500, steps=50, batch=32, world='track', bytes_per_unit=2223,
         unit_key='n_steps', cpu_trials=500),
 }

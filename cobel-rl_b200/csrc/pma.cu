@@ -463,6 +463,8 @@ __device__ __noinline__ int band_gth(const double* __restrict__ Tg, double* fac,
                                      int lane) {
   int flags = 0;
   const BandRing rg(ringmem, S, bw, lane);
+  const int bws = bw > 0 ? bw : 1;
+  const int ii0 = lane / bws + 1, jj0 = lane % bws + 1, di = 32 / bws, dj = 32 % bws;
   // elimination k = S-1 .. 1 works on rows k-bw .. k: stream upwards
 #pragma unroll 1
   for (int i = S - 1; i >= S - 1 - bw - kBandAhead; --i) rg.fetch_T(Tg, i);
@@ -477,11 +479,14 @@ __device__ __noinline__ int band_gth(const double* __restrict__ Tg, double* fac,
     if (!(ssum > 0.0)) { flags |= COBEL_FLAG_SINGULAR; ssum = 1.0; }
     const double inv = 1.0 / ssum;
 #pragma unroll 1
-    for (int e = lane; e < nb * nb; e += 32) {
-      const int ii = e / nb + 1, jj = e - (ii - 1) * nb + 1;        // i = k - ii, j = k - jj
-      double* ri = rg.row(k - ii);
-      const double f = ri[bw + ii] * inv;                          // P[i][k] / s
-      ri[bw + ii - jj] = fma(f, rk[bw - jj], ri[bw + ii - jj]);
+    for (int e = lane, ii = ii0, jj = jj0; e < bw * bw; e += 32) {  // i = k - ii, j = k - jj over bw x bw, guarded
+      if (ii <= nb && jj <= nb) {
+        double* ri = rg.row(k - ii);
+        const double f = ri[bw + ii] * inv;                        // P[i][k] / s
+        ri[bw + ii - jj] = fma(f, rk[bw - jj], ri[bw + ii - jj]);
+      }
+      jj += dj; ii += di;
+      if (jj > bw) { jj -= bw; ++ii; }
     }
     __syncwarp();
     if (lane < nb) rg.row(k - 1 - lane)[bw + 1 + lane] *= inv;     // column k keeps P[i][k] / s
