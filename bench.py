@@ -63,7 +63,7 @@ WORKLOADS = {
         desc='C5: SR agents with visited-set compaction, 100x100 open field, 1048576 agents in total (strong scaling: '
              'sharded over the GPUs), 2 trials x <=48 steps, max_visited 100',
         metric='agent-steps/sec', unit='agent-steps/s', kernel='sr_compact_kernel<4,PLAIN>',
-        agents_total=1048576, trials=2, steps=48, batch=0, world='open100', bytes_per_unit=8 * 50 * 8 + 24,
+        agents_total=1048576, trials=2, steps=48, batch=0, world='open100', bytes_per_unit=3 * 8 * 25 + 24,   # refined from the measured visited counts in measure()
         unit_key='n_steps', cpu_trials=2, scaling='strong', max_visited=100),
     'q': dict(
         desc='QAgent on the linear_track(10,2) topology graph, 4096 agents/GPU, 500 trials x <=50 steps, batch 32',
@@ -395,6 +395,20 @@ def measure(job, k, warmup, cdist, dev, flush, e2e=True):
     ms, wall, res = timed(job.step, job.reset)
     launches = L.cobel_launch_count() - l0
     units = float(res[job.wl['unit_key']].sum().item())
+    if job.name == 'sr100':
+        # algorithmic bytes of a compact-SR step: rows SRc[s], SRc[s'] read and SRc[s] written over the V states
+        # visited so far; V grows from 1 to the final count, so its mean over the run is taken as half of that
+        vbar = 0.5 * float(job.agent._n_visited.double().mean().item())
+        job.wl = dict(job.wl, bytes_per_unit=int(3 * 8 * vbar) + 24)
+        WORKLOADS['sr100'] = job.wl
+    if job.name == 'sfma':
+        # per agent-step: 138 B of step work + the reactivations of the trial-end replay (8N + 24S + 61 B each,
+        # DESIGN.md K5) spread over the steps actually taken
+        S_, A_ = job.env.n_states, job.env.n_actions
+        per_react = 8 * S_ * A_ + 24 * S_ + 61
+        job.wl = dict(job.wl, bytes_per_unit=int(138 + per_react * float(res['n_replay'].sum().item()) /
+                                                 max(float(res['n_steps'].sum().item()), 1.0)))
+        WORKLOADS['sfma'] = job.wl
     out = {'ms': sum(ms) / len(ms), 'wall': wall, 'units': units, 'launches': int(launches), 'res': res,
            'steps_units': float(res['n_steps'].sum().item()), 'replay_units': float(res['n_replay'].sum().item())}
     if e2e:
