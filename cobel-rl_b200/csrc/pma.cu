@@ -952,10 +952,11 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       unsigned tm = 0;
 #pragma unroll 1
       for (int i = lane, c = 0; i < N; i += 32, ++c) {
-        const double v = util[i];
-        if (v > lmax) { l2 = lmax; lmax = v; tm = 1u << c; }
-        else if (v == lmax) tm |= 1u << c;
-        else if (v > l2) l2 = v;
+        const double v = util[i];                        // branch-free: the three cases are selects
+        const bool gt = v > lmax, eq = v == lmax;
+        l2 = gt ? lmax : ((!eq && v > l2) ? v : l2);
+        tm = gt ? (1u << c) : (eq ? (tm | (1u << c)) : tm);
+        lmax = gt ? v : lmax;
       }
       const double umax = warp_max_f64(lmax);
       if (lmax != umax) { tm = 0; l2 = lmax; }
