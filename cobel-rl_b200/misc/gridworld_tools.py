@@ -80,3 +80,63 @@ def make_windy_gridworld(height, width, columns, goal_state=0, reward=1, directi
     wind = np.stack([idx, np.asarray(columns)[idx % width] * sign, np.zeros_like(idx)], axis=1)
     return make_gridworld(height, width, terminals=[goal_state], rewards=np.array([[goal_state, reward]]),
                           goals=[goal_state], wind=wind)
+
+
+# ---------------------------------------------------------------------------
+# Maze templates (reference: misc/gridworld_tools.py:237-507).  A maze is a set of corridor cells on
+# the full rectangular grid; the walls are the transitions, in both directions, between a corridor
+# cell and an adjacent cell outside the corridor (the outside cells stay valid but unreachable
+# states, as in the reference).  The templates produce the same WorldDict as the reference's; the
+# order of `invalid_transitions` (a set semantically: make_gridworld only tests membership) is
+# row-major by corridor cell here.
+# ---------------------------------------------------------------------------
+def _corridor_walls(height, width, corridor):
+    """Both directions of every transition between a corridor cell and a 4-neighbour outside it."""
+    inside = np.zeros((height, width), dtype=bool)
+    for r, c in corridor:
+        inside[r, c] = True
+    walls = []
+    for r, c in sorted(set(corridor)):
+        for dr, dc in ((0, -1), (-1, 0), (0, 1), (1, 0)):
+            rr, cc = r + dr, c + dc
+            if 0 <= rr < height and 0 <= cc < width and not inside[rr, cc]:
+                a, b = r * width + c, rr * width + cc
+                walls += [(a, b), (b, a)]
+    return walls
+
+
+def _maze(height, width, corridor, goal_state, start_state, reward):
+    return make_gridworld(height, width, [goal_state], np.array([[goal_state, reward]]), [goal_state], [start_state],
+                          invalid_transitions=_corridor_walls(height, width, corridor))
+
+
+def make_t_maze(stem_length, arm_length, goal_arm='right', reward=1):
+    """T-maze (misc/gridworld_tools.py:237-298): the arms are the top row, the stem hangs from its middle."""
+    assert stem_length > 0 and arm_length > 0, 'Stem and arm length must be greater than zero!'
+    height, width = stem_length + 1, arm_length * 2 + 1
+    corridor = [(0, c) for c in range(width)] + [(r, arm_length) for r in range(1, height)]
+    goal = 0 if goal_arm == 'left' else width - 1
+    return _maze(height, width, corridor, goal, height * width - arm_length - 1, reward)
+
+
+def make_double_t_maze(stem_length, arm_length, goal_arm='right-right', reward=1):
+    """Double T-maze (misc/gridworld_tools.py:301-432): a stem, a cross bar, and a T on either end of the bar."""
+    assert stem_length > 0 and arm_length > 0, 'Stem and arm length must be greater than zero!'
+    height, width = stem_length * 2 + 2, arm_length * 4 + 3
+    mid, left, right, bar = 2 * arm_length + 1, arm_length, width - 1 - arm_length, stem_length + 1
+    corridor = [(r, mid) for r in range(bar + 1, height)]                     # lower stem
+    corridor += [(bar, c) for c in range(left, right + 1)]                    # cross bar
+    corridor += [(r, c) for r in range(1, bar) for c in (left, right)]        # the two upper stems
+    corridor += [(0, c) for c in range(width) if c != mid]                    # the four arms (top row without its middle)
+    goal = {'left-left': 0, 'left-right': arm_length * 2, 'right-left': arm_length * 2 + 2,
+            'right-right': arm_length * 4 + 2}.get(goal_arm, 0)
+    return _maze(height, width, corridor, goal, height * width - arm_length * 2 - 2, reward)
+
+
+def make_two_sided_t_maze(stem_length, arm_length, goal_arm='right-right', reward=1):
+    """Two-sided T-maze (misc/gridworld_tools.py:435-506): a horizontal stem with vertical arms at both ends."""
+    assert stem_length > 0 and arm_length > 0, 'Stem and arm length must be greater than zero!'
+    height, width = arm_length * 2 + 1, stem_length + 2
+    corridor = [(arm_length, c) for c in range(width)] + [(r, c) for r in range(height) for c in (0, width - 1)]
+    goal = {'right-left': width - 1, 'left-left': width * (height - 1), 'right-right': width * height - 1}.get(goal_arm, 0)
+    return _maze(height, width, corridor, goal, arm_length * width + int(stem_length / 2), reward)

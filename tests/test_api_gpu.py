@@ -284,3 +284,28 @@ def test_unsupported_shapes_and_options_fail_loudly():
     cpu_stream = cb.BatchStream(2, device='cpu')
     with pytest.raises(_lib.CobelError):
         cpu_stream.next(1)
+
+
+def test_maze_template_worlds_run_bit_exact():
+    """The T-maze templates (misc/gridworld_tools.py:237-507) through Dyna-Q, PLAIN and recorded kernels, vs the oracle."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.policy import EpsilonGreedy
+    from cobel_rl_b200.misc.gridworld_tools import make_double_t_maze, make_t_maze
+    for world in (make_t_maze(3, 2), make_double_t_maze(2, 1, 'left-right')):
+        W = tb.compile_gridworld(world)
+        S = world['states']
+        for record in (True, False):
+            stream = cb.BatchStream(3, seed=77, device='cuda:0')
+            env = Gridworld(world, rng=stream)
+            ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream))
+            ag.record = record
+            res = ag.train(env, 8, 30, 32)
+            torch.cuda.synchronize()
+            for i in range(3):
+                rng = tb.Draws(LazyStream(77, i), 1)
+                st = tb.dynaq_init(S, 4)
+                rec = tb.dynaq_train(W, st, rng, 8, 30, 32).arrays()
+                assert np.array_equal(ag.Q[i].cpu().numpy(), st['Q']) and int(stream.draw_count[i]) == rng.k
+                assert np.array_equal(res['trial_steps'][i].cpu().numpy(), rec['trial_steps'])

@@ -32,6 +32,47 @@ def test_gridworld_builders(reference):
     assert big['sas'] is None and big['succ'].shape == (10000, 4)
 
 
+def same_maze(a, b):
+    """Like same_world, with `invalid_transitions` compared as the set it is (make_gridworld only tests membership)."""
+    for k in b:
+        x, y = a[k], b[k]
+        if k == 'invalid_transitions':
+            as_set = lambda w: {(int(s), int(t)) for s, t in w}
+            assert as_set(x) == as_set(y) and len(x) == len(y)
+        elif isinstance(y, np.ndarray):
+            assert x.dtype == y.dtype and np.array_equal(x, y), k
+        else:
+            assert x == y, (k, x, y)
+
+
+def test_maze_templates(reference):
+    from cobel.misc import gridworld_tools as rg
+    for stem in (1, 2, 3, 4):
+        for arm in (1, 2, 3):
+            for goal in ('left', 'right'):
+                same_maze(mg.make_t_maze(stem, arm, goal, 2.5), rg.make_t_maze(stem, arm, goal, 2.5))
+            for goal in ('left-left', 'left-right', 'right-left', 'right-right'):
+                same_maze(mg.make_double_t_maze(stem, arm, goal), rg.make_double_t_maze(stem, arm, goal))
+                same_maze(mg.make_two_sided_t_maze(stem, arm, goal), rg.make_two_sided_t_maze(stem, arm, goal))
+
+
+def test_maze_templates_known_answers():
+    """Runs everywhere (no reference needed): the T-maze of the reference's demo, drawn from the successor table."""
+    w = mg.make_t_maze(3, 2)
+    assert (w['height'], w['width']) == (4, 5) and list(w['starting_states']) == [17] and w['goals'] == [4]
+    assert w['rewards'][4] == 1 and w['terminals'][4] == 1 and len(w['invalid_transitions']) == 20
+    succ = w['succ']
+    # stem: only up / down moves; arms: left / right along the top row, down only at the junction
+    assert list(succ[17]) == [17, 12, 17, 17] and list(succ[12]) == [12, 7, 12, 17] and list(succ[7]) == [7, 2, 7, 12]
+    assert list(succ[2]) == [1, 2, 3, 7] and list(succ[0]) == [0, 0, 1, 0] and list(succ[4]) == [3, 4, 4, 4]
+    d = mg.make_double_t_maze(2, 1)
+    assert (d['height'], d['width']) == (6, 7) and list(d['starting_states']) == [38] and d['goals'] == [6]
+    assert len(d['invalid_transitions']) == 54
+    t = mg.make_two_sided_t_maze(2, 2)
+    assert (t['height'], t['width']) == (5, 4) and list(t['starting_states']) == [9] and t['goals'] == [19]
+    assert len(t['invalid_transitions']) == 24
+
+
 def test_topology_builders(reference):
     from cobel.misc import topology_tools as rt
     for args in [(10, 2, 1.0, 20., 'right'), (5, 1, 0.5, 1., 'left'), (4, 3)]:
