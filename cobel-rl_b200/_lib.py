@@ -73,8 +73,8 @@ class SFMAParams(C.Structure):
                 ('c_step', C.c_double), ('i_step', C.c_double), ('blend', C.c_double), ('interp_fwd', C.c_double),
                 ('interp_rev', C.c_double), ('mode', C.c_int32), ('recency', C.c_int32), ('deterministic', C.c_int32),
                 ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32), ('nb_replays', C.c_int32),
-                ('start_replay', C.c_int32), ('random_replay', C.c_int32), ('reserved', C.c_int32),
-                ('no_replay', C.c_int32), ('learn', C.c_int32)]
+                ('start_replay', C.c_int32), ('random_replay', C.c_int32), ('dynamic', C.c_int32),
+                ('no_replay', C.c_int32), ('learn', C.c_int32), ('td_acc', c_ptr), ('trial_mode', c_ptr)]
 
 
 PMA_MAX_SEQ = 64
@@ -89,7 +89,7 @@ class PMAParams(C.Structure):
                 ('pow_stride', C.c_int64), ('min_gap', c_ptr), ('carry', c_ptr), ('need_scratch', c_ptr),
                 ('lr_T', C.c_double), ('min_gain', C.c_double),
                 ('min_gain_original', C.c_int32), ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32),
-                ('no_replay', C.c_int32), ('learn', C.c_int32), ('sr_band', C.c_int32), ('reserved', C.c_int32),
+                ('no_replay', C.c_int32), ('learn', C.c_int32), ('sr_band', C.c_int32), ('options', C.c_int32),
                 ('band_scratch', c_ptr)]
 
 

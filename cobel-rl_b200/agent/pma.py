@@ -78,7 +78,7 @@ class PMA(Agent):
                 M._min_gap.data_ptr(), M._carry.data_ptr(), M._need_scratch.data_ptr(),
                 float(M.learning_rate_T), float(M.min_gain),
                 1 if M.min_gain_mode == 'original' else 0, n_tr, steps, batch_size, 1 if no_replay else 0,
-                1 if learn else 0, band, 0, _lib.ptr(bscratch))
+                1 if learn else 0, band, M.options(), _lib.ptr(bscratch))
             keep.append(par)
             _lib.call('cobel_pma_run', st.device, p, launch_stream(st))
             self._check_flags(res)

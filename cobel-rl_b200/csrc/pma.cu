@@ -743,6 +743,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   const double lrq = p.lr_q[n], gq = p.gamma_q[n];
   const double min_gain = p.min_gain;
   const bool original = p.min_gain_original != 0;
+  const int opt = PLAIN ? 0 : p.options;        // COBEL_PMA_OPT_* (the PLAIN kernel is built for none of them)
   PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
   PolicyTab mpt; mpt.init(mkind, mpar, lane);
   const bool learn = PLAIN || p.learn != 0;
@@ -789,13 +790,16 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     for (int c = 0; c < A; ++c) t[c] = xmul(po[c], qn[c]);
     const double gold = sum_seq<A>(t);
     const double g = xsub(gnew, gold);
+    if (opt & COBEL_PMA_OPT_EQUAL_GAIN) return 1.0;                  // gain.fill(1), memory/pma.py:241-242
     return g > min_gain ? g : min_gain;
   };
 
   // utility of the one-step backup i: gain * need * update_mask (memory/pma.py:247-249)
   auto util_one = [&](int i) -> double {
     const int a = act_of(i), s = i - a * S;
-    return xmul(xmul(gain_one(i), need[s]), (Pk[s * A + a] & kUm) ? 1.0 : 0.0);
+    const double gn = xmul(gain_one(i), need[s]);
+    if (opt & COBEL_PMA_OPT_KEEP_BARRIERS) return gn;               // ignore_barriers False, memory/pma.py:248-249
+    return xmul(gn, (Pk[s * A + a] & kUm) ? 1.0 : 0.0);
   };
 
   // PMAMemory.replay, memory/pma.py:168-267.  nsrc = the need vector in HBM (an SR row or the stationary
@@ -804,6 +808,11 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     if (nsrc) {
 #pragma unroll 1
       for (int e = lane; e < S; e += 32) need[e] = nsrc[e];
+    }
+    if (opt & COBEL_PMA_OPT_EQUAL_NEED) {                              // need.fill(1), memory/pma.py:244-245
+      __syncwarp();
+#pragma unroll 1
+      for (int e = lane; e < S; e += 32) need[e] = 1.0;
     }
     // CSR of the backups grouped by their next state (M.states does not change during a replay):
     // the backups that read Q row t are row t itself and pitems[poff[t] .. poff[t+1])
@@ -934,6 +943,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
           for (int l = 0; l < m; ++l) total = xadd(total, shfl_f64(sg, l));       // gain += step_gain, in order
         }
         gext = total > min_gain ? total : min_gain;
+        if (opt & COBEL_PMA_OPT_EQUAL_GAIN) gext = 1.0;
       }
       // ---- (4) arg-max of the utilities with exact ties (memory/pma.py:247-254); the candidate's
       // n-step gain overrides the one-step entry `ext` for this iteration only
@@ -942,7 +952,10 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         const int ea = act_of(ext), es = ext - ea * S;
         saved = util[ext];
         __syncwarp();
-        if (lane == 0) util[ext] = xmul(xmul(gext, need[es]), (Pk[es * A + ea] & kUm) ? 1.0 : 0.0);
+        if (lane == 0) {
+          const double gn = xmul(gext, need[es]);
+          util[ext] = (opt & COBEL_PMA_OPT_KEEP_BARRIERS) ? gn : xmul(gn, (Pk[es * A + ea] & kUm) ? 1.0 : 0.0);
+        }
         __syncwarp();
       }
       const double ninf = -__longlong_as_double(0x7FF0000000000000ll);
@@ -1195,7 +1208,7 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
   const size_t sm_main = (size_t)kMainWarps * so.bytes;
   COBEL_REQUIRE(sm_main <= 227 * 1024, COBEL_EUNSUPPORTED, "PMA: %d states x %d actions do not fit in shared memory", S, A);
   const bool plain = p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.mem_policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn &&
-                     !p.no_replay && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx &&
+                     !p.no_replay && !p.options && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx &&
                      !p.trace.replay_len && !p.stream.user_stream;
   const bool do_replay = p.learn && !p.no_replay;
   // the banded path needs its row ring to fit into the replay buffers it aliases; otherwise dense update_sr

@@ -223,6 +223,16 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
   int64_t nsteps = 0, nrep = 0, ncalls = 0;
   int flags = 0;
   const double* D = p.D;
+  int mode = p.mode;                   // CTA-uniform; re-chosen per trial when agent.dynamic is set
+  double tdacc = p.td_acc ? p.td_acc[n] : 0.0;   // agent.td (maintained by warp 0)
+
+  // agent.td += |td| for a batch of replayed updates, in replay order (agent/sfma.py:456); warp 0
+  auto acc_td = [&](double tdl, bool active) {
+    if (!p.td_acc) return;
+    const unsigned act = __ballot_sync(kFull, active);
+#pragma unroll 1
+    for (int l = 0; l < 32 && (act >> l & 1u); ++l) tdacc = xadd(tdacc, fabs(shfl_f64(tdl, l)));
+  };
 
   // similarity of experience i = (a, s') to the current experience, by replay mode
   // (memory/sfma.py:283-306)
@@ -230,7 +240,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     const int ms = Mx[sp * A + a] & 0x7FFF;                 // states.flatten('F')[a*S + sp]
     const double* Dc = D + (size_t)cur * S;
     const double* Dn = D + (size_t)nxt * S;
-    switch (p.mode) {
+    switch (mode) {
       case MODE_FORWARD: return Dn[sp];
       case MODE_REVERSE: return Dc[ms];
       case MODE_BLEND_FORWARD: return xadd(Dc[sp], xmul(p.blend, Dn[sp]));
@@ -291,8 +301,10 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
             const uint16_t v = Mx[es * A + ea];
             es2 = v & 0x7FFF; ent = v >> 15;
           }
+          double tdl = 0.0;
           td_batch_level_parallel<A>(Q, wm, rm, S, lane, active, es, ea, er, es2, ent, lr, gamma,
-                                     masked ? mbits : nullptr);
+                                     masked ? mbits : nullptr, &tdl);
+          acc_td(tdl, active);
         }
       }
       if (tr.replay_len && tid == 0) {
@@ -420,8 +432,10 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
           const uint16_t v = Mx[es * A + ea];
           es2 = v & 0x7FFF; ent = v >> 15;
         }
+        double tdl = 0.0;
         td_batch_level_parallel<A>(Q, wm, rm, S, lane, active, es, ea, er, es2, ent, lr, gamma,
-                                   masked ? mbits : nullptr);
+                                   masked ? mbits : nullptr, &tdl);
+        acc_td(tdl, active);
       }
     }
     if (tr.replay_len && tid == 0) {
@@ -487,6 +501,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
           double td = xadd(r, xmul(nt ? gamma : 0.0, mx));
           td = xsub(td, q);
           const double qn = xadd(q, xmul(lr, td));
+          tdacc = xadd(tdacc, fabs(td));
           __syncwarp();
           if (lane == 0) {
             Mr[s * A + a] = m1;
@@ -511,6 +526,23 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     __syncthreads();
     if (do_replay) {
       const int last = sh.last;
+      if (p.dynamic) {
+        // agent/sfma.py:311-318: p('reverse') = 1 / (1 + exp(-(5 td - 2))), one categorical draw over
+        // [p, 1 - p] (cdf normalised by its last entry), the accumulator restarts
+        if (warp == 0) {
+          win.ensure(1, lane);
+          const double u = win.next();
+          const double pm = xdiv(1.0, xadd(1.0, exp(-xsub(xmul(tdacc, 5.0), 2.0))));
+          const double c0 = xdiv(pm, xadd(pm, xsub(1.0, pm)));
+          if (fabs(c0 - u) < 1e-12) flags |= COBEL_FLAG_CDF_NEAR_TIE;      // exp() is not NumPy's bit for bit
+          tdacc = 0.0;
+          if (lane == 0) sh.idx = c0 > u ? MODE_REVERSE : MODE_DEFAULT;
+        }
+        __syncthreads();
+        mode = sh.idx;
+        if (p.trial_mode && tid == 0) p.trial_mode[n * p.trials + trial] = mode;
+        __syncthreads();
+      }
       for (int rpl = 0; rpl < p.nb_replays; ++rpl) replay(last, true);
       if (track_t) {
 #pragma unroll 1
@@ -542,6 +574,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     tr.n_steps[n] += nsteps;
     tr.n_replay[n] += nrep;
     if (tr.flags && flags) tr.flags[n] |= flags;
+    if (p.td_acc) p.td_acc[n] = tdacc;
   }
 }
 

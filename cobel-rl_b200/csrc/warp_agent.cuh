@@ -300,10 +300,11 @@ COBEL_DEV int select_action_eps_tab(const double (&v)[A], const double* tab, dou
 // ---------------------------------------------------------------------------
 // `mbits` (optional) holds one byte per state with bit a set = action a may enter the max over
 // Q[s2,:] (SFMA.update_q honours the action mask, agent/sfma.py:440-449; DynaQ / QAgent do not).
+// `td_out` (optional): receives this lane's TD error (SFMA accumulates |td|, agent/sfma.py:456).
 template <int A>
 COBEL_DEV void td_batch_level_parallel(double* Q, uint32_t* wm, uint32_t* rm, int S, int lane, bool active,
                                        int s, int a, double r, int s2, int nt, double lr, double gamma,
-                                       const uint8_t* mbits = nullptr) {
+                                       const uint8_t* mbits = nullptr, double* td_out = nullptr) {
   const unsigned act = __ballot_sync(kFull, active);
   const unsigned below = (1u << lane) - 1u;
   // writers / readers per state (wm / rm are all-zero on entry and are re-zeroed on exit)
@@ -358,6 +359,7 @@ COBEL_DEV void td_batch_level_parallel(double* Q, uint32_t* wm, uint32_t* rm, in
       double td = xadd(r, xmul(g, mx));
       td = xsub(td, q);
       qn = xadd(q, xmul(lr, td));
+      if (td_out) *td_out = td;
     }
     __syncwarp();
     if (ready) Q[s * A + a] = qn;

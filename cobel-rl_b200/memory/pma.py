@@ -30,11 +30,10 @@ class PMAMemory(TableMemory):
         self.gamma_q = gamma_q
         self.min_gain = 10 ** -6
         self.min_gain_mode = 'original'
-        # options of the reference that the B200 path does not implement (must stay at their defaults)
         self.equal_need = False
         self.equal_gain = False
         self.ignore_barriers = True
-        self.allow_loops = False
+        self.allow_loops = False          # True is not implemented by the B200 path (check_supported)
         if rng is None and getattr(policy, 'rng', None) is not None:
             rng = policy.rng
         super().__init__(self.nb_states, self.nb_actions, learning_rate, rng, init_self_loops=False)
@@ -105,10 +104,12 @@ class PMAMemory(TableMemory):
         self._SR.copy_(torch.linalg.inv(eye - g * self._T))
 
     def check_supported(self):
-        bad = [k for k in ('equal_need', 'equal_gain', 'allow_loops') if getattr(self, k)]
-        if bad or not self.ignore_barriers:
-            raise NotImplementedError('PMAMemory options not implemented by the B200 path: %s'
-                                      % (bad or ['ignore_barriers=False']))
+        if self.allow_loops:
+            raise NotImplementedError('PMAMemory.allow_loops is not implemented by the B200 path')
+
+    def options(self):
+        """COBEL_PMA_OPT_* bits (include/cobel_b200.h) of the reference's replay switches, memory/pma.py:238-249."""
+        return (1 if self.equal_need else 0) | (2 if self.equal_gain else 0) | (0 if self.ignore_barriers else 4)
 
     def power_tables(self, stream, keep):
         """``float(gamma) ** k`` for k = 0..MAX_SEQ+1 with Python's pow, like the reference

@@ -236,15 +236,21 @@ typedef struct CobelSFMAParams {
   int32_t nb_replays;        /* agent.nb_replays */
   int32_t start_replay;      /* agent.start_replay */
   int32_t random_replay;     /* agent.random: uniform batches over the unmasked experiences (memory/sfma.py:375-416) */
-  int32_t reserved;
+  int32_t dynamic;           /* agent.dynamic: 'reverse' / 'default' chosen per trial from td_acc (agent/sfma.py:311-318) */
   int32_t no_replay;
   int32_t learn;             /* 1 = train(), 0 = test() */
+  double*  td_acc;           /* optional [N] in/out: agent.td, the |TD error| accumulated by update_q (agent/sfma.py:456) */
+  int32_t* trial_mode;       /* optional [N,trials] out: replay mode chosen at the end of each trial (dynamic) */
 } CobelSFMAParams;
 
 int cobel_sfma_run(const CobelSFMAParams* p, void* stream);
 
 /* ---- PMA: agent/pma.py:137-369 + memory/pma.py:20-496 (Mattar & Daw gain x need replay) ---- */
 #define COBEL_PMA_MAX_SEQ 64      /* longest n-step sequence = largest replay batch */
+/* CobelPMAParams.options (memory/pma.py:238-249) */
+#define COBEL_PMA_OPT_EQUAL_NEED    1   /* M.equal_need: need.fill(1) */
+#define COBEL_PMA_OPT_EQUAL_GAIN    2   /* M.equal_gain: gain.fill(1) */
+#define COBEL_PMA_OPT_KEEP_BARRIERS 4   /* M.ignore_barriers == False: utility is not multiplied by update_mask */
 
 typedef struct CobelPMAParams {
   int64_t n_agents;
@@ -287,7 +293,7 @@ typedef struct CobelPMAParams {
    * refreshed once, densely, at the end of the call.  A violated guarantee raises COBEL_FLAG_BAND_VIOLATION.
    * sr_band < 0: dense update_sr after every trial (any T). */
   int32_t sr_band;
-  int32_t reserved;
+  int32_t options;           /* COBEL_PMA_OPT_* bits */
   double*  band_scratch;     /* scratch [N, 2, S*(2*sr_band+1)] when sr_band >= 0 */
 } CobelPMAParams;
 

@@ -85,6 +85,9 @@ CASES = {
     'sfma_walls5_random':   ('sfma', 'walls5', 27, dict(trials=15, steps=30, batch=32, mode='default', mask_actions=True,
                                                        valid_mask=True, random_replay=True)),
     'sfma_slip5':           ('sfma', 'slip5', 25, dict(trials=15, steps=40, batch=16, mode='default', mask_actions=False)),
+    # agent.dynamic (agent/sfma.py:311-318): 'reverse' / 'default' chosen per trial from the accumulated TD error
+    'sfma_walls5_dynamic':  ('sfma', 'walls5', 31, dict(trials=25, steps=50, batch=32, mode='default', mask_actions=True,
+                                                       valid_mask=True, dynamic=True)),
     # PMA (demo/gridworld/demo_pma.py:29-72; unit_tests/test_pma.py:15-78)
     'pma_walls5':           ('pma', 'walls5', 19, dict(trials=6, steps=50, batch=16, gamma_q=0.99, mask_actions=True,
                                                        valid_mask=True)),

@@ -165,7 +165,7 @@ def run_sr(world, u, trials, steps, *, policy=('eps', 0.1), lr=0.1, gamma=0.99, 
 
 def run_sfma(world, D, u, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99, gamma=0.99,
              mem_lr=0.9, mask_actions=False, mode='default', recency=False, start_replay=False,
-             nb_replays=1, metric=None, action_mask=None, random_replay=False):
+             nb_replays=1, metric=None, action_mask=None, random_replay=False, dynamic=False):
     cobel = ref_loader.load()
     rng = StreamRNG(u)
     env = _gridworld(cobel, world, rng)
@@ -194,8 +194,15 @@ def run_sfma(world, D, u, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99,
     agent.start_replay = start_replay
     agent.random = random_replay
     agent.nb_replays = nb_replays
+    agent.dynamic = dynamic
+    modes = []
+    if dynamic:
+        cbs['on_trial_end'] = list(cbs.get('on_trial_end', [])) + [lambda logs: modes.append(['reverse', 'default'].index(logs['replay_mode']))]
     agent.train(env, trials, steps, batch)
     out = cap.arrays()
+    if dynamic:
+        out['modes'] = np.array(modes, dtype=np.int32)
+        out['td'] = np.float64(agent.td)
     out.update(Q=agent.Q.copy(), Mr=mem.rewards.copy(), Ms=mem.states.astype(np.int32),
                Mt=mem.terminals.astype(np.int32), C=mem.C.copy(), T=mem.T.copy(), I=mem.I.copy(),
                draws=rng.k)
@@ -204,7 +211,8 @@ def run_sfma(world, D, u, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99,
 
 def run_pma(world, u, trials, steps, batch, *, policy=('eps', 0.1), mem_policy=('eps', 0.1), lr=0.9,
             gamma=0.99, mem_lr=0.9, lr_q=0.9, gamma_sr=0.9, gamma_q=0.99, mask_actions=True,
-            prefill=False, min_gain_mode='original', action_mask=None):
+            prefill=False, min_gain_mode='original', action_mask=None, equal_need=False, equal_gain=False,
+            ignore_barriers=True):
     cobel = ref_loader.load()
     rng = StreamRNG(u)
     env = _gridworld(cobel, world, rng)
@@ -213,6 +221,7 @@ def run_pma(world, u, trials, steps, batch, *, policy=('eps', 0.1), mem_policy=(
     mem = cobel.memory.PMAMemory(world['sas'], _policy(cobel, mem_policy, rng), mem_lr, lr_q,
                                  gamma_sr, gamma_q, rng=rng)
     mem.min_gain_mode = min_gain_mode
+    mem.equal_need, mem.equal_gain, mem.ignore_barriers = equal_need, equal_gain, ignore_barriers
     if prefill:   # unit_tests/test_pma.py:69-73
         for s in range(S):
             for a in range(4):

@@ -457,15 +457,17 @@ def sfma_memory_replay(st, D, rng, length, current_state, *, mode='default', bet
 def sfma_train(W, st, D, rng, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99, gamma=0.99,
                mem_lr=0.9, mask_actions=False, mode='default', decay_strength=1.0,
                decay_recency=0.9, no_replay=False, nb_replays=1, start_replay=False,
-               random_replay=False, replay_kwargs=None, rec=None):
+               random_replay=False, dynamic=False, replay_kwargs=None, rec=None):
     """SFMA.train, agent/sfma.py:233-328 (store before update_q; replay at trial end
     from the terminal state, or from a strength-sampled experience when the trial
     timed out; ``M.T`` zeroed after every trial, 324).  ``random_replay`` restates ``agent.random``;
-    ``dynamic`` mode selection is not restated."""
+    ``dynamic`` restates the per-trial choice between 'reverse' and 'default' from the accumulated
+    |TD error| (agent/sfma.py:311-318; chosen modes are returned in ``st['modes']``)."""
     S, A = W['S'], W['A']
     Q, Mr, Ms, Mt, C, T = st['Q'], st['Mr'], st['Ms'], st['Mt'], st['C'], st['T']
     rec = rec if rec is not None else Record()
     kw = dict(replay_kwargs or {})
+    st.setdefault('modes', [])
 
     def replay(state, apply=True):
         # agent/sfma.py:392-421: the batch is sampled first, then applied in order.  The replay at
@@ -515,6 +517,14 @@ def sfma_train(W, st, D, rng, trials, steps, batch, *, policy=('eps', 0.1), lr=0
                 break
         rec.trial_steps.append(step); rec.trial_reward.append(treward)
         if not no_replay:
+            if dynamic:
+                # agent/sfma.py:311-318: p('reverse') is a logistic function of the TD error accumulated since
+                # the last choice; one Generator.choice draw; the accumulator restarts
+                p_mode = 1 / (1 + np.exp(-(st['td_acc'] * 5 - 2)))
+                pick = draw_categorical(np.array([p_mode, 1 - p_mode]), rng.next())
+                mode = ['reverse', 'default'][pick]
+                st['modes'].append(pick)
+                st['td_acc'] = 0.0
             for _r in range(nb_replays):
                 replay(last)
             T.fill(0)

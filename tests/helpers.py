@@ -101,6 +101,8 @@ def oracle_case(name, agent=None, golden=None):
         a['random_replay'] = a.pop('random_replay', False)
         out = tb.sfma_train(W, st, D, rng, trials, steps, a.pop('batch'), replay_kwargs=rk, **a).arrays()
         out.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], C=st['C'], T=st['T'], I=st['I'], draws=rng.k)
+        if a.get('dynamic'):
+            out.update(modes=np.array(st['modes'], dtype=np.int32), td=np.float64(st['td_acc']))
     elif kind == 'pma':
         st = tb.pma_init(tb.t0_from_succ(W['succ']), S, A)
         if valid_mask:
@@ -222,6 +224,7 @@ def cuda_case(name, n_extra=2, device='cuda:0'):
                      rng=stream)
         ag.mask_actions = a.pop('mask_actions', False)
         ag.random = a.pop('random_replay', False)
+        ag.dynamic = a.pop('dynamic', False)
         if valid_mask:
             ag.action_mask = tb.valid_move_mask(succ)
         ag.record = True
@@ -231,6 +234,10 @@ def cuda_case(name, n_extra=2, device='cuda:0'):
         out.update(Q=ag._Q[0].cpu().numpy(), Mr=mem._rewards[0].cpu().numpy(), Ms=mem._states[0].cpu().numpy(),
                    Mt=mem._terminals[0].cpu().numpy(), C=mem._C[0].cpu().numpy(), T=mem._T[0].cpu().numpy(),
                    I=mem._I[0].cpu().numpy(), draws=int(stream.draw_count[0]), flags=int(res['flags'][0]))
+        if ag.dynamic:      # golden 'modes' indexes ['reverse', 'default']; the kernel reports COBEL_SFMA_* ids
+            rm = res['replay_mode'][0].cpu().numpy()
+            assert set(np.unique(rm)) <= {0, 2}
+            out.update(modes=np.where(rm == 2, 0, 1).astype(np.int32), td=np.float64(ag._td[0].item()))
         assert not a, 'unused case arguments %s' % a
         return out
     if kind == 'pma':

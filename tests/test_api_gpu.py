@@ -267,10 +267,6 @@ def test_unsupported_shapes_and_options_fail_loudly():
     env = Gridworld(world, rng=stream)
     smem = SFMAMemory(Euclidean(5, 5), 25, 4, rng=stream)
     sfma = SFMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), smem, rng=stream)
-    sfma.dynamic = True
-    with pytest.raises(NotImplementedError):
-        sfma.train(env, 1, 5, 4)
-    sfma.dynamic = False
     smem.reward_mod = True
     with pytest.raises(NotImplementedError):
         sfma.train(env, 1, 5, 4)

@@ -14,5 +14,7 @@ def test_oracle_matches_golden(name):
     keys = list(KEYS[kind])
     if kind == 'dynaq':
         keys += ['test_states', 'test_actions', 'test_trial_steps', 'test_trial_reward', 'draws_after_test']
+    if 'modes' in want:          # SFMA dynamic mode: the per-trial replay modes and the TD accumulator
+        keys += ['modes', 'td']
     # same NumPy / LAPACK on both sides in this image: even PMA's SR is bit-equal
     assert_equal_records(got, want, keys, what=name)

@@ -61,12 +61,38 @@ def test_sfma_and_pma_live(reference):
                         nb_replays=2).arrays()
     got.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], C=st['C'], T=st['T'], I=st['I'], draws=rng.k)
     assert_equal_records(got, ref, KEYS['sfma'])
+    # dynamic replay mode (agent/sfma.py:311-318) with two replays per trial
+    u = LazyStream(8, 3)
+    ref = ref_runs.run_sfma(world, D, u, 12, 30, 16, mask_actions=True, nb_replays=2, dynamic=True)
+    rng = tb.Draws(LazyStream(8, 3), 1)
+    st = tb.sfma_init(25, 4)
+    got = tb.sfma_train(W, st, D, rng, 12, 30, 16, mask_actions=True, nb_replays=2, dynamic=True).arrays()
+    got.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], C=st['C'], T=st['T'], I=st['I'], draws=rng.k,
+               modes=np.array(st['modes'], dtype=np.int32), td=np.float64(st['td_acc']))
+    assert_equal_records(got, ref, KEYS['sfma'] + ['modes', 'td'])
+    u = LazyStream(7, 9)
     ref = ref_runs.run_pma(world, u, 4, 12, 12, policy=('eps', 0.2), mem_policy=('eps', 0.05), lr_q=0.7, gamma_q=0.95,
                            mask_actions=True, min_gain_mode='')
     rng = tb.Draws(LazyStream(7, 9), 1)
     st = tb.pma_init(tb.t0_from_succ(W['succ']), 25, 4)
     got = tb.pma_train(W, st, rng, 4, 12, 12, policy=('eps', 0.2), mem_policy=('eps', 0.05), lr_q=0.7, gamma_q=0.95,
                        mask_actions=True, replay_kwargs={'original': False}).arrays()
+    got.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], T=st['T'], SR=st['SR'], update_mask=st['update_mask'],
+               draws=rng.k)
+    assert_equal_records(got, ref, KEYS['pma'])
+
+
+@pytest.mark.parametrize('opts', [dict(equal_need=True), dict(equal_gain=True), dict(ignore_barriers=False),
+                                  dict(equal_need=True, equal_gain=True, ignore_barriers=False)])
+def test_pma_replay_switches_live(reference, opts):
+    """PMAMemory.equal_need / equal_gain / ignore_barriers (memory/pma.py:238-249): oracle vs the reference."""
+    world = _world(reference, 'walls5')
+    W = tb.compile_gridworld(world)
+    u = LazyStream(11, 2)
+    ref = ref_runs.run_pma(world, u, 3, 15, 10, mask_actions=True, **opts)
+    rng = tb.Draws(LazyStream(11, 2), 1)
+    st = tb.pma_init(tb.t0_from_succ(W['succ']), 25, 4)
+    got = tb.pma_train(W, st, rng, 3, 15, 10, gamma_q=0.99, mask_actions=True, replay_kwargs=dict(opts)).arrays()
     got.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], T=st['T'], SR=st['SR'], update_mask=st['update_mask'],
                draws=rng.k)
     assert_equal_records(got, ref, KEYS['pma'])

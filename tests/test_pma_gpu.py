@@ -134,3 +134,38 @@ def test_pma_band_violation_is_reported():
     mem.sr_band = lambda wb: (3, real(wb)[1])            # lie: the world's band is 10
     with pytest.raises(_lib.CobelError, match='band'):
         ag.train(env, 1, 20, 4)
+
+
+@pytest.mark.parametrize('opts', [dict(equal_need=True), dict(equal_gain=True), dict(ignore_barriers=False),
+                                  dict(equal_need=True, equal_gain=True, ignore_barriers=False)])
+def test_pma_replay_switches_vs_oracle(opts):
+    """PMAMemory.equal_need / equal_gain / ignore_barriers (memory/pma.py:238-249) on the GPU vs the oracle (which
+    tests/test_oracle_vs_reference.py pins against the reference for the same switches)."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import PMA
+    from cobel_rl_b200.memory import PMAMemory
+    from cobel_rl_b200.policy import EpsilonGreedy
+    world = make_world('walls5')
+    W = tb.compile_gridworld(world)
+    n, trials, steps, batch = 3, 3, 15, 10
+    stream = cb.BatchStream(n, seed=1212, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = PMAMemory(world['sas'], EpsilonGreedy(0.1, rng=stream), 0.9, 0.9, 0.9, 0.99, rng=stream)
+    for k, v in opts.items():
+        setattr(mem, k, v)
+    ag = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem)
+    ag.mask_actions = True
+    ag.record = True
+    res = ag.train(env, trials, steps, batch)
+    torch.cuda.synchronize()
+    assert int(res['flags'].sum()) == 0
+    for i in range(n):
+        rng = tb.Draws(LazyStream(1212, i), 1)
+        st = tb.pma_init(tb.t0_from_succ(W['succ']), 25, 4)
+        rec = tb.pma_train(W, st, rng, trials, steps, batch, gamma_q=0.99, mask_actions=True, replay_kwargs=dict(opts)).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got.update(Q=ag.Q[i].cpu().numpy(), T=mem.T[i].cpu().numpy(), SR=mem.SR[i].cpu().numpy(), draws=int(stream.draw_count[i]))
+        rec.update(Q=st['Q'], T=st['T'], SR=st['SR'], draws=rng.k)
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q', 'T', 'SR', 'draws'],
+                             rtol=RTOL, what='agent %d %s' % (i, opts))
