@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
 #pragma unroll 1
         for (int j = last_seq + lane; j < count; j += 32) loop |= st_of(perf[j]) == ext;
         loop = __any_sync(kFull, loop);
-        if (!loop) {
+        if (!loop || (opt & COBEL_PMA_OPT_ALLOW_LOOPS)) {
           win.ensure(2, lane);
           double row[A];
           load_row<A>(Q + ext * A, row);
@@ -1033,8 +1033,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         __syncwarp();
         ndst = 0;
         if (ok) {
-#pragma unroll 1
-          for (int j = lane; j < nseq; j += 32) {
+          auto update_element = [&](int j) {
             const int i = seq[j];
             const int a = act_of(i), s = i - a * S;
             double r = 0.0;
@@ -1043,8 +1042,17 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
             double td = xadd(r, xmul(fv, powq[nseq - j]));
             const double q = Q[s * A + a];
             td = xsub(td, q);
-            Q[s * A + a] = xadd(q, xmul(lrq, td));     // states of a sequence are distinct (no loops)
+            Q[s * A + a] = xadd(q, xmul(lrq, td));
             dst[j] = (uint16_t)s;
+          };
+          if (opt & COBEL_PMA_OPT_ALLOW_LOOPS) {      // a sequence may revisit (s, a): in order, like the reference's loop
+            if (lane == 0) {
+#pragma unroll 1
+              for (int j = 0; j < nseq; ++j) update_element(j);
+            }
+          } else {                                    // the states of a sequence are distinct: one element per lane
+#pragma unroll 1
+            for (int j = lane; j < nseq; j += 32) update_element(j);
           }
           ndst = nseq;
         }

@@ -33,7 +33,7 @@ class PMAMemory(TableMemory):
         self.equal_need = False
         self.equal_gain = False
         self.ignore_barriers = True
-        self.allow_loops = False          # True is not implemented by the B200 path (check_supported)
+        self.allow_loops = False
         if rng is None and getattr(policy, 'rng', None) is not None:
             rng = policy.rng
         super().__init__(self.nb_states, self.nb_actions, learning_rate, rng, init_self_loops=False)
@@ -104,12 +104,12 @@ class PMAMemory(TableMemory):
         self._SR.copy_(torch.linalg.inv(eye - g * self._T))
 
     def check_supported(self):
-        if self.allow_loops:
-            raise NotImplementedError('PMAMemory.allow_loops is not implemented by the B200 path')
+        pass        # every replay switch of the reference's PMAMemory is implemented
 
     def options(self):
         """COBEL_PMA_OPT_* bits (include/cobel_b200.h) of the reference's replay switches, memory/pma.py:238-249."""
-        return (1 if self.equal_need else 0) | (2 if self.equal_gain else 0) | (0 if self.ignore_barriers else 4)
+        return ((1 if self.equal_need else 0) | (2 if self.equal_gain else 0) | (0 if self.ignore_barriers else 4) |
+                (8 if self.allow_loops else 0))
 
     def power_tables(self, stream, keep):
         """``float(gamma) ** k`` for k = 0..MAX_SEQ+1 with Python's pow, like the reference

@@ -251,6 +251,7 @@ int cobel_sfma_run(const CobelSFMAParams* p, void* stream);
 #define COBEL_PMA_OPT_EQUAL_NEED    1   /* M.equal_need: need.fill(1) */
 #define COBEL_PMA_OPT_EQUAL_GAIN    2   /* M.equal_gain: gain.fill(1) */
 #define COBEL_PMA_OPT_KEEP_BARRIERS 4   /* M.ignore_barriers == False: utility is not multiplied by update_mask */
+#define COBEL_PMA_OPT_ALLOW_LOOPS   8   /* M.allow_loops: a sequence is extended even if it revisits a state */
 
 typedef struct CobelPMAParams {
   int64_t n_agents;

@@ -212,7 +212,7 @@ def run_sfma(world, D, u, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99,
 def run_pma(world, u, trials, steps, batch, *, policy=('eps', 0.1), mem_policy=('eps', 0.1), lr=0.9,
             gamma=0.99, mem_lr=0.9, lr_q=0.9, gamma_sr=0.9, gamma_q=0.99, mask_actions=True,
             prefill=False, min_gain_mode='original', action_mask=None, equal_need=False, equal_gain=False,
-            ignore_barriers=True):
+            ignore_barriers=True, allow_loops=False):
     cobel = ref_loader.load()
     rng = StreamRNG(u)
     env = _gridworld(cobel, world, rng)
@@ -222,6 +222,7 @@ def run_pma(world, u, trials, steps, batch, *, policy=('eps', 0.1), mem_policy=(
                                  gamma_sr, gamma_q, rng=rng)
     mem.min_gain_mode = min_gain_mode
     mem.equal_need, mem.equal_gain, mem.ignore_barriers = equal_need, equal_gain, ignore_barriers
+    mem.allow_loops = allow_loops
     if prefill:   # unit_tests/test_pma.py:69-73
         for s in range(S):
             for a in range(4):

@@ -258,9 +258,6 @@ def test_unsupported_shapes_and_options_fail_loudly():
     pma = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem)
     with pytest.raises(NotImplementedError):
         pma.train(env, 1, 5, 4)
-    mem.allow_loops = True
-    with pytest.raises(NotImplementedError):
-        pma.train(env, 1, 5, 4)
     # SFMA: options of the reference that are not implemented
     world = make_world('open5')
     stream = cb.BatchStream(2, seed=1, device='cuda:0')

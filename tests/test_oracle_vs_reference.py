@@ -83,7 +83,8 @@ def test_sfma_and_pma_live(reference):
 
 
 @pytest.mark.parametrize('opts', [dict(equal_need=True), dict(equal_gain=True), dict(ignore_barriers=False),
-                                  dict(equal_need=True, equal_gain=True, ignore_barriers=False)])
+                                  dict(equal_need=True, equal_gain=True, ignore_barriers=False), dict(allow_loops=True),
+                                  dict(allow_loops=True, equal_need=True)])
 def test_pma_replay_switches_live(reference, opts):
     """PMAMemory.equal_need / equal_gain / ignore_barriers (memory/pma.py:238-249): oracle vs the reference."""
     world = _world(reference, 'walls5')

@@ -137,7 +137,8 @@ def test_pma_band_violation_is_reported():
 
 
 @pytest.mark.parametrize('opts', [dict(equal_need=True), dict(equal_gain=True), dict(ignore_barriers=False),
-                                  dict(equal_need=True, equal_gain=True, ignore_barriers=False)])
+                                  dict(equal_need=True, equal_gain=True, ignore_barriers=False), dict(allow_loops=True),
+                                  dict(allow_loops=True, equal_need=True)])
 def test_pma_replay_switches_vs_oracle(opts):
     """PMAMemory.equal_need / equal_gain / ignore_barriers (memory/pma.py:238-249) on the GPU vs the oracle (which
     tests/test_oracle_vs_reference.py pins against the reference for the same switches)."""
