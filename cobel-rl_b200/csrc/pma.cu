@@ -868,6 +868,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         } else if (lane == 0) {
           seq[0] = (uint16_t)ext;                                       // failed extension: one-step(ext, action 0)
         }
+        __syncwarp();                                                   // seq[] is read by all lanes in (3)
       }
       // ---- (2) re-evaluate the backups that read a Q row changed by the previous update ----------
       // (one code site for the compact list and for the full pass keeps the loop body small:
