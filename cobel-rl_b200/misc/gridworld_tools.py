@@ -140,3 +140,71 @@ def make_two_sided_t_maze(stem_length, arm_length, goal_arm='right-right', rewar
     corridor = [(arm_length, c) for c in range(width)] + [(r, c) for r in range(height) for c in (0, width - 1)]
     goal = {'right-left': width - 1, 'left-left': width * (height - 1), 'right-right': width * height - 1}.get(goal_arm, 0)
     return _maze(height, width, corridor, goal, arm_length * width + int(stem_length / 2), reward)
+
+
+def _ring(height, width):
+    return [(r, c) for r in range(height) for c in range(width) if r in (0, height - 1) or c in (0, width - 1)]
+
+
+def make_8_maze(center_height, lap_width, goal_location='right', reward=1):
+    """Figure-8 maze (misc/gridworld_tools.py:669-735): the outer ring of the grid plus its centre column."""
+    assert center_height > 0 and lap_width > 0, 'Center height and lap width must be greater than zero!'
+    height, width = center_height + 2, lap_width * 2 + 3
+    corridor = _ring(height, width) + [(r, lap_width + 1) for r in range(height)]
+    goal = (height // 2) * width + (width - 1 if goal_location == 'right' else 0)
+    return _maze(height, width, corridor, goal, lap_width + 2, reward)
+
+
+def make_two_choice_t_maze(center_height, lap_width, arm_length, chirality='right', goal_location='right', reward=1):
+    """Two-choice T-maze (misc/gridworld_tools.py:509-666): an outer ring whose centre column only reaches down to the
+    arm row of an inner T; the T's stem rises from the bottom of the ring on the `chirality` side of the centre column
+    and one of its arms ends in that column.  (Like the reference, the reward at the goal is 1 whatever `reward` says.)"""
+    assert arm_length > 0, '!'
+    assert center_height > 2, '!'
+    assert lap_width >= arm_length * 2 + 1, '!'
+    assert chirality in ['left', 'right'], 'Invalid chirality!'
+    height, width = center_height + 2, lap_width * 2 + 3
+    centre, arm_row = lap_width + 1, (center_height - 1) // 2 + 1
+    if chirality == 'left':
+        first, last, stem = centre - 2 * arm_length, centre, centre - arm_length
+    else:
+        first, last, stem = centre, centre + 2 * arm_length, centre + arm_length
+    corridor = _ring(height, width) + [(r, centre) for r in range(1, arm_row + 1)]
+    corridor += [(arm_row, c) for c in range(first, last + 1)] + [(r, stem) for r in range(arm_row + 1, height - 1)]
+    goal = (height // 2) * width + (width - 1 if goal_location == 'right' else 0)
+    return _maze(height, width, corridor, goal, width * (height - 1) + lap_width + arm_length, 1.0)
+
+
+def make_detour_maze(width_small, height_small, width_large, height_large, reward=1):
+    """Detour maze (misc/gridworld_tools.py:738-895): a straight stem from the start (bottom) to the goal (top),
+    a large rectangular loop to its right and a small one to its left, which meet on one crossing row."""
+    assert width_small > 0 and height_small > 0, 'Width and height of the small side piece must be greater than zero!'
+    assert width_large > width_small and height_large > height_small, \
+        'Width and height of the large side piece must be greater than those of the small side piece!'
+    width, height = width_small + width_large + 3, height_small + height_large + 5
+    stem, cross_row = width_small + 1, height_large + 2
+
+    def rectangle(r0, r1, c0, c1):
+        return [(r, c) for r in range(r0, r1 + 1) for c in range(c0, c1 + 1) if r in (r0, r1) or c in (c0, c1)]
+    corridor = [(r, stem) for r in range(height)]
+    corridor += rectangle(1, cross_row, stem, width - 1) + rectangle(cross_row, height - 2, 0, stem)
+    return _maze(height, width, corridor, stem, stem + width * (height - 1), reward)
+
+
+def make_cross_maze(arm_length, arm_width, goal_arm='top', reward=1.0):
+    """Cross maze (misc/gridworld_tools.py:898-974): two bands of width `arm_width` crossing in the middle; the agent
+    starts anywhere on the central square, the goal is the far end of one arm.  (Like the reference, the reward at
+    the goal cells is 1 whatever `reward` says.)"""
+    assert arm_length > 0 and arm_width > 0
+    assert goal_arm in ('left', 'top', 'right', 'bottom'), 'Invalid goal arm!'
+    size = arm_length * 2 + arm_width
+    band = range(arm_length, arm_length + arm_width)
+    corridor = [(r, c) for r in range(size) for c in range(size) if r in band or c in band]
+    starting = [r * size + c for r in band for c in band]
+    ends = {'top': [(0, c) for c in band], 'bottom': [(size - 1, c) for c in band],
+            'left': [(r, 0) for r in band], 'right': [(r, size - 1) for r in band]}[goal_arm]
+    terminals = [np.int64(r * size + c) for r, c in ends]
+    rewards = np.ones((arm_width, 2))
+    rewards[:, 0] = terminals
+    return make_gridworld(size, size, terminals, rewards, terminals, starting_states=starting,
+                          invalid_transitions=_corridor_walls(size, size, corridor))

@@ -54,6 +54,22 @@ def test_maze_templates(reference):
             for goal in ('left-left', 'left-right', 'right-left', 'right-right'):
                 same_maze(mg.make_double_t_maze(stem, arm, goal), rg.make_double_t_maze(stem, arm, goal))
                 same_maze(mg.make_two_sided_t_maze(stem, arm, goal), rg.make_two_sided_t_maze(stem, arm, goal))
+    for ch in (1, 2, 3, 4, 5):
+        for lw in (1, 2, 3):
+            for goal in ('left', 'right'):
+                same_maze(mg.make_8_maze(ch, lw, goal, 3.0), rg.make_8_maze(ch, lw, goal, 3.0))
+    for ch in (3, 4, 5, 6):
+        for lw, arm in ((3, 1), (4, 1), (5, 2), (7, 2), (7, 3)):
+            for chirality in ('left', 'right'):
+                for goal in ('left', 'right'):
+                    same_maze(mg.make_two_choice_t_maze(ch, lw, arm, chirality, goal, 2.0),
+                              rg.make_two_choice_t_maze(ch, lw, arm, chirality, goal, 2.0))
+    for ws, hs, dw, dh in ((1, 1, 1, 1), (2, 2, 2, 1), (1, 3, 4, 2), (3, 2, 1, 3)):
+        same_maze(mg.make_detour_maze(ws, hs, ws + dw, hs + dh, 2.0), rg.make_detour_maze(ws, hs, ws + dw, hs + dh, 2.0))
+    for arm in (1, 2, 3, 4):
+        for aw in (1, 2, 3):
+            for goal in ('left', 'top', 'right', 'bottom'):
+                same_maze(mg.make_cross_maze(arm, aw, goal, 2.0), rg.make_cross_maze(arm, aw, goal, 2.0))
 
 
 def test_maze_templates_known_answers():
@@ -71,6 +87,18 @@ def test_maze_templates_known_answers():
     t = mg.make_two_sided_t_maze(2, 2)
     assert (t['height'], t['width']) == (5, 4) and list(t['starting_states']) == [9] and t['goals'] == [19]
     assert len(t['invalid_transitions']) == 24
+    e = mg.make_8_maze(3, 2)
+    assert (e['height'], e['width']) == (5, 7) and list(e['starting_states']) == [4] and e['goals'] == [20]
+    assert len(e['invalid_transitions']) == 40
+    c = mg.make_two_choice_t_maze(3, 3, 1)
+    assert (c['height'], c['width']) == (5, 9) and list(c['starting_states']) == [40] and c['goals'] == [26]
+    assert len(c['invalid_transitions']) == 56
+    d = mg.make_detour_maze(2, 2, 4, 3)
+    assert (d['height'], d['width']) == (10, 9) and list(d['starting_states']) == [84] and d['goals'] == [3]
+    assert len(d['invalid_transitions']) == 98
+    x = mg.make_cross_maze(2, 2, 'left')
+    assert x['height'] == x['width'] == 6 and list(x['starting_states']) == [14, 15, 20, 21] and list(x['goals']) == [12, 18]
+    assert len(x['invalid_transitions']) == 32 and x['rewards'][12] == 1 and x['terminals'][18] == 1
 
 
 def test_topology_builders(reference):
