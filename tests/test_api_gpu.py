@@ -302,3 +302,32 @@ def test_maze_template_worlds_run_bit_exact():
                 rec = tb.dynaq_train(W, st, rng, 8, 30, 32).arrays()
                 assert np.array_equal(ag.Q[i].cpu().numpy(), st['Q']) and int(stream.draw_count[i]) == rng.k
                 assert np.array_equal(res['trial_steps'][i].cpu().numpy(), rec['trial_steps'])
+
+
+def test_trajectory_monitor_and_occupancy_map_on_device():
+    """TrajectoryMonitor (monitor/behavior.py:304-385) rebuilt from the recorded step buffers, and the occupancy map
+    (analysis/behavior_spatial.py:9-73) computed on the GPU from it, against the oracle's trajectory."""
+    from cobel_rl_b200.monitor import TrajectoryMonitor
+    from cobel_rl_b200.analysis import get_occupancy_map
+    stream, env, ag = _dynaq(3, seed=31)
+    ag.record = True
+    res = ag.train(env, 5, 12, 8)
+    torch.cuda.synchronize()
+    mon = TrajectoryMonitor(5, env)
+    pos = mon.from_result(res)                                   # [N, trials, max_steps, 2] on the device, NaN padded
+    assert pos.is_cuda and pos.shape[:2] == (3, 5) and pos.shape[3] == 2
+    world = make_world('open5')
+    W = tb.compile_gridworld(world)
+    for i in range(3):
+        rng = tb.Draws(LazyStream(31, i), 1)
+        st = tb.dynaq_init(25, 4)
+        rec = tb.dynaq_train(W, st, rng, 5, 12, 8).arrays()
+        lists = mon.from_result(res, agent=i)                    # the reference's list (trials) of lists (steps)
+        flat = np.array([p for trial in lists for p in trial])
+        assert [len(t) for t in lists] == list(rec['trial_steps'] + 1)
+        assert np.array_equal(flat, world['coordinates'][rec['next_states']])
+    occ = get_occupancy_map(pos, 5.0, 5.0, 1.0)
+    assert occ.is_cuda and occ.shape == (5, 5)
+    valid = pos[~torch.isnan(pos).any(dim=-1)].cpu().numpy()
+    want = np.histogram2d(valid[:, 0], valid[:, 1], bins=(5, 5), range=[[0, 5], [0, 5]])[0]
+    assert np.array_equal(occ.cpu().numpy(), want) and occ.sum().item() == float(res['n_steps'].sum().item())

@@ -68,3 +68,71 @@ def test_monitors_from_callbacks_and_results():
     single = EscapeLatencyMonitor(2, 50)
     single.update({'trial': 1, 'steps': 7})
     assert single.get_trace().tolist() == [0, 7]
+
+
+def test_response_and_q_monitors_match_reference(reference):
+    """monitor/behavior.py:212-301, 388-464: same traces as the reference's monitors fed the same logs."""
+    import importlib
+    import numpy as np
+    from cobel_rl_b200.monitor import QMonitor, ResponseMonitor
+    rb = importlib.import_module('cobel.monitor.behavior')
+    rewards = [0.0, 1.0, 0.0, 2.5, 0.0, 1.0]
+    ref, mine = rb.ResponseMonitor(6), ResponseMonitor(6)
+    for t, r in enumerate(rewards):
+        logs = {'trial': t, 'trial_reward': r}
+        if t == 4:
+            logs['response'] = 3
+        ref.update(dict(logs)); mine.update(dict(logs))
+    assert np.array_equal(ref.get_trace(), mine.get_trace()) and np.array_equal(ref.CRC, mine.get_cumulative())
+
+    class _Agent:
+        def __init__(self):
+            self.k = 0
+
+        def predict_on_batch(self, batch):
+            self.k += 1
+            return np.arange(len(batch) * 4, dtype=float).reshape(len(batch), 4) * self.k
+    a1, a2 = _Agent(), _Agent()
+    ref, mine = rb.QMonitor(3, [0, 2, 5]), QMonitor(3, [0, 2, 5])
+    for t in range(3):
+        ref.update({'trial': t, 'agent': a1}); mine.update({'trial': t, 'agent': a2})
+    assert all(np.array_equal(x, y) for x, y in zip(ref.get_trace(), mine.get_trace())) and len(mine.get_trace()) == 3
+    # batched response monitor: one row per agent
+    m = ResponseMonitor(3, n_agents=2)
+    for t, r in enumerate(([0.0, 1.0], [2.0, 0.0], [0.0, 0.0])):
+        m.update({'trial': t, 'trial_reward': np.array(r)})
+    assert np.array_equal(m.get_trace(), [[0, 1, 0], [1, 0, 0]]) and np.array_equal(m.get_cumulative(), [[0, 1, 1], [1, 1, 1]])
+
+
+def test_occupancy_map_and_match(reference):
+    """analysis/behavior_spatial.py:9-111 against the reference over random inputs, plus known answers."""
+    import importlib
+    import numpy as np
+    import torch
+    from cobel_rl_b200.analysis import get_occupancy_map, match
+    ra = importlib.import_module('cobel.analysis.behavior_spatial')
+    rs = np.random.default_rng(0)
+    for k in range(120):
+        w, h = rs.uniform(1, 6, 2)
+        b = rs.uniform(0.2, min(w, h))
+        if k % 4 == 0:
+            b, w, h = [0.5, 1.0, 0.25][k % 3], float(int(w) + 1), float(int(h) + 1)
+        margins = ['expand', 'include', 'ignore'][k % 3]
+        trajs = [np.round(rs.uniform(0, max(w, h) + 0.5, (int(rs.integers(1, 30)), 2)), 1 if k % 2 else 6) for _ in range(3)]
+        want = ra.get_occupancy_map(trajs, w, h, b, margins)
+        got = get_occupancy_map(trajs, w, h, b, margins).numpy()
+        assert got.shape == want.shape and np.array_equal(got, want), (k, w, h, b, margins)
+    for k in range(60):
+        seq, tpl = rs.integers(0, 4, int(rs.integers(1, 20))), rs.integers(0, 4, int(rs.integers(1, 8)))
+        assert np.array_equal(ra.match(seq, tpl), match(seq, tpl))
+    # a NaN-padded [N, T, 2] tensor gives the same map as the list of its valid rows
+    pos = torch.tensor([[[0.5, 0.5], [1.5, 0.5], [float('nan')] * 2], [[0.5, 1.5], [0.5, 1.5], [1.5, 1.5]]], dtype=torch.float64)
+    occ = get_occupancy_map(pos, 2.0, 2.0, 1.0)
+    assert occ.tolist() == [[1.0, 2.0], [1.0, 1.0]]
+
+
+def test_match_known_answers():
+    import numpy as np
+    from cobel_rl_b200.analysis import match
+    assert match(np.array([1, 2, 3, 1, 2]), np.array([1, 2])).tolist() == [2, 0, 0, 2, 0]
+    assert match(np.array([5]), np.array([5, 5, 5])).tolist() == [1]
