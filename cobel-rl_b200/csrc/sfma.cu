@@ -224,6 +224,8 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
   int flags = 0;
   const double* D = p.D;
   int mode = p.mode;                   // CTA-uniform; re-chosen per trial when agent.dynamic is set
+  const int mf = p.mod_flags;          // COBEL_SFMA_MOD_* / *_NORMALIZE switches
+  double cmax = 1.0, dmax = 1.0;       // np.amax(C) / np.amax(D[current_state]) when C_normalize / D_normalize
   double tdacc = p.td_acc ? p.td_acc[n] : 0.0;   // agent.td (maintained by warp 0)
 
   // agent.td += |td| for a batch of replayed updates, in replay order (agent/sfma.py:456); warp 0
@@ -240,14 +242,16 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     const int ms = Mx[sp * A + a] & 0x7FFF;                 // states.flatten('F')[a*S + sp]
     const double* Dc = D + (size_t)cur * S;
     const double* Dn = D + (size_t)nxt * S;
+    // D_normalize divides the current state's row by its maximum before the mode is applied (memory/sfma.py:286-288)
+    auto dc = [&](int x) -> double { return (mf & COBEL_SFMA_D_NORMALIZE) ? xdiv(Dc[x], dmax) : Dc[x]; };
     switch (mode) {
       case MODE_FORWARD: return Dn[sp];
-      case MODE_REVERSE: return Dc[ms];
-      case MODE_BLEND_FORWARD: return xadd(Dc[sp], xmul(p.blend, Dn[sp]));
-      case MODE_BLEND_REVERSE: return xadd(Dc[sp], xmul(p.blend, Dc[ms]));
-      case MODE_INTERPOLATE: return xadd(xmul(p.interp_fwd, Dn[sp]), xmul(p.interp_rev, Dc[ms]));
+      case MODE_REVERSE: return dc(ms);
+      case MODE_BLEND_FORWARD: return xadd(dc(sp), xmul(p.blend, Dn[sp]));
+      case MODE_BLEND_REVERSE: return xadd(dc(sp), xmul(p.blend, dc(ms)));
+      case MODE_INTERPOLATE: return xadd(xmul(p.interp_fwd, Dn[sp]), xmul(p.interp_rev, dc(ms)));
       case MODE_SWEEPING: return Dn[ms];
-      default: return Dc[sp];
+      default: return dc(sp);
     }
   };
 
@@ -341,6 +345,17 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
         if (C[i] > 0.0) { const int a = i / S; L[off++] = ((uint32_t)a << 16) | (uint32_t)(i - a * S); }
     }
     __syncthreads();
+    if (mf & COBEL_SFMA_C_NORMALIZE) {                                     // np.amax(C): C is constant during a replay
+      double lm = -__longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll 1
+      for (int e = tid; e < N; e += T) lm = C[e] > lm ? C[e] : lm;
+      for (int d = 16; d > 0; d >>= 1) { const double o = shfl_f64_xor(lm, d); lm = o > lm ? o : lm; }
+      if (lane == 0) part[warp] = lm;
+      __syncthreads();
+      cmax = part[0];
+      for (int w = 1; w < (T >> 5); ++w) cmax = part[w] > cmax ? part[w] : cmax;
+      __syncthreads();
+    }
     if (cur < 0) {                                                         // start ~ clip(C, 0) / sum
 #pragma unroll 1
       for (int j = tid; j < nnz; j += T) { const uint32_t l = L[j]; R[j] = C[(l >> 16) * S + (l & 0xFFFF)]; }
@@ -354,12 +369,25 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     __syncthreads();
     int count = 0;
     for (int it = 0; it < B; ++it) {
+      if (mf & COBEL_SFMA_D_NORMALIZE) {                                   // np.amax(D[current_state])
+        const double* Dc = D + (size_t)cur * S;
+        double lm = -__longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll 1
+        for (int e = tid; e < S; e += T) lm = Dc[e] > lm ? Dc[e] : lm;
+        for (int d = 16; d > 0; d >>= 1) { const double o = shfl_f64_xor(lm, d); lm = o > lm ? o : lm; }
+        if (lane == 0) part[warp] = lm;
+        __syncthreads();
+        dmax = part[0];
+        for (int w = 1; w < (T >> 5); ++w) dmax = part[w] > dmax ? part[w] : dmax;
+        __syncthreads();
+      }
       double lmax = 0.0;
 #pragma unroll 1
       for (int j = tid; j < nnz; j += T) {
         const uint32_t l = L[j];
         const int a = l >> 16, sp = l & 0xFFFF, i = a * S + sp;
-        double r = xmul(xmul(C[i], dvec(a, sp, cur, nxt)), xsub(1.0, I[sp]));  // C * D * (1 - I)
+        const double cn = (mf & COBEL_SFMA_C_NORMALIZE) ? xdiv(C[i], cmax) : C[i];
+        double r = xmul(xmul(cn, dvec(a, sp, cur, nxt)), xsub(1.0, I[sp]));    // C * D * (1 - I)
         if (recency) r = xmul(r, Tr[i]);
         if (r < thr) r = 0.0;
         R[j] = r;
@@ -385,7 +413,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
       } else {
         // probs ~ exp(beta * R / max) - 1  (softmax(R, -1, beta), sfma.py:349-373); exp(0) - 1 == 0 exactly
 #pragma unroll 1
-        for (int j = tid; j < nnz; j += T) { const double r = R[j]; R[j] = r > 0.0 ? xadd(exp(xmul(xdiv(r, m), beta)), -1.0) : 0.0; }
+        for (int j = tid; j < nnz; j += T) { const double r = R[j]; R[j] = r > 0.0 ? xadd(exp(xmul((mf & COBEL_SFMA_R_RAW) ? r : xdiv(r, m), beta)), -1.0) : 0.0; }
         if (warp == 0) {
           win.ensure(1, lane);
           const double u = win.next();
@@ -511,6 +539,20 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
             Q[s * A + a] = qn;
           }
           __syncwarp();
+          if (mf & (COBEL_SFMA_MOD_REWARD_LOCAL | COBEL_SFMA_MOD_REWARD | COBEL_SFMA_MOD_STATE)) {
+            // strength modulation of SFMAMemory.store, in the reference's order (memory/sfma.py:216-236)
+            if ((mf & COBEL_SFMA_MOD_REWARD_LOCAL) && lane == 0)
+              C[a * S + s] = xadd(C[a * S + s], xmul(r, p.reward_modulation));
+            __syncwarp();
+            if (mf & COBEL_SFMA_MOD_REWARD) {
+              const double* Ds = D + (size_t)s * S;
+#pragma unroll 1
+              for (int e = lane; e < N; e += 32) C[e] = xadd(C[e], xmul(xmul(r, Ds[e % S]), p.reward_modulation));
+              __syncwarp();
+            }
+            if ((mf & COBEL_SFMA_MOD_STATE) && lane < A) C[lane * S + s] = xadd(C[lane * S + s], 1.0);
+            __syncwarp();
+          }
         }
         s = s2;
         treward = xadd(treward, r);

@@ -35,6 +35,7 @@ class SFMAMemory(TableMemory):
         self.R_normalize = True
         self.reward_mod_local = self.error_mod_local = self.reward_mod = self.error_mod = False
         self.policy_mod = self.state_mod = False
+        self.reward_modulation = 1.0
         self._D_dev = None
         super().__init__(nb_states, nb_actions, learning_rate, rng, init_self_loops=True)
 
@@ -58,12 +59,16 @@ class SFMAMemory(TableMemory):
         return self._D_dev
 
     def check_supported(self):
-        assert self.mode in MODES or True
-        unsupported = [k for k in ('C_normalize', 'D_normalize', 'reward_mod_local', 'error_mod_local', 'reward_mod',
-                                   'error_mod', 'policy_mod', 'state_mod') if getattr(self, k)]
-        if unsupported or not self.R_normalize:
-            raise NotImplementedError('SFMAMemory options not implemented by the B200 path: %s'
-                                      % (unsupported or ['R_normalize=False']))
+        # error_mod / error_mod_local read experience['td'], which the reference's SFMA.train() has not computed
+        # when it calls store() (agent/sfma.py:289-291) -- they cannot run there either
+        unsupported = [k for k in ('error_mod_local', 'error_mod') if getattr(self, k)]
+        if unsupported:
+            raise NotImplementedError('SFMAMemory options not implemented by the B200 path: %s' % unsupported)
+
+    def mod_flags(self):
+        """COBEL_SFMA_MOD_* / *_NORMALIZE bits (include/cobel_b200.h), memory/sfma.py:216-236, 283-288, 319-320."""
+        return ((1 if self.reward_mod_local else 0) | (2 if self.reward_mod else 0) | (4 if self.state_mod else 0) |
+                (8 if self.C_normalize else 0) | (16 if self.D_normalize else 0) | (0 if self.R_normalize else 32))
 
     def mode_id(self):
         # an unknown mode string behaves like 'default' in the reference (memory/sfma.py:289-306)

@@ -203,6 +203,14 @@ int cobel_sr_compact_run(const CobelSRCompactParams* p, void* stream);
 enum { COBEL_SFMA_DEFAULT = 0, COBEL_SFMA_FORWARD = 1, COBEL_SFMA_REVERSE = 2, COBEL_SFMA_BLEND_FORWARD = 3,
        COBEL_SFMA_BLEND_REVERSE = 4, COBEL_SFMA_INTERPOLATE = 5, COBEL_SFMA_SWEEPING = 6 };
 
+/* CobelSFMAParams.mod_flags (memory/sfma.py:216-236, 283-288, 319-320) */
+#define COBEL_SFMA_MOD_REWARD_LOCAL 1   /* M.reward_mod_local: C[a,s] += r * reward_modulation on store */
+#define COBEL_SFMA_MOD_REWARD       2   /* M.reward_mod: C += r * tile(D[s]) * reward_modulation on store */
+#define COBEL_SFMA_MOD_STATE        4   /* M.state_mod: C[.,s] += 1 on store */
+#define COBEL_SFMA_C_NORMALIZE      8   /* M.C_normalize */
+#define COBEL_SFMA_D_NORMALIZE     16   /* M.D_normalize */
+#define COBEL_SFMA_R_RAW           32   /* M.R_normalize == False */
+
 typedef struct CobelSFMAParams {
   int64_t n_agents;
   CobelWorld world;
@@ -241,6 +249,9 @@ typedef struct CobelSFMAParams {
   int32_t learn;             /* 1 = train(), 0 = test() */
   double*  td_acc;           /* optional [N] in/out: agent.td, the |TD error| accumulated by update_q (agent/sfma.py:456) */
   int32_t* trial_mode;       /* optional [N,trials] out: replay mode chosen at the end of each trial (dynamic) */
+  double   reward_modulation;/* M.reward_modulation (1.0) */
+  int32_t  mod_flags;        /* COBEL_SFMA_MOD_* bits: strength modulation and normalisation switches */
+  int32_t  reserved2;
 } CobelSFMAParams;
 
 int cobel_sfma_run(const CobelSFMAParams* p, void* stream);

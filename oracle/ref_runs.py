@@ -165,7 +165,7 @@ def run_sr(world, u, trials, steps, *, policy=('eps', 0.1), lr=0.1, gamma=0.99, 
 
 def run_sfma(world, D, u, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99, gamma=0.99,
              mem_lr=0.9, mask_actions=False, mode='default', recency=False, start_replay=False,
-             nb_replays=1, metric=None, action_mask=None, random_replay=False, dynamic=False):
+             nb_replays=1, metric=None, action_mask=None, random_replay=False, dynamic=False, mem_flags=None):
     cobel = ref_loader.load()
     rng = StreamRNG(u)
     env = _gridworld(cobel, world, rng)
@@ -180,6 +180,9 @@ def run_sfma(world, D, u, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99,
     mem = cobel.memory.SFMAMemory(metric, S, 4, learning_rate=mem_lr, rng=rng)
     mem.mode = mode
     mem.recency = recency
+    for k, v in (mem_flags or {}).items():      # reward_mod_local, reward_mod, state_mod, C_normalize, ...
+        assert hasattr(mem, k), k
+        setattr(mem, k, v)
     cbs = cap.callbacks()
 
     def on_replay_end(logs):

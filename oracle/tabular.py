@@ -398,7 +398,8 @@ def sfma_init(S, A):
 
 def sfma_memory_replay(st, D, rng, length, current_state, *, mode='default', beta=20.0,
                        decay_inhibition=0.9, threshold=1e-6, recency=False, deterministic=False,
-                       blend=0.1, interp=(0.5, 0.5), i_step=1.0):
+                       blend=0.1, interp=(0.5, 0.5), i_step=1.0, c_normalize=False, d_normalize=False,
+                       r_normalize=True):
     """SFMAMemory.replay, memory/sfma.py:238-347.  Returns the flat indices
     ``a*S + s`` of the reactivated experiences."""
     S, A = st['Q'].shape
@@ -416,7 +417,11 @@ def sfma_memory_replay(st, D, rng, length, current_state, *, mode='default', bet
     statesF = Ms.flatten(order='F')
     for _ in range(length):
         Cc = np.copy(C)
+        if c_normalize:                                         # 283-284
+            Cc /= np.amax(Cc)
         Dv = np.tile(D[current_state], A)
+        if d_normalize:                                         # 287-288
+            Dv /= np.amax(Dv)
         if mode == 'forward':
             Dv = np.tile(D[next_state], A)
         elif mode == 'reverse':
@@ -435,7 +440,8 @@ def sfma_memory_replay(st, D, rng, length, current_state, *, mode='default', bet
         R[R < threshold] = 0.0
         if np.sum(R) == 0.0:                                    # 316
             break
-        R /= np.amax(R)
+        if r_normalize:                                         # 319-320
+            R /= np.amax(R)
         e = int(np.argmax(R))
         if not deterministic:
             ex = np.exp(R * beta) + (-1)                        # softmax(R, -1, beta), 349-373
@@ -457,7 +463,8 @@ def sfma_memory_replay(st, D, rng, length, current_state, *, mode='default', bet
 def sfma_train(W, st, D, rng, trials, steps, batch, *, policy=('eps', 0.1), lr=0.99, gamma=0.99,
                mem_lr=0.9, mask_actions=False, mode='default', decay_strength=1.0,
                decay_recency=0.9, no_replay=False, nb_replays=1, start_replay=False,
-               random_replay=False, dynamic=False, replay_kwargs=None, rec=None):
+               random_replay=False, dynamic=False, reward_mod_local=False, reward_mod=False, state_mod=False,
+               reward_modulation=1.0, replay_kwargs=None, rec=None):
     """SFMA.train, agent/sfma.py:233-328 (store before update_q; replay at trial end
     from the terminal state, or from a strength-sampled experience when the trial
     timed out; ``M.T`` zeroed after every trial, 324).  ``random_replay`` restates ``agent.random``;
@@ -506,6 +513,12 @@ def sfma_train(W, st, D, rng, trials, steps, batch, *, policy=('eps', 0.1), lr=0
             Mr[s, a] += mem_lr * (r - Mr[s, a]); Ms[s, a] = s2; Mt[s, a] = nt
             C *= decay_strength; C[S * a + s] += 1.0
             T *= decay_recency; T[S * a + s] = 1.0
+            if reward_mod_local:                                # memory/sfma.py:216-220
+                C[S * a + s] += r * reward_modulation
+            if reward_mod:                                      # 221-224
+                C += r * np.tile(D[s], A) * reward_modulation
+            if state_mod:                                       # 235-236
+                C[[s + S * b for b in range(A)]] += 1.0
             td = _td_update(Q, s, a, r, s2, nt, lr, gamma,
                             st['action_mask'][s2] if mask_actions else None)
             st['td_acc'] += np.abs(td)

@@ -264,10 +264,10 @@ def test_unsupported_shapes_and_options_fail_loudly():
     env = Gridworld(world, rng=stream)
     smem = SFMAMemory(Euclidean(5, 5), 25, 4, rng=stream)
     sfma = SFMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), smem, rng=stream)
-    smem.reward_mod = True
+    smem.error_mod = True                   # reads experience['td'] before it exists: broken in the reference too
     with pytest.raises(NotImplementedError):
         sfma.train(env, 1, 5, 4)
-    smem.reward_mod = False
+    smem.error_mod = False
     sfma.train(env, 2, 10, 4)              # and the supported configuration runs (Euclidean metric)
     # environment / agent mismatch and a CPU device are rejected
     other = Gridworld(make_open_field(4, 4, 0, 1), rng=cb.BatchStream(2, seed=1, device='cuda:0'))

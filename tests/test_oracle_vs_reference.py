@@ -97,3 +97,38 @@ def test_pma_replay_switches_live(reference, opts):
     got.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], T=st['T'], SR=st['SR'], update_mask=st['update_mask'],
                draws=rng.k)
     assert_equal_records(got, ref, KEYS['pma'])
+
+
+SFMA_FLAG_CASES = [
+    (dict(reward_mod_local=True, reward_modulation=2.5), 'default'),
+    (dict(reward_mod=True, reward_modulation=0.5), 'reverse'),
+    (dict(state_mod=True), 'default'),
+    (dict(C_normalize=True), 'blend_reverse'),
+    (dict(D_normalize=True), 'blend_forward'),
+    (dict(D_normalize=True, C_normalize=True), 'interpolate'),
+    (dict(R_normalize=False, beta=2.0), 'default'),
+    (dict(reward_mod_local=True, reward_mod=True, state_mod=True, C_normalize=True, D_normalize=True), 'reverse'),
+]
+
+
+def sfma_flag_kwargs(flags):
+    """Reference attribute names -> oracle keyword arguments (store-time flags, replay-time flags)."""
+    store = {k: flags[k] for k in ('reward_mod_local', 'reward_mod', 'state_mod', 'reward_modulation') if k in flags}
+    names = {'C_normalize': 'c_normalize', 'D_normalize': 'd_normalize', 'R_normalize': 'r_normalize', 'beta': 'beta'}
+    return store, {names[k]: flags[k] for k in names if k in flags}
+
+
+@pytest.mark.parametrize('flags,mode', SFMA_FLAG_CASES)
+def test_sfma_modulation_flags_live(reference, flags, mode):
+    """SFMAMemory strength modulation and normalisation switches (memory/sfma.py:216-236, 283-288, 319-320)."""
+    world = _world(reference, 'walls5')
+    W = tb.compile_gridworld(world)
+    D = reference.memory.utils.metrics.DR(5, 5, world['sas'], 0.9, world['invalid_transitions']).D
+    u = LazyStream(21, 4)
+    ref = ref_runs.run_sfma(world, D, u, 8, 30, 16, mode=mode, mask_actions=True, mem_flags=flags)
+    rng = tb.Draws(LazyStream(21, 4), 1)
+    st = tb.sfma_init(25, 4)
+    store, rk = sfma_flag_kwargs(flags)
+    got = tb.sfma_train(W, st, D, rng, 8, 30, 16, mode=mode, mask_actions=True, replay_kwargs=rk, **store).arrays()
+    got.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], C=st['C'], T=st['T'], I=st['I'], draws=rng.k)
+    assert_equal_records(got, ref, KEYS['sfma'])

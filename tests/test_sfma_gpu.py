@@ -106,3 +106,57 @@ def test_sfma_no_replay_and_test_mode():
         got2 = unpack_run(rt, i, 4, W['succ'], W['reward'])
         assert_equal_records(got2, rec2, ['states', 'actions', 'trial_steps'], what='test agent %d' % i)
         assert int(stream.draw_count[i]) == rng.k
+
+
+@pytest.mark.parametrize('flags,mode', [
+    (dict(reward_mod_local=True, reward_modulation=2.5), 'default'),
+    (dict(reward_mod=True, reward_modulation=0.5), 'reverse'),
+    (dict(state_mod=True), 'default'),
+    (dict(C_normalize=True), 'blend_reverse'),
+    (dict(D_normalize=True), 'blend_forward'),
+    (dict(D_normalize=True, C_normalize=True), 'interpolate'),
+    (dict(R_normalize=False, beta=2.0), 'default'),
+    (dict(reward_mod_local=True, reward_mod=True, state_mod=True, C_normalize=True, D_normalize=True), 'reverse'),
+])
+def test_sfma_modulation_flags_vs_oracle(flags, mode):
+    """SFMAMemory strength-modulation / normalisation switches (memory/sfma.py:216-236, 283-288, 319-320) on the GPU
+    against the oracle (pinned to the reference for the same switches by tests/test_oracle_vs_reference.py)."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import SFMA
+    from cobel_rl_b200.memory import SFMAMemory
+    from cobel_rl_b200.memory.utils.metrics import DR
+    from cobel_rl_b200.policy import EpsilonGreedy
+    world = make_world('walls5')
+    W = tb.compile_gridworld(world)
+    # a world with a negative reward as well: modulated strengths can go negative
+    world['rewards'][7] = -0.5
+    W['reward'][7] = -0.5
+    n, trials, steps, batch = 3, 8, 30, 16
+    stream = cb.BatchStream(n, seed=909, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    metric = DR(5, 5, world['sas'], 0.9, world['invalid_transitions'])
+    mem = SFMAMemory(metric, 25, 4, rng=stream)
+    mem.mode = mode
+    for k, v in flags.items():
+        assert hasattr(mem, k), k
+        setattr(mem, k, v)
+    ag = SFMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem, rng=stream)
+    ag.mask_actions = True
+    ag.record = True
+    res = ag.train(env, trials, steps, batch)
+    torch.cuda.synchronize()
+    assert int((res['flags'] & 2).sum()) == 0
+    store = {k: flags[k] for k in ('reward_mod_local', 'reward_mod', 'state_mod', 'reward_modulation') if k in flags}
+    names = {'C_normalize': 'c_normalize', 'D_normalize': 'd_normalize', 'R_normalize': 'r_normalize', 'beta': 'beta'}
+    rk = {names[k]: flags[k] for k in names if k in flags}
+    D = np.asarray(metric.D)
+    for i in range(n):
+        rng = tb.Draws(LazyStream(909, i), 1)
+        st = tb.sfma_init(25, 4)
+        rec = tb.sfma_train(W, st, D, rng, trials, steps, batch, mode=mode, mask_actions=True, replay_kwargs=rk, **store).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got.update(Q=ag.Q[i].cpu().numpy(), C=mem._C[i].cpu().numpy(), I=mem._I[i].cpu().numpy(), draws=int(stream.draw_count[i]))
+        rec.update(Q=st['Q'], C=st['C'], I=st['I'], draws=rng.k)
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q', 'C', 'I', 'draws'],
+                             what='agent %d %s' % (i, flags))
