@@ -308,12 +308,11 @@ COBEL_DEV void td_batch_level_parallel(double* Q, uint32_t* wm, uint32_t* rm, in
   const unsigned act = __ballot_sync(kFull, active);
   const unsigned below = (1u << lane) - 1u;
   // writers / readers per state (wm / rm are all-zero on entry and are re-zeroed on exit)
-  unsigned same_s = 0;
   if (active) {
-    // all lanes with the same key store the same mask: a benign same-value race
-    same_s = __match_any_sync(act, s);
-    wm[s] = same_s;
-    rm[s2] = __match_any_sync(act, s2);
+    // shared-memory OR reductions (fire-and-forget RED.OR) instead of two MATCH.ANY: the masks are only needed
+    // after the barrier below
+    atomicOr(&wm[s], 1u << lane);
+    atomicOr(&rm[s2], 1u << lane);
   }
   // lanes with my action, from A cheap ballots instead of a third MATCH
   unsigned same_a = 0;
@@ -325,7 +324,7 @@ COBEL_DEV void td_batch_level_parallel(double* Q, uint32_t* wm, uint32_t* rm, in
   __syncwarp();
   unsigned strict = 0, weak = 0;
   if (active) {
-    const unsigned same_sa = same_s & same_a;                       // i writes the entry j reads+writes
+    const unsigned same_sa = wm[s] & same_a;                        // i writes the entry j reads+writes
     strict = (wm[s2] | same_sa) & below;                            // i writes into the row j reads
     weak = rm[s] & below;                                           // j writes into the row i reads
   }
