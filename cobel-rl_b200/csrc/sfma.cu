@@ -142,7 +142,9 @@ COBEL_DEV int block_sample(const double* w, int N, double u, double* part, Block
   return idx;
 }
 
-template <int A>
+// MODS = the memory's strength-modulation / normalisation switches (mod_flags) may be set; the common case
+// (none) gets an instantiation without that code.
+template <int A, bool MODS>
 __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ CobelSFMAParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ BlockShared sh;
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
   int flags = 0;
   const double* D = p.D;
   int mode = p.mode;                   // CTA-uniform; re-chosen per trial when agent.dynamic is set
-  const int mf = p.mod_flags;          // COBEL_SFMA_MOD_* / *_NORMALIZE switches
+  const int mf = MODS ? p.mod_flags : 0;   // COBEL_SFMA_MOD_* / *_NORMALIZE switches
   double cmax = 1.0, dmax = 1.0;       // np.amax(C) / np.amax(D[current_state]) when C_normalize / D_normalize
   double tdacc = p.td_acc ? p.td_acc[n] : 0.0;   // agent.td (maintained by warp 0)
 
@@ -628,8 +630,13 @@ int launch(const CobelSFMAParams& p, cudaStream_t st) {
   const SfmaSmem so(S, A, T, p.batch, p.recency != 0 || p.no_replay != 0, p.random_replay != 0);
   COBEL_REQUIRE(so.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
                 "SFMA tables of %d states x %d actions need %d bytes of shared memory", S, A, so.bytes);
-  COBEL_CUDA_OK(cudaFuncSetAttribute(sfma_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, so.bytes));
-  sfma_kernel<A><<<(unsigned)p.n_agents, T, so.bytes, st>>>(p);
+  if (p.mod_flags) {
+    COBEL_CUDA_OK(cudaFuncSetAttribute(sfma_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, so.bytes));
+    sfma_kernel<A, true><<<(unsigned)p.n_agents, T, so.bytes, st>>>(p);
+  } else {
+    COBEL_CUDA_OK(cudaFuncSetAttribute(sfma_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, so.bytes));
+    sfma_kernel<A, false><<<(unsigned)p.n_agents, T, so.bytes, st>>>(p);
+  }
   cobel_count_launch();
   COBEL_CUDA_OK(cudaGetLastError());
   return COBEL_OK;
