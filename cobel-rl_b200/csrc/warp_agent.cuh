@@ -336,7 +336,8 @@ COBEL_DEV void td_batch_level_parallel(double* Q, uint32_t* wm, uint32_t* rm, in
   while (done != kFull) {
     const bool ready = active && !(done >> lane & 1u) && (dep & ~done) == 0;
     const unsigned R = __ballot_sync(kFull, ready);
-    double qn = 0.0;
+    // the lanes of a round touch disjoint data (every read-write and write-write overlap is a dependence above),
+    // so a lane writes straight after its reads; one barrier per round orders the rounds
     if (ready) {
       double row[A];
       load_row<A>(Q + s2 * A, row);
@@ -352,11 +353,9 @@ COBEL_DEV void td_batch_level_parallel(double* Q, uint32_t* wm, uint32_t* rm, in
       }
       double td = xadd(r, xmul(g, mx));
       td = xsub(td, q);
-      qn = xadd(q, xmul(lr, td));
+      Q[s * A + a] = xadd(q, xmul(lr, td));
       if (td_out) *td_out = td;
     }
-    __syncwarp();
-    if (ready) Q[s * A + a] = qn;
     __syncwarp();
     done |= R;
   }
