@@ -6,12 +6,13 @@
 //
 // Mapping: ONE WARP PER AGENT, agent tables resident in shared memory for the whole launch
 // (HBM is touched once: coalesced stage-in / stage-out).  Per environment step the warp
-//   * generates the step's 34 uniforms lane-parallel (one Philox block per lane),
-//   * selects the action and steps the environment warp-uniformly,
+//   * takes the step's 34 uniforms from the agent's stream window (one Philox block per lane per refill;
+//     the PLAIN kernel keeps 256 draws in shared memory, i.e. seven steps per refill),
+//   * selects the action and steps the environment warp-uniformly (PLAIN: tie-pattern CDF table),
 //   * draws the 32 replay indices one per lane, gathers the 32 experiences in parallel and
 //     applies the 32 TD updates in dependency levels (td_batch_level_parallel): updates that
 //     do not touch each other's rows run in the same round, so the reference's strictly
-//     sequential 32-update chain collapses to ~6-8 rounds with bit-identical results.
+//     sequential 32-update chain collapses to about five rounds with bit-identical results.
 // (v1 of this kernel used one thread per agent: 180 warp-instructions per update at one
 //  instruction per 5 cycles, profiles/r1_dynaq_v1_thread_per_agent.txt.)
 #include "warp_agent.cuh"

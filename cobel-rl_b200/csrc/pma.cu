@@ -5,27 +5,33 @@
 // memory/pma.py:104-496 (store, replay, compute_gain_batch, compute_gain, compute_need,
 // update_sr, update_q).  Semantics: SURVEY.md Appendix A.7.
 //
-// The trial loop is split into two kernels launched alternately by cobel_pma_run (all agents
-// advance trial by trial; per-agent state is carried in HBM between launches):
+// Kernels (cobel_pma_run picks the path, see run<A>()):
 //
-//   pma_main_kernel  ONE WARP PER AGENT.  [end-of-trial replay of the previous trial] + reset +
-//                    start-of-trial replay + the online steps.  Q, M.rewards, M.states|terminals,
-//                    the gain vector and the need row live in shared memory (13 KB per agent at
-//                    10x10, 16 agents per SM); T stays in HBM (one row read+written per step).
-//                    Replay: the gain of every one-step backup depends on two Q rows, so after the
-//                    first iteration of a replay call only the backups whose rows were touched by
-//                    the previous update are re-evaluated (compacted to one lane-parallel pass) --
-//                    bit-identical to the reference's full recomputation; gain x need x mask,
-//                    the exact-tie arg-max draw and the n-step update are warp passes with
-//                    shuffle reductions (no block barriers).
-//   pma_sr_kernel    ONE CTA PER AGENT.  update_sr: SR = inv(I - gamma T) by register-tiled
-//                    Gauss-Jordan (no pivoting: I - gamma T is strictly diagonally dominant), T
-//                    read from and SR written to HBM; for agents whose trial timed out also the
-//                    stationary distribution (the reference's LAPACK dgeev `need`) by the
-//                    subtraction-free GTH elimination.
+//   pma_main_kernel  ONE WARP PER AGENT.  reset + start-of-trial replay + the online steps [+ update_sr +
+//                    end-of-trial replay].  Q, M.rewards, M.states|terminals, the utility vector and the need
+//                    row live in shared memory (14 KB per agent at 10x10, 16 agents per SM); T stays in HBM
+//                    (one row read+written per step).  Replay: the gain of every one-step backup depends on two
+//                    Q rows, so after the first iteration of a replay call only the backups whose rows were
+//                    touched by the previous update are re-evaluated (compacted to one lane-parallel pass) --
+//                    bit-identical to the reference's full recomputation; gain x need x mask, the exact-tie
+//                    arg-max draw and the n-step update are warp passes with shuffle reductions (no block
+//                    barriers).
+//   update_sr, banded (CobelPMAParams.sr_band >= 0, BAND = true): replay reads ONE row of SR per call, and T of
+//                    a W-wide gridworld has half bandwidth W, so the agent's warp factorises the band of
+//                    I - gamma T itself (band_lu) and solves for the row it needs (band_solve_row; band_gth for
+//                    the stationary need of timed-out trials): all trials run in ONE launch, and SR is
+//                    refreshed once per call by pma_sr_band_kernel from the stored factors.
+//   update_sr, dense (any T): pma_sr_kernel, ONE CTA PER AGENT, after every trial (the main kernel is then
+//                    launched once per trial, per-agent state carried in HBM): SR = inv(I - gamma T) by
+//                    register-tiled Gauss-Jordan (no pivoting: I - gamma T is strictly diagonally dominant); for
+//                    agents whose trial timed out also the stationary distribution (the reference's LAPACK
+//                    dgeev `need`) by the subtraction-free GTH elimination.
 //
 // (v1 ran everything in one CTA per agent and was barrier-bound: 7 of 8 warps waited for warp 0
 //  through ~12 block barriers per replay iteration, profiles/r1_pma_v1_cta_per_agent.txt.)
+// The main kernel is instruction-fetch bound (its replay loop is as large as the L1.5 instruction cache): the
+// rarely executed routines are __noinline__, runtime loops are not unrolled, fp64 division and the Philox refill
+// are single shared copies.
 //
 // Exactness: everything except SR / the stationary vector follows the reference's operation
 // order bit for bit; those two come from a different (but 1e-13-accurate) factorisation than
