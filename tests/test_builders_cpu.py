@@ -1,7 +1,6 @@
 """CPU (build container only: needs /root/reference): the product's world / graph builders produce
 exactly the reference's WorldDicts and node dictionaries (keys, dtypes, values, neighbour order)."""
 import numpy as np
-import pytest
 
 from cobel_rl_b200.misc import gridworld_tools as mg, topology_tools as mt
 from cobel_rl_b200.memory.utils import metrics as mm

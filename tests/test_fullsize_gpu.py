@@ -7,7 +7,7 @@ import torch
 
 from oracle import tabular as tb
 from oracle.philox import LazyStream
-from helpers import assert_equal_records, make_world
+from helpers import make_world
 
 pytestmark = pytest.mark.gpu
 SEED = 0x5EED

@@ -5,7 +5,6 @@ bit-equal.  SR and the stationary `need` vector come from an in-kernel Gauss-Jor
 factorisation instead of LAPACK: tolerance 1e-12 relative to the matrix scale (BASELINE.json
 north_star: "within 1e-12 relative"; see helpers.assert_equal_records), and the kernel's top-2
 utility gap certificate must stay far above that tolerance."""
-import numpy as np
 import pytest
 import torch
 

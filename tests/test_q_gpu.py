@@ -6,7 +6,7 @@ import torch
 
 from oracle import cases, tabular as tb
 from oracle.philox import LazyStream
-from helpers import KEYS, assert_equal_records, cuda_case, load_golden, make_topology, unpack_run
+from helpers import KEYS, assert_equal_records, cuda_case, load_golden, unpack_run
 
 pytestmark = pytest.mark.gpu
 
@@ -26,9 +26,7 @@ def test_q_hexagonal_six_actions_and_continue_training():
     from cobel_rl_b200.interface import Topology
     from cobel_rl_b200.agent import QAgent
     from cobel_rl_b200.policy import EpsilonGreedy
-    from oracle import ref_loader
-    # hexagonal() is not part of the product builders yet: build the node dict with the oracle-side
-    # restatement of the graph (any dict of nodes with 6 neighbours works)
+    # a hand-built 6-neighbour graph (any dict of nodes with 6 neighbours works)
     n_side = 4
     ids = [str(i) for i in range(n_side * n_side)]
     nodes = {}
