@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sr_compact_kernel(const __g
   auto locate = [&](int g) -> int {
     unsigned hit = 0;
     int where = -1;
-    for (int e0 = 0; e0 < V; e0 += 32) {
+    // newest entries first: a walk mostly returns to states it has just left (entries are unique: at most one hit)
+    for (int e0 = (V - 1) & ~31; e0 >= 0; e0 -= 32) {
       const int e = e0 + lane;
       hit = __ballot_sync(kFull, e < V && vis[e] == g);
       if (hit) { where = e0 + __ffs(hit) - 1; break; }
