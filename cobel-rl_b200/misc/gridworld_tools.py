@@ -208,3 +208,21 @@ def make_cross_maze(arm_length, arm_width, goal_arm='top', reward=1.0):
     rewards[:, 0] = terminals
     return make_gridworld(size, size, terminals, rewards, terminals, starting_states=starting,
                           invalid_transitions=_corridor_walls(size, size, corridor))
+
+
+def load_world(file_name):
+    """A WorldDict pickled by the reference's gridworld editor (misc/gridworld_gui.py:203-239 saves / loads
+    ``self.world`` with pickle) or by ``save_world``; the successor table is added if the file has none."""
+    import pickle
+    with open(file_name, 'rb') as f:
+        world = pickle.load(f)
+    if 'succ' not in world and world.get('sas') is not None:
+        world['succ'] = np.argmax(np.asarray(world['sas']), axis=2).astype(np.int32)    # interface/gridworld.py:116-117
+    return world
+
+
+def save_world(world, file_name):
+    """The counterpart of ``load_world``, in the editor's format (a pickled WorldDict)."""
+    import pickle
+    with open(file_name, 'wb') as f:
+        pickle.dump(world, f)

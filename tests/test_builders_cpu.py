@@ -122,3 +122,20 @@ def test_metrics(reference):
     np.testing.assert_array_equal(mm.DR(5, 5, world['sas'], 0.9, []).D, rm.DR(5, 5, world['sas'], 0.9, []).D)
     np.testing.assert_array_equal(mm.SR(world['sas'], 0.8).D, rm.SR(world['sas'], 0.8).D)
     np.testing.assert_allclose(mm.Euclidean(4, 3).D, rm.Euclidean(4, 3).D, rtol=1e-15)
+
+
+def test_pickled_world_round_trip(reference, tmp_path):
+    """The gridworld editor's file format (misc/gridworld_gui.py:203-239: a pickled WorldDict)."""
+    import pickle
+    from cobel.misc import gridworld_tools as rg
+    from cobel_rl_b200.interface.gridworld import successor_table
+    ref_world = rg.make_t_maze(3, 2)                 # as the reference's editor would have saved it (no 'succ' key)
+    path = tmp_path / 'maze.pkl'
+    with open(path, 'wb') as f:
+        pickle.dump(ref_world, f)
+    world = mg.load_world(path)
+    same_world(world, ref_world)
+    assert np.array_equal(world['succ'], mg.make_t_maze(3, 2)['succ']) and np.array_equal(successor_table(world), world['succ'])
+    mg.save_world(world, tmp_path / 'again.pkl')
+    again = mg.load_world(tmp_path / 'again.pkl')
+    same_world(again, world)
