@@ -132,3 +132,32 @@ def test_sfma_modulation_flags_live(reference, flags, mode):
     got = tb.sfma_train(W, st, D, rng, 8, 30, 16, mode=mode, mask_actions=True, replay_kwargs=rk, **store).arrays()
     got.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], C=st['C'], T=st['T'], I=st['I'], draws=rng.k)
     assert_equal_records(got, ref, KEYS['sfma'])
+
+
+@pytest.mark.parametrize('k', range(6))
+def test_dynaq_random_configurations_live(reference, k):
+    """Randomised Dyna-Q configurations (policy kind and parameter, masks, replay schedule, batch, learning rates)
+    on the maze templates: the oracle against the unmodified reference."""
+    rs = np.random.default_rng(300 + k)
+    tools = reference.misc.gridworld_tools
+    world = [tools.make_t_maze(3, 2), tools.make_double_t_maze(2, 1), tools.make_8_maze(3, 2),
+             tools.make_cross_maze(2, 2, 'left'), tools.make_detour_maze(1, 1, 2, 2),
+             tools.make_two_choice_t_maze(3, 3, 1)][k]
+    S = world['states']
+    kind = ['eps', 'xeps', 'softmax'][k % 3]
+    par = float(np.round(rs.uniform(0.05, 0.5) if kind != 'softmax' else rs.uniform(0.5, 3.0), 3))
+    kw = dict(policy=(kind, par), lr=float(np.round(rs.uniform(0.3, 1.0), 3)), gamma=float(np.round(rs.uniform(0.5, 0.99), 3)),
+              mem_lr=float(np.round(rs.uniform(0.3, 1.0), 3)), mask_actions=bool(k % 2),
+              no_replay=(k == 4), episodic_replay=(k == 5))
+    batch = int(rs.choice([4, 16, 32]))
+    W = tb.compile_gridworld(world)
+    mask = tb.valid_move_mask(W['succ'])
+    mask[np.arange(S), 0] |= ~mask.any(axis=1)        # dead-end cells keep one valid action
+    u = LazyStream(40 + k, 1)
+    ref = ref_runs.run_dynaq(world, u, 10, 25, batch, action_mask=mask if kw['mask_actions'] else None, **kw)
+    rng = tb.Draws(LazyStream(40 + k, 1), 1)
+    st = tb.dynaq_init(S, 4)
+    st['action_mask'] = mask
+    got = tb.dynaq_train(W, st, rng, 10, 25, batch, **kw).arrays()
+    got.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'], draws=rng.k)
+    assert_equal_records(got, ref, KEYS['dynaq'])
