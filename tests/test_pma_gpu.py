@@ -5,6 +5,7 @@ bit-equal.  SR and the stationary `need` vector come from an in-kernel Gauss-Jor
 factorisation instead of LAPACK: tolerance 1e-12 relative to the matrix scale (BASELINE.json
 north_star: "within 1e-12 relative"; see helpers.assert_equal_records), and the kernel's top-2
 utility gap certificate must stay far above that tolerance."""
+import numpy as np
 import pytest
 import torch
 
@@ -169,3 +170,43 @@ def test_pma_replay_switches_vs_oracle(opts):
         rec.update(Q=st['Q'], T=st['T'], SR=st['SR'], draws=rng.k)
         assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q', 'T', 'SR', 'draws'],
                              rtol=RTOL, what='agent %d %s' % (i, opts))
+
+
+@pytest.mark.parametrize('shape', [(6, 7), (4, 9), (7, 5)])
+def test_pma_on_other_grid_shapes_vs_oracle(shape):
+    """PMA on walled grids of other shapes (bandwidths 7, 9 and 5; state counts 42, 36, 35): the banded update_sr
+    against the oracle's dense LAPACK inverse.  (Worlds with unreachable cells, e.g. the maze templates, have no unique
+    stationary distribution: a timed-out trial there raises COBEL_FLAG_SINGULAR, and the reference's `eig` need is
+    not defined either.)"""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import PMA
+    from cobel_rl_b200.memory import PMAMemory
+    from cobel_rl_b200.misc import gridworld_tools as mg
+    from cobel_rl_b200.policy import EpsilonGreedy
+    h, w = shape
+    goal = w - 1
+    walls = [(1, 2), (2, 1), (w + 1, w + 2), (w + 2, w + 1), (2 * w + 3, 3 * w + 3), (3 * w + 3, 2 * w + 3)]
+    world = mg.make_gridworld(h, w, terminals=[goal], rewards=np.array([[goal, 5.0]]), goals=[goal],
+                              starting_states=[h * w - w], invalid_transitions=walls)
+    W = tb.compile_gridworld(world)
+    S = world['states']
+    n, trials, steps, batch = 3, 3, 30, 12
+    stream = cb.BatchStream(n, seed=77, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = PMAMemory(world['sas'], EpsilonGreedy(0.1, rng=stream), 0.9, 0.9, 0.9, 0.99, rng=stream)
+    ag = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem)
+    ag.record = True
+    assert mem.sr_band(env.transition_band)[0] == w
+    res = ag.train(env, trials, steps, batch)
+    torch.cuda.synchronize()
+    assert int(res['flags'].sum()) == 0
+    for i in range(n):
+        rng = tb.Draws(LazyStream(77, i), 1)
+        st = tb.pma_init(tb.t0_from_succ(W['succ']), S, 4)
+        rec = tb.pma_train(W, st, rng, trials, steps, batch, gamma_q=0.99).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got.update(Q=ag.Q[i].cpu().numpy(), T=mem.T[i].cpu().numpy(), SR=mem.SR[i].cpu().numpy(), draws=int(stream.draw_count[i]))
+        rec.update(Q=st['Q'], T=st['T'], SR=st['SR'], draws=rng.k)
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q', 'T', 'SR', 'draws'],
+                             rtol=RTOL, what='%s agent %d' % (shape, i))
