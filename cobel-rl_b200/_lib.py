@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcobel_b200.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_f64p = C.c_void_p   # device pointers travel as raw addresses
 c_ptr = C.c_void_p
@@ -91,7 +91,13 @@ class PMAParams(C.Structure):
                 ('lr_T', C.c_double), ('min_gain', C.c_double),
                 ('min_gain_original', C.c_int32), ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32),
                 ('no_replay', C.c_int32), ('learn', C.c_int32), ('sr_band', C.c_int32), ('options', C.c_int32),
-                ('band_scratch', c_ptr)]
+                ('band_scratch', c_ptr), ('n_tab', C.c_int32), ('reserved3', C.c_int32), ('tab_kind', c_ptr),
+                ('tab_param', c_ptr), ('tab_of_agent', c_ptr), ('tab_scratch', c_ptr)]
+
+
+def pma_tab_doubles(n_actions):
+    """COBEL_PMA_TAB_DOUBLES(A) of include/cobel_b200.h."""
+    return 3 * (1 << (2 * n_actions)) * n_actions
 
 
 STRUCTS = {'CobelWorld': World, 'CobelStream': Stream, 'CobelPolicy': Policy, 'CobelTrace': Trace,

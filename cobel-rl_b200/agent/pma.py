@@ -69,6 +69,7 @@ class PMA(Agent):
             psr, pq, pstride = M.power_tables(st, keep)
             mptr, mstride = self._mask_args(keep)
             band, bscratch = M.sr_band(interface.transition_band) if (learn and not no_replay) else (-1, None)
+            n_tab, tkind, tpar, tof, tscr = M.policy_tables(st, pol, A, keep)
             p = _lib.PMAParams(
                 st.n_agents, interface.c_world(), st.c_struct(), pol.c_struct(st, keep), M.policy.c_struct(st, keep), tr,
                 self._Q.data_ptr(), M._rewards.data_ptr(), M._states.data_ptr(), M._terminals.data_ptr(),
@@ -78,7 +79,8 @@ class PMA(Agent):
                 M._min_gap.data_ptr(), M._carry.data_ptr(), M._need_scratch.data_ptr(),
                 float(M.learning_rate_T), float(M.min_gain),
                 1 if M.min_gain_mode == 'original' else 0, n_tr, steps, batch_size, 1 if no_replay else 0,
-                1 if learn else 0, band, M.options(), _lib.ptr(bscratch))
+                1 if learn else 0, band, M.options(), _lib.ptr(bscratch),
+                n_tab, 0, _lib.ptr(tkind), _lib.ptr(tpar), _lib.ptr(tof), _lib.ptr(tscr))
             keep.append(par)
             _lib.call('cobel_pma_run', st.device, p, launch_stream(st))
             self._check_flags(res)

@@ -121,6 +121,21 @@ COBEL_DEV double row_max(const double (&v)[A]) {
   }
 }
 
+// np.sum over A contiguous doubles: a plain loop below 8 elements; for exactly 8 NumPy's
+// pairwise routine keeps 8 accumulators and combines them as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).
+template <int A>
+COBEL_DEV double np_sum(const double (&x)[A]) {
+  static_assert(A <= 8, "np_sum: longer rows need the blocked pairwise tree");
+  if constexpr (A == 8) {
+    return xadd(xadd(xadd(x[0], x[1]), xadd(x[2], x[3])), xadd(xadd(x[4], x[5]), xadd(x[6], x[7])));
+  } else {
+    double s = x[0];
+#pragma unroll
+    for (int a = 1; a < A; ++a) s = xadd(s, x[a]);
+    return s;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Host-side error plumbing shared by the entry points.
 // ---------------------------------------------------------------------------

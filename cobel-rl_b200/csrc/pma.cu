@@ -74,6 +74,7 @@ COBEL_DEV void probs_row(const double (&v)[A], uint32_t mask, int kind, double p
       p[a] = 0.0;
       if (mask >> a & 1u) { p[a] = exp(xmul(xsub(v[a], m), par)); sum = xadd(sum, p[a]); }
     }
+    if (A == 8 && nv == 8) sum = np_sum<A>(p);             // np.sum over exactly 8 values is a tree, not a loop
 #pragma unroll
     for (int a = 0; a < A; ++a)
       if (mask >> a & 1u) p[a] = pdiv(p[a], sum);
@@ -98,12 +99,7 @@ COBEL_DEV void probs_row(const double (&v)[A], uint32_t mask, int kind, double p
 }
 
 template <int A>
-COBEL_DEV double sum_seq(const double (&x)[A]) {     // np.sum over < 8 elements: sequential
-  double s = x[0];
-#pragma unroll
-  for (int a = 1; a < A; ++a) s = xadd(s, x[a]);
-  return s;
-}
+COBEL_DEV double sum_seq(const double (&x)[A]) { return np_sum<A>(x); }    // np.sum over one row of A values
 
 // ---------------------------------------------------------------------------
 // Register-tiled dense eliminations on an S x S matrix distributed over the 16 x 16 thread
@@ -633,22 +629,150 @@ __global__ void __launch_bounds__(256) pma_band_check_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------
+// Tie-pattern policy tables (CobelPMAParams.tab_*): for the two epsilon-greedy kinds get_action_probs depends only
+// on idx = valid-action mask << A | tie pattern, so per distinct (kind, parameter) three tables of (1 << 2A) rows
+// of A doubles are built once per call -- with exactly the operations of probs_row / select_action_warp:
+//   raw   get_action_probs(v, mask)                                  policy/greedy.py:60-88, 117-147
+//   norm  raw / np.sum(raw)       (action_probs_batch)               memory/pma.py:423-450
+//   cdf   cumsum(raw) / cumsum(raw)[-1], last entry 2.0 (never <= u) policy/greedy.py:58
+// ---------------------------------------------------------------------------
+template <int A>
+struct PolTab {
+  static constexpr int kIdx = 1 << (2 * A);
+  static constexpr int kDoubles = 3 * kIdx * A;
+  const double* base;
+  COBEL_DEV const double* raw(int idx) const { return base + idx * A; }
+  COBEL_DEV const double* norm(int idx) const { return base + (kIdx + idx) * A; }
+  COBEL_DEV const double* cdf(int idx) const { return base + (2 * kIdx + idx) * A; }
+};
+
+template <int A>
+__global__ void __launch_bounds__(256) pma_policy_table_kernel(const int32_t* __restrict__ kind, const double* __restrict__ param,
+                                                               double* out) {
+  constexpr int kIdx = PolTab<A>::kIdx;
+  const int c = blockIdx.x;
+  const int kd = kind[c];
+  const double par = param[c];
+  double* raw = out + (size_t)c * PolTab<A>::kDoubles;
+  double* norm = raw + kIdx * A;
+  double* cdf = norm + kIdx * A;
+  for (int idx = threadIdx.x; idx < kIdx; idx += blockDim.x) {
+    const uint32_t mask = (uint32_t)idx >> A, ties = (uint32_t)idx & ((1u << A) - 1u);
+    const bool ok = ties != 0 && (ties & ~mask) == 0 && kd != COBEL_POLICY_SOFTMAX;
+    double p[A], pn[A], cd[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) { p[a] = 0.0; pn[a] = 0.0; cd[a] = 2.0; }
+    if (ok) {
+      const int nv = __popc(mask), k = __popc(ties);
+      const double tie = xdiv(xsub(1.0, par), (double)k);
+      double top, low;
+      if (kd == COBEL_POLICY_EPS_GREEDY) {
+        const double base = xdiv(par, (double)nv);
+        top = xadd(base, tie); low = xadd(base, 0.0);
+      } else {
+        const int d = nv - k > 1 ? nv - k : 1;
+        top = xadd(tie, 0.0); low = xadd(0.0, xdiv(par, (double)d));
+      }
+#pragma unroll
+      for (int a = 0; a < A; ++a) p[a] = (mask >> a & 1u) ? ((ties >> a & 1u) ? top : low) : 0.0;
+      double s = p[0], c2 = p[0];
+      cd[0] = c2;
+#pragma unroll
+      for (int a = 1; a < A; ++a) { s = xadd(s, p[a]); c2 = xadd(c2, p[a]); cd[a] = c2; }
+#pragma unroll
+      for (int a = 0; a < A; ++a) pn[a] = xdiv(p[a], s);
+      if (c2 != 1.0) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) cd[a] = xdiv(cd[a], c2);
+      }
+      cd[A - 1] = 2.0;
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) { raw[idx * A + a] = p[a]; norm[idx * A + a] = pn[a]; cdf[idx * A + a] = cd[a]; }
+  }
+}
+
+// read-only row of A doubles from a 16-byte aligned global table (A even -> LDG.128)
+template <int A>
+COBEL_DEV void ldg_row(const double* r, double (&v)[A]) {
+  if constexpr (A % 2 == 0) {
+#pragma unroll
+    for (int x = 0; x < A; x += 2) {
+      const double2 t = __ldg(reinterpret_cast<const double2*>(r + x));
+      v[x] = t.x; v[x + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int x = 0; x < A; ++x) v[x] = __ldg(r + x);
+  }
+}
+
+// table row of a Q row: valid mask << A | (valid entries equal to the maximum over the valid entries)
+template <int A>
+COBEL_DEV int tie_index(const double (&v)[A], uint32_t mb) {
+  const double ninf = -__longlong_as_double(0x7FF0000000000000ll);
+  double w[A];
+#pragma unroll
+  for (int a = 0; a < A; ++a) w[a] = (mb >> a & 1u) ? v[a] : ninf;
+  const double m = row_max<A>(w);
+  uint32_t ties = 0;
+#pragma unroll
+  for (int a = 0; a < A; ++a) ties |= (w[a] == m ? 1u : 0u) << a;
+  return (int)((mb << A) | ties);
+}
+
+// Policy.select_action from the cdf table: the number of bin edges <= u (every lane computes the same)
+template <int A>
+COBEL_DEV int select_action_tab(const double (&v)[A], uint32_t mb, const PolTab<A>& tab, double u) {
+  double c[A];
+  ldg_row<A>(tab.cdf(tie_index<A>(v, mb)), c);
+  int a = 0;
+#pragma unroll
+  for (int x = 0; x < A - 1; ++x) a += c[x] <= u ? 1 : 0;
+  return a;
+}
+
+// ---------------------------------------------------------------------------
+// Utilities are kept as order-preserving integer keys: (hi signed, lo unsigned) compares like the double, equal
+// keys <=> equal doubles (-0.0 is canonicalised to +0.0 first; utilities are never NaN).  A warp maximum is then
+// two REDUX instructions instead of a five-level fp64 shuffle butterfly.
+// ---------------------------------------------------------------------------
+COBEL_DEV int2 key_of(double v) {                     // .x = lo, .y = hi
+  v = xadd(v, 0.0);
+  int hi = __double2hiint(v), lo = __double2loint(v);
+  const int s = hi >> 31;
+  return make_int2(lo ^ s, hi ^ (s & 0x7FFFFFFF));
+}
+COBEL_DEV double key_value(int2 k) {
+  const int s = k.y >> 31;
+  return __hiloint2double(k.y ^ (s & 0x7FFFFFFF), k.x ^ s);
+}
+constexpr int kKeyMinHi = (int)0x80000000;            // below the key of every double (-inf included)
+COBEL_DEV int2 warp_max_key(int2 k) {
+  const int mh = __reduce_max_sync(kFull, k.y);
+  const unsigned ml = __reduce_max_sync(kFull, k.y == mh ? (unsigned)k.x : 0u);
+  return make_int2((int)ml, mh);
+}
+
+// ---------------------------------------------------------------------------
 // pma_main_kernel: one warp per agent.
 // ---------------------------------------------------------------------------
 struct MainSmem {      // byte offsets inside one agent's shared-memory block
-  int q, mr, util, need, poff, pk, pitems, list, seq, perf, dst, rs, mbits, bytes;
+  int q, mr, need, pk, mbits, ukey, poff, pitems, list, seq, perf, dst, rs, bytes;
+  int np;              // utility entries padded to a multiple of 32 (chunks of one entry per lane)
   static constexpr int kListCap = 256;     // stale-gain list; larger sets fall back to a full pass
   __host__ __device__ MainSmem(int S, int A) {
     const int N = S * A;
+    np = (N + 31) & ~31;
     q = 0;
     mr = q + N * 8;
     need = mr + N * 8;
     pk = need + ((S + 1) & ~1) * 8;
     mbits = pk + N * 2;
     // from here on: buffers that are dead between replay calls -- the banded solver's row ring aliases them
-    util = (mbits + S + 7) & ~7;
-    poff = util + N * 8;
-    pitems = poff + ((S + 2) & ~1) * 4;
+    ukey = (mbits + S + 7) & ~7;
+    poff = ukey + np * 8;
+    pitems = poff + ((S + 3) & ~1) * 4;
     list = pitems + N * 2;
     seq = list + kListCap * 2;
     perf = seq + (kMaxSeq + 2) * 2;
@@ -656,14 +780,9 @@ struct MainSmem {      // byte offsets inside one agent's shared-memory block
     rs = (dst + (kMaxSeq + 2) * 2 + 7) & ~7;
     bytes = (rs + (kMaxSeq + 2) * 8 + 15) & ~15;
   }
-  // doubles available to the banded solver's ring (from `util` to the end of the block)
-  __host__ __device__ int ring_doubles() const { return (bytes - util) / 8; }
+  // doubles available to the banded solver's ring (from `ukey` to the end of the block)
+  __host__ __device__ int ring_doubles() const { return (bytes - ukey) / 8; }
 };
-
-COBEL_DEV double warp_max_f64(double v) {
-  for (int d = 16; d > 0; d >>= 1) { const double o = shfl_f64_xor(v, d); v = o > v ? o : v; }
-  return v;
-}
 
 // launch phases of pma_main_kernel
 struct MainPhase {
@@ -673,9 +792,9 @@ struct MainPhase {
   int n_trials;         // trials run by this launch (0 or 1 when replays are enabled)
 };
 
-// PLAIN = epsilon-greedy agent and memory policies, training with replay, deterministic world, no optional
-// trace buffers, generated stream: the other policies' code (fp64 exp) and the per-step checks are compiled out
-// (the kernel is instruction-fetch bound: profiles/r1_pma_v3.txt).
+// PLAIN = epsilon-greedy agent and memory policies from the tie-pattern tables, training with replay,
+// deterministic world, no optional trace buffers, generated stream: the per-row policy evaluation (fp64
+// divisions, exp) and the per-step checks are compiled out.
 // BAND = banded update_sr inside this kernel (all trials in one launch), see band_lu above.
 template <int A, bool PLAIN, bool BAND>
 __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __grid_constant__ CobelPMAParams p,
@@ -689,11 +808,11 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   unsigned char* blk = smem + (size_t)warp * so.bytes;
   double* Q = reinterpret_cast<double*>(blk + so.q);         // [s][a]
   double* Mr = reinterpret_cast<double*>(blk + so.mr);       // [s][a]
-  double* util = reinterpret_cast<double*>(blk + so.util);   // [a*S+s] gain * need * update_mask of the one-step backups
+  int2* ukey = reinterpret_cast<int2*>(blk + so.ukey);       // [a*S+s] key of gain * need * update_mask of the one-step backups
   double* need = reinterpret_cast<double*>(blk + so.need);   // [s] need of the current replay call
-  int32_t* poff = reinterpret_cast<int32_t*>(blk + so.poff); // [S+1] CSR offsets: backups whose next state is t
+  int32_t* poff = reinterpret_cast<int32_t*>(blk + so.poff); // [S+2] CSR: backups that bootstrap from row t are pitems[poff[t+1] .. poff[t+2])
   uint16_t* Pk = reinterpret_cast<uint16_t*>(blk + so.pk);   // [s][a] M.states | update_mask << 13 | M.terminals << 15
-  uint16_t* pitems = reinterpret_cast<uint16_t*>(blk + so.pitems); // [N] CSR items (flat indices a*S+s)
+  uint16_t* pitems = reinterpret_cast<uint16_t*>(blk + so.pitems); // CSR items (flat indices a*S+s)
   uint16_t* list = reinterpret_cast<uint16_t*>(blk + so.list);     // flat indices of the stale gains
   uint16_t* seq = reinterpret_cast<uint16_t*>(blk + so.seq);   // candidate n-step sequence (flat indices)
   uint16_t* perf = reinterpret_cast<uint16_t*>(blk + so.perf); // performed updates of this replay call
@@ -701,6 +820,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   double* rs = reinterpret_cast<double*>(blk + so.rs);         // M.rewards of the candidate sequence's elements
   uint8_t* mbits = blk + so.mbits;                             // [s] valid-action bits (all ones if unmasked)
   constexpr int kSt = 0x1FFF, kUm = 0x2000;
+  const int nch = so.np >> 5;                                  // chunks of 32 consecutive utilities (N <= 1024: at most 32)
   // flat backup index i = a*S + s (the reference's order, memory/pma.py:205) -> a, s, s*A + a without integer
   // division: i < 1024 and S <= 160, so (i * ceil(2^20 / S)) >> 20 == i / S exactly
   const uint32_t magicS = ((1u << 20) + (uint32_t)S - 1u) / (uint32_t)S;
@@ -731,12 +851,25 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   const double* powsr = p.pow_gamma_sr + n * p.pow_stride;     // float(M.gamma) ** k
   const double* powq = p.pow_gamma_q + n * p.pow_stride;       // float(M.gamma_q) ** k
   constexpr int kPol = PLAIN ? COBEL_POLICY_EPS_GREEDY : -1;
-  const int mkind = PLAIN ? COBEL_POLICY_EPS_GREEDY : p.mem_policy.kind;
+  const int mkind = p.mem_policy.kind;
   const double mpar = p.mem_policy.param[n];
-  // cached quotients par/n and (1-par)/n of the memory policy (n = 1..A), every lane holds all of them
+  // tie-pattern tables of the agent's and the memory's policy (PLAIN: both guaranteed by the host)
+  const bool have_tab = PLAIN || (p.n_tab > 0 && A <= 4);
+  PolTab<A> tabA{nullptr}, tabM{nullptr};
+  if (have_tab) {
+    const int ta = p.tab_of_agent ? p.tab_of_agent[2 * n] : 0;
+    const int tm = p.tab_of_agent ? p.tab_of_agent[2 * n + 1] : p.n_tab - 1;
+    tabA.base = p.tab_scratch + (size_t)ta * PolTab<A>::kDoubles;
+    tabM.base = p.tab_scratch + (size_t)tm * PolTab<A>::kDoubles;
+  }
+  const bool useA = PLAIN || (have_tab && p.policy.kind != COBEL_POLICY_SOFTMAX);
+  const bool useM = PLAIN || (have_tab && mkind != COBEL_POLICY_SOFTMAX);
+  // per-row evaluation (generic kernel only): cached quotients par/n and (1-par)/n of the memory policy
   double qpar[A], qom[A];
+  if (!PLAIN) {
 #pragma unroll
-  for (int a = 0; a < A; ++a) { qpar[a] = xdiv(mpar, (double)(a + 1)); qom[a] = xdiv(xsub(1.0, mpar), (double)(a + 1)); }
+    for (int a = 0; a < A; ++a) { qpar[a] = xdiv(mpar, (double)(a + 1)); qom[a] = xdiv(xsub(1.0, mpar), (double)(a + 1)); }
+  }
   __syncwarp();
 
   int64_t* carry = p.carry + n * 4;           // [0] last state (-1: timed out)  [1] steps  [2] replayed  [3] replay calls
@@ -750,13 +883,15 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   const double min_gain = p.min_gain;
   const bool original = p.min_gain_original != 0;
   const int opt = PLAIN ? 0 : p.options;        // COBEL_PMA_OPT_* (the PLAIN kernel is built for none of them)
-  PolicyTab pt; pt.init(p.policy.kind, p.policy.param[n], lane);
-  PolicyTab mpt; mpt.init(mkind, mpar, lane);
+  PolicyTab pt, mpt;
+  if (!PLAIN) { pt.init(p.policy.kind, p.policy.param[n], lane); mpt.init(mkind, mpar, lane); }
   const bool learn = PLAIN || p.learn != 0;
   const bool do_replay = PLAIN || (learn && !p.no_replay);
   const CobelTrace& tr = p.trace;
   int flags = 0;
-  double min_gap = __longlong_as_double(0x7FF0000000000000ll);
+  // certificate: the smallest relative gap (umax - u2) / |umax| between the two largest distinct utilities, kept
+  // as a fraction (one division per launch instead of one per selection)
+  double gap_num = __longlong_as_double(0x7FF0000000000000ll), gap_den = 1.0;
 
   // gain of the one-step backup i = (a, s): PMAMemory.compute_gain_batch, memory/pma.py:333-386
   auto gain_one = [&](int i) -> double {
@@ -769,25 +904,28 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     load_row<A>(Q + ms * A, tr_);
     const double boot = xmul(xmul(gq, row_max<A>(tr_)), mt ? 1.0 : 0.0);
     {
-      double qa = q[0];
-#pragma unroll
-      for (int c = 1; c < A; ++c) qa = c == a ? q[c] : qa;
+      const double qa = pick<A>(q, a);
       const double upd = xadd(qa, xmul(lrq, xsub(xadd(Mr[s * A + a], boot), qa)));
 #pragma unroll
       for (int c = 0; c < A; ++c) qn[c] = c == a ? upd : q[c];
     }
     const uint32_t mb = mbits[s];
-    probs_row<A>(q, mb, mkind, mpar, qpar, qom, po);
-    probs_row<A>(qn, mb, mkind, mpar, qpar, qom, pn);
-    const double so_ = sum_seq<A>(po), sn_ = sum_seq<A>(pn);
-    // p / sum(p): x / 1.0 == x, so the (frequent) exactly-normalised case skips the divisions
-    if (sn_ != 1.0) {
+    if (PLAIN || useM) {
+      ldg_row<A>(tabM.norm(tie_index<A>(q, mb)), po);
+      ldg_row<A>(tabM.norm(tie_index<A>(qn, mb)), pn);
+    } else {
+      probs_row<A>(q, mb, mkind, mpar, qpar, qom, po);
+      probs_row<A>(qn, mb, mkind, mpar, qpar, qom, pn);
+      const double so_ = sum_seq<A>(po), sn_ = sum_seq<A>(pn);
+      // p / sum(p): x / 1.0 == x, so the (frequent) exactly-normalised case skips the divisions
+      if (sn_ != 1.0) {
 #pragma unroll
-      for (int c = 0; c < A; ++c) pn[c] = pdiv(pn[c], sn_);
-    }
-    if (so_ != 1.0) {
+        for (int c = 0; c < A; ++c) pn[c] = pdiv(pn[c], sn_);
+      }
+      if (so_ != 1.0) {
 #pragma unroll
-      for (int c = 0; c < A; ++c) po[c] = pdiv(po[c], so_);
+        for (int c = 0; c < A; ++c) po[c] = pdiv(po[c], so_);
+      }
     }
 #pragma unroll
     for (int c = 0; c < A; ++c) t[c] = xmul(pn[c], qn[c]);
@@ -800,12 +938,11 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     return g > min_gain ? g : min_gain;
   };
 
-  // utility of the one-step backup i: gain * need * update_mask (memory/pma.py:247-249)
-  auto util_one = [&](int i) -> double {
-    const int a = act_of(i), s = i - a * S;
-    const double gn = xmul(gain_one(i), need[s]);
-    if (opt & COBEL_PMA_OPT_KEEP_BARRIERS) return gn;               // ignore_barriers False, memory/pma.py:248-249
-    return xmul(gn, (Pk[s * A + a] & kUm) ? 1.0 : 0.0);
+  // utility of a backup with gain g at (s, a): gain * need * update_mask (memory/pma.py:247-249), as a key
+  auto util_key = [&](double g, int s, int a) -> int2 {
+    const double gn = xmul(g, need[s]);
+    if (opt & COBEL_PMA_OPT_KEEP_BARRIERS) return key_of(gn);       // ignore_barriers False, memory/pma.py:248-249
+    return key_of(xmul(gn, (Pk[s * A + a] & kUm) ? 1.0 : 0.0));
   };
 
   // PMAMemory.replay, memory/pma.py:168-267.  nsrc = the need vector in HBM (an SR row or the stationary
@@ -820,37 +957,44 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
 #pragma unroll 1
       for (int e = lane; e < S; e += 32) need[e] = 1.0;
     }
-    // CSR of the backups grouped by their next state (M.states does not change during a replay):
-    // the backups that read Q row t are row t itself and pitems[poff[t] .. poff[t+1])
+    // CSR of the backups grouped by the Q row they bootstrap from (M.states does not change during a replay).
+    // Only backups with M.terminals != 0 take part: a zero flag multiplies the bootstrap value away
+    // (memory/pma.py:362-363), so their gain does not depend on that row -- in particular the never-experienced
+    // backups, which all point at state 0.  The backups that read Q row t are row t itself and group t.
 #pragma unroll 1
-    for (int e = lane; e <= S; e += 32) poff[e] = 0;
+    for (int e = lane; e < S + 2; e += 32) poff[e] = 0;
+    if (lane < so.np - N) ukey[N + lane] = make_int2(0, kKeyMinHi);   // padding of the last chunk never wins
     __syncwarp();
 #pragma unroll 1
-    for (int e = lane; e < N; e += 32) atomicAdd(&poff[(Pk[e] & kSt) + 1], 1);
+    for (int e = lane; e < N; e += 32) { const uint16_t pk = Pk[e]; if (pk >> 15) atomicAdd(&poff[(pk & kSt) + 1], 1); }
     __syncwarp();
-    if (lane == 0) {
+    {                                               // inclusive prefix sum of poff[1..S]: a segment per lane + a warp scan
+      const int seg = (S + 31) >> 5, b0 = lane * seg;
+      int sum = 0;
 #pragma unroll 1
-      for (int t = 0; t < S; ++t) poff[t + 1] += poff[t];
+      for (int x = 0; x < seg; ++x) { const int t = b0 + x; if (t < S) sum += poff[t + 1]; }
+      int incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
+      int run = incl - sum;
+#pragma unroll 1
+      for (int x = 0; x < seg; ++x) { const int t = b0 + x; if (t < S) { run += poff[t + 1]; poff[t + 1] = run; } }
+      const int tot = __shfl_sync(kFull, incl, 31);
+      if (lane == 0) poff[S + 1] = tot;
     }
     __syncwarp();
 #pragma unroll 1
-    for (int e = lane; e < N; e += 32) {            // fill from the back of each group, then the offsets are the starts again
-      const int s_ = e / A, a_ = e - s_ * A;
-      const int t = Pk[e] & kSt;
-      pitems[atomicSub(&poff[t + 1], 1) - 1] = (uint16_t)(a_ * S + s_);
+    for (int e = lane; e < N; e += 32) {            // fill each group from its back: poff[t+1] ends as the start of group t
+      const uint16_t pk = Pk[e];
+      if (pk >> 15) {
+        const int s_ = e / A, a_ = e - s_ * A;
+        pitems[atomicSub(&poff[(pk & kSt) + 1], 1) - 1] = (uint16_t)(a_ * S + s_);
+      }
     }
-    __syncwarp();
-    // poff[t+1] now holds the start of group t; shift so that poff[t] = start, poff[S] = N
-    int nxt[6];                                     // S <= 160: at most 6 entries per lane
-#pragma unroll
-    for (int x = 0; x < 6; ++x) { const int t = lane + 32 * x; nxt[x] = t < S ? poff[t + 1] : 0; }
-    __syncwarp();
-#pragma unroll
-    for (int x = 0; x < 6; ++x) { const int t = lane + 32 * x; if (t < S) poff[t] = nxt[x]; }
-    if (lane == 0) poff[S] = N;
     __syncwarp();
     int count = 0, last_seq = 0, ndst = -1;          // ndst < 0: first iteration, every backup is stale
-    __syncwarp();
+    unsigned dirty = nch >= 32 ? kFull : ((1u << nch) - 1u);   // chunks whose maximum has to be recomputed
+    int cm_hi = kKeyMinHi; unsigned cm_lo = 0;       // lane c: the largest key of chunk c
     for (int it = 0; it < B; ++it) {
       // ---- (1) extension of the current sequence (memory/pma.py:219-235) -------------------------
       int ext = -1, clen = 0;
@@ -865,7 +1009,9 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
           win.ensure(2, lane);
           double row[A];
           load_row<A>(Q + ext * A, row);
-          const int ea = select_action_warp<A, kPol>(row, mbits[ext], mpt, win.next(), lane);
+          const double u = win.next();
+          const int ea = (PLAIN || useM) ? select_action_tab<A>(row, mbits[ext], tabM, u)
+                                         : select_action_warp<A, kPol>(row, mbits[ext], mpt, u, lane);
           ext += ea * S;
           clen = count - last_seq + 1;
 #pragma unroll 1
@@ -877,15 +1023,14 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         __syncwarp();                                                   // seq[] is read by all lanes in (3)
       }
       // ---- (2) re-evaluate the backups that read a Q row changed by the previous update ----------
-      // (one code site for the compact list and for the full pass keeps the loop body small:
-      //  the kernel was instruction-cache bound with three inlined copies of the gain evaluation)
+      // (one code site for the compact list and for the full pass keeps the loop body small)
       if (ndst != 0) {
         int nd = 0;
         bool full = ndst < 0;
 #pragma unroll 1
         for (int d = 0; d < ndst && !full; ++d) {
           const int t = dst[d];
-          const int p0 = poff[t], np = poff[t + 1] - p0;
+          const int p0 = poff[t + 1], np = poff[t + 2] - p0;
           if (nd + A + np <= MainSmem::kListCap) {
 #pragma unroll 1
             for (int x = lane; x < A + np; x += 32) list[nd + x] = x < A ? (uint16_t)(x * S + t) : pitems[p0 + x - A];
@@ -896,11 +1041,18 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         }
         __syncwarp();
         const int total = full ? N : nd;
+        unsigned myd = 0;
 #pragma unroll 1
         for (int j0 = 0; j0 < total; j0 += 32) {
           const int j = j0 + lane;
-          if (j < total) { const int i = full ? j : list[j]; util[i] = util_one(i); }
+          if (j < total) {
+            const int i = full ? j : list[j];
+            const int a = act_of(i), s = i - a * S;
+            ukey[i] = util_key(gain_one(i), s, a);
+            myd |= 1u << (i >> 5);
+          }
         }
+        dirty |= __reduce_or_sync(kFull, myd);
         __syncwarp();
       }
       // ---- (3) n-step gain of the candidate (memory/pma.py:269-331), lane j = element j -----------
@@ -926,7 +1078,6 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
             double q[A], qn[A], pb[A], pa[A], t[A];
             load_row<A>(Q + s * A, q);
             const uint32_t mb = mbits[s];
-            probs_row<A>(q, mb, mkind, mpar, qpar, qom, pb);
             double r = 0.0;
 #pragma unroll 1
             for (int f = 0; f < nseq - j; ++f) r = xadd(r, xmul(rs[j + f], powsr[f]));
@@ -936,7 +1087,13 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
               const double qt = c == a ? target : q[c];
               qn[c] = xadd(q[c], xmul(lrq, xsub(qt, q[c])));
             }
-            probs_row<A>(qn, mb, mkind, mpar, qpar, qom, pa);
+            if (PLAIN || useM) {
+              ldg_row<A>(tabM.raw(tie_index<A>(q, mb)), pb);
+              ldg_row<A>(tabM.raw(tie_index<A>(qn, mb)), pa);
+            } else {
+              probs_row<A>(q, mb, mkind, mpar, qpar, qom, pb);
+              probs_row<A>(qn, mb, mkind, mpar, qpar, qom, pa);
+            }
 #pragma unroll
             for (int c = 0; c < A; ++c) t[c] = xmul(qn[c], pa[c]);
             const double ga = sum_seq<A>(t);
@@ -954,52 +1111,65 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       }
       // ---- (4) arg-max of the utilities with exact ties (memory/pma.py:247-254); the candidate's
       // n-step gain overrides the one-step entry `ext` for this iteration only
-      double saved = 0.0;
+      int2 saved = make_int2(0, 0);
       if (ext >= 0) {
         const int ea = act_of(ext), es = ext - ea * S;
-        saved = util[ext];
+        saved = ukey[ext];
         __syncwarp();
-        if (lane == 0) {
-          const double gn = xmul(gext, need[es]);
-          util[ext] = (opt & COBEL_PMA_OPT_KEEP_BARRIERS) ? gn : xmul(gn, (Pk[es * A + ea] & kUm) ? 1.0 : 0.0);
-        }
+        if (lane == 0) ukey[ext] = util_key(gext, es, ea);
+        dirty |= 1u << (ext >> 5);
         __syncwarp();
       }
-      const double ninf = -__longlong_as_double(0x7FF0000000000000ll);
-      // one pass: per-lane maximum, its tie mask over the lane's entries (bit c = entry lane + 32 c) and the lane's
-      // second-largest distinct value; then the warp maximum decides which lanes' masks count
-      double lmax = ninf, l2 = ninf;
-      unsigned tm = 0;
-#pragma unroll 1
-      for (int i = lane, c = 0; i < N; i += 32, ++c) {
-        const double v = util[i];                        // branch-free: the three cases are selects
-        const bool gt = v > lmax, eq = v == lmax;
-        l2 = gt ? lmax : ((!eq && v > l2) ? v : l2);
-        tm = gt ? (1u << c) : (eq ? (tm | (1u << c)) : tm);
-        lmax = gt ? v : lmax;
+      // chunk maxima are kept across iterations: only the chunks that received a new utility are reduced again
+      while (dirty) {
+        const int c = __ffs(dirty) - 1;
+        dirty &= dirty - 1;
+        const int2 m = warp_max_key(ukey[c * 32 + lane]);
+        if (lane == c) { cm_hi = m.y; cm_lo = (unsigned)m.x; }
       }
-      const double umax = warp_max_f64(lmax);
-      if (lmax != umax) { tm = 0; l2 = lmax; }
-      // ties in flat-index order: lane c keeps the tie ballot of chunk c (N <= 1024); the certificate is the gap
-      // to the largest utility below the maximum
-      unsigned mytb = 0;
-#pragma unroll 1
-      for (int c = 0; c * 32 < N; ++c) {
-        const unsigned b = __ballot_sync(kFull, (tm >> c & 1u) != 0);
+      const int2 cmine = make_int2((int)cm_lo, lane < nch ? cm_hi : kKeyMinHi);
+      const int2 umax = warp_max_key(cmine);
+      const bool cwin = cmine.y == umax.y && cmine.x == umax.x;          // chunk holds a maximum
+      unsigned tchunks = __ballot_sync(kFull, cwin);
+      // the largest utility below the maximum: over the other chunks' maxima and the rest of the winning chunks
+      int2 second = warp_max_key(cwin ? make_int2(0, kKeyMinHi) : cmine);
+      // ties in flat-index order: lane c keeps the tie ballot of chunk c
+      unsigned mytb = 0, onlyb = 0;
+      const int c0 = __ffs(tchunks) - 1;
+      while (tchunks) {
+        const int c = __ffs(tchunks) - 1;
+        tchunks &= tchunks - 1;
+        const int2 k = ukey[c * 32 + lane];
+        const bool eq = k.y == umax.y && k.x == umax.x;
+        const unsigned b = __ballot_sync(kFull, eq);
+        const int2 r2 = warp_max_key(eq ? make_int2(0, kKeyMinHi) : k);
+        if (r2.y > second.y || (r2.y == second.y && (unsigned)r2.x > (unsigned)second.x)) second = r2;
         mytb = lane == c ? b : mytb;
+        onlyb = b;
       }
       const int mycnt = __popc(mytb);
-      int incl = mycnt;                                  // inclusive scan of the per-chunk tie counts
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
-      const int ktot = __shfl_sync(kFull, incl, 31);
-      const double u2 = warp_max_f64(l2);
-      if (umax != 0.0 && u2 > -1e300) { const double gp = (umax - u2) / fabs(umax); min_gap = gp < min_gap ? gp : min_gap; }
+      const int ktot = __reduce_add_sync(kFull, mycnt);
+      {
+        const double vmax = key_value(umax);
+        if (second.y != kKeyMinHi && vmax != 0.0) {
+          const double v2 = key_value(second);
+          if (v2 > -1e300) {
+            const double num = xsub(vmax, v2), den = fabs(vmax);
+            if (num * gap_den < gap_num * den) { gap_num = num; gap_den = den; }
+          }
+        }
+      }
       win.ensure(1, lane);
       const double u = win.next();
-      // Generator.choice(p = ties / k): cdf_m = m-fold sequential sum of fl(1/k), normalised by cdf_k
-      int pick = ktot - 1;
-      if (ktot > 1) {
+      int chosen;
+      if (ktot == 1) {
+        chosen = c0 * 32 + __ffs(onlyb) - 1;
+      } else {
+        // Generator.choice(p = ties / k): cdf_m = m-fold sequential sum of fl(1/k), normalised by cdf_k
+        int incl = mycnt;                                // inclusive scan of the per-chunk tie counts
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
+        int pick = ktot - 1;
         const double pk_ = pdiv(1.0, int_to_f64(ktot));
         double ck = 0.0;
 #pragma unroll 1
@@ -1010,14 +1180,15 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
           c = xadd(c, pk_);
           if (pdiv(c, ck) > u) { pick = m; break; }
         }
+        // the chunk whose [incl - cnt, incl) range contains `pick`, then the pick-th set bit of its ballot
+        const unsigned owner = __ballot_sync(kFull, pick >= incl - mycnt && pick < incl);
+        const int oc = __ffs(owner) - 1;
+        chosen = oc * 32 + __shfl_sync(kFull, (int)__fns(mytb, 0, pick - (incl - mycnt) + 1), oc);
       }
-      // the chunk whose [incl - cnt, incl) range contains `pick`, then the pick-th set bit of its ballot
-      const unsigned owner = __ballot_sync(kFull, pick >= incl - mycnt && pick < incl);
-      const int oc = __ffs(owner) - 1;
-      const int chosen = oc * 32 + __shfl_sync(kFull, (int)__fns(mytb, 0, pick - (incl - mycnt) + 1), oc);
       if (ext >= 0) {
         __syncwarp();
-        if (lane == 0) util[ext] = saved;
+        if (lane == 0) ukey[ext] = saved;
+        dirty = 1u << (ext >> 5);
       }
       // ---- (5) apply the chosen (n-step) update: PMAMemory.update_q, memory/pma.py:452-496 --------
       {
@@ -1090,6 +1261,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   const int bw = p.sr_band;
   double* bscr = BAND ? p.band_scratch + (size_t)n * 2 * S * (2 * bw + 1) : nullptr;   // [0]: LU factors, [1]: GTH rows
   double* bgth = BAND ? bscr + S * (2 * bw + 1) : nullptr;
+  double* ring = reinterpret_cast<double*>(ukey);      // the band solver's row ring aliases the replay buffers
   const double gsr = p.gamma_sr[n];
   bool have_lu = false;        // bscr holds the factors of I - gamma T for the current T
   bool sr_given = true;        // no update_sr yet in this call: the start replay reads the caller's SR
@@ -1101,11 +1273,11 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     if (stage == 0) {
       if (BAND) {                                        // M.update_sr() + compute_need(last)
         if (c_last < 0) {
-          flags |= band_gth(Tg, bgth, util, S, bw, need, lane);
+          flags |= band_gth(Tg, bgth, ring, S, bw, need, lane);
         } else {
-          flags |= band_lu(Tg, gsr, bscr, util, S, bw, lane);
+          flags |= band_lu(Tg, gsr, bscr, ring, S, bw, lane);
           have_lu = true;
-          band_solve_row(bscr, util, S, bw, (int)c_last, need, lane);
+          band_solve_row(bscr, ring, S, bw, (int)c_last, need, lane);
         }
         sr_given = false;
       } else {
@@ -1119,10 +1291,10 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       if (rep) {
         if (BAND && !sr_given) {
           if (!have_lu) {
-            flags |= band_lu(Tg, gsr, bscr, util, S, bw, lane);
+            flags |= band_lu(Tg, gsr, bscr, ring, S, bw, lane);
             have_lu = true;
           }
-          band_solve_row(bscr, util, S, bw, s, need, lane);
+          band_solve_row(bscr, ring, S, bw, s, need, lane);
         } else {
           nsrc = SRg + (size_t)s * S;
         }
@@ -1140,7 +1312,9 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       for (int x = 0; x < 5; ++x) { const int j = lane + 32 * x; trow[x] = (learn && j < S) ? Tg[(size_t)s * S + j] : 0.0; }
       double row[A];
       load_row<A>(Q + s * A, row);
-      const int a = select_action_warp<A, kPol>(row, mbits[s], pt, win.next(), lane);
+      const double ua = win.next();
+      const int a = (PLAIN || useA) ? select_action_tab<A>(row, mbits[s], tabA, ua)
+                                    : select_action_warp<A, kPol>(row, mbits[s], pt, ua, lane);
       const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : __ldg(p.world.succ + s * A + a);
       const double r = __ldg(p.world.reward + s2);
       const int end = __ldg(p.world.terminal + s2);
@@ -1192,7 +1366,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   }
 
   // banded call: leave the factors of the final I - gamma T for pma_sr_band_kernel (SR is refreshed once per call)
-  if (BAND && do_replay && !sr_given && !have_lu) flags |= band_lu(Tg, gsr, bscr, util, S, bw, lane);
+  if (BAND && do_replay && !sr_given && !have_lu) flags |= band_lu(Tg, gsr, bscr, ring, S, bw, lane);
   __syncwarp();
   if (learn) {
 #pragma unroll 1
@@ -1210,7 +1384,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     tr.n_steps[n] += nsteps - nsteps0;
     tr.n_replay[n] += nrep - nrep0;
     if (tr.flags && flags) tr.flags[n] |= flags;
-    if (p.min_gap) p.min_gap[n] = fmin(p.min_gap[n], min_gap);
+    if (p.min_gap && gap_num < 1e300) p.min_gap[n] = fmin(p.min_gap[n], gap_num / gap_den);
   }
 }
 
@@ -1222,7 +1396,10 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
   const MainSmem so(S, A);
   const size_t sm_main = (size_t)kMainWarps * so.bytes;
   COBEL_REQUIRE(sm_main <= 227 * 1024, COBEL_EUNSUPPORTED, "PMA: %d states x %d actions do not fit in shared memory", S, A);
-  const bool plain = p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.mem_policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn &&
+  const bool tabs = p.n_tab > 0 && A <= 4;
+  COBEL_REQUIRE(p.n_tab == 0 || (p.tab_kind && p.tab_param && p.tab_scratch), COBEL_EINVAL,
+                "n_tab > 0 needs tab_kind, tab_param and tab_scratch[n_tab, COBEL_PMA_TAB_DOUBLES(A)]");
+  const bool plain = tabs && p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.mem_policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn &&
                      !p.no_replay && !p.options && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx &&
                      !p.trace.replay_len && !p.stream.user_stream;
   const bool do_replay = p.learn && !p.no_replay;
@@ -1233,6 +1410,12 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
   const size_t sm_sr = (size_t)(4 * (tile * 16 + 2) + ((S + 1) & ~1) + S * S) * 8;
   if (tile == 7) COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
   else COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
+  if constexpr (A <= 4) {
+    if (tabs) {                                        // the tie-pattern policy tables of this call
+      pma_policy_table_kernel<A><<<(unsigned)p.n_tab, 256, 0, st>>>(p.tab_kind, p.tab_param, p.tab_scratch);
+      cobel_count_launch();
+    }
+  }
   const unsigned grid_main = (unsigned)((p.n_agents + kMainWarps - 1) / kMainWarps);
   auto main_launch = [&](MainPhase ph) -> int {
     auto go = [&](auto kernel) -> int {
@@ -1241,8 +1424,10 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
       cobel_count_launch();
       return COBEL_OK;
     };
-    if (band) return plain ? go(pma_main_kernel<A, true, true>) : go(pma_main_kernel<A, false, true>);
-    return plain ? go(pma_main_kernel<A, true, false>) : go(pma_main_kernel<A, false, false>);
+    if constexpr (A <= 4) {
+      if (plain) return band ? go(pma_main_kernel<A, true, true>) : go(pma_main_kernel<A, true, false>);
+    }
+    return band ? go(pma_main_kernel<A, false, true>) : go(pma_main_kernel<A, false, false>);
   };
   auto sr_launch = [&](int final_only) {
     if (tile == 7) pma_sr_kernel<7><<<(unsigned)p.n_agents, kThreads, sm_sr, st>>>(p, final_only);

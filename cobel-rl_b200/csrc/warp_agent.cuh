@@ -210,6 +210,7 @@ COBEL_DEV int select_action_warp(const double (&v)[A], uint32_t mask, const Poli
       p[a] = 0.0;
       if (mask >> a & 1u) { p[a] = exp(xmul(xsub(v[a], m), pt.par)); sum = xadd(sum, p[a]); }
     }
+    if (A == 8 && mask == kAll) sum = np_sum<A>(p);        // np.sum over exactly 8 values is a tree, not a loop
 #pragma unroll
     for (int a = 0; a < A; ++a)
       if (mask >> a & 1u) p[a] = xdiv(p[a], sum);

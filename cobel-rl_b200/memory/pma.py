@@ -111,6 +111,43 @@ class PMAMemory(TableMemory):
         return ((1 if self.equal_need else 0) | (2 if self.equal_gain else 0) | (0 if self.ignore_barriers else 4) |
                 (8 if self.allow_loops else 0))
 
+    def policy_tables(self, stream, agent_policy, n_actions, keep):
+        """Tie-pattern policy tables of a call (include/cobel_b200.h: CobelPMAParams.tab_*): one table per distinct
+        (kind, parameter) among the agents' online policy and the memory's policy.  Returns
+        ``(n_tab, kinds, params, table-of-agent [N,2] or None, scratch)``; ``n_tab = 0`` when the kernels
+        evaluate the policies per row instead (more than 4 actions, or no epsilon-greedy policy at all)."""
+        pols = (agent_policy, self.policy)
+        if n_actions > 4 or all(pl.kind == 2 for pl in pols):
+            return 0, None, None, None, None
+        dev = stream.device
+        kinds, params, cols = [], [], []
+        for pl in pols:
+            par = pl._param()
+            if not torch.is_tensor(par) and np.ndim(par) == 0:
+                key = (pl.kind, float(par))
+                if key not in list(zip(kinds, params)):
+                    kinds.append(key[0]); params.append(key[1])
+                cols.append(list(zip(kinds, params)).index(key))
+            else:
+                uniq, inv = torch.unique(stream.param(par, pl.param_name), return_inverse=True)
+                base = len(kinds)
+                kinds += [pl.kind] * uniq.numel()
+                params += uniq.cpu().tolist()
+                cols.append(inv.to(torch.int32) + base)
+        n_tab = len(kinds)
+        tof = None
+        if not (all(isinstance(c, int) for c in cols) and cols == [0, n_tab - 1]):
+            # not the kernel's default assignment (agent: table 0, memory: the last one)
+            tof = torch.stack([c if torch.is_tensor(c) else torch.full((stream.n_agents,), c, dtype=torch.int32, device=dev)
+                               for c in cols], dim=1).contiguous()
+        tkind = torch.tensor(kinds, dtype=torch.int32, device=dev)
+        tpar = torch.tensor(params, dtype=torch.float64, device=dev)
+        n = n_tab * _lib.pma_tab_doubles(n_actions)
+        if getattr(self, '_tab_scratch', None) is None or self._tab_scratch.numel() < n:
+            self._tab_scratch = torch.empty(n, dtype=torch.float64, device=dev)
+        keep += [tkind, tpar, tof]
+        return n_tab, tkind, tpar, tof, self._tab_scratch
+
     def power_tables(self, stream, keep):
         """``float(gamma) ** k`` for k = 0..MAX_SEQ+1 with Python's pow, like the reference
         (memory/pma.py:310,315,485,491).  Returns (sr table, q table, per-agent stride)."""

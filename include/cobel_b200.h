@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define COBEL_ABI_VERSION 2
+#define COBEL_ABI_VERSION 3
 
 enum {
   COBEL_OK = 0,
@@ -307,7 +307,20 @@ typedef struct CobelPMAParams {
   int32_t sr_band;
   int32_t options;           /* COBEL_PMA_OPT_* bits */
   double*  band_scratch;     /* scratch [N, 2, S*(2*sr_band+1)] when sr_band >= 0 */
+  /* Tie-pattern policy tables (optional, A <= 4, the two epsilon-greedy kinds).  get_action_probs of those
+   * policies (policy/greedy.py:60-88,117-147) depends only on which actions are valid and which of them tie for
+   * the row maximum, so raw probabilities, action_probs_batch's p / sum(p) (memory/pma.py:423-450) and
+   * select_action's cumsum(p) / cumsum(p)[-1] (policy/greedy.py:58) are tabulated once per distinct
+   * (kind, parameter) -- with exactly the per-row operations -- and a gain evaluation becomes a row maximum,
+   * A compares and one table row.  n_tab = 0: probabilities are evaluated per row (any policy, any A). */
+  int32_t  n_tab;            /* number of tables */
+  int32_t  reserved3;
+  const int32_t* tab_kind;   /* [n_tab] COBEL_POLICY_* of table t (a Softmax entry leaves its table unused) */
+  const double*  tab_param;  /* [n_tab] its epsilon */
+  const int32_t* tab_of_agent;/* optional [N,2]: tables of (agent.policy, M.policy) of agent n; NULL = (0, n_tab-1) */
+  double*  tab_scratch;      /* scratch [n_tab, COBEL_PMA_TAB_DOUBLES(A)], filled by the call */
 } CobelPMAParams;
+#define COBEL_PMA_TAB_DOUBLES(A) (3 * (1 << (2 * (A))) * (A))
 
 int cobel_pma_run(const CobelPMAParams* p, void* stream);
 
