@@ -316,6 +316,17 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_sr_kernel(con
 // row goes back to global scratch with a fire-and-forget store.
 constexpr int kBandAhead = 4;
 
+// 1 / x to ~1 ulp without the IEEE division's slow path: MUFU.RCP64H seed + two Newton steps.  Only the banded
+// eliminations use it (not bit-exact by design); their pivots and row sums are far from the subnormal range, and
+// anything below 1e-300 raises COBEL_FLAG_SINGULAR first.
+COBEL_DEV double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = fma(fma(-x, y, 1.0), y, y);
+  y = fma(fma(-x, y, 1.0), y, y);
+  return y;
+}
+
 COBEL_DEV void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   const int sz = valid ? 8 : 0;                       // src-size 0: the 8 bytes are zero-filled
@@ -346,12 +357,6 @@ struct BandRing {
         const bool ok = j >= 0 && j < S;
         cp_async8(row(i) + d, Tg + (size_t)i * S + (ok ? j : i), ok);
       }
-    cp_async_commit();
-  }
-  COBEL_DEV void fetch_band(const double* __restrict__ b, int i) const {   // row i of a stored band
-    if (i >= 0 && i < S)
-#pragma unroll 1
-      for (int d = lane; d < W; d += 32) cp_async8(row(i) + d, b + (size_t)i * W + d, true);
     cp_async_commit();
   }
   COBEL_DEV void store_band(double* b, int i) const {
@@ -394,7 +399,7 @@ __device__ __noinline__ int band_lu(const double* __restrict__ Tg, double g, dou
     const double* rk = rg.row(k);
     const double piv = rk[bw];
     if (!(fabs(piv) > 1e-300)) flags |= COBEL_FLAG_SINGULAR;
-    const double ipiv = 1.0 / piv;
+    const double ipiv = fast_rcp(piv);
 #pragma unroll 1
     for (int e = lane, ii = ii0, jj = jj0; e < bw * bw; e += 32) {  // (ii, jj) enumerate bw x bw; the last steps guard
       if (ii <= nb && jj <= nb) {
@@ -418,45 +423,51 @@ __device__ __noinline__ int band_lu(const double* __restrict__ Tg, double g, dou
   return flags;
 }
 
-// x = row c of inv(M) from the factors: U^T y = e_c (forward, column sweeps), then L^T x = y (backward).
-// x lives in shared memory; the factor rows stream through the ring.
-__device__ __noinline__ void band_solve_row(const double* __restrict__ fac, double* ringmem, int S, int bw, int c, double* x,
-                                            int lane) {
-  const BandRing rg(ringmem, S, bw, lane);
+// x = row c of inv(M) from the factors: U^T y = e_c (forward, column sweeps), then L^T x = y (backward, in place).
+// x lives in shared memory, `w` (shared scratch of S doubles) holds the right-hand side of the forward sweep; each
+// step reads one factor row straight from the global scratch, the loads running four steps ahead of the recurrence.
+__device__ __noinline__ void band_solve_row(const double* fac, double* w, int S, int bw, int c, double* x, int lane) {
+  const int W = 2 * bw + 1;
 #pragma unroll 1
-  for (int e = lane; e < S; e += 32) x[e] = e == c ? 1.0 : 0.0;
-#pragma unroll 1
-  for (int j = c; j <= c + kBandAhead; ++j) rg.fetch_band(fac, j);
-#pragma unroll 1
-  for (int j = c; j < S; ++j) {                       // y_j = rhs_j / U[j][j]; rhs_i -= U[j][i] y_j, i in (j, j+bw]
-    cp_async_wait<kBandAhead>();
-    __syncwarp();
-    const double* rj = rg.row(j);
-    const double yj = x[j] * rj[bw];
-    const int nb = min(bw, S - 1 - j);
-    __syncwarp();
-    if (lane == 0) x[j] = yj;
-    if (lane < nb) x[j + 1 + lane] = fma(-rj[bw + 1 + lane], yj, x[j + 1 + lane]);
-    __syncwarp();
-    rg.fetch_band(fac, j + kBandAhead + 1);
-  }
-  cp_async_wait<0>();
+  for (int e = lane; e < S; e += 32) { w[e] = e == c ? 1.0 : 0.0; x[e] = 0.0; }
   __syncwarp();
+  double dg[4], ov[4];                                // 1 / U[j][j] and this lane's off-diagonal entry of row j
+  auto diag = [&](int j) -> double { return (j >= 0 && j < S) ? fac[(size_t)j * W + bw] : 0.0; };
+  auto upper = [&](int j) -> double { return (j >= 0 && j < S && lane < bw) ? fac[(size_t)j * W + bw + 1 + lane] : 0.0; };
+  auto lower = [&](int j) -> double { return (j >= 0 && j < S && lane < bw) ? fac[(size_t)j * W + bw - 1 - lane] : 0.0; };
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { dg[u] = diag(c + u); ov[u] = upper(c + u); }
 #pragma unroll 1
-  for (int j = S - 1; j >= S - 1 - kBandAhead; --j) rg.fetch_band(fac, j);
-#pragma unroll 1
-  for (int j = S - 1; j > 0; --j) {                   // x_j final; x_i -= L[j][i] x_j, i in [j-bw, j)
-    cp_async_wait<kBandAhead>();
-    __syncwarp();
-    const double* rj = rg.row(j);
-    const double xj = x[j];
-    const int nb = min(bw, j);
-    if (lane < nb) x[j - 1 - lane] = fma(-rj[bw - 1 - lane], xj, x[j - 1 - lane]);
-    __syncwarp();
-    rg.fetch_band(fac, j - kBandAhead - 1);
+  for (int j0 = c; j0 < S; j0 += 4) {                 // y_j = rhs_j / U[j][j]; rhs_i -= U[j][i] y_j, i in (j, j+bw]
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      if (j < S) {
+        const double yj = w[j] * dg[u];
+        const int nb = min(bw, S - 1 - j);
+        if (lane == 0) x[j] = yj;
+        if (lane < nb) w[j + 1 + lane] = fma(-ov[u], yj, w[j + 1 + lane]);
+        __syncwarp();
+        dg[u] = diag(j + 4); ov[u] = upper(j + 4);
+      }
+    }
   }
-  cp_async_wait<0>();
-  __syncwarp();
+#pragma unroll
+  for (int u = 0; u < 4; ++u) ov[u] = lower(S - 1 - u);
+#pragma unroll 1
+  for (int j0 = S - 1; j0 > 0; j0 -= 4) {             // x_j final; x_i -= L[j][i] x_j, i in [j-bw, j)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 - u;
+      if (j > 0) {
+        const double xj = x[j];
+        const int nb = min(bw, j);
+        if (lane < nb) x[j - 1 - lane] = fma(-ov[u], xj, x[j - 1 - lane]);
+        __syncwarp();
+        ov[u] = lower(j - 4);
+      }
+    }
+  }
 }
 
 // Stationary distribution of the banded row-stochastic T by GTH elimination (see gth_stationary), scaled to
@@ -479,7 +490,7 @@ __device__ __noinline__ int band_gth(const double* __restrict__ Tg, double* fac,
     double ssum = lane < nb ? rk[bw - 1 - lane] : 0.0;
     for (int d = 16; d > 0; d >>= 1) ssum += shfl_f64_xor(ssum, d);
     if (!(ssum > 0.0)) { flags |= COBEL_FLAG_SINGULAR; ssum = 1.0; }
-    const double inv = 1.0 / ssum;
+    const double inv = fast_rcp(ssum);
 #pragma unroll 1
     for (int e = lane, ii = ii0, jj = jj0; e < bw * bw; e += 32) {  // i = k - ii, j = k - jj over bw x bw, guarded
       if (ii <= nb && jj <= nb) {
@@ -651,6 +662,23 @@ __global__ void __launch_bounds__(256) pma_policy_table_kernel(const int32_t* __
                                                                double* out) {
   constexpr int kIdx = PolTab<A>::kIdx;
   const int c = blockIdx.x;
+  if (c == (int)gridDim.x - 1) {
+    // last block: Generator.choice(p = ones(k) / k) for k = 1..32 (memory/pma.py:252-254), row k-1 holds the bin
+    // edges cdf_m / cdf_k, m < k-1 (cdf_m = m+1 sequential additions of fl(1/k)); other entries 2.0 (never <= u)
+    double* tie = out + (size_t)c * PolTab<A>::kDoubles;
+    if (threadIdx.x < 32) {
+      const int k = threadIdx.x + 1;
+      const double pk = xdiv(1.0, (double)k);
+      double ck = 0.0;
+      for (int m = 0; m < k; ++m) ck = xadd(ck, pk);
+      double cm = 0.0;
+      for (int m = 0; m < 32; ++m) {
+        cm = xadd(cm, pk);
+        tie[threadIdx.x * 32 + m] = m < k - 1 ? xdiv(cm, ck) : 2.0;
+      }
+    }
+    return;
+  }
   const int kd = kind[c];
   const double par = param[c];
   double* raw = out + (size_t)c * PolTab<A>::kDoubles;
@@ -758,7 +786,7 @@ COBEL_DEV int2 warp_max_key(int2 k) {
 // pma_main_kernel: one warp per agent.
 // ---------------------------------------------------------------------------
 struct MainSmem {      // byte offsets inside one agent's shared-memory block
-  int q, mr, need, pk, mbits, ukey, poff, pitems, list, seq, perf, dst, rs, bytes;
+  int q, mr, need, pk, mbits, ukey, poff, pitems, list, perf, dst, rs, bytes;
   int np;              // utility entries padded to a multiple of 32 (chunks of one entry per lane)
   static constexpr int kListCap = 256;     // stale-gain list; larger sets fall back to a full pass
   __host__ __device__ MainSmem(int S, int A) {
@@ -774,8 +802,7 @@ struct MainSmem {      // byte offsets inside one agent's shared-memory block
     poff = ukey + np * 8;
     pitems = poff + ((S + 3) & ~1) * 4;
     list = pitems + N * 2;
-    seq = list + kListCap * 2;
-    perf = seq + (kMaxSeq + 2) * 2;
+    perf = list + kListCap * 2;
     dst = perf + (kMaxSeq + 2) * 2;
     rs = (dst + (kMaxSeq + 2) * 2 + 7) & ~7;
     bytes = (rs + (kMaxSeq + 2) * 8 + 15) & ~15;
@@ -814,7 +841,6 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   uint16_t* Pk = reinterpret_cast<uint16_t*>(blk + so.pk);   // [s][a] M.states | update_mask << 13 | M.terminals << 15
   uint16_t* pitems = reinterpret_cast<uint16_t*>(blk + so.pitems); // CSR items (flat indices a*S+s)
   uint16_t* list = reinterpret_cast<uint16_t*>(blk + so.list);     // flat indices of the stale gains
-  uint16_t* seq = reinterpret_cast<uint16_t*>(blk + so.seq);   // candidate n-step sequence (flat indices)
   uint16_t* perf = reinterpret_cast<uint16_t*>(blk + so.perf); // performed updates of this replay call
   uint16_t* dst = reinterpret_cast<uint16_t*>(blk + so.dst);   // states whose Q row changed in the last update
   double* rs = reinterpret_cast<double*>(blk + so.rs);         // M.rewards of the candidate sequence's elements
@@ -862,6 +888,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     tabA.base = p.tab_scratch + (size_t)ta * PolTab<A>::kDoubles;
     tabM.base = p.tab_scratch + (size_t)tm * PolTab<A>::kDoubles;
   }
+  const double* tie_cdf = have_tab ? p.tab_scratch + (size_t)p.n_tab * PolTab<A>::kDoubles : nullptr;   // [32][32]
   const bool useA = PLAIN || (have_tab && p.policy.kind != COBEL_POLICY_SOFTMAX);
   const bool useM = PLAIN || (have_tab && mkind != COBEL_POLICY_SOFTMAX);
   // per-row evaluation (generic kernel only): cached quotients par/n and (1-par)/n of the memory policy
@@ -892,51 +919,6 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   // certificate: the smallest relative gap (umax - u2) / |umax| between the two largest distinct utilities, kept
   // as a fraction (one division per launch instead of one per selection)
   double gap_num = __longlong_as_double(0x7FF0000000000000ll), gap_den = 1.0;
-
-  // gain of the one-step backup i = (a, s): PMAMemory.compute_gain_batch, memory/pma.py:333-386
-  auto gain_one = [&](int i) -> double {
-    const int a = act_of(i), s = i - a * S;
-    double q[A], qn[A], po[A], pn[A], t[A];
-    load_row<A>(Q + s * A, q);
-    const uint16_t pk = Pk[s * A + a];
-    const int ms = pk & kSt, mt = pk >> 15;
-    double tr_[A];
-    load_row<A>(Q + ms * A, tr_);
-    const double boot = xmul(xmul(gq, row_max<A>(tr_)), mt ? 1.0 : 0.0);
-    {
-      const double qa = pick<A>(q, a);
-      const double upd = xadd(qa, xmul(lrq, xsub(xadd(Mr[s * A + a], boot), qa)));
-#pragma unroll
-      for (int c = 0; c < A; ++c) qn[c] = c == a ? upd : q[c];
-    }
-    const uint32_t mb = mbits[s];
-    if (PLAIN || useM) {
-      ldg_row<A>(tabM.norm(tie_index<A>(q, mb)), po);
-      ldg_row<A>(tabM.norm(tie_index<A>(qn, mb)), pn);
-    } else {
-      probs_row<A>(q, mb, mkind, mpar, qpar, qom, po);
-      probs_row<A>(qn, mb, mkind, mpar, qpar, qom, pn);
-      const double so_ = sum_seq<A>(po), sn_ = sum_seq<A>(pn);
-      // p / sum(p): x / 1.0 == x, so the (frequent) exactly-normalised case skips the divisions
-      if (sn_ != 1.0) {
-#pragma unroll
-        for (int c = 0; c < A; ++c) pn[c] = pdiv(pn[c], sn_);
-      }
-      if (so_ != 1.0) {
-#pragma unroll
-        for (int c = 0; c < A; ++c) po[c] = pdiv(po[c], so_);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < A; ++c) t[c] = xmul(pn[c], qn[c]);
-    const double gnew = sum_seq<A>(t);
-#pragma unroll
-    for (int c = 0; c < A; ++c) t[c] = xmul(po[c], qn[c]);
-    const double gold = sum_seq<A>(t);
-    const double g = xsub(gnew, gold);
-    if (opt & COBEL_PMA_OPT_EQUAL_GAIN) return 1.0;                  // gain.fill(1), memory/pma.py:241-242
-    return g > min_gain ? g : min_gain;
-  };
 
   // utility of a backup with gain g at (s, a): gain * need * update_mask (memory/pma.py:247-249), as a key
   auto util_key = [&](double g, int s, int a) -> int2 {
@@ -995,16 +977,16 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     int count = 0, last_seq = 0, ndst = -1;          // ndst < 0: first iteration, every backup is stale
     unsigned dirty = nch >= 32 ? kFull : ((1u << nch) - 1u);   // chunks whose maximum has to be recomputed
     int cm_hi = kKeyMinHi; unsigned cm_lo = 0;       // lane c: the largest key of chunk c
+    unsigned seqmask = 0;                            // lane w: bits of the states 32 w .. 32 w + 31 in performed[last_seq:]
     for (int it = 0; it < B; ++it) {
       // ---- (1) extension of the current sequence (memory/pma.py:219-235) -------------------------
-      int ext = -1, clen = 0;
+      // The candidate sequence is performed[last_seq:] + [ext]: it is read in place from perf[] (perf[count] holds
+      // the candidate until the chosen update overwrites it); seqmask = the states of performed[last_seq:].
+      int ext = -1, clen = 0, seq_base = 0;
       if (count > 0) {
         const int lp = perf[count - 1];
         ext = Pk[sa_of(lp)] & kSt;                          // next_state of the last update
-        bool loop = false;
-#pragma unroll 1
-        for (int j = last_seq + lane; j < count; j += 32) loop |= st_of(perf[j]) == ext;
-        loop = __any_sync(kFull, loop);
+        const bool loop = (__shfl_sync(kFull, seqmask, ext >> 5) >> (ext & 31)) & 1u;
         if (!loop || (opt & COBEL_PMA_OPT_ALLOW_LOOPS)) {
           win.ensure(2, lane);
           double row[A];
@@ -1014,101 +996,123 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
                                          : select_action_warp<A, kPol>(row, mbits[ext], mpt, u, lane);
           ext += ea * S;
           clen = count - last_seq + 1;
-#pragma unroll 1
-          for (int j = lane; j < clen - 1; j += 32) seq[j] = perf[last_seq + j];
-          if (lane == 0) seq[clen - 1] = (uint16_t)ext;
-        } else if (lane == 0) {
-          seq[0] = (uint16_t)ext;                                       // failed extension: one-step(ext, action 0)
+          seq_base = last_seq;
+        } else {
+          seq_base = count;                                 // failed extension: one-step(ext, action 0)
         }
-        __syncwarp();                                                   // seq[] is read by all lanes in (3)
+        if (lane == 0) perf[count] = (uint16_t)ext;
+        __syncwarp();                                       // seq[] is read by all lanes in (2)
       }
-      // ---- (2) re-evaluate the backups that read a Q row changed by the previous update ----------
-      // (one code site for the compact list and for the full pass keeps the loop body small)
-      if (ndst != 0) {
-        int nd = 0;
-        bool full = ndst < 0;
+      const uint16_t* seq = perf + seq_base;
+      // ---- (2) work list of this iteration: the one-step backups whose gain is stale (they read a Q row changed
+      // by the previous update; everything on the first iteration) followed by the elements of the candidate
+      // n-step sequence.  Both kinds are "the gain of moving Q[s,a] towards a target" (memory/pma.py:269-386):
+      //   one-step   target = M.rewards + gamma_q max Q[s'] M.terminals, probabilities p / sum(p), clipped
+      //   n-step     target = discounted reward sum + bootstrap, raw probabilities, clipped per element if 'original'
+      // so ONE evaluation pass serves both (lane = work item).
+      int nd = 0;
+      bool full = ndst < 0;
 #pragma unroll 1
-        for (int d = 0; d < ndst && !full; ++d) {
-          const int t = dst[d];
-          const int p0 = poff[t + 1], np = poff[t + 2] - p0;
-          if (nd + A + np <= MainSmem::kListCap) {
+      for (int d = 0; d < ndst && !full; ++d) {
+        const int t = dst[d];
+        const int p0 = poff[t + 1], np = poff[t + 2] - p0;
+        if (nd + A + np <= MainSmem::kListCap) {
 #pragma unroll 1
-            for (int x = lane; x < A + np; x += 32) list[nd + x] = x < A ? (uint16_t)(x * S + t) : pitems[p0 + x - A];
-            nd += A + np;
-          } else {
-            full = true;
-          }
+          for (int x = lane; x < A + np; x += 32) list[nd + x] = x < A ? (uint16_t)(x * S + t) : pitems[p0 + x - A];
+          nd += A + np;
+        } else {
+          full = true;
         }
-        __syncwarp();
-        const int total = full ? N : nd;
-        unsigned myd = 0;
-#pragma unroll 1
-        for (int j0 = 0; j0 < total; j0 += 32) {
-          const int j = j0 + lane;
-          if (j < total) {
-            const int i = full ? j : list[j];
-            const int a = act_of(i), s = i - a * S;
-            ukey[i] = util_key(gain_one(i), s, a);
-            myd |= 1u << (i >> 5);
-          }
-        }
-        dirty |= __reduce_or_sync(kFull, myd);
-        __syncwarp();
       }
-      // ---- (3) n-step gain of the candidate (memory/pma.py:269-331), lane j = element j -----------
-      double gext = 0.0;
-      if (ext >= 0) {
-        const int nseq = clen > 0 ? clen : 1;
+      const int n1 = full ? N : nd;
+      const int nseq = ext >= 0 ? (clen > 0 ? clen : 1) : 0;
+      double fv = 0.0;
+      if (nseq) {
 #pragma unroll 1
         for (int j = lane; j < nseq; j += 32) rs[j] = Mr[sa_of(seq[j])];
-        __syncwarp();
-        const int lastI = seq[nseq - 1];
-        const uint16_t lpk = Pk[sa_of(lastI)];
+        const uint16_t lpk = Pk[sa_of(seq[nseq - 1])];
         double lrow[A];
         load_row<A>(Q + (lpk & kSt) * A, lrow);
-        const double fv = xmul(row_max<A>(lrow), (lpk >> 15) ? 1.0 : 0.0);
-        double total = 0.0;
+        fv = xmul(row_max<A>(lrow), (lpk >> 15) ? 1.0 : 0.0);
+      }
+      __syncwarp();
+      double total = 0.0;                                  // gain of the candidate: its elements' gains added in order
+      unsigned myd = 0;
 #pragma unroll 1
-        for (int j0 = 0; j0 < nseq; j0 += 32) {
-          const int j = j0 + lane;
-          double sg = 0.0;
-          if (j < nseq) {
-            const int i = seq[j];
-            const int a = act_of(i), s = i - a * S;
-            double q[A], qn[A], pb[A], pa[A], t[A];
-            load_row<A>(Q + s * A, q);
-            const uint32_t mb = mbits[s];
+      for (int j0 = 0; j0 < n1 + nseq; j0 += 32) {
+        const int j = j0 + lane;
+        const bool one = j < n1;
+        double g = 0.0;
+        if (j < n1 + nseq) {
+          const int e = j - n1;
+          const int i = one ? (full ? j : list[j]) : seq[e];
+          const int a = act_of(i), s = i - a * S;
+          double q[A], qn[A], po[A], pn[A], t[A];
+          load_row<A>(Q + s * A, q);
+          double target;
+          if (one) {
+            const uint16_t pk = Pk[s * A + a];
+            double tr_[A];
+            load_row<A>(Q + (pk & kSt) * A, tr_);
+            target = xadd(Mr[s * A + a], xmul(xmul(gq, row_max<A>(tr_)), (pk >> 15) ? 1.0 : 0.0));
+          } else {
             double r = 0.0;
 #pragma unroll 1
-            for (int f = 0; f < nseq - j; ++f) r = xadd(r, xmul(rs[j + f], powsr[f]));
-            const double target = xadd(r, xmul(fv, powq[nseq - j]));
-#pragma unroll
-            for (int c = 0; c < A; ++c) {
-              const double qt = c == a ? target : q[c];
-              qn[c] = xadd(q[c], xmul(lrq, xsub(qt, q[c])));
-            }
-            if (PLAIN || useM) {
-              ldg_row<A>(tabM.raw(tie_index<A>(q, mb)), pb);
-              ldg_row<A>(tabM.raw(tie_index<A>(qn, mb)), pa);
-            } else {
-              probs_row<A>(q, mb, mkind, mpar, qpar, qom, pb);
-              probs_row<A>(qn, mb, mkind, mpar, qpar, qom, pa);
-            }
-#pragma unroll
-            for (int c = 0; c < A; ++c) t[c] = xmul(qn[c], pa[c]);
-            const double ga = sum_seq<A>(t);
-#pragma unroll
-            for (int c = 0; c < A; ++c) t[c] = xmul(qn[c], pb[c]);
-            sg = xsub(ga, sum_seq<A>(t));
-            if (original) sg = sg > min_gain ? sg : min_gain;
+            for (int f = 0; f < nseq - e; ++f) r = xadd(r, xmul(rs[e + f], powsr[f]));
+            target = xadd(r, xmul(fv, powq[nseq - e]));
           }
-          const int m = nseq - j0 < 32 ? nseq - j0 : 32;
-#pragma unroll 1
-          for (int l = 0; l < m; ++l) total = xadd(total, shfl_f64(sg, l));       // gain += step_gain, in order
+          {
+            const double qa = pick<A>(q, a);
+            const double upd = xadd(qa, xmul(lrq, xsub(target, qa)));
+#pragma unroll
+            for (int c = 0; c < A; ++c) qn[c] = c == a ? upd : q[c];
+          }
+          const uint32_t mb = mbits[s];
+          if (PLAIN || useM) {
+            const double* tb = one ? tabM.norm(0) : tabM.raw(0);
+            ldg_row<A>(tb + tie_index<A>(q, mb) * A, po);
+            ldg_row<A>(tb + tie_index<A>(qn, mb) * A, pn);
+          } else {
+            probs_row<A>(q, mb, mkind, mpar, qpar, qom, po);
+            probs_row<A>(qn, mb, mkind, mpar, qpar, qom, pn);
+            if (one) {
+              const double so_ = sum_seq<A>(po), sn_ = sum_seq<A>(pn);
+              // p / sum(p): x / 1.0 == x, so the (frequent) exactly-normalised case skips the divisions
+              if (sn_ != 1.0) {
+#pragma unroll
+                for (int c = 0; c < A; ++c) pn[c] = pdiv(pn[c], sn_);
+              }
+              if (so_ != 1.0) {
+#pragma unroll
+                for (int c = 0; c < A; ++c) po[c] = pdiv(po[c], so_);
+              }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < A; ++c) t[c] = xmul(pn[c], qn[c]);
+          const double gnew = sum_seq<A>(t);
+#pragma unroll
+          for (int c = 0; c < A; ++c) t[c] = xmul(po[c], qn[c]);
+          g = xsub(gnew, sum_seq<A>(t));
+          if (one) {
+            g = g > min_gain ? g : min_gain;
+            if (opt & COBEL_PMA_OPT_EQUAL_GAIN) g = 1.0;               // gain.fill(1), memory/pma.py:241-242
+            ukey[i] = util_key(g, s, a);
+            myd |= 1u << (i >> 5);
+          } else if (original) {
+            g = g > min_gain ? g : min_gain;
+          }
         }
-        gext = total > min_gain ? total : min_gain;
-        if (opt & COBEL_PMA_OPT_EQUAL_GAIN) gext = 1.0;
+        if (nseq) {                                        // gain += step_gain, in sequence order
+          const int lo = n1 - j0 > 0 ? n1 - j0 : 0, hi = n1 + nseq - j0 < 32 ? n1 + nseq - j0 : 32;
+#pragma unroll 1
+          for (int l = lo; l < hi; ++l) total = xadd(total, shfl_f64(g, l));
+        }
       }
+      dirty |= __reduce_or_sync(kFull, myd);
+      __syncwarp();
+      double gext = total > min_gain ? total : min_gain;
+      if (opt & COBEL_PMA_OPT_EQUAL_GAIN) gext = 1.0;
       // ---- (4) arg-max of the utilities with exact ties (memory/pma.py:247-254); the candidate's
       // n-step gain overrides the one-step entry `ext` for this iteration only
       int2 saved = make_int2(0, 0);
@@ -1131,6 +1135,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       const int2 umax = warp_max_key(cmine);
       const bool cwin = cmine.y == umax.y && cmine.x == umax.x;          // chunk holds a maximum
       unsigned tchunks = __ballot_sync(kFull, cwin);
+      const unsigned tchunks0 = tchunks;
       // the largest utility below the maximum: over the other chunks' maxima and the rest of the winning chunks
       int2 second = warp_max_key(cwin ? make_int2(0, kKeyMinHi) : cmine);
       // ties in flat-index order: lane c keeps the tie ballot of chunk c
@@ -1147,8 +1152,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         mytb = lane == c ? b : mytb;
         onlyb = b;
       }
-      const int mycnt = __popc(mytb);
-      const int ktot = __reduce_add_sync(kFull, mycnt);
+      const int ktot = __reduce_add_sync(kFull, __popc(mytb));
       {
         const double vmax = key_value(umax);
         if (second.y != kKeyMinHi && vmax != 0.0) {
@@ -1165,25 +1169,41 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       if (ktot == 1) {
         chosen = c0 * 32 + __ffs(onlyb) - 1;
       } else {
-        // Generator.choice(p = ties / k): cdf_m = m-fold sequential sum of fl(1/k), normalised by cdf_k
-        int incl = mycnt;                                // inclusive scan of the per-chunk tie counts
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
-        int pick = ktot - 1;
-        const double pk_ = pdiv(1.0, int_to_f64(ktot));
-        double ck = 0.0;
+        // Generator.choice(p = ties / k): cdf_m = m-fold sequential sum of fl(1/k), normalised by cdf_k; the pick is
+        // the number of bin edges <= u (tabulated per k <= 32 next to the policy tables)
+        int pick;
+        if ((PLAIN || have_tab) && ktot <= 32) {
+          const double edge = __ldg(tie_cdf + (ktot - 1) * 32 + lane);
+          pick = __popc(__ballot_sync(kFull, edge <= u));
+        } else {
+          pick = ktot - 1;
+          const double pk_ = pdiv(1.0, int_to_f64(ktot));
+          double ck = 0.0;
 #pragma unroll 1
-        for (int m = 0; m < ktot; ++m) ck = xadd(ck, pk_);
-        double c = 0.0;
+          for (int m = 0; m < ktot; ++m) ck = xadd(ck, pk_);
+          double c = 0.0;
 #pragma unroll 1
-        for (int m = 0; m < ktot; ++m) {
-          c = xadd(c, pk_);
-          if (pdiv(c, ck) > u) { pick = m; break; }
+          for (int m = 0; m < ktot; ++m) {
+            c = xadd(c, pk_);
+            if (pdiv(c, ck) > u) { pick = m; break; }
+          }
         }
-        // the chunk whose [incl - cnt, incl) range contains `pick`, then the pick-th set bit of its ballot
-        const unsigned owner = __ballot_sync(kFull, pick >= incl - mycnt && pick < incl);
-        const int oc = __ffs(owner) - 1;
-        chosen = oc * 32 + __shfl_sync(kFull, (int)__fns(mytb, 0, pick - (incl - mycnt) + 1), oc);
+        // the pick-th tie in flat-index order: walk the winning chunks (ascending) until their tie counts cover it
+        chosen = 0;
+        unsigned tc = tchunks0;
+        int base = 0;
+        while (tc) {
+          const int c = __ffs(tc) - 1;
+          tc &= tc - 1;
+          const unsigned b = __shfl_sync(kFull, mytb, c);
+          const int nb = __popc(b);
+          if (pick < base + nb) {
+            const unsigned sel = __ballot_sync(kFull, (b >> lane & 1u) && __popc(b & ((1u << lane) - 1u)) == pick - base);
+            chosen = c * 32 + __ffs(sel) - 1;
+            break;
+          }
+          base += nb;
+        }
       }
       if (ext >= 0) {
         __syncwarp();
@@ -1193,31 +1213,34 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       // ---- (5) apply the chosen (n-step) update: PMAMemory.update_q, memory/pma.py:452-496 --------
       {
         const bool use_seq = clen > 0 && chosen == ext;
-        const int nseq = use_seq ? clen : 1;
-        if (!use_seq && lane == 0) { seq[0] = (uint16_t)chosen; rs[0] = Mr[sa_of(chosen)]; }
-        __syncwarp();
-        const int lastI = seq[nseq - 1];
-        const uint16_t lpk = Pk[sa_of(lastI)];
-        double lrow[A];
-        load_row<A>(Q + (lpk & kSt) * A, lrow);
-        const double fv = xmul(row_max<A>(lrow), (lpk >> 15) ? 1.0 : 0.0);
-        bool ok = true;                               // n >= 2: every transition must be non-terminal & experienced
-        if (nseq >= 2) {
-          bool bad = false;
-#pragma unroll 1
-          for (int j = lane; j < nseq; j += 32) { const int k = seq[j]; bad |= (Pk[sa_of(k)] >> 15) == 0; }
-          ok = !__any_sync(kFull, bad);
+        const int nseq5 = use_seq ? clen : 1;
+        const uint16_t* sq = use_seq ? seq : perf + count;
+        double fv5 = fv;                              // the candidate's bootstrap value is still valid (Q unchanged)
+        if (!use_seq) {
+          const int csa = sa_of(chosen);
+          if (lane == 0) { perf[count] = (uint16_t)chosen; rs[0] = Mr[csa]; }
+          const uint16_t lpk = Pk[csa];
+          double lrow[A];
+          load_row<A>(Q + (lpk & kSt) * A, lrow);
+          fv5 = xmul(row_max<A>(lrow), (lpk >> 15) ? 1.0 : 0.0);
         }
         __syncwarp();
+        bool ok = true;                               // n >= 2: every transition must be non-terminal & experienced
+        if (nseq5 >= 2) {
+          bool bad = false;
+#pragma unroll 1
+          for (int j = lane; j < nseq5; j += 32) { const int k = sq[j]; bad |= (Pk[sa_of(k)] >> 15) == 0; }
+          ok = !__any_sync(kFull, bad);
+        }
         ndst = 0;
         if (ok) {
           auto update_element = [&](int j) {
-            const int i = seq[j];
+            const int i = sq[j];
             const int a = act_of(i), s = i - a * S;
             double r = 0.0;
 #pragma unroll 1
-            for (int f = 0; f < nseq - j; ++f) r = xadd(r, xmul(rs[j + f], powq[f]));
-            double td = xadd(r, xmul(fv, powq[nseq - j]));
+            for (int f = 0; f < nseq5 - j; ++f) r = xadd(r, xmul(rs[j + f], powq[f]));
+            double td = xadd(r, xmul(fv5, powq[nseq5 - j]));
             const double q = Q[s * A + a];
             td = xsub(td, q);
             Q[s * A + a] = xadd(q, xmul(lrq, td));
@@ -1226,17 +1249,18 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
           if (opt & COBEL_PMA_OPT_ALLOW_LOOPS) {      // a sequence may revisit (s, a): in order, like the reference's loop
             if (lane == 0) {
 #pragma unroll 1
-              for (int j = 0; j < nseq; ++j) update_element(j);
+              for (int j = 0; j < nseq5; ++j) update_element(j);
             }
           } else {                                    // the states of a sequence are distinct: one element per lane
 #pragma unroll 1
-            for (int j = lane; j < nseq; j += 32) update_element(j);
+            for (int j = lane; j < nseq5; j += 32) update_element(j);
           }
-          ndst = nseq;
+          ndst = nseq5;
         }
-        if (lane == 0) perf[count] = (uint16_t)chosen;
         ++count;
-        if (ext != chosen) last_seq = it;
+        const int cs = st_of(chosen);
+        if (ext != chosen) { last_seq = it; seqmask = 0; }
+        if (lane == (cs >> 5)) seqmask |= 1u << (cs & 31);
         __syncwarp();
       }
     }
@@ -1412,7 +1436,7 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
   else COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
   if constexpr (A <= 4) {
     if (tabs) {                                        // the tie-pattern policy tables of this call
-      pma_policy_table_kernel<A><<<(unsigned)p.n_tab, 256, 0, st>>>(p.tab_kind, p.tab_param, p.tab_scratch);
+      pma_policy_table_kernel<A><<<(unsigned)p.n_tab + 1, 256, 0, st>>>(p.tab_kind, p.tab_param, p.tab_scratch);
       cobel_count_launch();
     }
   }

@@ -142,7 +142,7 @@ class PMAMemory(TableMemory):
                                for c in cols], dim=1).contiguous()
         tkind = torch.tensor(kinds, dtype=torch.int32, device=dev)
         tpar = torch.tensor(params, dtype=torch.float64, device=dev)
-        n = n_tab * _lib.pma_tab_doubles(n_actions)
+        n = n_tab * _lib.pma_tab_doubles(n_actions) + 1024      # + COBEL_PMA_TIE_DOUBLES
         if getattr(self, '_tab_scratch', None) is None or self._tab_scratch.numel() < n:
             self._tab_scratch = torch.empty(n, dtype=torch.float64, device=dev)
         keep += [tkind, tpar, tof]

@@ -318,9 +318,11 @@ typedef struct CobelPMAParams {
   const int32_t* tab_kind;   /* [n_tab] COBEL_POLICY_* of table t (a Softmax entry leaves its table unused) */
   const double*  tab_param;  /* [n_tab] its epsilon */
   const int32_t* tab_of_agent;/* optional [N,2]: tables of (agent.policy, M.policy) of agent n; NULL = (0, n_tab-1) */
-  double*  tab_scratch;      /* scratch [n_tab, COBEL_PMA_TAB_DOUBLES(A)], filled by the call */
+  double*  tab_scratch;      /* scratch [n_tab * COBEL_PMA_TAB_DOUBLES(A) + COBEL_PMA_TIE_DOUBLES], filled by the call (the
+                                tail holds the bin edges of Generator.choice over k <= 32 tied utilities) */
 } CobelPMAParams;
 #define COBEL_PMA_TAB_DOUBLES(A) (3 * (1 << (2 * (A))) * (A))
+#define COBEL_PMA_TIE_DOUBLES 1024
 
 int cobel_pma_run(const CobelPMAParams* p, void* stream);
 
