@@ -75,7 +75,7 @@ class SFMAParams(C.Structure):
                 ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32), ('nb_replays', C.c_int32),
                 ('start_replay', C.c_int32), ('random_replay', C.c_int32), ('dynamic', C.c_int32),
                 ('no_replay', C.c_int32), ('learn', C.c_int32), ('td_acc', c_ptr), ('trial_mode', c_ptr),
-                ('reward_modulation', C.c_double), ('mod_flags', C.c_int32), ('reserved2', C.c_int32)]
+                ('reward_modulation', C.c_double), ('mod_flags', C.c_int32), ('reserved2', C.c_int32), ('carry', c_ptr)]
 
 
 PMA_MAX_SEQ = 64
@@ -100,7 +100,15 @@ def pma_tab_doubles(n_actions):
     return 3 * (1 << (2 * n_actions)) * n_actions
 
 
-STRUCTS = {'CobelWorld': World, 'CobelStream': Stream, 'CobelPolicy': Policy, 'CobelTrace': Trace,
+class Experiences(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('reserved', C.c_int32), ('state', c_ptr), ('action', c_ptr), ('reward', c_ptr),
+                ('next_state', c_ptr), ('terminal', c_ptr), ('td', c_ptr)]
+
+
+# COBEL_OP_* (include/cobel_b200.h)
+OP_STORE, OP_UPDATE_Q, OP_RETRIEVE_BATCH, OP_REPLAY, OP_RETRIEVE_Q, OP_GATHER, OP_GAIN_BATCH, OP_NEED = range(1, 9)
+
+STRUCTS = {'CobelExperiences': Experiences, 'CobelWorld': World, 'CobelStream': Stream, 'CobelPolicy': Policy, 'CobelTrace': Trace,
            'CobelDynaQParams': DynaQParams, 'CobelQParams': QParams, 'CobelSRParams': SRParams, 'CobelSRCompactParams': SRCompactParams, 'CobelSFMAParams': SFMAParams, 'CobelPMAParams': PMAParams}
 
 _SIGNATURES = {
@@ -116,6 +124,17 @@ _SIGNATURES = {
     'cobel_sr_compact_run': (C.c_int, [C.POINTER(SRCompactParams), c_ptr]),
     'cobel_sfma_run': (C.c_int, [C.POINTER(SFMAParams), c_ptr]),
     'cobel_pma_run': (C.c_int, [C.POINTER(PMAParams), c_ptr]),
+    'cobel_env_reset': (C.c_int, [C.POINTER(World), C.POINTER(Stream), C.c_int64, c_ptr, c_ptr]),
+    'cobel_env_step': (C.c_int, [C.POINTER(World), C.POINTER(Stream), C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'cobel_policy_probs': (C.c_int, [C.POINTER(Policy), C.c_int64, C.c_int64, C.c_int32, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'cobel_policy_select': (C.c_int, [C.POINTER(Policy), C.POINTER(Stream), C.c_int64, C.c_int32, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'cobel_dynaq_op': (C.c_int, [C.POINTER(DynaQParams), C.c_int, C.POINTER(Experiences), c_ptr]),
+    'cobel_q_op': (C.c_int, [C.POINTER(QParams), C.c_int, C.POINTER(Experiences), c_ptr]),
+    'cobel_sr_op': (C.c_int, [C.POINTER(SRParams), C.c_int, C.POINTER(Experiences), c_ptr, c_ptr, c_ptr]),
+    'cobel_sfma_op': (C.c_int, [C.POINTER(SFMAParams), C.c_int, C.POINTER(Experiences), c_ptr]),
+    'cobel_sfma_replay': (C.c_int, [C.POINTER(SFMAParams), c_ptr, C.c_int, c_ptr]),
+    'cobel_pma_op': (C.c_int, [C.POINTER(PMAParams), C.c_int, C.POINTER(Experiences), c_ptr, c_ptr, c_ptr]),
+    'cobel_pma_replay': (C.c_int, [C.POINTER(PMAParams), c_ptr, C.c_int, c_ptr]),
 }
 
 _lib = None

@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..experience import Experience, ExperienceBatch  # noqa: F401
 from ..memory.dyna_q import DynaQMemory
 from ..spaces import Discrete
 from .agent import Agent, launch_stream
@@ -96,6 +97,29 @@ class DynaQ(Agent):
     def test(self, interface, trials, steps):
         """agent/dyna_q.py:217-273 for all agents (``policy_test``; nothing is learned)."""
         return self._run(interface, trials, steps, 0, True, learn=False)
+
+    # ---- stand-alone methods: for callers that drive the loop themselves (agent/dyna_q.py:176-203) -------------
+    def _op(self, op, batch):
+        st = self._stream
+        keep = []
+        lr, gm = st.param(self.learning_rate, 'learning_rate'), st.param(self.gamma, 'gamma')
+        p, e = self.M._table_params(keep, self._Q, lr, gm), batch.c_struct()
+        _lib.call('cobel_dynaq_op', st.device, p, op, e, launch_stream(st))
+        return batch
+
+    def update_q(self, experience):
+        """agent/dyna_q.py:275-301 for all agents; returns the experience with its TD error (``'td'``)."""
+        batch = ExperienceBatch.from_dicts(self._stream, experience, with_td=True)
+        self.M._check_experience(batch)
+        self._op(_lib.OP_UPDATE_Q, batch)
+        out = dict(experience)
+        out['td'] = batch.td[0, 0].item() if self._stream.single else batch.td[:, 0]
+        return out
+
+    def replay(self, batch_size):
+        """agent/dyna_q.py:319-330: ``M.retrieve_batch(batch_size)``, then ``update_q`` for each experience in order."""
+        if batch_size > 0:
+            self._op(_lib.OP_REPLAY, ExperienceBatch(self._stream, batch_size))
 
     def predict_on_batch(self, batch):
         """agent/dyna_q.py:303-317: Q-values of a batch of states (``[N, B, A]``, or ``[B, A]`` for one agent)."""

@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..experience import Experience, ExperienceBatch  # noqa: F401  (Experience: agent/q.py:17-23)
 from ..spaces import Box, Discrete
 from ..stream import BatchStream
 from .agent import Agent, launch_stream
@@ -116,6 +117,55 @@ class QAgent(Agent):
     def test(self, interface, trials, steps=32):
         """agent/q.py:230-295 for all agents."""
         return self._run(interface, trials, steps, 0, learn=False)
+
+    # ---- stand-alone methods (agent/q.py:196-216: the body of the reference's step loop) ------------------------
+    def _op(self, op, batch, interface=None):
+        st = self._stream
+        obs_key = getattr(interface, '_obs_key', None) if interface is not None else getattr(self, '_op_obs_key', None)
+        self._op_obs_key = obs_key
+        keep = []
+        key_t = None
+        if obs_key is not None:
+            key_t = torch.as_tensor(obs_key, dtype=torch.int32, device=st.device).contiguous()
+            keep.append(key_t)
+        n_keys = self._Q.shape[1]
+        lr, gm = st.param(self.learning_rate, 'learning_rate'), st.param(self.gamma, 'gamma')
+        world = _lib.World(n_keys if key_t is None else key_t.numel(), self.nb_actions, 0, 0, None, None, None, None, None, None, None)
+        flags = torch.zeros(st.n_agents, dtype=torch.int32, device=st.device)
+        tr = _lib.Trace(None, None, None, None, None, 0, None, 0, None, 0, flags.data_ptr(), None)
+        p = _lib.QParams(st.n_agents, world, st.c_struct(), _lib.Policy(0, 0, None), tr, self._Q.data_ptr(),
+                         _lib.ptr(key_t), n_keys, 0, _lib.ptr(self._log), 0 if self._log is None else self._log.shape[1],
+                         self._log_len.data_ptr(), lr.data_ptr(), gm.data_ptr(), 0, 0, 0, 1)
+        e = batch.c_struct()
+        _lib.call('cobel_q_op', st.device, p, op, e, launch_stream(st))
+        return batch
+
+    def bind_interface(self, interface):
+        """Allocate the Q rows for the observations of ``interface`` (the reference's dict grows on demand,
+        agent/q.py:152-158) before the agent is driven step by step."""
+        if self._stream is None:
+            self._bind(interface.rng)
+        self._alloc_q(interface.n_states)
+        self._op_obs_key = getattr(interface, '_obs_key', None)
+
+    def append(self, experience):
+        """``self.M.append(experience)`` of the reference's step loop (agent/q.py:213)."""
+        self._ensure_log(1)
+        self._op(_lib.OP_STORE, ExperienceBatch.from_dicts(self._stream, experience))
+
+    def update_q(self, experience):
+        """agent/q.py:297-322 for all agents; returns the experience with its TD error."""
+        batch = ExperienceBatch.from_dicts(self._stream, experience, with_td=True)
+        self._op(_lib.OP_UPDATE_Q, batch)
+        out = dict(experience)
+        out['td'] = batch.td[0, 0].item() if self._stream.single else batch.td[:, 0]
+        return out
+
+    def replay(self, batch_size=32):
+        """agent/q.py:344-354: ``for i in rng.choice(len(M), batch_size): update_q(M[i])``."""
+        if batch_size > 0:
+            assert bool((self._log_len > 0).all()), 'replay from an empty memory'
+            self._op(_lib.OP_REPLAY, ExperienceBatch(self._stream, batch_size))
 
     def predict_on_batch(self, batch):
         """agent/q.py:324-342 for Discrete observations (state indices)."""

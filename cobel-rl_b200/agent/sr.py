@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..experience import Experience, ExperienceBatch  # noqa: F401  (Experience: agent/sr.py:16-22)
 from ..spaces import Discrete
 from .agent import Agent, launch_stream
 
@@ -138,14 +139,38 @@ class SR(Agent):
         """agent/sr.py:199-253 for all agents."""
         return self._run(interface, trials, steps, learn=False)
 
-    def retrieve_q(self, state):
-        """agent/sr.py:288-308 (host-side convenience; same pairwise order is NOT guaranteed here)."""
+    # ---- stand-alone methods -----------------------------------------------------------------------------------
+    def _op_params(self):
         st = self._stream
-        s = torch.as_tensor(state, device=st.device).reshape(-1).long().expand(st.n_agents)
-        n = torch.arange(st.n_agents, device=st.device)
-        values = (self._SR * self._rewards.unsqueeze(1)).sum(dim=2)          # [N, S]
-        m = self._model[n, s].long()                                          # [N, A]
-        return self._view(torch.gather(values, 1, m))
+        assert not self.compact, 'the stand-alone SR methods act on the dense tables'
+        S, A = self._SR.shape[1], self._model.shape[2]
+        lr, gm = st.param(self.learning_rate, 'learning_rate'), st.param(self.gamma, 'gamma')
+        world = _lib.World(S, A, 0, 0, None, None, None, None, None, None, None)
+        p = _lib.SRParams(st.n_agents, world, st.c_struct(), _lib.Policy(0, 0, None), _lib.Trace(), self._SR.data_ptr(),
+                          self._rewards.data_ptr(), self._model.data_ptr(), None, 0, lr.data_ptr(), gm.data_ptr(), 0, 0, 1, 0)
+        return p, (lr, gm)
+
+    def update(self, experience):
+        """agent/sr.py:255-286 for all agents: learned reward, transition model and the SR row of ``state``."""
+        st = self._stream
+        batch = ExperienceBatch.from_dicts(st, experience)
+        S = self._SR.shape[1]
+        if bool(((batch.state < 0) | (batch.state >= S) | (batch.next_state < 0) | (batch.next_state >= S)).any()):
+            raise IndexError('experience with a state outside the tables')
+        p, keep = self._op_params()
+        e = batch.c_struct()
+        _lib.call('cobel_sr_op', st.device, p, _lib.OP_STORE, e, None, None, launch_stream(st))
+        return experience
+
+    def retrieve_q(self, state):
+        """agent/sr.py:288-308: ``Q[a] = np.sum(SR[m(s, a)] * rewards)`` in NumPy's pairwise order (csrc/ops.cu)."""
+        st = self._stream
+        s = torch.as_tensor(state, device=st.device).reshape(-1).to(torch.int32)
+        s = (s.expand(st.n_agents) if s.numel() == 1 else s).contiguous()
+        q = torch.empty((st.n_agents, self._model.shape[2]), dtype=torch.float64, device=st.device)
+        p, keep = self._op_params()
+        _lib.call('cobel_sr_op', st.device, p, _lib.OP_RETRIEVE_Q, None, s.data_ptr(), q.data_ptr(), launch_stream(st))
+        return self._view(q)
 
     def predict_on_batch(self, batch):
         idx = np.array(batch).astype(int).reshape(-1)

@@ -16,16 +16,18 @@
 //                    bit-identical to the reference's full recomputation; gain x need x mask, the exact-tie
 //                    arg-max draw and the n-step update are warp passes with shuffle reductions (no block
 //                    barriers).
-//   update_sr, banded (CobelPMAParams.sr_band >= 0, BAND = true): replay reads ONE row of SR per call, and T of
-//                    a W-wide gridworld has half bandwidth W, so the agent's warp factorises the band of
-//                    I - gamma T itself (band_lu) and solves for the row it needs (band_solve_row; band_gth for
-//                    the stationary need of timed-out trials): all trials run in ONE launch, and SR is
-//                    refreshed once per call by pma_sr_band_kernel from the stored factors.
+//   update_sr, banded (CobelPMAParams.sr_band >= 0): replay reads ONE row of SR per call, and T of a W-wide
+//                    gridworld has half bandwidth W: pma_band_factor_kernel / pma_band_solve_kernel, ONE WARP PER
+//                    AGENT between the main kernel's launches, factorise the band of I - gamma T (or run the
+//                    banded GTH elimination for the stationary need of timed-out trials) and solve for the rows
+//                    the replays need; SR is refreshed once per call by pma_sr_band_kernel from the last factors.
 //   update_sr, dense (any T): pma_sr_kernel, ONE CTA PER AGENT, after every trial (the main kernel is then
 //                    launched once per trial, per-agent state carried in HBM): SR = inv(I - gamma T) by
 //                    register-tiled Gauss-Jordan (no pivoting: I - gamma T is strictly diagonally dominant); for
 //                    agents whose trial timed out also the stationary distribution (the reference's LAPACK
 //                    dgeev `need`) by the subtraction-free GTH elimination.
+//   With replays on, the main kernel is launched per phase (MainPhase): update_sr sits between a trial's steps
+//   and its end replay, and the per-agent state travels in `carry`.
 //
 // (v1 ran everything in one CTA per agent and was barrier-bound: 7 of 8 warps waited for warp 0
 //  through ~12 block barriers per replay iteration, profiles/r1_pma_v1_cta_per_agent.txt.)
@@ -285,15 +287,15 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_sr_kernel(con
   double* Mat = xv + ((S + 1) & ~1);                              // [S*S] GTH scratch
   int flags = 0;
   const double* Tg = p.T + (size_t)n * S * S;
-  gauss_jordan_inverse<TILE>(Tg, p.gamma_sr[n], p.SR + (size_t)n * S * S, S, elim, tid, flags);
-  if (final_only) {
+  if (final_only != 2) gauss_jordan_inverse<TILE>(Tg, p.gamma_sr[n], p.SR + (size_t)n * S * S, S, elim, tid, flags);
+  if (final_only == 1) {
     // end of a banded call (sr_band >= 0): SR is refreshed once, and the caller's band guarantee is verified
     const int bw = p.sr_band;
     for (int e = tid; e < S * S; e += kThreads) {
       const int i = e / S, j = e - i * S;
       if (abs(i - j) > bw && Tg[e] != 0.0) flags |= COBEL_FLAG_BAND_VIOLATION;
     }
-  } else if (p.carry[n * 4 + 0] < 0) {
+  } else if (p.carry[n * 8 + 0] < 0) {               // (final_only == 2: the stationary need only, SR is left alone)
     gth_stationary<TILE>(Tg, Mat, xv, S, elim, tid, flags);
     for (int e = tid; e < S; e += kThreads) p.need_scratch[(size_t)n * S + e] = xv[e];
   }
@@ -302,19 +304,13 @@ __global__ void __launch_bounds__(kThreads, TILE <= 7 ? 2 : 1) pma_sr_kernel(con
 }
 
 // ---------------------------------------------------------------------------
-// Banded update_sr for one agent by one warp (CobelPMAParams.sr_band): replay reads ONE row of
-// SR = inv(M), M = I - gamma T (memory/pma.py:401-411), and T of a W-wide gridworld has half bandwidth
-// bw = W, so instead of the S^3 dense inverse the warp factorises the band (S * bw^2 operations, no
-// pivoting: M is strictly diagonally dominant, the factors stay inside the band) and solves
-// x^T M = e_c^T for the row (2 * S * bw).  The result is what the dense elimination gives with the
-// multiplications by the exact zeros outside the band left out.
-// Band storage in global scratch (L1/L2 resident): b[i * W + (j - i + bw)] = M[i][j], W = 2 bw + 1.
+// Banded update_sr (CobelPMAParams.sr_band): replay reads ONE row of SR = inv(M), M = I - gamma T
+// (memory/pma.py:401-411), and T of a W-wide gridworld has half bandwidth bw = W, so instead of the S^3 dense
+// inverse the band is factorised (S * bw^2 operations, no pivoting: M is strictly diagonally dominant, the
+// factors stay inside the band) and x^T M = e_c^T is solved for the row (2 * S * bw).  The result is what the
+// dense elimination gives with the multiplications by the exact zeros outside the band left out.
+// Band storage in global scratch: b[i * W + (j - i + bw)] = M[i][j], W = 2 bw + 1.
 // ---------------------------------------------------------------------------
-// The factorisation is latency-critical (S dependent steps), so rows are STREAMED through a small
-// shared-memory ring with cp.async kBandAhead rows ahead of the step that needs them: the HBM/L2
-// latency of T (dense source) and of the stored factors is off the dependency chain, and a finished
-// row goes back to global scratch with a fire-and-forget store.
-constexpr int kBandAhead = 4;
 
 // 1 / x to ~1 ulp without the IEEE division's slow path: MUFU.RCP64H seed + two Newton steps.  Only the banded
 // eliminations use it (not bit-exact by design); their pivots and row sums are far from the subnormal range, and
@@ -336,6 +332,10 @@ COBEL_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "me
 template <int N>
 COBEL_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// The eliminations are latency-critical (S dependent steps), so rows are STREAMED through a small shared-memory
+// ring with cp.async kBandAhead rows ahead of the step that needs them: the HBM/L2 latency of T is off the
+// dependency chain, and a finished row goes to the global scratch with a fire-and-forget store.
+constexpr int kBandAhead = 4;
 // rows of the ring: the bw + 1 active rows, one being replaced and kBandAhead in flight, rounded up to a power of two
 __host__ __device__ inline int band_ring_rows(int bw) {
   int r = 1;
@@ -426,7 +426,7 @@ __device__ __noinline__ int band_lu(const double* __restrict__ Tg, double g, dou
 // x = row c of inv(M) from the factors: U^T y = e_c (forward, column sweeps), then L^T x = y (backward, in place).
 // x lives in shared memory, `w` (shared scratch of S doubles) holds the right-hand side of the forward sweep; each
 // step reads one factor row straight from the global scratch, the loads running four steps ahead of the recurrence.
-__device__ __noinline__ void band_solve_row(const double* fac, double* w, int S, int bw, int c, double* x, int lane) {
+__device__ __forceinline__ void band_solve_row(const double* fac, double* w, int S, int bw, int c, double* x, int lane) {
   const int W = 2 * bw + 1;
 #pragma unroll 1
   for (int e = lane; e < S; e += 32) { w[e] = e == c ? 1.0 : 0.0; x[e] = 0.0; }
@@ -469,6 +469,7 @@ __device__ __noinline__ void band_solve_row(const double* fac, double* w, int S,
     }
   }
 }
+
 
 // Stationary distribution of the banded row-stochastic T by GTH elimination (see gth_stationary), scaled to
 // unit 2-norm, into x (shared memory).  fac receives the eliminated rows (column k holds P[i][k] / s_k).
@@ -544,8 +545,74 @@ __device__ __noinline__ int band_gth(const double* __restrict__ Tg, double* fac,
 }
 
 // ---------------------------------------------------------------------------
+// pma_band_factor_kernel / pma_band_solve_kernel: M.update_sr() at a trial boundary, launched between the phases of
+// pma_main_kernel.  Inside the main kernel (16 warps per SM, all of its shared memory taken by the replay tables)
+// the eliminations ran at 0.5 instructions / cycle / scheduler and made up 36 % of the PMA run
+// (profiles/r2_pma_v5.txt).
+//   factor: carry[.,0] < 0 (the trial timed out): GTH elimination of T, the stationary vector -> need_scratch;
+//           always: LU of I - gamma T -> band_scratch (diagonal = 1 / pivot, sub-diagonal part = multipliers)
+//   solve:  one row of the inverse from the stored factors -> need_scratch:
+//           row carry[.,0] for the end replay of a trial that reached a terminal state, row carry[.,4] (the next
+//           trial's start state) for the start replay
+// ---------------------------------------------------------------------------
+constexpr int kBandWarps = 8;
+struct BandSmem {                                     // per warp (agent)
+  int ring, x, w, bytes;
+  __host__ __device__ BandSmem(int S, int bw) {
+    ring = 0;
+    x = ring + band_ring_rows(bw) * (2 * bw + 1) * 8;
+    w = x + ((S + 1) & ~1) * 8;
+    bytes = (w + ((S + 1) & ~1) * 8 + 15) & ~15;
+  }
+};
+
+// (A one-thread-per-agent factor kernel -- window of bw + 2 rows lane-interleaved in shared memory, 5.5
+//  instructions per element update, 3x fewer instructions per agent -- measured 1.28 ms against 1.0 ms for this one
+//  at 16384 agents: 32 KB of window per 16 agents leave 1.75 warps per scheduler on strictly dependent steps.)
+__global__ void __launch_bounds__(kBandWarps * 32) pma_band_factor_kernel(const __grid_constant__ CobelPMAParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int S = p.world.n_states, bw = p.sr_band, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n = (int64_t)blockIdx.x * kBandWarps + warp;
+  if (n >= p.n_agents) return;
+  const BandSmem so(S, bw);
+  unsigned char* blk = smem + (size_t)warp * so.bytes;
+  double* ring = reinterpret_cast<double*>(blk + so.ring);
+  double* x = reinterpret_cast<double*>(blk + so.x);
+  const double* Tg = p.T + (size_t)n * S * S;
+  double* fac = p.band_scratch + (size_t)n * S * (2 * bw + 1);
+  int flags = 0;
+  if (p.carry[n * 8 + 0] < 0) {
+    flags |= band_gth(Tg, fac, ring, S, bw, x, lane);
+    double* need = p.need_scratch + (size_t)n * S;
+#pragma unroll 1
+    for (int e = lane; e < S; e += 32) need[e] = x[e];
+    __syncwarp();
+  }
+  flags |= band_lu(Tg, p.gamma_sr[n], fac, ring, S, bw, lane);
+  flags = __reduce_or_sync(kFull, flags);
+  if (lane == 0 && flags && p.trace.flags) p.trace.flags[n] |= flags;
+}
+
+__global__ void __launch_bounds__(kBandWarps * 32) pma_band_solve_kernel(const __grid_constant__ CobelPMAParams p, const int which) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int S = p.world.n_states, bw = p.sr_band, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n = (int64_t)blockIdx.x * kBandWarps + warp;
+  if (n >= p.n_agents) return;
+  const int64_t c = p.carry[n * 8 + which];          // which = 0: the last state of the trial, 4: the next start state
+  if (c < 0) return;                                  // timed-out trial: need_scratch holds the stationary need
+  const BandSmem so(S, bw);
+  unsigned char* blk = smem + (size_t)warp * so.bytes;
+  double* x = reinterpret_cast<double*>(blk + so.x);
+  double* w = reinterpret_cast<double*>(blk + so.w);
+  band_solve_row(p.band_scratch + (size_t)n * S * (2 * bw + 1), w, S, bw, (int)c, x, lane);
+  double* need = p.need_scratch + (size_t)n * S;
+#pragma unroll 1
+  for (int e = lane; e < S; e += 32) need[e] = x[e];
+}
+
+// ---------------------------------------------------------------------------
 // pma_sr_band_kernel: the full SR = inv(I - gamma T) of a banded T, once at the end of a banded call.
-// One CTA per agent, from the band factors pma_main_kernel leaves in band_scratch: thread r solves row r of the
+// One CTA per agent, from the band factors pma_band_factor_kernel leaves in band_scratch: thread r solves row r of the
 // inverse (x^T M = e_r^T) in its own row of a shared-memory S x S matrix -- no barriers between the S steps,
 // the factor rows are broadcast loads.  2 S^2 bw operations instead of the S^3 of the dense Gauss-Jordan.
 // ---------------------------------------------------------------------------
@@ -559,7 +626,7 @@ __global__ void __launch_bounds__(160) pma_sr_band_kernel(const __grid_constant_
   constexpr int WP = 2 * BW + 1;                                   // padded factor row: entry [BW + i] = M-factor[j][j + i]
   double* fac = X + (size_t)S * LD;                                // [S][WP] the factors left by pma_main_kernel, staged
   {                                                                // once and zero-padded to the window length
-    const double* fg = p.band_scratch + (size_t)n * 2 * S * W;
+    const double* fg = p.band_scratch + (size_t)n * S * W;
     for (int e = tid; e < S * WP; e += blockDim.x) {
       const int j = e / WP, d = e - j * WP - BW;                   // d = column offset -BW .. BW
       fac[e] = (d >= -bw && d <= bw) ? fg[(size_t)j * W + bw + d] : 0.0;
@@ -797,7 +864,7 @@ struct MainSmem {      // byte offsets inside one agent's shared-memory block
     need = mr + N * 8;
     pk = need + ((S + 1) & ~1) * 8;
     mbits = pk + N * 2;
-    // from here on: buffers that are dead between replay calls -- the banded solver's row ring aliases them
+    // from here on: buffers that are dead between replay calls
     ukey = (mbits + S + 7) & ~7;
     poff = ukey + np * 8;
     pitems = poff + ((S + 3) & ~1) * 4;
@@ -807,23 +874,24 @@ struct MainSmem {      // byte offsets inside one agent's shared-memory block
     rs = (dst + (kMaxSeq + 2) * 2 + 7) & ~7;
     bytes = (rs + (kMaxSeq + 2) * 8 + 15) & ~15;
   }
-  // doubles available to the banded solver's ring (from `ukey` to the end of the block)
-  __host__ __device__ int ring_doubles() const { return (bytes - ukey) / 8; }
 };
 
-// launch phases of pma_main_kernel
+// launch phases of pma_main_kernel: [end-of-trial replay of the previous trial] [reset] [n_trials x (start-of-trial
+// replay + online steps)].  With replays on, update_sr sits between a trial's steps and its end replay, so a launch
+// runs one trial at most and the per-agent state travels in `carry`.
 struct MainPhase {
   int init_carry;       // first launch of a run: reset the per-agent carry
-  int end_replay;       // replay(last) of the previous trial first (SR / need_scratch are fresh)
+  int end_replay;       // replay(last) of the previous trial first
+  int reset;            // draw the start state of the next trial (else it comes from carry[4])
+  int n_trials;         // trials run by this launch (several only without replays; later ones reset themselves)
   int trial_first;      // index of the first trial run by this launch
-  int n_trials;         // trials run by this launch (0 or 1 when replays are enabled)
+  int scratch_need;     // banded update_sr: both replays read their need vector from need_scratch
 };
 
 // PLAIN = epsilon-greedy agent and memory policies from the tie-pattern tables, training with replay,
 // deterministic world, no optional trace buffers, generated stream: the per-row policy evaluation (fp64
 // divisions, exp) and the per-step checks are compiled out.
-// BAND = banded update_sr inside this kernel (all trials in one launch), see band_lu above.
-template <int A, bool PLAIN, bool BAND>
+template <int A, bool PLAIN>
 __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __grid_constant__ CobelPMAParams p,
                                                                       const __grid_constant__ MainPhase ph) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -899,7 +967,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   }
   __syncwarp();
 
-  int64_t* carry = p.carry + n * 4;           // [0] last state (-1: timed out)  [1] steps  [2] replayed  [3] replay calls
+  int64_t* carry = p.carry + n * 8;           // [0] last state (-1: timed out)  [1] steps  [2] replayed  [3] replay calls  [4] start state
   int64_t c_last = ph.init_carry ? -1 : carry[0];
   int64_t nsteps = ph.init_carry ? 0 : carry[1], nrep = ph.init_carry ? 0 : carry[2], ncalls = ph.init_carry ? 0 : carry[3];
   const int64_t nsteps0 = nsteps, nrep0 = nrep;
@@ -1279,53 +1347,26 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     __syncwarp();
   };
 
-  // Launch phases with a single (inlined) replay site: stage 0 = end-of-trial replay of the previous
-  // trial (agent/pma.py:248-256), stage 1 = reset + start-of-trial replay (206-213) + online steps.
-  // Dense mode: one trial per launch, pma_sr_kernel in between.  BAND: stage 1, stage 0, stage 1, ... in one launch.
+  // Launch phases with a single (inlined) replay site: stage 0 = end-of-trial replay of the previous trial
+  // (agent/pma.py:248-256), stage 1 = [reset] + start-of-trial replay (206-213) + online steps.
   const int bw = p.sr_band;
-  double* bscr = BAND ? p.band_scratch + (size_t)n * 2 * S * (2 * bw + 1) : nullptr;   // [0]: LU factors, [1]: GTH rows
-  double* bgth = BAND ? bscr + S * (2 * bw + 1) : nullptr;
-  double* ring = reinterpret_cast<double*>(ukey);      // the band solver's row ring aliases the replay buffers
-  const double gsr = p.gamma_sr[n];
-  bool have_lu = false;        // bscr holds the factors of I - gamma T for the current T
-  bool sr_given = true;        // no update_sr yet in this call: the start replay reads the caller's SR
+  const double* nscr = p.need_scratch + (size_t)n * S;
   int trial = ph.trial_first, ntr = ph.n_trials;
-  for (int stage = ph.end_replay ? 0 : 1;;) {
-    const double* nsrc = nullptr;
-    bool rep = true;
-    int s = 0;
+  int s = ph.init_carry ? 0 : (int)carry[4];
+  bool reset = ph.reset != 0;
+  for (int stage = (ph.end_replay && do_replay) ? 0 : 1;;) {
     if (stage == 0) {
-      if (BAND) {                                        // M.update_sr() + compute_need(last)
-        if (c_last < 0) {
-          flags |= band_gth(Tg, bgth, ring, S, bw, need, lane);
-        } else {
-          flags |= band_lu(Tg, gsr, bscr, ring, S, bw, lane);
-          have_lu = true;
-          band_solve_row(bscr, ring, S, bw, (int)c_last, need, lane);
-        }
-        sr_given = false;
-      } else {
-        nsrc = c_last >= 0 ? SRg + (size_t)c_last * S : p.need_scratch + (size_t)n * S;   // terminal state / stationary need
-      }
-    } else {
-      if (ntr == 0) break;
+      // need = SR[last] for a trial that ended in a terminal state, else the stationary distribution
+      replay((ph.scratch_need || c_last < 0) ? nscr : SRg + (size_t)c_last * S);
+      stage = 1;
+      continue;
+    }
+    if (reset) {
       win.ensure(2, lane);
       s = __ldg(p.world.starts + draw_integer(win.next(), K));
-      rep = do_replay;                                   // awake replay, need = SR[start]
-      if (rep) {
-        if (BAND && !sr_given) {
-          if (!have_lu) {
-            flags |= band_lu(Tg, gsr, bscr, ring, S, bw, lane);
-            have_lu = true;
-          }
-          band_solve_row(bscr, ring, S, bw, s, need, lane);
-        } else {
-          nsrc = SRg + (size_t)s * S;
-        }
-      }
     }
-    if (rep) replay(nsrc);
-    if (stage == 0) { stage = 1; continue; }
+    if (ntr == 0) break;
+    if (do_replay) replay(ph.scratch_need ? nscr : SRg + (size_t)s * S);     // awake replay, need = SR[start]
     double treward = 0.0;
     int step = 0, last = -1;
     for (;; ++step) {
@@ -1343,7 +1384,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       const double r = __ldg(p.world.reward + s2);
       const int end = __ldg(p.world.terminal + s2);
       const int nt = 1 - end;
-      if (BAND && abs(s2 - s) > bw) flags |= COBEL_FLAG_BAND_VIOLATION;
+      if (bw >= 0 && abs(s2 - s) > bw) flags |= COBEL_FLAG_BAND_VIOLATION;
       if (!PLAIN && tr.step_sa && lane == 0) {
         if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
@@ -1385,12 +1426,10 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     }
     c_last = last;
     ++trial; --ntr;
-    have_lu = false;                                     // T changed
-    if (BAND && do_replay) stage = 0;
+    reset = true;                                        // further trials of this launch (no replays) reset themselves
+    if (ntr == 0) break;
   }
 
-  // banded call: leave the factors of the final I - gamma T for pma_sr_band_kernel (SR is refreshed once per call)
-  if (BAND && do_replay && !sr_given && !have_lu) flags |= band_lu(Tg, gsr, bscr, ring, S, bw, lane);
   __syncwarp();
   if (learn) {
 #pragma unroll 1
@@ -1404,7 +1443,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   flags = __reduce_or_sync(kFull, flags);
   if (lane == 0) {
     p.stream.draw_count[n] = (int64_t)win.position();
-    carry[0] = c_last; carry[1] = nsteps; carry[2] = nrep; carry[3] = ncalls;
+    carry[0] = c_last; carry[1] = nsteps; carry[2] = nrep; carry[3] = ncalls; carry[4] = s;
     tr.n_steps[n] += nsteps - nsteps0;
     tr.n_replay[n] += nrep - nrep0;
     if (tr.flags && flags) tr.flags[n] |= flags;
@@ -1427,9 +1466,7 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
                      !p.no_replay && !p.options && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx &&
                      !p.trace.replay_len && !p.stream.user_stream;
   const bool do_replay = p.learn && !p.no_replay;
-  // the banded path needs its row ring to fit into the replay buffers it aliases; otherwise dense update_sr
-  const bool band = do_replay && p.sr_band >= 0 &&
-                    band_ring_rows(p.sr_band) * (2 * p.sr_band + 1) <= so.ring_doubles();
+  const bool band = do_replay && p.sr_band >= 0;
   const int tile = S <= 7 * 16 ? 7 : 10;
   const size_t sm_sr = (size_t)(4 * (tile * 16 + 2) + ((S + 1) & ~1) + S * S) * 8;
   if (tile == 7) COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
@@ -1449,9 +1486,9 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
       return COBEL_OK;
     };
     if constexpr (A <= 4) {
-      if (plain) return band ? go(pma_main_kernel<A, true, true>) : go(pma_main_kernel<A, true, false>);
+      if (plain) return go(pma_main_kernel<A, true>);
     }
-    return band ? go(pma_main_kernel<A, false, true>) : go(pma_main_kernel<A, false, false>);
+    return go(pma_main_kernel<A, false>);
   };
   auto sr_launch = [&](int final_only) {
     if (tile == 7) pma_sr_kernel<7><<<(unsigned)p.n_agents, kThreads, sm_sr, st>>>(p, final_only);
@@ -1459,13 +1496,34 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
     cobel_count_launch();
   };
   int rc = COBEL_OK;
+  // MainPhase{init_carry, end_replay, reset, n_trials, trial_first, scratch_need}
   if (!do_replay) {
-    rc = main_launch(MainPhase{1, 0, 0, p.trials});            // no replay: all trials in one launch
+    rc = main_launch(MainPhase{1, 0, 1, p.trials, 0, 0});      // no replay: all trials in one launch
   } else if (band) {
-    // banded update_sr inside the main kernel: all trials in one launch, then SR = inv(I - gamma T) once
+    // banded update_sr, its own kernels (one warp per agent, full occupancy) between the launches of the main kernel:
+    //   main(reset, start replay from the caller's SR, steps of trial 0)
+    //   trial t: factor(update_sr; need of the end replay) -> main(end replay t, reset t+1)
+    //            -> solve(need = SR[start]) -> main(start replay, steps of trial t+1)
+    // and SR = inv(I - gamma T) once, densely, from the last factors
+    const unsigned grid_band = (unsigned)((p.n_agents + kBandWarps - 1) / kBandWarps);
+    const BandSmem bso(S, p.sr_band);
+    const size_t sm_bandk = (size_t)kBandWarps * bso.bytes;
+    COBEL_CUDA_OK(cudaFuncSetAttribute(pma_band_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_bandk));
+    COBEL_CUDA_OK(cudaFuncSetAttribute(pma_band_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_bandk));
     pma_band_check_kernel<<<(unsigned)p.n_agents, 256, 0, st>>>(p);
     cobel_count_launch();
-    rc = main_launch(MainPhase{1, 0, 0, p.trials});
+    rc = main_launch(MainPhase{1, 0, 1, 1, 0, 0});
+    for (int t = 0; t < p.trials && !rc; ++t) {
+      const int more = t + 1 < p.trials ? 1 : 0;
+      pma_band_factor_kernel<<<grid_band, kBandWarps * 32, sm_bandk, st>>>(p);
+      pma_band_solve_kernel<<<grid_band, kBandWarps * 32, sm_bandk, st>>>(p, 0);
+      cobel_count_launch(2);
+      rc = main_launch(MainPhase{0, 1, more, 0, t + 1, 1});
+      if (rc || !more) break;
+      pma_band_solve_kernel<<<grid_band, kBandWarps * 32, sm_bandk, st>>>(p, 4);
+      cobel_count_launch();
+      rc = main_launch(MainPhase{0, 0, 0, 1, t + 1, 1});
+    }
     if (rc) return rc;
     const int LD = S | 1;
     const int bwp = p.sr_band <= 4 ? 4 : p.sr_band <= 8 ? 8 : p.sr_band <= 12 ? 12 : p.sr_band <= 16 ? 16 : p.sr_band <= 24 ? 24 : 32;
@@ -1486,13 +1544,57 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
     }
   } else {
     // trial t: main(reset, start replay, steps) -> sr(update_sr [+ stationary]) -> main(end replay, then trial t+1)
-    rc = main_launch(MainPhase{1, 0, 0, 1});
+    rc = main_launch(MainPhase{1, 0, 1, 1, 0, 0});
     for (int t = 0; t < p.trials && !rc; ++t) {
       sr_launch(0);
-      rc = main_launch(MainPhase{0, 1, t + 1, t + 1 < p.trials ? 1 : 0});
+      const int more = t + 1 < p.trials ? 1 : 0;
+      rc = main_launch(MainPhase{0, 1, more, more, t + 1, 0});
     }
   }
   if (rc) return rc;
+  COBEL_CUDA_OK(cudaGetLastError());
+  return COBEL_OK;
+}
+
+// carry <- {state, 0, 0, 0, 0, ...}: the per-agent state a stand-alone replay starts from
+__global__ void pma_set_carry_kernel(int64_t* carry, const int32_t* state, int64_t n_agents) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_agents) return;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) carry[n * 8 + k] = 0;
+  carry[n * 8 + 0] = state[n];
+}
+
+// PMAMemory.replay(Q, action_mask, batch, current_state) as a stand-alone call: the end-of-trial phase of the main kernel
+template <int A>
+int replay_only(const CobelPMAParams& p, const int32_t* state, int update_sr, cudaStream_t st) {
+  const int S = p.world.n_states;
+  COBEL_REQUIRE(S <= 160 && S * A <= 1024, COBEL_EUNSUPPORTED,
+                "PMA kernels support at most 160 states (register-tiled S x S eliminations), got %d", S);
+  const MainSmem so(S, A);
+  const size_t sm_main = (size_t)kMainWarps * so.bytes;
+  COBEL_REQUIRE(sm_main <= 227 * 1024, COBEL_EUNSUPPORTED, "PMA: %d states x %d actions do not fit in shared memory", S, A);
+  if constexpr (A <= 4) {
+    if (p.n_tab > 0) {
+      pma_policy_table_kernel<A><<<(unsigned)p.n_tab + 1, 256, 0, st>>>(p.tab_kind, p.tab_param, p.tab_scratch);
+      cobel_count_launch();
+    }
+  }
+  pma_set_carry_kernel<<<(unsigned)((p.n_agents + 127) / 128), 128, 0, st>>>(p.carry, state, p.n_agents);
+  // M.update_sr() and / or the stationary need of the agents whose current state is None
+  const int tile = S <= 7 * 16 ? 7 : 10;
+  const size_t sm_sr = (size_t)(4 * (tile * 16 + 2) + ((S + 1) & ~1) + S * S) * 8;
+  if (tile == 7) {
+    COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
+    pma_sr_kernel<7><<<(unsigned)p.n_agents, kThreads, sm_sr, st>>>(p, update_sr ? 0 : 2);
+  } else {
+    COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
+    pma_sr_kernel<10><<<(unsigned)p.n_agents, kThreads, sm_sr, st>>>(p, update_sr ? 0 : 2);
+  }
+  auto kernel = pma_main_kernel<A, false>;
+  COBEL_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_main));
+  kernel<<<(unsigned)((p.n_agents + kMainWarps - 1) / kMainWarps), kMainWarps * 32, sm_main, st>>>(p, MainPhase{0, 1, 0, 0, 0, 0});
+  cobel_count_launch(3);
   COBEL_CUDA_OK(cudaGetLastError());
   return COBEL_OK;
 }
@@ -1522,6 +1624,30 @@ extern "C" int cobel_pma_run(const CobelPMAParams* pp, void* stream) {
     case 4: return run<4>(p, st);
     case 6: return run<6>(p, st);
     case 8: return run<8>(p, st);
+    default:
+      cobel_set_error("unsupported number of actions %d (built for 2,3,4,6,8)", p.world.n_actions);
+      return COBEL_EUNSUPPORTED;
+  }
+}
+
+extern "C" int cobel_pma_replay(const CobelPMAParams* pp, const int32_t* state, int update_sr, void* stream) {
+  COBEL_REQUIRE(pp != nullptr && state != nullptr, COBEL_EINVAL, "null params");
+  const CobelPMAParams& p = *pp;
+  COBEL_REQUIRE(p.n_agents > 0 && p.stream.draw_count && p.trace.n_steps && p.trace.n_replay, COBEL_EINVAL, "stream / trace missing");
+  COBEL_REQUIRE(p.Q && p.Mr && p.Ms && p.Mt && p.T && p.SR && p.update_mask && p.lr && p.gamma && p.mem_lr && p.lr_q &&
+                p.gamma_q && p.gamma_sr && p.pow_gamma_sr && p.pow_gamma_q && p.mem_policy.param && p.policy.param && p.carry &&
+                p.need_scratch, COBEL_EINVAL, "agent tables missing");
+  COBEL_REQUIRE(p.mem_policy.kind >= 0 && p.mem_policy.kind <= 2, COBEL_EINVAL, "bad memory policy");
+  COBEL_REQUIRE(p.batch >= 0 && p.batch <= kMaxSeq, COBEL_EUNSUPPORTED, "PMA replay batch must be in 0..%d", kMaxSeq);
+  COBEL_REQUIRE(p.learn && !p.no_replay, COBEL_EINVAL, "cobel_pma_replay needs learn = 1 and no_replay = 0");
+  COBEL_REQUIRE(p.n_tab == 0 || (p.tab_kind && p.tab_param && p.tab_scratch), COBEL_EINVAL, "policy tables incomplete");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (p.world.n_actions) {
+    case 2: return replay_only<2>(p, state, update_sr, st);
+    case 3: return replay_only<3>(p, state, update_sr, st);
+    case 4: return replay_only<4>(p, state, update_sr, st);
+    case 6: return replay_only<6>(p, state, update_sr, st);
+    case 8: return replay_only<8>(p, state, update_sr, st);
     default:
       cobel_set_error("unsupported number of actions %d (built for 2,3,4,6,8)", p.world.n_actions);
       return COBEL_EUNSUPPORTED;

@@ -17,6 +17,7 @@
 // and only decide the sampled index, so a draw that falls within 1e-12 of a bin edge raises
 // COBEL_FLAG_CDF_NEAR_TIE instead of silently risking a different index.
 #include "warp_agent.cuh"
+#include "thread_agent.cuh"
 
 namespace {
 
@@ -140,6 +141,442 @@ COBEL_DEV int block_sample(const double* w, int N, double u, double* part, Block
   if (sh->flag) flags |= COBEL_FLAG_CDF_NEAR_TIE;
   __syncthreads();
   return idx;
+}
+
+// ---------------------------------------------------------------------------
+// Split path (the common configuration: no per-step decay of C or T, no strength modulation that touches every
+// experience).  A trial is two launches:
+//   sfma_step_kernel    ONE THREAD PER AGENT: reset + the online steps.  A step reads one Q row, draws an action,
+//                       looks the successor up and updates one entry each of Q, M.rewards, M.states, M.terminals and
+//                       C -- a dozen scattered 8-byte accesses to the agent's tables in HBM and ~150 scalar
+//                       instructions.  In the fused kernel warp 0 of the agent's CTA does this while 7 warps wait at
+//                       a barrier (61 % of the kernel's time at 3 CTAs per SM, profiles/r1_sfma_v2.txt); here a warp
+//                       advances 32 agents at once and every agent of the batch is in flight.
+//   sfma_replay_kernel  ONE CTA PER AGENT: SFMAMemory.replay + the replayed Q updates.  Only what a replay reads is
+//                       staged: the compact list of experienced (s, a) with their strengths and next states, the
+//                       inhibition vector and the priority scratch (41 KB at 20x20 instead of 67 KB: 5 CTAs per SM);
+//                       Q stays in HBM and receives the <= batch updates at the end.
+// The per-agent state between the launches (current / last state, counters) travels in CobelSFMAParams.carry.
+// ---------------------------------------------------------------------------
+struct SfmaPhase {
+  int init;           // step kernel: first launch of a call (the carry's counters restart)
+  int reset;          // step kernel: draw the start state of the first trial of this launch
+  int n_trials;       // step kernel: trials run by this launch (0: reset only; several only without any replay)
+  int trial;          // index of the (first) trial (trace rows)
+  int start_replay;   // replay kernel: the trace-only replay at trial start (cur = start state, no Q updates)
+};
+
+template <int A>
+__global__ void __launch_bounds__(64) sfma_step_kernel(const __grid_constant__ CobelSFMAParams p, const __grid_constant__ SfmaPhase ph) {
+  const int64_t n = (int64_t)blockIdx.x * 64 + threadIdx.x;
+  if (n >= p.n_agents) return;
+  const int S = p.world.n_states, K = p.world.n_starts, N = S * A;
+  const size_t g0 = (size_t)n * N;
+  double* Q = p.Q + g0;
+  double* Mr = p.Mr + g0;
+  int32_t* Ms = p.Ms + g0;
+  int32_t* Mt = p.Mt + g0;
+  double* C = p.C + g0;
+  const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
+  int64_t* carry = p.carry + n * 4;        // [0] current state / last state (-1: timed out)  [1] steps  [2] replayed  [3] replay calls
+  const CobelTrace& tr = p.trace;
+  Rng rng; rng.init(p.stream, n);
+  const bool learn = p.learn != 0;
+  const int kind = p.policy.kind;
+  const double par = p.policy.param[n];
+  const double lr = p.lr[n], gamma = p.gamma[n], mlr = p.mem_lr[n];
+  const int mf = p.mod_flags;
+  int flags = 0;
+  if (ph.init) { carry[0] = 0; carry[1] = 0; carry[2] = 0; carry[3] = 0; }
+  int s = (int)carry[0];
+  for (int t = 0; t < ph.n_trials || t == 0; ++t) {
+    if (ph.reset || t > 0) s = __ldg(p.world.starts + draw_integer(rng.next(), K));
+    if (t >= ph.n_trials) break;
+    int64_t nsteps = carry[1];
+    double tdacc = p.td_acc ? p.td_acc[n] : 0.0;
+    double treward = 0.0;
+    int step = 0, last = -1;
+    for (;; ++step) {
+      double row[A];
+      load_row_t<A>(Q + (size_t)s * A, row);
+      const int a = select_action_thread<A>(row, mask_bits<A>(amask, s), kind, par, rng.next());
+      const int s2 = p.world.tp_off ? stochastic_successor_t(p.world, s * A + a, rng.next()) : __ldg(p.world.succ + s * A + a);
+      const double r = __ldg(p.world.reward + s2);
+      const int end = __ldg(p.world.terminal + s2);
+      const int nt = 1 - end;
+      if (tr.step_sa) {
+        if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
+        else flags |= COBEL_FLAG_TRACE_OVERFLOW;
+      }
+      ++nsteps;
+      if (learn) {
+        // SFMAMemory.store (memory/sfma.py:206-215; decay_strength == 1 and M.T is not tracked on this path), then
+        // SFMA.update_q (agent/sfma.py:423-458): max over the unmasked actions of s'
+        const double m0 = Mr[s * A + a];
+        Mr[s * A + a] = xadd(m0, xmul(mlr, xsub(r, m0)));
+        Ms[s * A + a] = s2;
+        Mt[s * A + a] = nt;
+        double c = xadd(C[a * S + s], p.c_step);
+        if (mf & COBEL_SFMA_MOD_REWARD_LOCAL) c = xadd(c, xmul(r, p.reward_modulation));   // memory/sfma.py:216-218
+        C[a * S + s] = c;
+        if (mf & COBEL_SFMA_MOD_STATE) {                                                    // memory/sfma.py:233-236
+#pragma unroll
+          for (int x = 0; x < A; ++x) C[x * S + s] = xadd(C[x * S + s], 1.0);
+        }
+        const double td = td_update_thread<A>(Q, s, a, r, s2, nt, lr, gamma, mask_bits<A>(amask, s2));
+        tdacc = xadd(tdacc, fabs(td));
+      }
+      s = s2;
+      treward = xadd(treward, r);
+      if (end) last = s2;
+      if (end || step + 1 == p.steps) break;
+    }
+    tr.trial_steps[n * p.trials + ph.trial + t] = step;
+    tr.trial_reward[n * p.trials + ph.trial + t] = treward;
+    tr.n_steps[n] += nsteps - carry[1];
+    carry[1] = nsteps;
+    if (p.td_acc) p.td_acc[n] = tdacc;
+    s = last;
+  }
+  carry[0] = s;
+  p.stream.draw_count[n] = (int64_t)rng.k;
+  if (flags && tr.flags) tr.flags[n] |= flags;
+}
+
+struct ReplaySmem {
+  int l, cc, msc, r, inh, part, rep, mbits, cdf, bytes;
+  __host__ __device__ ReplaySmem(int S, int A, int T, int B, bool random_replay) {
+    const int N = S * A;
+    r = 0;                                   // priority scratch [nnz] (aliased by the dependency masks of the TD batch)
+    cc = r + N * 8;                          // strengths of the listed experiences
+    inh = cc + N * 8;                        // I [S]
+    part = inh + S * 8;                      // scan partials
+    cdf = part + (T + 32) * 8;               // random replay: m-fold sums of fl(1 / n_valid)
+    l = cdf + (random_replay ? N * 8 : 0);   // experienced experiences: action << 16 | state, ascending flat index
+    rep = l + N * 4;                         // reactivated flat indices of one replay
+    msc = rep + ((B + 1) & ~1) * 4;          // next state of the listed experiences
+    mbits = msc + N * 2;                     // valid-action bits per state
+    bytes = (mbits + S + 15) & ~15;
+  }
+};
+
+template <int A>
+__global__ void __launch_bounds__(256) sfma_replay_kernel(const __grid_constant__ CobelSFMAParams p, const __grid_constant__ SfmaPhase ph) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ BlockShared sh;
+  const int S = p.world.n_states, N = S * A, B = p.batch;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n = blockIdx.x;
+  const ReplaySmem so(S, A, T, B, p.random_replay != 0);
+  double* R = reinterpret_cast<double*>(smem + so.r);
+  double* Cc = reinterpret_cast<double*>(smem + so.cc);
+  double* I = reinterpret_cast<double*>(smem + so.inh);
+  double* part = reinterpret_cast<double*>(smem + so.part);
+  double* cdft = reinterpret_cast<double*>(smem + so.cdf);
+  uint32_t* L = reinterpret_cast<uint32_t*>(smem + so.l);
+  int32_t* rep = reinterpret_cast<int32_t*>(smem + so.rep);
+  uint16_t* Msc = reinterpret_cast<uint16_t*>(smem + so.msc);
+  uint8_t* mbits = smem + so.mbits;
+  uint32_t* wm = reinterpret_cast<uint32_t*>(R);
+  uint32_t* rm = wm + S;
+
+  const size_t g0 = (size_t)n * N;
+  double* Q = p.Q + g0;
+  const double* Mr = p.Mr + g0;
+  const int32_t* Ms = p.Ms + g0;
+  const int32_t* Mt = p.Mt + g0;
+  const double* Cg = p.C + g0;
+  const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
+  int64_t* carry = p.carry + n * 4;
+  const CobelTrace& tr = p.trace;
+  const bool masked = amask != nullptr;
+  const bool apply_updates = ph.start_replay == 0;
+  // agent.random batches (retrieve_random_batch); start_replay == 2: the stand-alone memory call, without Q updates
+  const bool random_path = p.random_replay && (apply_updates || ph.start_replay == 2);
+  const double lr = apply_updates ? p.lr[n] : 0.0, gamma = apply_updates ? p.gamma[n] : 0.0;
+  const double beta = p.beta, thr = p.threshold, dinh = p.decay_inhibition;
+  const double* D = p.D;
+  const int mf = p.mod_flags;
+  double cmax = 1.0, dmax = 1.0;
+  int mode = p.mode;
+  int64_t nrep = carry[2], ncalls = carry[3];
+  const int64_t nrep0 = nrep;
+  const int last = (int)carry[0];
+  int flags = 0;
+  DrawWindow win; win.init(p.stream, n, (uint64_t)p.stream.draw_count[n]);      // used by warp 0 only
+  double tdacc = p.td_acc ? p.td_acc[n] : 0.0;                                   // agent.td (maintained by warp 0)
+
+#pragma unroll 1
+  for (int e = tid; e < S; e += T) mbits[e] = (uint8_t)mask_bits<A>(amask, e);
+  __syncthreads();
+
+  auto acc_td = [&](double tdl, bool active) {
+    if (!p.td_acc) return;
+    const unsigned act = __ballot_sync(kFull, active);
+#pragma unroll 1
+    for (int l = 0; l < 32 && (act >> l & 1u); ++l) tdacc = xadd(tdacc, fabs(shfl_f64(tdl, l)));
+  };
+  // the replayed TD updates, in order, on the Q table in HBM (agent/sfma.py:416-419); warp 0
+  auto apply_batch = [&](int count) {
+#pragma unroll 1
+    for (int e = tid; e < 2 * S; e += T) wm[e] = 0;                        // wm, rm alias R
+    __syncthreads();
+    if (warp == 0 && apply_updates) {
+#pragma unroll 1
+      for (int b0 = 0; b0 < count; b0 += 32) {
+        const bool active = b0 + lane < count;
+        int es = 0, ea = 0, es2 = 0, ent = 0;
+        double er = 0.0;
+        if (active) {
+          const int e = rep[b0 + lane];
+          ea = e / S; es = e - ea * S;
+          er = Mr[es * A + ea];
+          es2 = Ms[es * A + ea]; ent = Mt[es * A + ea] ? 1 : 0;
+        }
+        double tdl = 0.0;
+        td_batch_level_parallel<A>(Q, wm, rm, S, lane, active, es, ea, er, es2, ent, lr, gamma,
+                                   masked ? mbits : nullptr, &tdl);
+        acc_td(tdl, active);
+      }
+    }
+  };
+  auto log_replay = [&](int count) {
+    if (tr.replay_idx)
+#pragma unroll 1
+      for (int j = tid; j < count; j += T) {
+        if (nrep + j < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + j] = rep[j];
+        else flags |= COBEL_FLAG_TRACE_OVERFLOW;
+      }
+    if (tr.replay_len && tid == 0) {
+      if (ncalls < tr.replay_calls_cap) tr.replay_len[n * tr.replay_calls_cap + ncalls] = count;
+      else flags |= COBEL_FLAG_TRACE_OVERFLOW;
+    }
+    nrep += count;
+    ++ncalls;
+  };
+
+  if (!ph.start_replay && p.dynamic) {
+    // agent/sfma.py:311-318: p('reverse') = 1 / (1 + exp(-(5 td - 2))), one categorical draw over
+    // [p, 1 - p] (cdf normalised by its last entry), the accumulator restarts
+    if (warp == 0) {
+      win.ensure(1, lane);
+      const double u = win.next();
+      const double pm = xdiv(1.0, xadd(1.0, exp(-xsub(xmul(tdacc, 5.0), 2.0))));
+      const double c0 = xdiv(pm, xadd(pm, xsub(1.0, pm)));
+      if (fabs(c0 - u) < 1e-12) flags |= COBEL_FLAG_CDF_NEAR_TIE;      // exp() is not NumPy's bit for bit
+      tdacc = 0.0;
+      if (lane == 0) sh.idx = c0 > u ? MODE_REVERSE : MODE_DEFAULT;
+    }
+    __syncthreads();
+    mode = sh.idx;
+    if (p.trial_mode && tid == 0) p.trial_mode[n * p.trials + ph.trial] = mode;
+    __syncthreads();
+  }
+
+  // similarity of experience (a, s') with modelled next state ms to the current experience, by replay mode
+  // (memory/sfma.py:283-306)
+  auto dvec = [&](int sp, int ms, int cur, int nxt) -> double {
+    const double* Dc = D + (size_t)cur * S;
+    const double* Dn = D + (size_t)nxt * S;
+    auto dc = [&](int x) -> double { return (mf & COBEL_SFMA_D_NORMALIZE) ? xdiv(Dc[x], dmax) : Dc[x]; };
+    switch (mode) {
+      case MODE_FORWARD: return Dn[sp];
+      case MODE_REVERSE: return dc(ms);
+      case MODE_BLEND_FORWARD: return xadd(dc(sp), xmul(p.blend, Dn[sp]));
+      case MODE_BLEND_REVERSE: return xadd(dc(sp), xmul(p.blend, dc(ms)));
+      case MODE_INTERPOLATE: return xadd(xmul(p.interp_fwd, Dn[sp]), xmul(p.interp_rev, dc(ms)));
+      case MODE_SWEEPING: return Dn[ms];
+      default: return dc(sp);
+    }
+  };
+
+  const int n_replays = ph.start_replay ? 1 : p.nb_replays;
+  for (int rpl = 0; rpl < n_replays; ++rpl) {
+    if (random_path) {
+      // agent.random: uniform batches over the unmasked experiences (retrieve_random_batch, memory/sfma.py:375-416):
+      // probs = mask / sum(mask); NumPy's choice() searches u in the m-fold sequential sums of fl(1 / n_valid)
+      if (tid == 0) {
+        int m = 0;
+        for (int a = 0; a < A; ++a)
+          for (int sp = 0; sp < S; ++sp)
+            if (mbits[sp] >> a & 1) ++m;
+        const double pv = xdiv(1.0, int_to_f64(m));
+        double c = 0.0;
+        for (int j = 0; j < m; ++j) { c = xadd(c, pv); cdft[j] = c; }
+        sh.idx = m;
+      }
+      __syncthreads();
+      const int nvalid = sh.idx;
+      __syncthreads();
+      if (warp == 0) {
+        const double tot = cdft[nvalid - 1];
+#pragma unroll 1
+        for (int b0 = 0; b0 < B; b0 += 32) {
+          const int nb = B - b0 < 32 ? B - b0 : 32;
+          win.ensure(nb, lane);
+          const double u = win.peek(lane < nb ? lane : 0);
+          win.advance(nb);
+          if (lane < nb) {
+            int lo = 0, hi = nvalid - 1;                       // invariant: answer in [lo, hi]
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (xdiv(cdft[mid], tot) > u) hi = mid; else lo = mid + 1;
+            }
+            int m = lo, e = -1;                                // m-th valid experience in F order
+            for (int a = 0; a < A && e < 0; ++a)
+              for (int sp = 0; sp < S; ++sp)
+                if ((mbits[sp] >> a & 1) && m-- == 0) { e = a * S + sp; break; }
+            rep[b0 + lane] = e;
+          }
+        }
+      }
+      __syncthreads();
+      log_replay(B);
+      apply_batch(B);
+      __syncthreads();
+      continue;
+    }
+    if (warp == 0) {
+      win.ensure(2, lane);
+      const int act0 = draw_integer(win.next(), A);                        // sfma.py:264 (always drawn)
+      double u = 0.0;
+      if (last < 0) u = win.next();                                        // sfma.py:272
+      if (lane == 0) { sh.action = act0; sh.u = u; }
+    }
+    __syncthreads();
+    int cur = last, action = sh.action;
+    // Experiences that were never stored have strength 0, hence priority 0 and weight exp(0) - 1 = 0:
+    // they can never be drawn and add exact zeros to every sum.  All passes below run over the compact,
+    // index-ordered list L of experiences with C > 0 (C is constant during a replay).
+    int nnz;
+    {
+      const int chunk = (N + T - 1) / T;
+      const int lo = tid * chunk < N ? tid * chunk : N, hi = lo + chunk < N ? lo + chunk : N;
+      int cnt = 0;
+#pragma unroll 1
+      for (int i = lo; i < hi; ++i) cnt += Cg[i] > 0.0 ? 1 : 0;
+      int off = block_exclusive_scan_int(cnt, part, tid, T, nnz);
+#pragma unroll 1
+      for (int i = lo; i < hi; ++i) {
+        const double c = Cg[i];
+        if (c > 0.0) {
+          const int a = i / S, sp = i - a * S;
+          L[off] = ((uint32_t)a << 16) | (uint32_t)sp;
+          Cc[off] = c;
+          Msc[off] = (uint16_t)Ms[sp * A + a];
+          ++off;
+        }
+      }
+    }
+    __syncthreads();
+    if (mf & COBEL_SFMA_C_NORMALIZE) {                                     // np.amax(C): C is constant during a replay
+      double lm = -__longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll 1
+      for (int e = tid; e < N; e += T) lm = Cg[e] > lm ? Cg[e] : lm;
+      for (int d = 16; d > 0; d >>= 1) { const double o = shfl_f64_xor(lm, d); lm = o > lm ? o : lm; }
+      if (lane == 0) part[warp] = lm;
+      __syncthreads();
+      cmax = part[0];
+      for (int w = 1; w < (T >> 5); ++w) cmax = part[w] > cmax ? part[w] : cmax;
+      __syncthreads();
+    }
+    if (cur < 0) {                                                         // start ~ clip(C, 0) / sum
+#pragma unroll 1
+      for (int j = tid; j < nnz; j += T) R[j] = Cc[j];
+      __syncthreads();
+      const uint32_t l = L[block_sample(R, nnz, sh.u, part, &sh, tid, T, flags)];
+      cur = l & 0xFFFF; action = l >> 16;
+    }
+    int nxt = Ms[cur * A + action];
+#pragma unroll 1
+    for (int e = tid; e < S; e += T) I[e] = 0.0;                           // sfma.py:277
+    __syncthreads();
+    int count = 0;
+    for (int it = 0; it < B; ++it) {
+      if (mf & COBEL_SFMA_D_NORMALIZE) {                                   // np.amax(D[current_state])
+        const double* Dc = D + (size_t)cur * S;
+        double lm = -__longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll 1
+        for (int e = tid; e < S; e += T) lm = Dc[e] > lm ? Dc[e] : lm;
+        for (int d = 16; d > 0; d >>= 1) { const double o = shfl_f64_xor(lm, d); lm = o > lm ? o : lm; }
+        if (lane == 0) part[warp] = lm;
+        __syncthreads();
+        dmax = part[0];
+        for (int w = 1; w < (T >> 5); ++w) dmax = part[w] > dmax ? part[w] : dmax;
+        __syncthreads();
+      }
+      double lmax = 0.0;
+#pragma unroll 1
+      for (int j = tid; j < nnz; j += T) {
+        const uint32_t l = L[j];
+        const int sp = l & 0xFFFF;
+        const double cn = (mf & COBEL_SFMA_C_NORMALIZE) ? xdiv(Cc[j], cmax) : Cc[j];
+        double r = xmul(xmul(cn, dvec(sp, Msc[j], cur, nxt)), xsub(1.0, I[sp]));    // C * D * (1 - I)
+        if (r < thr) r = 0.0;
+        R[j] = r;
+        lmax = r > lmax ? r : lmax;
+      }
+      // block max (R >= 0): all-zero <=> np.sum(R) == 0 (sfma.py:316)
+      for (int d = 16; d > 0; d >>= 1) { const double o = shfl_f64_xor(lmax, d); lmax = o > lmax ? o : lmax; }
+      if (lane == 0) part[warp] = lmax;
+      __syncthreads();
+      double m = part[0];
+      for (int w = 1; w < (T >> 5); ++w) m = part[w] > m ? part[w] : m;
+      __syncthreads();
+      if (!(m > 0.0)) break;
+      int jsel;
+      if (p.deterministic) {                                               // argmax(R): first maximum
+        if (tid == 0) sh.idx = 0x7fffffff;
+        __syncthreads();
+#pragma unroll 1
+        for (int j = tid; j < nnz; j += T) if (R[j] == m) { atomicMin(&sh.idx, j); break; }
+        __syncthreads();
+        jsel = sh.idx;
+        __syncthreads();
+      } else {
+        // probs ~ exp(beta * R / max) - 1  (softmax(R, -1, beta), sfma.py:349-373); exp(0) - 1 == 0 exactly
+#pragma unroll 1
+        for (int j = tid; j < nnz; j += T) { const double r = R[j]; R[j] = r > 0.0 ? xadd(exp(xmul((mf & COBEL_SFMA_R_RAW) ? r : xdiv(r, m), beta)), -1.0) : 0.0; }
+        if (warp == 0) {
+          win.ensure(1, lane);
+          const double u = win.next();
+          if (lane == 0) sh.u = u;
+        }
+        __syncthreads();
+        jsel = block_sample(R, nnz, sh.u, part, &sh, tid, T, flags);
+      }
+      const uint32_t l = L[jsel];
+      action = l >> 16;
+      cur = l & 0xFFFF;
+      nxt = Msc[jsel];
+#pragma unroll 1
+      for (int s = tid; s < S; s += T) {                                   // sfma.py:333-335
+        double v = xmul(I[s], dinh);
+        if (s == cur) { v = xadd(v, p.i_step); v = v < 1.0 ? v : 1.0; }
+        I[s] = v;
+      }
+      if (tid == 0) rep[count] = action * S + cur;
+      ++count;
+      __syncthreads();
+    }
+    log_replay(count);
+    apply_batch(count);
+    __syncthreads();
+  }
+
+  // M.I survives the replay (the next one resets it); M.T is zeroed after a trial with replay by the host side
+  if (!random_path) {
+#pragma unroll 1
+    for (int e = tid; e < S; e += T) p.I[(size_t)n * S + e] = I[e];
+  }
+  flags = __syncthreads_or(flags);
+  if (tid == 0) {
+    p.stream.draw_count[n] = (int64_t)win.position();
+    tr.n_replay[n] += nrep - nrep0;
+    carry[2] = nrep; carry[3] = ncalls;
+    if (tr.flags && flags) tr.flags[n] |= flags;
+    if (p.td_acc) p.td_acc[n] = tdacc;
+  }
 }
 
 // MODS = the memory's strength-modulation / normalisation switches (mod_flags) may be set; the common case
@@ -627,6 +1064,38 @@ int launch(const CobelSFMAParams& p, cudaStream_t st) {
   const int S = p.world.n_states, N = S * A;
   COBEL_REQUIRE(S <= 0x7FFF, COBEL_EUNSUPPORTED, "SFMA kernel supports at most 32767 states");
   const int T = N <= 128 ? 64 : N <= 512 ? 128 : 256;
+  // Split path: per-step work that touches single table entries only (no decay of C, M.T neither read nor kept,
+  // no strength modulation over all experiences), and the caller provided the carry scratch
+  const bool track_t = p.recency != 0 || (p.learn && p.no_replay);
+  const bool split = p.carry != nullptr && p.decay_strength == 1.0 && !track_t && !(p.mod_flags & COBEL_SFMA_MOD_REWARD);
+  if (split) {
+    const ReplaySmem rso(S, A, T, p.batch, p.random_replay != 0);
+    COBEL_REQUIRE(rso.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
+                  "SFMA replay of %d states x %d actions needs %d bytes of shared memory", S, A, rso.bytes);
+    COBEL_CUDA_OK(cudaFuncSetAttribute(sfma_replay_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, rso.bytes));
+    const unsigned grid_step = (unsigned)((p.n_agents + 63) / 64);
+    auto step = [&](SfmaPhase ph) { sfma_step_kernel<A><<<grid_step, 64, 0, st>>>(p, ph); cobel_count_launch(); };
+    auto replay = [&](SfmaPhase ph) { sfma_replay_kernel<A><<<(unsigned)p.n_agents, T, rso.bytes, st>>>(p, ph); cobel_count_launch(); };
+    // SfmaPhase{init, reset, n_trials, trial, start_replay}
+    if (!p.learn) {
+      step(SfmaPhase{1, 1, p.trials, 0, 0});                       // test(): all trials in one launch
+    } else {
+      for (int t = 0; t < p.trials; ++t) {
+        if (p.start_replay) {                                      // agent/sfma.py:272-275: trace only, no Q updates
+          step(SfmaPhase{t == 0, 1, 0, t, 0});
+          replay(SfmaPhase{0, 0, 0, t, 1});
+          step(SfmaPhase{0, 0, 1, t, 0});
+        } else {
+          step(SfmaPhase{t == 0, 1, 1, t, 0});
+        }
+        replay(SfmaPhase{0, 0, 0, t, 0});                          // agent/sfma.py:300-324 (no_replay keeps M.T: fused path)
+      }
+      // M.T.fill(0) after every trial with replay (agent/sfma.py:324); M.T is not tracked on this path
+      if (p.trials > 0) COBEL_CUDA_OK(cudaMemsetAsync(p.T, 0, (size_t)p.n_agents * N * sizeof(double), st));
+    }
+    COBEL_CUDA_OK(cudaGetLastError());
+    return COBEL_OK;
+  }
   const SfmaSmem so(S, A, T, p.batch, p.recency != 0 || p.no_replay != 0, p.random_replay != 0);
   COBEL_REQUIRE(so.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
                 "SFMA tables of %d states x %d actions need %d bytes of shared memory", S, A, so.bytes);
@@ -638,6 +1107,30 @@ int launch(const CobelSFMAParams& p, cudaStream_t st) {
     sfma_kernel<A, false><<<(unsigned)p.n_agents, T, so.bytes, st>>>(p);
   }
   cobel_count_launch();
+  COBEL_CUDA_OK(cudaGetLastError());
+  return COBEL_OK;
+}
+
+__global__ void sfma_set_carry_kernel(int64_t* carry, const int32_t* state, int64_t n_agents) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_agents) return;
+  carry[n * 4 + 0] = state[n];
+  carry[n * 4 + 1] = 0; carry[n * 4 + 2] = 0; carry[n * 4 + 3] = 0;
+}
+
+// SFMAMemory.replay(batch, state) / SFMA.replay(batch, state) as a stand-alone call: the replay kernel of the split path
+template <int A>
+int replay_only(const CobelSFMAParams& p, const int32_t* state, int apply_updates, cudaStream_t st) {
+  const int S = p.world.n_states, N = S * A;
+  COBEL_REQUIRE(S <= 0x7FFF, COBEL_EUNSUPPORTED, "SFMA kernel supports at most 32767 states");
+  const int T = N <= 128 ? 64 : N <= 512 ? 128 : 256;
+  const ReplaySmem rso(S, A, T, p.batch, p.random_replay != 0);
+  COBEL_REQUIRE(rso.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
+                "SFMA replay of %d states x %d actions needs %d bytes of shared memory", S, A, rso.bytes);
+  COBEL_CUDA_OK(cudaFuncSetAttribute(sfma_replay_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, rso.bytes));
+  sfma_set_carry_kernel<<<(unsigned)((p.n_agents + 127) / 128), 128, 0, st>>>(p.carry, state, p.n_agents);
+  sfma_replay_kernel<A><<<(unsigned)p.n_agents, T, rso.bytes, st>>>(p, SfmaPhase{0, 0, 0, 0, apply_updates == 1 ? 0 : (apply_updates == 2 ? 2 : 1)});
+  cobel_count_launch(2);
   COBEL_CUDA_OK(cudaGetLastError());
   return COBEL_OK;
 }
@@ -664,6 +1157,28 @@ extern "C" int cobel_sfma_run(const CobelSFMAParams* pp, void* stream) {
     case 4: return launch<4>(p, st);
     case 6: return launch<6>(p, st);
     case 8: return launch<8>(p, st);
+    default:
+      cobel_set_error("unsupported number of actions %d (built for 2,3,4,6,8)", p.world.n_actions);
+      return COBEL_EUNSUPPORTED;
+  }
+}
+
+extern "C" int cobel_sfma_replay(const CobelSFMAParams* pp, const int32_t* state, int apply_updates, void* stream) {
+  COBEL_REQUIRE(pp != nullptr && state != nullptr, COBEL_EINVAL, "null params");
+  const CobelSFMAParams& p = *pp;
+  COBEL_REQUIRE(p.n_agents > 0 && p.stream.draw_count && p.trace.n_replay && p.trace.replay_idx && p.trace.replay_len && p.carry,
+                COBEL_EINVAL, "cobel_sfma_replay needs the stream, trace.replay_idx / replay_len / n_replay and the carry scratch");
+  COBEL_REQUIRE(p.Mr && p.Ms && p.Mt && p.C && p.I && p.D, COBEL_EINVAL, "memory tables missing");
+  COBEL_REQUIRE(apply_updates != 1 || (p.Q && p.lr && p.gamma), COBEL_EINVAL, "Q / lr / gamma missing");
+  COBEL_REQUIRE(p.batch >= 0 && p.nb_replays >= 0 && !p.recency, COBEL_EINVAL, "batch and nb_replays must be >= 0; recency runs inside train() only");
+  COBEL_REQUIRE(p.mode >= MODE_DEFAULT && p.mode <= MODE_SWEEPING, COBEL_EINVAL, "unknown replay mode %d", p.mode);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (p.world.n_actions) {
+    case 2: return replay_only<2>(p, state, apply_updates, st);
+    case 3: return replay_only<3>(p, state, apply_updates, st);
+    case 4: return replay_only<4>(p, state, apply_updates, st);
+    case 6: return replay_only<6>(p, state, apply_updates, st);
+    case 8: return replay_only<8>(p, state, apply_updates, st);
     default:
       cobel_set_error("unsupported number of actions %d (built for 2,3,4,6,8)", p.world.n_actions);
       return COBEL_EUNSUPPORTED;

@@ -72,7 +72,7 @@ extern "C" size_t cobel_sizeof(const char* name) {
   if (!name) return 0;
 #define COBEL_SZ(T) if (!strcmp(name, #T)) return sizeof(T);
   COBEL_SZ(CobelWorld) COBEL_SZ(CobelStream) COBEL_SZ(CobelPolicy) COBEL_SZ(CobelTrace)
-  COBEL_SZ(CobelDynaQParams) COBEL_SZ(CobelQParams) COBEL_SZ(CobelSRParams) COBEL_SZ(CobelSRCompactParams) COBEL_SZ(CobelSFMAParams) COBEL_SZ(CobelPMAParams)
+  COBEL_SZ(CobelDynaQParams) COBEL_SZ(CobelQParams) COBEL_SZ(CobelSRParams) COBEL_SZ(CobelSRCompactParams) COBEL_SZ(CobelSFMAParams) COBEL_SZ(CobelPMAParams) COBEL_SZ(CobelExperiences)
 #undef COBEL_SZ
   return 0;
 }

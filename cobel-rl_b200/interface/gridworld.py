@@ -51,35 +51,25 @@ class Gridworld(Interface):
         self._set_tables(successor_table(world), world['rewards'], world['terminals'], world['starting_states'],
                          None if self.deterministic else world['sas'])
         self._coordinates = torch.as_tensor(np.asarray(world['coordinates']), dtype=torch.float64).to(self.rng.device)
-        self._current = torch.zeros(self.rng.n_agents, dtype=torch.int64, device=self.rng.device)
+        self._current = torch.zeros(self.rng.n_agents, dtype=torch.int32, device=self.rng.device)
         self.reset()      # gridworld.py:89 -- consumes one draw per agent, like the reference
 
     @property
     def current_state(self):
-        return self._out(self._current)
+        return self._out(self._current.long())
 
     @property
     def current_coordinates(self):
-        return self._out(self._coordinates[self._current])
+        return self._out(self._coordinates[self._current.long()])
 
     def step(self, action):
         """gridworld.py:92-129 for all agents: (state, reward, end_trial, False, {})."""
-        a = torch.as_tensor(action, device=self.rng.device).reshape(-1).to(torch.int64)
-        if self.deterministic:
-            self._current = self._succ[self._current, a].to(torch.int64)
-        else:   # gridworld.py:118-123: one categorical draw over the sas row per agent
-            rows = torch.as_tensor(np.asarray(self.world['sas']), device=self.rng.device)[self._current, a]
-            cdf = torch.cumsum(rows, dim=1)
-            cdf = cdf / cdf[:, -1:]
-            self._current = (cdf <= self.rng.next(1)).sum(dim=1)
-        reward = self._reward[self._current]
-        end = self._terminal[self._current].bool()
-        return self._out(self._current), self._out(reward), self._out(end), False, {}
+        cur, reward, end = self._launch_step(action)
+        return self._out(cur.long()), self._out(reward), self._out(end), False, {}
 
     def reset(self):
         """gridworld.py:131-145: uniform draw over the starting states."""
-        self._current = self._starts[self.rng.integers(self._starts.numel())].to(torch.int64)
-        return self._out(self._current), {}
+        return self._out(self._launch_reset().long()), {}
 
     def get_position(self):
-        return self._out(self._coordinates[self._current].clone())
+        return self._out(self._coordinates[self._current.long()].clone())

@@ -71,6 +71,35 @@ class Interface(abc.ABC):
                           self._reward.data_ptr(), self._terminal.data_ptr(), self._starts.data_ptr(),
                           _lib.ptr(tp[0]), _lib.ptr(tp[1]), _lib.ptr(tp[2]))
 
+    # -- Interface.reset() / step() for all agents: one launch of csrc/ops.cu each
+    def _launch_reset(self):
+        from ..stream import cuda_stream
+        st = self.rng
+        cur = torch.empty(st.n_agents, dtype=torch.int32, device=st.device)
+        w, s = self.c_world(), st.c_struct()
+        _lib.call('cobel_env_reset', st.device, w, s, st.n_agents, cur.data_ptr(), cuda_stream(st.device))
+        self._current = cur
+        return cur
+
+    def _launch_step(self, action):
+        from ..stream import cuda_stream
+        st = self.rng
+        a = torch.as_tensor(action, device=st.device).reshape(-1).to(torch.int32)
+        if a.numel() == 1:
+            a = a.expand(st.n_agents)
+        a = a.contiguous()
+        assert a.numel() == st.n_agents, 'one action per agent'
+        if bool(((a < 0) | (a >= self.n_actions)).any()):
+            raise IndexError('action out of range')          # the reference indexes sas[s, a] / neighbors[a]
+        cur = self._current.clone()
+        reward = torch.empty(st.n_agents, dtype=torch.float64, device=st.device)
+        end = torch.empty(st.n_agents, dtype=torch.uint8, device=st.device)
+        w, s = self.c_world(), st.c_struct()
+        _lib.call('cobel_env_step', st.device, w, s, st.n_agents, cur.data_ptr(), a.data_ptr(), reward.data_ptr(),
+                  end.data_ptr(), cuda_stream(st.device))
+        self._current = cur
+        return cur, reward, end.bool()
+
     def _out(self, t):
         """Squeeze the agent axis for single-agent streams (reference return types)."""
         if not self.rng.single:

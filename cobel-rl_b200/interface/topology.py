@@ -45,7 +45,7 @@ class Topology(Interface):
             self.observation_space = Box(low=np.array([-np.inf] * 3 + [0.0] * 3),
                                          high=np.array([np.inf] * 3 + [360.0] * 3), dtype=np.float64)
         # topology.py:109 -- one draw in the constructor
-        self._current = self._starts[self.rng.integers(self._starts.numel())].to(torch.int64)
+        self._launch_reset()
 
     @property
     def current_node(self):
@@ -53,21 +53,23 @@ class Topology(Interface):
             return self.node_ids[int(self._current[0])]
         return [self.node_ids[int(i)] for i in self._current.tolist()]
 
-    def _observation(self):
-        return self._out(self._current) if self.discrete else self._out(self._pose[self._current].clone())
+    def get_observation(self):
+        """topology.py:174-193: the pose of the current node (or its index with ``discrete=True``)."""
+        cur = self._current.long()
+        return self._out(cur) if self.discrete else self._out(self._pose[cur].clone())
+
+    _observation = get_observation
 
     def step(self, action):
         """topology.py:126-157: returns ``end_trial`` as both terminated and truncated."""
-        a = torch.as_tensor(action, device=self.rng.device).reshape(-1).to(torch.int64)
-        self._current = self._succ[self._current, a].to(torch.int64)
-        reward = self._out(self._reward[self._current])
-        end = self._out(self._terminal[self._current].bool())
-        return self._observation(), reward, end, end, {}
+        _, reward, end = self._launch_step(action)
+        end = self._out(end)
+        return self.get_observation(), self._out(reward), end, end, {}
 
     def reset(self):
         """topology.py:159-172."""
-        self._current = self._starts[self.rng.integers(self._starts.numel())].to(torch.int64)
-        return self._observation(), {}
+        self._launch_reset()
+        return self.get_observation(), {}
 
     def get_position(self):
-        return self._out(self._pose[self._current].clone())
+        return self._out(self._pose[self._current.long()].clone())

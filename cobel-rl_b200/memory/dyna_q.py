@@ -8,7 +8,9 @@ interactive use on the whole batch of agents.
 """
 import torch
 
-from ..stream import BatchStream
+from .. import _lib
+from ..experience import Experience, ExperienceBatch  # noqa: F401  (Experience: memory/dyna_q.py:8-14)
+from ..stream import BatchStream, cuda_stream
 
 
 class TableMemory:
@@ -55,18 +57,33 @@ class TableMemory:
         t = torch.as_tensor(x, dtype=dtype, device=self._alloc_for.device).reshape(-1)
         return t.expand(self._alloc_for.n_agents) if t.numel() == 1 else t
 
-    def store(self, experience):
-        """memory/dyna_q.py:77-96 for all agents (fields are scalars or ``[N]`` tensors)."""
+    def _table_params(self, keep, Q=None, lr=None, gamma=None):
+        """``CobelDynaQParams`` around the memory tables (and, for the agent-level calls, its Q table)."""
         st = self._alloc_for
-        n = torch.arange(st.n_agents, device=st.device)
-        s = self._batched(experience['state'], torch.int64)
-        a = self._batched(experience['action'], torch.int64)
-        r = self._batched(experience['reward'], torch.float64)
-        lr = st.param(self.learning_rate, 'learning_rate')
-        cur = self._rewards[n, s, a]
-        self._rewards[n, s, a] = cur + lr * (r - cur)
-        self._states[n, s, a] = self._batched(experience['next_state'], torch.int32)
-        self._terminals[n, s, a] = self._batched(experience['terminal'], torch.int32)
+        S, A = self.number_of_states, self.number_of_actions
+        mlr = st.param(self.learning_rate, 'memory learning_rate')
+        keep.append(mlr)
+        world = _lib.World(S, A, 0, 0, None, None, None, None, None, None, None)
+        return _lib.DynaQParams(st.n_agents, world, st.c_struct(), _lib.Policy(0, 0, None), _lib.Trace(),
+                                _lib.ptr(Q), self._rewards.data_ptr(), self._states.data_ptr(),
+                                self._terminals.data_ptr(), None, 0, _lib.ptr(lr), _lib.ptr(gamma), mlr.data_ptr(),
+                                0, 0, 0, 1, 0, 0)
+
+    def _check_experience(self, batch):
+        S, A = self.number_of_states, self.number_of_actions
+        bad = ((batch.state < 0) | (batch.state >= S) | (batch.action < 0) | (batch.action >= A) |
+               (batch.next_state < 0) | (batch.next_state >= S))
+        if bool(bad.any()):
+            raise IndexError('experience with a state / action outside the tables')
+
+    def store(self, experience):
+        """memory/dyna_q.py:77-96 for all agents (fields are scalars or ``[N]`` tensors); one launch of csrc/ops.cu."""
+        st = self._alloc_for
+        batch = ExperienceBatch.from_dicts(st, experience)
+        self._check_experience(batch)
+        keep = []
+        p, e = self._table_params(keep), batch.c_struct()
+        _lib.call('cobel_dynaq_op', st.device, p, _lib.OP_STORE, e, cuda_stream(st.device))
 
     def retrieve(self, state, action):
         """memory/dyna_q.py:98-120."""
@@ -84,13 +101,15 @@ class DynaQMemory(TableMemory):
         super().__init__(states, actions, learning_rate, rng, init_self_loops=True)
 
     def retrieve_batch(self, batch_size=32):
-        """memory/dyna_q.py:122-157: ``batch_size`` uniform draws over S*A per agent,
-        C-order unravel.  Returns a dict of ``[N, batch]`` tensors."""
+        """memory/dyna_q.py:122-157: ``batch_size`` uniform draws over S*A per agent, C-order unravel.  Returns the
+        list of ``batch_size`` Experience dicts (fields ``[N]`` tensors)."""
+        return self._retrieve(batch_size).to_dicts()
+
+    def _retrieve(self, batch_size):
         st = self._alloc_for
-        S, A = self.number_of_states, self.number_of_actions
-        u = st.next(batch_size)
-        idx = torch.clamp((u * (S * A)).floor().to(torch.int64), max=S * A - 1)
-        s, a = idx // A, idx % A
-        n = torch.arange(st.n_agents, device=st.device).reshape(-1, 1)
-        return {'state': s, 'action': a, 'reward': self._rewards[n, s, a],
-                'next_state': self._states[n, s, a], 'terminal': self._terminals[n, s, a]}
+        batch = ExperienceBatch(st, batch_size)
+        if batch_size > 0:
+            keep = []
+            p, e = self._table_params(keep), batch.c_struct()
+            _lib.call('cobel_dynaq_op', st.device, p, _lib.OP_RETRIEVE_BATCH, e, cuda_stream(st.device))
+        return batch

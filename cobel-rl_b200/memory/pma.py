@@ -8,6 +8,8 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..experience import Experience, ExperienceBatch  # noqa: F401  (Experience: memory/pma.py:11-17)
+from ..stream import cuda_stream
 from .dyna_q import TableMemory
 
 
@@ -52,7 +54,7 @@ class PMAMemory(TableMemory):
         self._SR = torch.as_tensor(SR).to(dev).contiguous()
         self._update_mask = torch.zeros((n, S * self.nb_actions), dtype=torch.uint8, device=dev)
         self._min_gap = torch.full((n,), float('inf'), dtype=torch.float64, device=dev)
-        self._carry = torch.zeros((n, 4), dtype=torch.int64, device=dev)            # kernel scratch
+        self._carry = torch.zeros((n, 8), dtype=torch.int64, device=dev)            # kernel scratch
         self._need_scratch = torch.zeros((n, S), dtype=torch.float64, device=dev)   # kernel scratch
         self._band_T = self._matrix_band(self._T0)     # half bandwidth of T; None = must be re-measured
         self._band_scratch = None
@@ -80,7 +82,7 @@ class PMAMemory(TableMemory):
         if bw > self.sr_band_max or 2 * bw + 1 >= S:
             return -1, None
         self._band_T = bw                              # experienced transitions stay inside the world's band
-        n = self._T.shape[0] * 2 * S * (2 * bw + 1)
+        n = self._T.shape[0] * S * (2 * bw + 1)
         if self._band_scratch is None or self._band_scratch.numel() < n:
             self._band_scratch = torch.empty(n, dtype=torch.float64, device=self._T.device)
         return bw, self._band_scratch
@@ -148,7 +150,137 @@ class PMAMemory(TableMemory):
         keep += [tkind, tpar, tof]
         return n_tab, tkind, tpar, tof, self._tab_scratch
 
-    def power_tables(self, stream, keep):
+    # ---- stand-alone methods -----------------------------------------------------------------------------------
+    def _mem_params(self, keep, agent=None, batch=0, tr=None):
+        """``CobelPMAParams`` around the memory's tables; ``agent`` (a PMA agent) adds Q, the action mask and the
+        agent's hyper-parameters."""
+        st = self._alloc_for
+        S, A = self.nb_states, self.nb_actions
+        if agent is not None:
+            world = _lib.World(S, A, 0, 0, None, None, None, None, None, None, None)
+            return agent._params(world, agent.policy, tr if tr is not None else _lib.Trace(), 0, 1, batch, False, True, -1, None, keep)
+        par = {k: st.param(v, k) for k, v in dict(mem_lr=self.learning_rate, lr_q=self.learning_rate_q,
+                                                  gamma_q=self.gamma_q, gamma_sr=self.gamma).items()}
+        psr, pq, pstride = self.power_tables(st, keep)
+        keep.append(par)
+        world = _lib.World(S, A, 0, 0, None, None, None, None, None, None, None)
+        return _lib.PMAParams(
+            st.n_agents, world, st.c_struct(), _lib.Policy(0, 0, None), self.policy.c_struct(st, keep), _lib.Trace(),
+            None, self._rewards.data_ptr(), self._states.data_ptr(), self._terminals.data_ptr(),
+            self._T.data_ptr(), self._SR.data_ptr(), self._update_mask.data_ptr(), None, 0,
+            None, None, par['mem_lr'].data_ptr(), par['lr_q'].data_ptr(), par['gamma_q'].data_ptr(),
+            par['gamma_sr'].data_ptr(), psr.data_ptr(), pq.data_ptr(), pstride, self._min_gap.data_ptr(),
+            self._carry.data_ptr(), self._need_scratch.data_ptr(), float(self.learning_rate_T), float(self.min_gain),
+            1 if self.min_gain_mode == 'original' else 0, 0, 1, batch, 0, 1, -1, self.options(), None,
+            0, 0, None, None, None, None)
+
+    def store(self, experience):
+        """memory/pma.py:148-166 for all agents: the table entry and ``T[s] += lr_T * (onehot(s') - T[s])``."""
+        st = self._alloc_for
+        batch = ExperienceBatch.from_dicts(st, experience)
+        self._check_experience(batch)
+        keep = []
+        p, e = self._mem_params(keep), batch.c_struct()
+        _lib.call('cobel_pma_op', st.device, p, _lib.OP_STORE, e, None, None, cuda_stream(st.device))
+        self._band_T = None
+
+    def _states_arg(self, current_state):
+        st = self._alloc_for
+        if current_state is None:
+            return torch.full((st.n_agents,), -1, dtype=torch.int32, device=st.device)
+        s = torch.as_tensor(current_state, device=st.device).reshape(-1).to(torch.int32)
+        return (s.expand(st.n_agents) if s.numel() == 1 else s).contiguous()
+
+    def replay(self, q_function, action_mask, replay_length, current_state, force_first=None, update_sr=False):
+        """memory/pma.py:168-267 for all agents.  ``q_function`` is the PMA agent whose Q table the replay reads and
+        updates IN PLACE (the reference copies Q and the agent rebinds ``self.Q``, agent/pma.py:207); ``current_state``
+        a state per agent, or None (need = stationary distribution of T).  Returns ``(performed, Q)``: the performed
+        updates as a padded ``[N, L]`` tensor of flat indices ``a*S + s`` (-1 = none) and the agent's Q table."""
+        assert force_first is None, 'force_first is not implemented by the B200 path'
+        agent = q_function
+        assert hasattr(agent, '_Q') and agent.M is self, 'pass the PMA agent that owns this memory as q_function'
+        st = self._alloc_for
+        n, dev = st.n_agents, st.device
+        saved_mask, saved_flag = agent._action_mask, agent.mask_actions
+        if action_mask is not None:
+            agent._action_mask, agent.mask_actions = torch.as_tensor(action_mask, device=dev).bool().contiguous(), True
+        else:
+            agent.mask_actions = False
+        try:
+            keep = []
+            L = max(int(replay_length), 1)
+            idx = torch.full((n, L), -1, dtype=torch.int32, device=dev)
+            ln = torch.zeros((n, 1), dtype=torch.int32, device=dev)
+            zeros = torch.zeros((2, n), dtype=torch.int64, device=dev)
+            flags = torch.zeros(n, dtype=torch.int32, device=dev)
+            tr = _lib.Trace(None, None, zeros[0].data_ptr(), zeros[1].data_ptr(), None, 0, idx.data_ptr(), L,
+                            ln.data_ptr(), 1, flags.data_ptr(), None)
+            p = self._mem_params(keep, agent, int(replay_length), tr)
+            state = self._states_arg(current_state)
+            _lib.call('cobel_pma_replay', dev, p, state.data_ptr(), 1 if update_sr else 0, cuda_stream(dev))
+        finally:
+            agent._action_mask, agent.mask_actions = saved_mask, saved_flag
+        if bool((flags & 8).any()):
+            raise _lib.CobelError('PMA: singular elimination (T has a closed class without a unique stationary distribution)')
+        return self._view(idx), agent.Q
+
+    def compute_gain_batch(self, q_function, action_mask=None):
+        """memory/pma.py:333-386: the gain of every one-step backup, ``[N, S*A]`` in the reference's order ``a*S + s``.
+        ``q_function`` is the PMA agent that owns this memory."""
+        agent = q_function
+        st = self._alloc_for
+        saved_mask, saved_flag = agent._action_mask, agent.mask_actions
+        if action_mask is not None:
+            agent._action_mask, agent.mask_actions = torch.as_tensor(action_mask, device=st.device).bool().contiguous(), True
+        else:
+            agent.mask_actions = False
+        try:
+            keep = []
+            p = self._mem_params(keep, agent)
+            out = torch.empty((st.n_agents, self.nb_states * self.nb_actions), dtype=torch.float64, device=st.device)
+            _lib.call('cobel_pma_op', st.device, p, _lib.OP_GAIN_BATCH, None, None, out.data_ptr(), cuda_stream(st.device))
+        finally:
+            agent._action_mask, agent.mask_actions = saved_mask, saved_flag
+        return self._view(out)
+
+    def compute_need(self, current_state=None):
+        """memory/pma.py:388-411: ``tile(SR[current_state], A)``, or the stationary distribution of T (|left Perron
+        vector|, unit 2-norm) tiled when ``current_state`` is None."""
+        st = self._alloc_for
+        keep = []
+        p = self._mem_params(keep)
+        state = self._states_arg(current_state)
+        if current_state is None:
+            # the stationary distribution comes from the GTH elimination of the replay path: a replay of length 0 on a
+            # scratch Q table leaves it in need_scratch
+            n, dev = st.n_agents, st.device
+            tmp = {'Q': torch.zeros((n, self.nb_states, self.nb_actions), dtype=torch.float64, device=dev),
+                   'one': torch.ones(n, dtype=torch.float64, device=dev), 'cnt': torch.zeros((2, n), dtype=torch.int64, device=dev),
+                   'dc': st.draw_count.clone()}
+            keep.append(tmp)
+            p.Q, p.lr, p.gamma = tmp['Q'].data_ptr(), tmp['one'].data_ptr(), tmp['one'].data_ptr()
+            p.policy = self.policy.c_struct(st, keep)
+            p.trace.n_steps, p.trace.n_replay = tmp['cnt'][0].data_ptr(), tmp['cnt'][1].data_ptr()
+            p.batch = 0
+            _lib.call('cobel_pma_replay', dev, p, state.data_ptr(), 0, cuda_stream(dev))
+        out = torch.empty((st.n_agents, self.nb_states * self.nb_actions), dtype=torch.float64, device=st.device)
+        _lib.call('cobel_pma_op', st.device, p, _lib.OP_NEED, None, state.data_ptr(), out.data_ptr(), cuda_stream(st.device))
+        return self._view(out)
+
+    def action_probs_batch(self, q_function, action_mask=None):
+        """memory/pma.py:423-450: ``policy.get_action_probs`` for every row of a ``[N, S, A]`` (or ``[S, A]``) table,
+        each row divided by its sum."""
+        p = self.policy.get_action_probs(q_function, action_mask)
+        cols = [p[..., a] for a in range(p.shape[-1])]
+        if len(cols) == 8:      # np.sum over exactly 8 values is a tree, below that a plain loop (SURVEY.md App. A.3)
+            tot = ((cols[0] + cols[1]) + (cols[2] + cols[3])) + ((cols[4] + cols[5]) + (cols[6] + cols[7]))
+        else:
+            tot = cols[0]
+            for c in cols[1:]:
+                tot = tot + c
+        return p / tot.unsqueeze(-1)
+
+    def power_tables(self, stream, keep, q_gamma=None):
         """``float(gamma) ** k`` for k = 0..MAX_SEQ+1 with Python's pow, like the reference
         (memory/pma.py:310,315,485,491).  Returns (sr table, q table, per-agent stride)."""
         L = _lib.PMA_MAX_SEQ + 2
@@ -161,7 +293,7 @@ class PMAMemory(TableMemory):
                 cache = {}
                 rows = [cache.setdefault(float(g), [float(g) ** k for k in range(L)]) for g in v]
             return np.array(rows, dtype=np.float64)
-        a, b = table(self.gamma), table(self.gamma_q)
+        a, b = table(self.gamma), table(self.gamma_q if q_gamma is None else q_gamma)
         if a.shape[0] != b.shape[0]:
             n = stream.n_agents
             a, b = np.broadcast_to(a, (n, L)).copy(), np.broadcast_to(b, (n, L)).copy()

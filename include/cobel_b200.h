@@ -252,6 +252,9 @@ typedef struct CobelSFMAParams {
   double   reward_modulation;/* M.reward_modulation (1.0) */
   int32_t  mod_flags;        /* COBEL_SFMA_MOD_* bits: strength modulation and normalisation switches */
   int32_t  reserved2;
+  int64_t* carry;            /* optional scratch [N,4]: per-agent state between the launches of the split path (one
+                                thread per agent for the online steps, one CTA per agent for the replays); NULL = the
+                                fused one-CTA-per-agent kernel */
 } CobelSFMAParams;
 
 int cobel_sfma_run(const CobelSFMAParams* p, void* stream);
@@ -290,7 +293,7 @@ typedef struct CobelPMAParams {
   const double* pow_gamma_q; /* same for M.gamma_q (the reference uses Python's float pow) */
   int64_t  pow_stride;       /* 0 = one table for all agents, COBEL_PMA_MAX_SEQ+2 = one per agent */
   double*  min_gap;          /* optional [N] in/out: smallest relative gap between the two largest distinct utilities */
-  int64_t* carry;            /* scratch [N,4]: per-agent state carried between the launches of one call */
+  int64_t* carry;            /* scratch [N,8]: per-agent state carried between the launches of one call */
   double*  need_scratch;     /* scratch [N,S]: stationary `need` of agents whose trial timed out */
   double   lr_T;             /* M.learning_rate_T (0.9) */
   double   min_gain;         /* M.min_gain (1e-6) */
@@ -300,13 +303,13 @@ typedef struct CobelPMAParams {
   int32_t learn;             /* 1 = train(), 0 = test() */
   /* Banded update_sr (memory/pma.py:413-415 needs only the SR rows that replay reads, :401-411).  sr_band >= 0 is
    * the caller's guarantee that T[i][j] == 0 for |i - j| > sr_band and that every world transition satisfies
-   * |s' - s| <= sr_band (a W-wide gridworld: sr_band = W): all trials then run in ONE launch, each agent
-   * factorising its banded I - gamma T and solving for the one SR row a replay call needs, and SR is
-   * refreshed once, densely, at the end of the call.  A violated guarantee raises COBEL_FLAG_BAND_VIOLATION.
+   * |s' - s| <= sr_band (a W-wide gridworld: sr_band = W): each agent then factorises its banded I - gamma T after
+   * every trial (its own kernels between the phases of the main kernel) and solves for the one SR row a replay call needs, and SR is refreshed
+   * once, densely, at the end of the call.  A violated guarantee raises COBEL_FLAG_BAND_VIOLATION.
    * sr_band < 0: dense update_sr after every trial (any T). */
   int32_t sr_band;
   int32_t options;           /* COBEL_PMA_OPT_* bits */
-  double*  band_scratch;     /* scratch [N, 2, S*(2*sr_band+1)] when sr_band >= 0 */
+  double*  band_scratch;     /* scratch [N, S*(2*sr_band+1)] when sr_band >= 0 (the band factors of I - gamma T) */
   /* Tie-pattern policy tables (optional, A <= 4, the two epsilon-greedy kinds).  get_action_probs of those
    * policies (policy/greedy.py:60-88,117-147) depends only on which actions are valid and which of them tie for
    * the row maximum, so raw probabilities, action_probs_batch's p / sum(p) (memory/pma.py:423-450) and
@@ -325,6 +328,68 @@ typedef struct CobelPMAParams {
 #define COBEL_PMA_TIE_DOUBLES 1024
 
 int cobel_pma_run(const CobelPMAParams* p, void* stream);
+
+/* ---- stand-alone methods ------------------------------------------------------------------------------------
+ * One call = one method of the reference's classes for all N agents, for callers that drive the loop themselves
+ * (env.step -> policy.select_action -> M.store -> agent.update_q -> agent.replay, agent/dyna_q.py:176-203) instead
+ * of the fused train().  Same arithmetic, same stream contract; one thread per agent (csrc/ops.cu), the two
+ * replay generators are phases of the fused kernels. */
+
+/* B experiences per agent, [N,B] each: the Experience dicts of memory/dyna_q.py:8-14, agent/q.py:17-23,
+ * agent/sr.py:16-22, memory/pma.py:11-17, memory/sfma.py:12-18 as a structure of arrays. */
+typedef struct CobelExperiences {
+  int32_t  batch;            /* B */
+  int32_t  reserved;
+  int32_t* state;            /* [N,B] */
+  int32_t* action;           /* [N,B] */
+  double*  reward;           /* [N,B] */
+  int32_t* next_state;       /* [N,B] */
+  int32_t* terminal;         /* [N,B] holds 1 - end_trial, like the reference's field of that name */
+  double*  td;               /* optional [N,B]: out, the TD error update_q adds to the dict */
+} CobelExperiences;
+
+enum {
+  COBEL_OP_STORE = 1,          /* Memory.store(e[.,0]) / QAgent: M.append / SR: SR.update(e[.,0]) */
+  COBEL_OP_UPDATE_Q = 2,       /* Agent.update_q for the B experiences in order (PMA: the batch is ONE n-step update) */
+  COBEL_OP_RETRIEVE_BATCH = 3, /* DynaQMemory.retrieve_batch(B) -> e */
+  COBEL_OP_REPLAY = 4,         /* Agent.replay(B): draw, then update_q in order; e receives the batch */
+  COBEL_OP_RETRIEVE_Q = 5,     /* SR.retrieve_q(state) -> q_out[N,A] */
+  COBEL_OP_GATHER = 6,         /* SFMA: e.state holds flat indices a*S+s (-1 = none); fills e with the stored experiences */
+  COBEL_OP_GAIN_BATCH = 7,     /* PMAMemory.compute_gain_batch -> out[N,S*A] */
+  COBEL_OP_NEED = 8            /* PMAMemory.compute_need(state) -> out[N,S*A]; state < 0: need_scratch (stationary) tiled */
+};
+
+/* Interface.reset() / Interface.step(action): interface/gridworld.py:92-145, interface/topology.py:126-172.
+ * state[N] in/out (reset: out), reward[N], end_trial[N] out. */
+int cobel_env_reset(const CobelWorld* w, const CobelStream* s, int64_t n_agents, int32_t* state, void* stream);
+int cobel_env_step(const CobelWorld* w, const CobelStream* s, int64_t n_agents, int32_t* state, const int32_t* action,
+                   double* reward, uint8_t* end_trial, void* stream);
+/* Policy.get_action_probs(values[., A], mask) for rows_per_agent rows per agent, and Policy.select_action (one row and one
+ * draw per agent): policy/greedy.py:40-147, policy/softmax.py:40-88.  mask: [rows, A] bytes or NULL. */
+int cobel_policy_probs(const CobelPolicy* pol, int64_t n_agents, int64_t rows_per_agent, int32_t n_actions,
+                       const double* values, const uint8_t* mask, double* probs, void* stream);
+int cobel_policy_select(const CobelPolicy* pol, const CobelStream* s, int64_t n_agents, int32_t n_actions,
+                        const double* values, const uint8_t* mask, int32_t* action, void* stream);
+/* DynaQMemory.store / retrieve_batch, DynaQ.update_q / replay: memory/dyna_q.py:77-157, agent/dyna_q.py:275-330 */
+int cobel_dynaq_op(const CobelDynaQParams* p, int op, const CobelExperiences* e, void* stream);
+/* QAgent: M.append (STORE), update_q, replay (e.state receives the replayed log indices): agent/q.py:205-215, 297-354 */
+int cobel_q_op(const CobelQParams* p, int op, const CobelExperiences* e, void* stream);
+/* SR.update (STORE) / SR.retrieve_q: agent/sr.py:255-308 */
+int cobel_sr_op(const CobelSRParams* p, int op, const CobelExperiences* e, const int32_t* state, double* q_out, void* stream);
+/* SFMAMemory.store, SFMA.update_q (learn = 0: no_update), GATHER: memory/sfma.py:195-236, agent/sfma.py:423-458 */
+int cobel_sfma_op(const CobelSFMAParams* p, int op, const CobelExperiences* e, void* stream);
+/* SFMAMemory.replay(batch, state) [apply_updates = 0] / SFMA.replay(batch, state) [apply_updates = 1] /
+ * SFMAMemory.retrieve_random_batch(batch, mask) [apply_updates = 2, random_replay = 1]
+ * (memory/sfma.py:238-347, 375-416, agent/sfma.py:392-421): state[N] = current state, -1 = None.  The reactivated
+ * flat indices go to trace.replay_idx / replay_len (mandatory here); needs p.carry. */
+int cobel_sfma_replay(const CobelSFMAParams* p, const int32_t* state, int apply_updates, void* stream);
+/* PMAMemory.store, PMA.update_q (pow_gamma_q must hold agent.gamma ** k), compute_gain_batch, compute_need:
+ * memory/pma.py:148-166, 333-411, agent/pma.py:319-353 */
+int cobel_pma_op(const CobelPMAParams* p, int op, const CobelExperiences* e, const int32_t* state, double* out, void* stream);
+/* PMAMemory.replay(Q, action_mask, batch, state) (memory/pma.py:168-267): state[N] = current state, -1 = None (the
+ * need is then the stationary distribution of T).  Q is updated in place, the performed updates go to
+ * trace.replay_idx / replay_len.  update_sr != 0: M.update_sr() first (dense inverse, memory/pma.py:413-415). */
+int cobel_pma_replay(const CobelPMAParams* p, const int32_t* state, int update_sr, void* stream);
 
 /* ---- utilities -------------------------------------------------------------- */
 int  cobel_abi_version(void);

@@ -113,8 +113,8 @@ def test_interactive_policy_and_memory_calls():
     mem.store({'state': torch.tensor([1, 2, 3]), 'action': 1, 'reward': 2.0, 'next_state': torch.tensor([6, 7, 8]), 'terminal': 1})
     got = mem.retrieve(torch.tensor([1, 2, 3]), 1)
     assert got['reward'].tolist() == [1.8, 1.8, 1.8] and got['next_state'].tolist() == [6, 7, 8]
-    b = mem.retrieve_batch(5)
-    assert b['state'].shape == (3, 5) and int(b['state'].max()) < 25
+    b = mem.retrieve_batch(5)          # a list of 5 Experience dicts, fields [N] tensors (memory/dyna_q.py:122-157)
+    assert len(b) == 5 and b[0]['state'].shape == (3,) and max(int(e['state'].max()) for e in b) < 25
 
 
 def test_topology_discrete_mode_runs_tabular_agents():
