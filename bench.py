@@ -163,6 +163,49 @@ class ClockSampler:
 # CPU baseline / reference arm: the reference's algorithm (oracle port) on host cores
 # --------------------------------------------------------------------------- #
 
+def reference_available():
+    """The unmodified reference package (baseline/_ref, placed by oracle/install_reference.py) is importable."""
+    try:
+        from oracle import ref_loader
+        return ref_loader.available()
+    except Exception:
+        return False
+
+
+def _ref_worker(args):
+    """One host core: a slice of agents run one after the other through the UNMODIFIED reference classes
+    (cobel.agent.* from baseline/_ref, driven by the same per-agent uniform streams)."""
+    name, agent_ids, trials = args
+    os.environ['OPENBLAS_NUM_THREADS'] = '1'
+    from oracle import ref_runs
+    from oracle.philox import LazyStream
+    wl = WORKLOADS[name]
+    steps, batch = wl['steps'], wl['batch']
+    units = 0
+    if name == 'q':
+        from cobel_rl_b200.misc.topology_tools import linear_track
+        nodes, starts = linear_track(10, 2, 1.0, 20.0, 'right')
+    else:
+        world = make_world(wl['world'])
+    for g in agent_ids:
+        u = LazyStream(SEED, g)
+        if name == 'dynaq':
+            units += len(ref_runs.run_dynaq(world, u, trials, steps, batch)['states'])
+        elif name == 'q':
+            units += len(ref_runs.run_q_topology(nodes, starts, u, trials, steps, batch)['states'])
+        elif name == 'sr':
+            units += len(ref_runs.run_sr(world, u, trials, steps)['states'])
+        elif name == 'sfma':
+            from cobel_rl_b200.memory.utils.metrics import DR
+            D = DR(world['width'], world['height'], world['sas'], 0.9, world['invalid_transitions']).D
+            units += len(ref_runs.run_sfma(world, D, u, trials, steps, batch, mask_actions=True)['states'])
+        elif name == 'pma':
+            units += len(ref_runs.run_pma(world, u, trials, steps, batch, gamma_q=0.99, mask_actions=True)['replay'])
+        else:
+            raise ValueError(name)
+    return units
+
+
 def _cpu_worker(args):
     name, agent_ids, trials = args
     os.environ['OPENBLAS_NUM_THREADS'] = '1'
@@ -205,27 +248,39 @@ def _cpu_worker(args):
     return units
 
 
+# agents per host core when the real reference runs (it is 2-3x slower than the vectorised oracle port)
+REF_AGENTS_PER_CORE = {'dynaq': 6, 'pma': 4, 'q': 6, 'sr': 4, 'sfma': 2}
+
+
 def cpu_run(name, agents_per_core=1, pool=None, cores=None, trials=None):
-    """Oracle port of the reference loop, one process per host core, each running a slice of agents
-    of the SAME workload (same world, hyper-parameters and per-agent streams)."""
+    """The reference's CPU loop, one process per host core, each running a slice of agents of the SAME workload
+    (same world, hyper-parameters and per-agent streams): the UNMODIFIED reference (baseline/_ref) when it is
+    present -- kind "reference" -- else the oracle port (kind "port"; always for sr100, whose dense tables do not
+    exist in the reference's form)."""
     import multiprocessing as mp
     wl = WORKLOADS[name]
     trials = trials or wl['cpu_trials']
     cores = cores or os.cpu_count() or 1
+    real = reference_available() and name in REF_AGENTS_PER_CORE
+    worker = _ref_worker if real else _cpu_worker
+    if real:
+        agents_per_core = min(agents_per_core, REF_AGENTS_PER_CORE[name])
     ids = [list(range(c * agents_per_core, (c + 1) * agents_per_core)) for c in range(cores)]
     own = pool is None
     if own:
         pool = mp.get_context('spawn').Pool(cores)
-        pool.map(_cpu_worker, [('dynaq', [0], 1)] * cores)       # import / warm the workers
+        pool.map(worker, [('dynaq', [0], 1)] * cores)            # import / warm the workers
     t0 = time.perf_counter()
-    units = sum(pool.map(_cpu_worker, [(name, i, trials) for i in ids]))
+    units = sum(pool.map(worker, [(name, i, trials) for i in ids]))
     dt = time.perf_counter() - t0
     if own:
         pool.close()
-    return {'value': units / dt, 'unit': wl['unit'], 'cores': cores, 'kind': 'port',
+    what = ('the unmodified reference classes (cobel.agent.* from baseline/_ref) under the same uniform streams'
+            if real else 'oracle/tabular.py (NumPy restatement validated bit-exact against the reference)')
+    return {'value': units / dt, 'unit': wl['unit'], 'cores': cores, 'kind': 'reference' if real else 'port',
             'sample': '%d agents (%d per core) of the same workload, %d trials x <=%d steps, batch %d: %d units in '
-                      '%.1f s; oracle/tabular.py (NumPy restatement validated bit-exact against the reference)'
-                      % (cores * agents_per_core, agents_per_core, trials, wl['steps'], wl['batch'], units, dt),
+                      '%.1f s; %s' % (cores * agents_per_core, agents_per_core, trials, wl['steps'], wl['batch'],
+                                      units, dt, what),
             'seconds': dt, 'units': units}
 
 
@@ -237,7 +292,8 @@ def run_reference(args):
     wl = WORKLOADS[name]
     cores = os.cpu_count() or 1
     pool = mp.get_context('spawn').Pool(cores)
-    pool.map(_cpu_worker, [('dynaq', [0], 1)] * cores)
+    pool.map(_ref_worker if (reference_available() and name in REF_AGENTS_PER_CORE) else _cpu_worker,
+             [('dynaq', [0], 1)] * cores)
     for _ in range(args.warmup):
         cpu_run(name, 1, pool, cores)
     t_tot, u_tot, last = 0.0, 0, None

@@ -344,10 +344,12 @@ __host__ __device__ inline int band_ring_rows(int bw) {
 }
 
 struct BandRing {
-  double* ring;      // [R][W] shared memory, row i lives in slot i % R (R a power of two)
+  double* ring;      // [R][W + 1] shared memory, row i lives in slot i % R (R a power of two).  The pitch W + 1 is even, so
+                     // the elements (row k + ii, column k + jj) that the lanes ii of an elimination step touch lie an odd
+                     // number of doubles apart: conflict-free
   int S, bw, W, R, lane;
   COBEL_DEV BandRing(double* r, int S_, int bw_, int lane_) : ring(r), S(S_), bw(bw_), W(2 * bw_ + 1), R(band_ring_rows(bw_)), lane(lane_) {}
-  COBEL_DEV double* row(int i) const { return ring + (i & (R - 1)) * W; }
+  COBEL_DEV double* row(int i) const { return ring + (i & (R - 1)) * (W + 1); }
   // one commit group per call, also for rows outside [0, S) (keeps the group arithmetic uniform)
   COBEL_DEV void fetch_T(const double* __restrict__ Tg, int i) const {     // band of row i of the dense T
     if (i >= 0 && i < S)
@@ -378,9 +380,6 @@ __device__ __noinline__ int band_lu(const double* __restrict__ Tg, double g, dou
       for (int d = lane; d < W; d += 32) { double* e = rg.row(i) + d; *e = (d == bw ? 1.0 : 0.0) - g * *e; }
     }
   };
-  // element e = lane + 32 x of the bw x bw update block is (ii, jj) = (e / bw + 1, e % bw + 1): advanced incrementally
-  const int bws = bw > 0 ? bw : 1;
-  const int ii0 = lane / bws + 1, jj0 = lane % bws + 1, di = 32 / bws, dj = 32 % bws;
 #pragma unroll 1
   for (int i = 0; i < bw; ++i) rg.fetch_T(Tg, i);
   cp_async_wait<0>();
@@ -396,23 +395,23 @@ __device__ __noinline__ int band_lu(const double* __restrict__ Tg, double g, dou
     to_M(k + bw);
     __syncwarp();
     const int nb = min(bw, S - 1 - k);
-    const double* rk = rg.row(k);
+    double* rk = rg.row(k);
     const double piv = rk[bw];
     if (!(fabs(piv) > 1e-300)) flags |= COBEL_FLAG_SINGULAR;
     const double ipiv = fast_rcp(piv);
-#pragma unroll 1
-    for (int e = lane, ii = ii0, jj = jj0; e < bw * bw; e += 32) {  // (ii, jj) enumerate bw x bw; the last steps guard
-      if (ii <= nb && jj <= nb) {
-        double* ri = rg.row(k + ii);
-        const double l = ri[bw - ii] * ipiv;
-        ri[bw - ii + jj] = fma(-l, rk[bw + jj], ri[bw - ii + jj]);
-      }
-      jj += dj; ii += di;
-      if (jj > bw) { jj -= bw; ++ii; }
+    // lane ii = row k + ii of the bw x bw update block: its multiplier, then its bw elements in sequence (the pivot
+    // row is a broadcast read).  A flattened (ii, jj) -> lane mapping keeps all 32 lanes busy but spends 24
+    // instructions of index arithmetic per element round: 96 per step against 45 here.
+    if (lane >= 1 && lane <= nb) {
+      double* ri = rg.row(k + lane) + (bw - lane);    // &M[k + ii][k]
+      const double* u = rk + bw;                      // &M[k][k]
+      const double l = ri[0] * ipiv;
+      ri[0] = l;
+#pragma unroll 2
+      for (int jj = 1; jj <= nb; ++jj) ri[jj] = fma(-l, u[jj], ri[jj]);
     }
     __syncwarp();
-    if (lane < nb) rg.row(k + 1 + lane)[bw - 1 - lane] *= ipiv;
-    if (lane == 0) rg.row(k)[bw] = ipiv;
+    if (lane == 0) rk[bw] = ipiv;
     __syncwarp();
     rg.store_band(fac, k);
     __syncwarp();
@@ -477,8 +476,6 @@ __device__ __noinline__ int band_gth(const double* __restrict__ Tg, double* fac,
                                      int lane) {
   int flags = 0;
   const BandRing rg(ringmem, S, bw, lane);
-  const int bws = bw > 0 ? bw : 1;
-  const int ii0 = lane / bws + 1, jj0 = lane % bws + 1, di = 32 / bws, dj = 32 % bws;
   // elimination k = S-1 .. 1 works on rows k-bw .. k: stream upwards
 #pragma unroll 1
   for (int i = S - 1; i >= S - 1 - bw - kBandAhead; --i) rg.fetch_T(Tg, i);
@@ -492,18 +489,14 @@ __device__ __noinline__ int band_gth(const double* __restrict__ Tg, double* fac,
     for (int d = 16; d > 0; d >>= 1) ssum += shfl_f64_xor(ssum, d);
     if (!(ssum > 0.0)) { flags |= COBEL_FLAG_SINGULAR; ssum = 1.0; }
     const double inv = fast_rcp(ssum);
-#pragma unroll 1
-    for (int e = lane, ii = ii0, jj = jj0; e < bw * bw; e += 32) {  // i = k - ii, j = k - jj over bw x bw, guarded
-      if (ii <= nb && jj <= nb) {
-        double* ri = rg.row(k - ii);
-        const double f = ri[bw + ii] * inv;                        // P[i][k] / s
-        ri[bw + ii - jj] = fma(f, rk[bw - jj], ri[bw + ii - jj]);
-      }
-      jj += dj; ii += di;
-      if (jj > bw) { jj -= bw; ++ii; }
+    if (lane >= 1 && lane <= nb) {                    // lane ii = row i = k - ii: P[i][k - jj] += P[i][k] / s * P[k][k - jj]
+      double* ri = rg.row(k - lane) + (bw + lane);    // &P[i][k]
+      const double* u = rk + bw;                      // &P[k][k]
+      const double f = ri[0] * inv;
+#pragma unroll 2
+      for (int jj = 1; jj <= nb; ++jj) ri[-jj] = fma(f, u[-jj], ri[-jj]);
+      ri[0] = f;                                      // column k keeps P[i][k] / s
     }
-    __syncwarp();
-    if (lane < nb) rg.row(k - 1 - lane)[bw + 1 + lane] *= inv;     // column k keeps P[i][k] / s
     __syncwarp();
     rg.store_band(fac, k);                                         // (only its scaled super-diagonal part is read again)
     __syncwarp();
@@ -550,7 +543,8 @@ __device__ __noinline__ int band_gth(const double* __restrict__ Tg, double* fac,
 // the eliminations ran at 0.5 instructions / cycle / scheduler and made up 36 % of the PMA run
 // (profiles/r2_pma_v5.txt).
 //   factor: carry[.,0] < 0 (the trial timed out): GTH elimination of T, the stationary vector -> need_scratch;
-//           always: LU of I - gamma T -> band_scratch (diagonal = 1 / pivot, sub-diagonal part = multipliers)
+//           always: LU of I - gamma T -> band_scratch (diagonal = 1 / pivot, sub-diagonal part = multipliers);
+//           carry[.,0] >= 0: row carry[.,0] of the inverse -> need_scratch
 //   solve:  one row of the inverse from the stored factors -> need_scratch:
 //           row carry[.,0] for the end replay of a trial that reached a terminal state, row carry[.,4] (the next
 //           trial's start state) for the start replay
@@ -560,7 +554,7 @@ struct BandSmem {                                     // per warp (agent)
   int ring, x, w, bytes;
   __host__ __device__ BandSmem(int S, int bw) {
     ring = 0;
-    x = ring + band_ring_rows(bw) * (2 * bw + 1) * 8;
+    x = ring + band_ring_rows(bw) * (2 * bw + 2) * 8;
     w = x + ((S + 1) & ~1) * 8;
     bytes = (w + ((S + 1) & ~1) * 8 + 15) & ~15;
   }
@@ -589,6 +583,13 @@ __global__ void __launch_bounds__(kBandWarps * 32) pma_band_factor_kernel(const 
     __syncwarp();
   }
   flags |= band_lu(Tg, p.gamma_sr[n], fac, ring, S, bw, lane);
+  if (p.carry[n * 8 + 0] >= 0) {                        // the trial ended in a terminal state: need = SR[last]
+    double* w = reinterpret_cast<double*>(blk + so.w);
+    band_solve_row(fac, w, S, bw, (int)p.carry[n * 8 + 0], x, lane);
+    double* need = p.need_scratch + (size_t)n * S;
+#pragma unroll 1
+    for (int e = lane; e < S; e += 32) need[e] = x[e];
+  }
   flags = __reduce_or_sync(kFull, flags);
   if (lane == 0 && flags && p.trace.flags) p.trace.flags[n] |= flags;
 }
@@ -611,84 +612,63 @@ __global__ void __launch_bounds__(kBandWarps * 32) pma_band_solve_kernel(const _
 }
 
 // ---------------------------------------------------------------------------
-// pma_sr_band_kernel: the full SR = inv(I - gamma T) of a banded T, once at the end of a banded call.
-// One CTA per agent, from the band factors pma_band_factor_kernel leaves in band_scratch: thread r solves row r of the
-// inverse (x^T M = e_r^T) in its own row of a shared-memory S x S matrix -- no barriers between the S steps,
-// the factor rows are broadcast loads.  2 S^2 bw operations instead of the S^3 of the dense Gauss-Jordan.
+// pma_sr_band_kernel: the full SR = inv(I - gamma T) of a banded T, once at the end of a banded call, from the band
+// factors pma_band_factor_kernel leaves in band_scratch.  One CTA per agent, thread c solves COLUMN c of the
+// inverse (L y = e_c forward, U x = y backward): at step i every thread touches SR[i][c], so the S x S result is
+// written (and the intermediate y read back) with fully coalesced rows and nothing but the factors has to be
+// staged -- 21 KB of shared memory per CTA instead of the 101 KB of a row-per-thread solve that kept its S x S
+// block on chip (2 CTAs per SM, 0.30 instructions / cycle / scheduler, profiles/r1_pma_v3_banded.txt).
+// 2 S^2 bw operations instead of the S^3 of the dense Gauss-Jordan.
 // ---------------------------------------------------------------------------
 template <int BW>      // BW >= sr_band: length of the per-thread register window
 __global__ void __launch_bounds__(160) pma_sr_band_kernel(const __grid_constant__ CobelPMAParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int S = p.world.n_states, bw = p.sr_band, W = 2 * bw + 1, tid = threadIdx.x;
   const int64_t n = blockIdx.x;
-  const int LD = S | 1;                                            // odd row stride: conflict-free column walks
-  double* X = reinterpret_cast<double*>(smem);                     // [S][LD]
-  constexpr int WP = 2 * BW + 1;                                   // padded factor row: entry [BW + i] = M-factor[j][j + i]
-  double* fac = X + (size_t)S * LD;                                // [S][WP] the factors left by pma_main_kernel, staged
-  {                                                                // once and zero-padded to the window length
+  constexpr int WP = 2 * BW + 2;                                   // padded factor row: entry [BW + d] = factor[j][j + d]
+  double* fac = reinterpret_cast<double*>(smem);                   // [S][WP], zero-padded to the window length
+  {
     const double* fg = p.band_scratch + (size_t)n * S * W;
     for (int e = tid; e < S * WP; e += blockDim.x) {
-      const int j = e / WP, d = e - j * WP - BW;                   // d = column offset -BW .. BW
+      const int j = e / WP, d = e - j * WP - BW;                   // d = column offset -BW .. BW + 1
       fac[e] = (d >= -bw && d <= bw) ? fg[(size_t)j * W + bw + d] : 0.0;
     }
   }
   __syncthreads();
-  // Thread r solves x^T M = e_r^T.  The right-hand side entries that a step can still change are kept in a
-  // register window, so a step is BW independent FMAs with broadcast factor loads (issued one step ahead)
-  // and one shared-memory store; the whole warp walks j from its first row (entries before a thread's own row
-  // are zero).
-  const int r = tid, j0 = tid & ~31;
-  if (j0 < S) {
-    double* x = X + (size_t)min(r, S - 1) * LD;
-    double w[BW], fc[BW + 1], fn[BW + 1];
+  const int c = tid, i0 = tid & ~31;                               // a warp walks i from its first column on (y_i = 0 above)
+  if (i0 >= S) return;
+  double* col = p.SR + (size_t)n * S * S + min(c, S - 1);          // element i of this thread's column: col[i * S]
+  const bool live = c < S;
+  double w[BW];                                                    // the last BW solution entries: w[d-1] = y_{i-d} / x_{i+d}
 #pragma unroll
-    for (int i = 0; i < BW; ++i) w[i] = 0.0;
+  for (int d = 0; d < BW; ++d) w[d] = 0.0;
+#pragma unroll 2
+  for (int i = i0; i < S; ++i) {                                   // L y = e_c (unit diagonal; multipliers l[i][i-d] at offset -d)
+    const double* f = fac + (size_t)i * WP + BW;
+    double acc = i == c ? 1.0 : 0.0;
 #pragma unroll
-    for (int i = 0; i <= BW; ++i) fc[i] = fac[(size_t)j0 * WP + BW + i];
-    double cur = 0.0;
-    for (int j = j0; j < S; ++j) {                                 // U^T y = e_r
-      const double* fnext = fac + (size_t)min(j + 1, S - 1) * WP + BW;
+    for (int d = 1; d <= BW; ++d) acc = fma(-f[-d], w[d - 1], acc);
+    if (live) col[(size_t)i * S] = acc;
 #pragma unroll
-      for (int i = 0; i <= BW; ++i) fn[i] = fnext[i];
-      const double yj = (cur + (j == r ? 1.0 : 0.0)) * fc[0];
-      if (r < S) x[j] = yj;
-#pragma unroll
-      for (int i = 1; i <= BW; ++i) w[i - 1] = fma(-fc[i], yj, w[i - 1]);
-      cur = w[0];
-#pragma unroll
-      for (int i = 1; i < BW; ++i) w[i - 1] = w[i];
-      w[BW - 1] = 0.0;
-#pragma unroll
-      for (int i = 0; i <= BW; ++i) fc[i] = fn[i];
-    }
-#pragma unroll
-    for (int i = 0; i < BW; ++i) w[i] = 0.0;
-#pragma unroll
-    for (int i = 1; i <= BW; ++i) fc[i] = fac[(size_t)(S - 1) * WP + BW - i];
-    cur = 0.0;
-    double yv = (r < S && S - 1 >= j0) ? x[S - 1] : 0.0;
-    for (int j = S - 1; j >= 0; --j) {                             // L^T x = y (unit diagonal)
-      const int jn = max(j - 1, 0);
-      const double* fnext = fac + (size_t)jn * WP + BW;
-#pragma unroll
-      for (int i = 1; i <= BW; ++i) fn[i] = fnext[-i];
-      const double ynext = (r < S && jn >= j0) ? x[jn] : 0.0;     // y_j = 0 before the warp's first row
-      const double xj = yv + cur;
-      if (r < S) x[j] = xj;
-#pragma unroll
-      for (int i = 1; i <= BW; ++i) w[i - 1] = fma(-fc[i], xj, w[i - 1]);
-      cur = w[0];
-#pragma unroll
-      for (int i = 1; i < BW; ++i) w[i - 1] = w[i];
-      w[BW - 1] = 0.0;
-#pragma unroll
-      for (int i = 1; i <= BW; ++i) fc[i] = fn[i];
-      yv = ynext;
-    }
+    for (int d = BW - 1; d > 0; --d) w[d] = w[d - 1];
+    w[0] = acc;
   }
-  __syncthreads();
-  double* SRg = p.SR + (size_t)n * S * S;
-  for (int e = tid; e < S * S; e += blockDim.x) { const int i = e / S; SRg[e] = X[i * LD + (e - i * S)]; }
+#pragma unroll
+  for (int d = 0; d < BW; ++d) w[d] = 0.0;
+  double ynext = live ? col[(size_t)(S - 1) * S] : 0.0;
+#pragma unroll 2
+  for (int i = S - 1; i >= 0; --i) {                               // U x = y (the diagonal holds 1 / pivot)
+    const double* f = fac + (size_t)i * WP + BW;
+    double acc = ynext;
+    ynext = (live && i - 1 >= i0) ? col[(size_t)(i - 1) * S] : 0.0;   // y_i = 0 above the warp's first column
+#pragma unroll
+    for (int d = 1; d <= BW; ++d) acc = fma(-f[d], w[d - 1], acc);
+    const double xi = acc * f[0];
+    if (live) col[(size_t)i * S] = xi;
+#pragma unroll
+    for (int d = BW - 1; d > 0; --d) w[d] = w[d - 1];
+    w[0] = xi;
+  }
 }
 
 // The caller's band guarantee on the initial T (a streaming read of T, once per banded call).
@@ -1516,8 +1496,7 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
     for (int t = 0; t < p.trials && !rc; ++t) {
       const int more = t + 1 < p.trials ? 1 : 0;
       pma_band_factor_kernel<<<grid_band, kBandWarps * 32, sm_bandk, st>>>(p);
-      pma_band_solve_kernel<<<grid_band, kBandWarps * 32, sm_bandk, st>>>(p, 0);
-      cobel_count_launch(2);
+      cobel_count_launch();
       rc = main_launch(MainPhase{0, 1, more, 0, t + 1, 1});
       if (rc || !more) break;
       pma_band_solve_kernel<<<grid_band, kBandWarps * 32, sm_bandk, st>>>(p, 4);
@@ -1525,9 +1504,8 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
       rc = main_launch(MainPhase{0, 0, 0, 1, t + 1, 1});
     }
     if (rc) return rc;
-    const int LD = S | 1;
     const int bwp = p.sr_band <= 4 ? 4 : p.sr_band <= 8 ? 8 : p.sr_band <= 12 ? 12 : p.sr_band <= 16 ? 16 : p.sr_band <= 24 ? 24 : 32;
-    const size_t sm_band = ((size_t)S * LD + (size_t)S * (2 * bwp + 1)) * 8;
+    const size_t sm_band = (size_t)S * (2 * bwp + 2) * 8;
     if (sm_band <= 227 * 1024) {
       auto go = [&](auto kernel) -> int {
         COBEL_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_band));

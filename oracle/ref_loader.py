@@ -1,18 +1,22 @@
 """Import the real, unmodified reference (build container only).
 
 Test infrastructure (see oracle/__init__.py).  ``/root/reference`` is read-only
-and does not exist on the GPU box, so this module is used only (a) by
-``oracle/make_golden.py`` to generate ``tests/golden/*.npz`` and (b) by CPU tests
-that pin the restatement against the reference (skipped when the reference is
-absent).  The GUI / gym packages the reference imports at module level are
+and does not exist on the GPU box; there the unmodified copy under ``baseline/_ref``
+(oracle/install_reference.py) is used.  This module serves (a) ``oracle/make_golden.py``
+to generate ``tests/golden/*.npz``, (b) the CPU tests that pin the restatement against
+the reference and (c) ``bench.py``'s reference arm / cpu_baseline leg.  The GUI / gym packages the reference imports at module level are
 replaced by the empty stand-ins under ``oracle/_stubs``;
 they never execute on the headless path.
 """
 import os
 import sys
 
-REFERENCE_SRC = os.environ.get('COBEL_REFERENCE_SRC', '/root/reference/src')
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_stubs')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the build container has the reference checkout; the GPU box only the copy oracle/install_reference.py placed under
+# baseline/_ref (git-ignored, travels with the snapshot)
+_CANDIDATES = [os.environ.get('COBEL_REFERENCE_SRC'), '/root/reference/src', os.path.join(os.path.dirname(_HERE), 'baseline', '_ref')]
+REFERENCE_SRC = next((c for c in _CANDIDATES if c and os.path.isdir(os.path.join(c, 'cobel'))), '/root/reference/src')
+_STUBS = os.path.join(_HERE, '_stubs')
 
 
 def available():
