@@ -15,7 +15,7 @@ from collections import Counter
 def sass_lines(so, cubin_sub, kernel_sub):
     d = tempfile.mkdtemp()
     subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(so)], cwd=d, capture_output=True)
-    cub = [f for f in os.listdir(d) if cubin_sub in f and 'sm_100a' in f][0]
+    cub = [f for f in os.listdir(d) if cubin_sub in f and 'sm_100a' in f][0] if any(cubin_sub in f for f in os.listdir(d)) else sorted(os.listdir(d))[0]
     txt = subprocess.run(['nvdisasm', '-gi', os.path.join(d, cub)], capture_output=True, text=True).stdout.split('\n')
     out, infn, loc = [], False, []
     pending = []
