@@ -127,7 +127,7 @@ class Agent(abc.ABC):
         S, A = m.shape[-2], m.shape[-1]
         return m.data_ptr(), (S * A if m.dim() == 3 else 0)
 
-    def _fire_trial_callbacks(self, res, first_trial, replay_calls=(0, 0), flat_order='F'):
+    def _fire_trial_callbacks(self, res, first_trial, replay_calls=(0, 0), flat_order='F', session_first=0):
         """Fire the per-trial hooks after a launch, once per trial in order, with batched values.
         ``replay_calls = (calls at trial start, calls at trial end)`` additionally fires
         ``on_replay_begin`` / ``on_replay_end`` (agent/pma.py:112-135, agent/sfma.py:139-187) with
@@ -161,7 +161,7 @@ class Agent(abc.ABC):
 
         for t in range(trials):
             steps_t, rew_t = res['trial_steps'][:, t], res['trial_reward'][:, t]
-            logs = {'trial_reward': 0.0, 'trial': first_trial + t, 'trial_session': t}
+            logs = {'trial_reward': 0.0, 'trial': first_trial + t, 'trial_session': session_first + t}
             logs = self.callbacks.on_trial_begin(logs)
             for c in range(per_trial):
                 if c == replay_calls[0]:      # the online steps lie between the start and the end replays
@@ -186,8 +186,27 @@ class Agent(abc.ABC):
 
     @staticmethod
     def _merge(results):
+        """One RunResult for a session that ran as several launches (``trials_per_launch``).  Per-trial arrays are
+        concatenated; the recorded per-step / per-replay buffers of a launch are padded with -1 behind the data of
+        each agent, so they are compacted per agent (the merged buffer is addressed by cumulative counts, exactly
+        like the buffer of a single launch)."""
         if len(results) == 1:
             return results[0]
+
+        def compact_cat(bufs, counts):
+            n = bufs[0].shape[0]
+            total = sum(c.long() for c in counts)
+            out = torch.full((n, max(int(total.max()), 1)), -1, dtype=bufs[0].dtype, device=bufs[0].device)
+            rows = torch.arange(n, device=out.device).unsqueeze(1)
+            offset = torch.zeros(n, dtype=torch.long, device=out.device)
+            for b, c in zip(bufs, counts):
+                pos = torch.arange(b.shape[1], device=out.device).unsqueeze(0)
+                valid = pos < c.long().unsqueeze(1)
+                dst = (offset.unsqueeze(1) + pos)
+                out[rows.expand_as(dst)[valid], dst[valid]] = b[valid]
+                offset += c.long()
+            return out
+
         out = RunResult()
         for k in results[0]:
             if k in ('n_steps', 'n_replay'):
@@ -196,13 +215,35 @@ class Agent(abc.ABC):
                 out[k] = results[0][k]
                 for r in results[1:]:
                     out[k] = out[k] | r[k]
+            elif k in ('step_sa', 'step_next'):
+                out[k] = compact_cat([r[k] for r in results], [r['n_steps'] for r in results])
+            elif k == 'replay_idx':
+                out[k] = compact_cat([r[k] for r in results], [r['n_replay'] for r in results])
+            elif k == 'replay_len':
+                out[k] = compact_cat([r[k] for r in results], [(r[k] >= 0).sum(dim=1) for r in results])
             else:
                 out[k] = torch.cat([r[k] for r in results], dim=1)
         return out
 
     def _check_flags(self, res):
-        if self.record and bool((res['flags'] & 1).any()):
+        """Raise / warn on the COBEL_FLAG_* bits a launch left behind (include/cobel_b200.h)."""
+        fl = res['flags']
+        if not fl.numel() or int(fl.max().item()) == 0:
+            return
+        if self.record and bool((fl & 1).any()):
             raise _lib.CobelError('trace buffer overflow (internal sizing error)')
+        if bool((fl & 32).any()):      # COBEL_FLAG_BAND_VIOLATION (a violated band promise also derails the eliminations)
+            raise _lib.CobelError('PMA: T or a transition left the band assumed by the banded update_sr')
+        if bool((fl & 8).any()):       # COBEL_FLAG_SINGULAR
+            raise _lib.CobelError('PMA: singular elimination -- T has no unique stationary distribution (unreachable cells '
+                                  'form closed classes of their own) or a pivot of I - gamma T underflowed')
+        if bool((fl & 64).any()):      # COBEL_FLAG_REPLAY_OVERFLOW
+            raise _lib.CobelError('SFMA: an agent has experienced more (state, action) pairs than the replay kernel can '
+                                  'stage in shared memory for this state space')
+        if bool((fl & 2).any()):       # COBEL_FLAG_CDF_NEAR_TIE: exp() / prefix sums are not bit-identical to NumPy's
+            import warnings
+            warnings.warn('SFMA replay: %d agent(s) drew within 1e-12 of a CDF bin edge; their sampled indices may '
+                          'differ from the reference' % int((fl & 2).bool().sum()))
 
     @abc.abstractmethod
     def train(self, interface, trials, steps):

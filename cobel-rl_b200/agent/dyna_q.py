@@ -67,7 +67,7 @@ class DynaQ(Agent):
         assert interface.n_states == S and interface.n_actions == A
         pol = self.policy if learn else self.policy_test
         results = []
-        for _, n_tr in self._chunks(trials):
+        for t0, n_tr in self._chunks(trials):
             keep = []
             tr, res = self._make_trace(n_tr, steps, 0 if (no_replay or self.episodic_replay or not learn) else 1,
                                        1 if (learn and not no_replay and self.episodic_replay) else 0,
@@ -82,7 +82,7 @@ class DynaQ(Agent):
                                  1 if no_replay else 0, 1 if self.episodic_replay else 0)
             _lib.call('cobel_dynaq_run', st.device, p, launch_stream(st))
             self._check_flags(res)
-            self._fire_trial_callbacks(res, self.current_trial)
+            self._fire_trial_callbacks(res, self.current_trial, session_first=t0)
             self.current_trial += n_tr
             results.append(res)
             if self.stop:

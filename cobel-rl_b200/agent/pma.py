@@ -85,7 +85,7 @@ class PMA(Agent):
         # the reference's PMA.test() also acts with `policy` (agent/pma.py:287)
         pol = self.policy
         results = []
-        for _, n_tr in self._chunks(trials):
+        for t0, n_tr in self._chunks(trials):
             keep = []
             tr, res = self._make_trace(n_tr, steps, 0, 2 if (learn and not no_replay) else 0, batch_size, keep)
             band, bscratch = M.sr_band(interface.transition_band) if (learn and not no_replay) else (-1, None)
@@ -94,7 +94,7 @@ class PMA(Agent):
             self._check_flags(res)
             if band >= 0 and bool((res['flags'] & 32).any()):      # COBEL_FLAG_BAND_VIOLATION
                 raise _lib.CobelError('PMA: T or a transition left the band of %d assumed by the banded update_sr' % band)
-            self._fire_trial_callbacks(res, self.current_trial, (1, 1) if (learn and not no_replay) else (0, 0))
+            self._fire_trial_callbacks(res, self.current_trial, (1, 1) if (learn and not no_replay) else (0, 0), session_first=t0)
             self.current_trial += n_tr
             results.append(res)
         self.last_run = self._merge(results)

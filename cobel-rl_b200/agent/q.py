@@ -85,7 +85,7 @@ class QAgent(Agent):
         assert interface.n_actions == self.nb_actions
         pol = self.policy if learn else self.policy_test
         results = []
-        for _, n_tr in self._chunks(trials):
+        for t0, n_tr in self._chunks(trials):
             keep = []
             if learn:
                 self._ensure_log(n_tr * steps)
@@ -102,7 +102,7 @@ class QAgent(Agent):
                              batch_size if learn else 0, 1 if learn else 0)
             _lib.call('cobel_q_run', st.device, p, launch_stream(st))
             self._check_flags(res)
-            self._fire_trial_callbacks(res, self.current_trial)
+            self._fire_trial_callbacks(res, self.current_trial, session_first=t0)
             self.current_trial += n_tr
             results.append(res)
             if self.stop:

@@ -102,7 +102,7 @@ class SR(Agent):
         assert interface.n_states == int(self.observation_space.n) and interface.n_actions == self._model.shape[2]
         pol = self.policy if learn else self.policy_test
         results = []
-        for _, n_tr in self._chunks(trials):
+        for t0, n_tr in self._chunks(trials):
             keep = []
             tr, res = self._make_trace(n_tr, steps, 0, 0, 0, keep)
             lr, gm = st.param(self.learning_rate, 'learning_rate'), st.param(self.gamma, 'gamma')
@@ -123,7 +123,7 @@ class SR(Agent):
                                   lr.data_ptr(), gm.data_ptr(), n_tr, steps, 1 if learn else 0, 0)
                 _lib.call('cobel_sr_run', st.device, p, launch_stream(st))
             self._check_flags(res)
-            self._fire_trial_callbacks(res, self.current_trial)
+            self._fire_trial_callbacks(res, self.current_trial, session_first=t0)
             self.current_trial += n_tr
             results.append(res)
             if self.stop:

@@ -23,9 +23,10 @@ constexpr int kWarpsPerCta = 4;
 
 struct AgentSmem {      // byte offsets inside one agent's shared-memory block
   int q, mr, mx, wm, rm, ptab, draws, bytes;
-  __host__ __device__ AgentSmem(int S, int A, bool plain) {
+  // tables = false: Q / M stay in HBM (state spaces whose tables do not fit), only the dependency masks are on chip
+  __host__ __device__ AgentSmem(int S, int A, bool plain, bool tables = true) {
     const bool eps_tab = plain && A <= 4;
-    const int SA = S * A;
+    const int SA = tables ? S * A : 0;
     q = 0;
     mr = q + SA * 8;
     wm = mr + SA * 8;
@@ -51,39 +52,62 @@ struct WorldSmem {      // byte offsets of the CTA-shared environment tables
 // PLAIN = the common production case (epsilon-greedy training with per-step replay, no optional trace buffers,
 // no action mask, deterministic world): a kernel without the per-step checks and the other policies' code
 // (the instruction count per step is what bounds this kernel).
-template <int A, bool PLAIN>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const __grid_constant__ CobelDynaQParams p) {
+// HBM = the agent's tables (and the environment's) are too large for shared memory: Q / M.rewards / M.states /
+// M.terminals are read and written in place in HBM / L2 (a replay is 32 independent gathers per lane-parallel
+// round, so the DRAM latency of a step is paid about six times, not 33), the world tables go through the read-only
+// path, only the two dependency masks of the level-parallel replay (8 bytes per state) stay on chip.
+template <int A, bool PLAIN, bool HBM = false>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, HBM ? 1 : 7) dynaq_warp_kernel(const __grid_constant__ CobelDynaQParams p) {
+  static_assert(!(PLAIN && HBM), "the HBM path is the generic kernel");
   extern __shared__ __align__(16) unsigned char smem[];
   const int S = p.world.n_states, K = p.world.n_starts, SA = S * A;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const WorldSmem wo(S, A, K);
+  const WorldSmem wo(HBM ? 0 : S, A, HBM ? 0 : K);
   constexpr bool kEpsTab = PLAIN && A <= 4;      // tie-pattern CDF table instead of per-step probabilities
-  const AgentSmem ao(S, A, PLAIN);
+  const AgentSmem ao(S, A, PLAIN, !HBM);
 
   double* rew_s = reinterpret_cast<double*>(smem + wo.rew);
   int32_t* succ_s = reinterpret_cast<int32_t*>(smem + wo.succ);
   int32_t* starts_s = reinterpret_cast<int32_t*>(smem + wo.starts);
   uint8_t* term_s = smem + wo.term;
-  for (int e = threadIdx.x; e < SA; e += blockDim.x) succ_s[e] = p.world.succ[e];
-  for (int e = threadIdx.x; e < S; e += blockDim.x) { rew_s[e] = p.world.reward[e]; term_s[e] = p.world.terminal[e]; }
-  for (int e = threadIdx.x; e < K; e += blockDim.x) starts_s[e] = p.world.starts[e];
-  __syncthreads();
+  if constexpr (!HBM) {
+    for (int e = threadIdx.x; e < SA; e += blockDim.x) succ_s[e] = p.world.succ[e];
+    for (int e = threadIdx.x; e < S; e += blockDim.x) { rew_s[e] = p.world.reward[e]; term_s[e] = p.world.terminal[e]; }
+    for (int e = threadIdx.x; e < K; e += blockDim.x) starts_s[e] = p.world.starts[e];
+    __syncthreads();
+  }
+  auto w_succ = [&](int sa) -> int { if constexpr (HBM) return __ldg(p.world.succ + sa); else return succ_s[sa]; };
+  auto w_rew = [&](int x) -> double { if constexpr (HBM) return __ldg(p.world.reward + x); else return rew_s[x]; };
+  auto w_term = [&](int x) -> int { if constexpr (HBM) return __ldg(p.world.terminal + x); else return term_s[x]; };
+  auto w_start = [&](int k) -> int { if constexpr (HBM) return __ldg(p.world.starts + k); else return starts_s[k]; };
 
-  const int64_t n = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x / 32 + warp;
   if (n >= p.n_agents) return;                      // whole warp leaves; no block-wide sync below
 
   unsigned char* blk = smem + wo.bytes + (size_t)warp * ao.bytes;
-  double* Q = reinterpret_cast<double*>(blk + ao.q);
-  double* Mr = reinterpret_cast<double*>(blk + ao.mr);
-  uint16_t* Mx = reinterpret_cast<uint16_t*>(blk + ao.mx);     // next state | non-terminal << 15
+  const size_t g0 = (size_t)n * SA;
+  double* Q = HBM ? p.Q + g0 : reinterpret_cast<double*>(blk + ao.q);
+  double* Mr = HBM ? p.Mr + g0 : reinterpret_cast<double*>(blk + ao.mr);
+  uint16_t* Mx = reinterpret_cast<uint16_t*>(blk + ao.mx);     // next state | non-terminal << 15 (on-chip tables)
+  int32_t* Msg = p.Ms + g0;                                    // (HBM tables)
+  int32_t* Mtg = p.Mt + g0;
   uint32_t* wm = reinterpret_cast<uint32_t*>(blk + ao.wm);
   uint32_t* rm = reinterpret_cast<uint32_t*>(blk + ao.rm);
+  auto m_next = [&](int i, int& s2, int& nt) {
+    if constexpr (HBM) { s2 = Msg[i]; nt = Mtg[i] ? 1 : 0; }
+    else { const uint16_t v = Mx[i]; s2 = v & 0x7FFF; nt = v >> 15; }
+  };
+  auto m_set = [&](int i, int s2, int nt) {
+    if constexpr (HBM) { Msg[i] = s2; Mtg[i] = nt; }
+    else Mx[i] = (uint16_t)(s2 | (nt << 15));
+  };
 
-  const size_t g0 = (size_t)n * SA;
-  for (int e = lane; e < SA; e += 32) {
-    Q[e] = p.Q[g0 + e];
-    Mr[e] = p.Mr[g0 + e];
-    Mx[e] = (uint16_t)(p.Ms[g0 + e] | ((p.Mt[g0 + e] ? 1 : 0) << 15));
+  if constexpr (!HBM) {
+    for (int e = lane; e < SA; e += 32) {
+      Q[e] = p.Q[g0 + e];
+      Mr[e] = p.Mr[g0 + e];
+      Mx[e] = (uint16_t)(p.Ms[g0 + e] | ((p.Mt[g0 + e] ? 1 : 0) << 15));
+    }
   }
   __syncwarp();
 
@@ -118,8 +142,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
         const int i = draw_integer(u, SA);
         rs = i / A; ra = i - rs * A;
         rr = Mr[i];
-        const uint16_t v = Mx[i];
-        rs2 = v & 0x7FFF; rnt = v >> 15;
+        m_next(i, rs2, rnt);
         if (!PLAIN && tr.replay_idx) {
           if (nrep + lane < tr.replay_cap) tr.replay_idx[n * tr.replay_cap + nrep + lane] = i;
           else flags |= COBEL_FLAG_TRACE_OVERFLOW;
@@ -138,7 +161,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   for (int trial = 0; trial < p.trials; ++trial) {
     // interface/gridworld.py:142: one uniform draw over the starting states
     win.ensure(3 + (step_replay && B <= 32 ? B : 0), lane);
-    int s = starts_s[draw_integer(win.next(), K)];
+    int s = w_start(draw_integer(win.next(), K));
     double treward = 0.0;
     int step = 0;
     for (;; ++step) {
@@ -154,9 +177,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
       int a;
       if constexpr (kEpsTab) a = select_action_eps_tab<A>(row, ptab, win.next(), lane);
       else a = select_action_warp<A, PLAIN ? COBEL_POLICY_EPS_GREEDY : -1>(row, mask, pt, win.next(), lane);
-      const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : succ_s[s * A + a];
-      const double r = rew_s[s2];
-      const int end = term_s[s2];
+      const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : w_succ(s * A + a);
+      const double r = w_rew(s2);
+      const int end = w_term(s2);
       const int nt = 1 - end;
       if (!PLAIN && tr.step_sa && lane == 0) {
         if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
@@ -178,7 +201,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
         __syncwarp();
         if (lane == 0) {
           Mr[s * A + a] = m1;
-          Mx[s * A + a] = (uint16_t)(s2 | (nt << 15));
+          m_set(s * A + a, s2, nt);
           Q[s * A + a] = qn;
         }
         __syncwarp();
@@ -196,7 +219,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
   }
 
   __syncwarp();
-  if (learn) {
+  if (learn && !HBM) {
     for (int e = lane; e < SA; e += 32) {
       p.Q[g0 + e] = Q[e];
       p.Mr[g0 + e] = Mr[e];
@@ -216,15 +239,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) dynaq_warp_kernel(const 
 template <int A>
 int launch(const CobelDynaQParams& p, cudaStream_t st) {
   const int S = p.world.n_states, K = p.world.n_starts;
-  COBEL_REQUIRE(S <= 0x7FFF, COBEL_EUNSUPPORTED, "Dyna-Q kernel supports at most 32767 states");
   const WorldSmem wo(S, A, K);
   const bool plain = !p.action_mask && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx && !p.trace.replay_len &&
                      p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn && !p.no_replay && !p.episodic_replay &&
                      p.batch == 32 && !p.stream.user_stream;
   const AgentSmem ao(S, A, plain);
   const size_t sm = (size_t)wo.bytes + (size_t)kWarpsPerCta * ao.bytes;
-  COBEL_REQUIRE(sm <= 227 * 1024, COBEL_EUNSUPPORTED,
-                "Dyna-Q tables of %d states x %d actions do not fit in shared memory (%zu bytes per CTA)", S, A, sm);
+  if (sm > 227 * 1024) {
+    // the tables do not fit: they stay in HBM / L2, only the dependency masks of the replay are staged
+    const AgentSmem go(S, A, false, false);
+    int warps = kWarpsPerCta;
+    while (warps > 1 && (size_t)warps * go.bytes > 227 * 1024) warps >>= 1;
+    const size_t smg = (size_t)warps * go.bytes;
+    COBEL_REQUIRE(smg <= 227 * 1024, COBEL_EUNSUPPORTED,
+                  "Dyna-Q: the replay's dependency masks of %d states do not fit in shared memory (%zu bytes)", S, smg);
+    COBEL_CUDA_OK(cudaFuncSetAttribute(dynaq_warp_kernel<A, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));
+    dynaq_warp_kernel<A, false, true><<<(unsigned)((p.n_agents + warps - 1) / warps), warps * 32, smg, st>>>(p);
+    cobel_count_launch();
+    COBEL_CUDA_OK(cudaGetLastError());
+    return COBEL_OK;
+  }
   const unsigned grid = (unsigned)((p.n_agents + kWarpsPerCta - 1) / kWarpsPerCta);
   if (plain) {
     COBEL_CUDA_OK(cudaFuncSetAttribute(dynaq_warp_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

@@ -26,8 +26,9 @@ static_assert(sizeof(LogRecord) == 16, "log record must be 16 bytes");
 
 struct QSmem {
   int q, wm, rm, ptab, draws, bytes;
-  __host__ __device__ QSmem(int NK, int A) {
-    q = 0; wm = q + NK * A * 8; rm = wm + NK * 4; ptab = (rm + NK * 4 + 15) & ~15;
+  // table = false: Q stays in HBM (key spaces whose table does not fit), only the dependency masks are on chip
+  __host__ __device__ QSmem(int NK, int A, bool table = true) {
+    q = 0; wm = q + (table ? NK * A * 8 : 0); rm = wm + NK * 4; ptab = (rm + NK * 4 + 15) & ~15;
     draws = ptab + kEpsTabDoubles * 8;   // tie-pattern CDF table and stream window of the PLAIN kernel (warp_agent.cuh)
     bytes = draws + kSmemDraws * 8;
   }
@@ -41,34 +42,44 @@ struct QWorldSmem {
 };
 
 // PLAIN = no optional trace buffers, deterministic world (see dynaq.cu)
-template <int A, bool PLAIN>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __grid_constant__ CobelQParams p) {
+// HBM = Q and the environment's tables stay in HBM / L2 (see dynaq.cu): only the dependency masks are on chip
+template <int A, bool PLAIN, bool HBM = false>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, HBM ? 1 : 7) q_warp_kernel(const __grid_constant__ CobelQParams p) {
+  static_assert(!(PLAIN && HBM), "the HBM path is the generic kernel");
   extern __shared__ __align__(16) unsigned char smem[];
   const int S = p.world.n_states, K = p.world.n_starts, NK = p.n_keys;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const QWorldSmem wo(S, A, K);
-  const QSmem ao(NK, A);
+  const QWorldSmem wo(HBM ? 0 : S, A, HBM ? 0 : K);
+  const QSmem ao(NK, A, !HBM);
   double* rew_s = reinterpret_cast<double*>(smem + wo.rew);
   int32_t* succ_s = reinterpret_cast<int32_t*>(smem + wo.succ);
   int32_t* starts_s = reinterpret_cast<int32_t*>(smem + wo.starts);
   int32_t* key_s = reinterpret_cast<int32_t*>(smem + wo.key);
   uint8_t* term_s = smem + wo.term;
-  for (int e = threadIdx.x; e < S * A; e += blockDim.x) succ_s[e] = p.world.succ[e];
-  for (int e = threadIdx.x; e < S; e += blockDim.x) {
-    rew_s[e] = p.world.reward[e]; term_s[e] = p.world.terminal[e];
-    key_s[e] = p.obs_key ? p.obs_key[e] : e;
+  if constexpr (!HBM) {
+    for (int e = threadIdx.x; e < S * A; e += blockDim.x) succ_s[e] = p.world.succ[e];
+    for (int e = threadIdx.x; e < S; e += blockDim.x) {
+      rew_s[e] = p.world.reward[e]; term_s[e] = p.world.terminal[e];
+      key_s[e] = p.obs_key ? p.obs_key[e] : e;
+    }
+    for (int e = threadIdx.x; e < K; e += blockDim.x) starts_s[e] = p.world.starts[e];
+    __syncthreads();
   }
-  for (int e = threadIdx.x; e < K; e += blockDim.x) starts_s[e] = p.world.starts[e];
-  __syncthreads();
+  auto w_succ = [&](int sa) -> int { if constexpr (HBM) return __ldg(p.world.succ + sa); else return succ_s[sa]; };
+  auto w_rew = [&](int x) -> double { if constexpr (HBM) return __ldg(p.world.reward + x); else return rew_s[x]; };
+  auto w_term = [&](int x) -> int { if constexpr (HBM) return __ldg(p.world.terminal + x); else return term_s[x]; };
+  auto w_start = [&](int k) -> int { if constexpr (HBM) return __ldg(p.world.starts + k); else return starts_s[k]; };
+  auto w_key = [&](int x) -> int { if constexpr (HBM) return p.obs_key ? __ldg(p.obs_key + x) : x; else return key_s[x]; };
 
-  const int64_t n = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x / 32 + warp;
   if (n >= p.n_agents) return;
   unsigned char* blk = smem + wo.bytes + (size_t)warp * ao.bytes;
-  double* Q = reinterpret_cast<double*>(blk + ao.q);
+  const size_t g0 = (size_t)n * NK * A;
+  double* Q = HBM ? p.Q + g0 : reinterpret_cast<double*>(blk + ao.q);
   uint32_t* wm = reinterpret_cast<uint32_t*>(blk + ao.wm);
   uint32_t* rm = reinterpret_cast<uint32_t*>(blk + ao.rm);
-  const size_t g0 = (size_t)n * NK * A;
-  for (int e = lane; e < NK * A; e += 32) Q[e] = p.Q[g0 + e];
+  if constexpr (!HBM)
+    for (int e = lane; e < NK * A; e += 32) Q[e] = p.Q[g0 + e];
   for (int e = lane; e < NK; e += 32) { wm[e] = 0; rm[e] = 0; }
   __syncwarp();
 
@@ -89,22 +100,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __gr
 
   for (int trial = 0; trial < p.trials; ++trial) {
     win.ensure(3 + (learn && B <= 32 ? B : 0), lane);
-    int s = starts_s[draw_integer(win.next(), K)];                // interface reset: one draw
+    int s = w_start(draw_integer(win.next(), K));                 // interface reset: one draw
     double treward = 0.0;
     int step = 0;
     for (;; ++step) {
       win.ensure(2 + (learn && B <= 32 ? B : 0), lane);
-      const int ks = key_s[s];
+      const int ks = w_key(s);
       double row[A];
       load_row<A>(Q + ks * A, row);
       int a;
       if constexpr (kEpsTab) a = select_action_eps_tab<A>(row, ptab, win.next(), lane);
       else a = select_action_warp<A, PLAIN ? COBEL_POLICY_EPS_GREEDY : -1>(row, (1u << A) - 1u, pt, win.next(), lane);
-      const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : succ_s[s * A + a];
-      const double r = rew_s[s2];
-      const int end = term_s[s2];
+      const int s2 = (!PLAIN && p.world.tp_off) ? stochastic_successor(p.world, s * A + a, win.next()) : w_succ(s * A + a);
+      const double r = w_rew(s2);
+      const int end = w_term(s2);
       const int nt = 1 - end;
-      const int ks2 = key_s[s2];
+      const int ks2 = w_key(s2);
       if (!PLAIN && tr.step_sa && lane == 0) {
         if (nsteps < tr.step_cap) { tr.step_sa[n * tr.step_cap + nsteps] = s * A + a; if (tr.step_next) tr.step_next[n * tr.step_cap + nsteps] = s2; }
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
@@ -168,7 +179,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 7) q_warp_kernel(const __gr
   }
 
   __syncwarp();
-  if (learn)
+  if (learn && !HBM)
     for (int e = lane; e < NK * A; e += 32) p.Q[g0 + e] = Q[e];
   flags = __reduce_or_sync(kFull, flags);
   if (lane == 0) {
@@ -185,8 +196,20 @@ int launch(const CobelQParams& p, cudaStream_t st) {
   const QWorldSmem wo(p.world.n_states, A, p.world.n_starts);
   const QSmem ao(p.n_keys, A);
   const size_t sm = (size_t)wo.bytes + (size_t)kWarpsPerCta * ao.bytes;
-  COBEL_REQUIRE(sm <= 227 * 1024, COBEL_EUNSUPPORTED,
-                "QAgent tables (%d states, %d keys, %d actions) do not fit in shared memory", p.world.n_states, p.n_keys, A);
+  if (sm > 227 * 1024) {
+    // the tables do not fit: Q stays in HBM / L2, only the dependency masks of the replay are staged
+    const QSmem go(p.n_keys, A, false);
+    int warps = kWarpsPerCta;
+    while (warps > 1 && (size_t)warps * go.bytes > 227 * 1024) warps >>= 1;
+    const size_t smg = (size_t)warps * go.bytes;
+    COBEL_REQUIRE(smg <= 227 * 1024, COBEL_EUNSUPPORTED,
+                  "QAgent: the replay's dependency masks of %d keys do not fit in shared memory (%zu bytes)", p.n_keys, smg);
+    COBEL_CUDA_OK(cudaFuncSetAttribute(q_warp_kernel<A, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smg));
+    q_warp_kernel<A, false, true><<<(unsigned)((p.n_agents + warps - 1) / warps), warps * 32, smg, st>>>(p);
+    cobel_count_launch();
+    COBEL_CUDA_OK(cudaGetLastError());
+    return COBEL_OK;
+  }
   const unsigned grid = (unsigned)((p.n_agents + kWarpsPerCta - 1) / kWarpsPerCta);
   const bool plain = !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx && !p.trace.replay_len &&
                      p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn && p.batch == 32 && !p.stream.user_stream;
@@ -215,8 +238,8 @@ extern "C" int cobel_q_run(const CobelQParams* pp, void* stream) {
   COBEL_REQUIRE(p.Q && p.lr && p.gamma, COBEL_EINVAL, "agent tables missing");
   COBEL_REQUIRE(p.n_keys > 0 && p.n_keys <= 65535, COBEL_EINVAL, "n_keys must be in 1..65535");
   COBEL_REQUIRE(p.batch >= 0, COBEL_EINVAL, "batch must be >= 0");
+  if (p.trials == 0) return COBEL_OK;                  // a zero-trial session is a no-op (no log needed)
   COBEL_REQUIRE(!p.learn || (p.log && p.log_len && p.log_cap > 0), COBEL_EINVAL, "experience log missing");
-  if (p.trials == 0) return COBEL_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (p.world.n_actions) {
     case 2: return launch<2>(p, st);

@@ -165,6 +165,7 @@ struct SfmaPhase {
   int n_trials;       // step kernel: trials run by this launch (0: reset only; several only without any replay)
   int trial;          // index of the (first) trial (trace rows)
   int start_replay;   // replay kernel: the trace-only replay at trial start (cur = start state, no Q updates)
+  int list_cap;       // replay kernel: capacity of the list of experienced (s, a) (ReplaySmem)
 };
 
 template <int A>
@@ -245,19 +246,34 @@ __global__ void __launch_bounds__(64) sfma_step_kernel(const __grid_constant__ C
 }
 
 struct ReplaySmem {
-  int l, cc, msc, r, inh, part, rep, mbits, cdf, bytes;
-  __host__ __device__ ReplaySmem(int S, int A, int T, int B, bool random_replay) {
+  int l, cc, msc, r, inh, part, rep, mbits, cdf, bytes, cap;
+  // cap = capacity of the list of experienced (s, a): all S*A of them when that fits, else what shared memory
+  // holds (an agent that has experienced more raises COBEL_FLAG_REPLAY_OVERFLOW)
+  __host__ __device__ ReplaySmem(int S, int A, int T, int B, bool random_replay, int cap_ = -1) {
     const int N = S * A;
+    cap = cap_ < 0 ? N : cap_;
+    const int R = cap > S ? cap : S;         // the priority scratch also hosts the 2 S dependency-mask words (8 S bytes)
     r = 0;                                   // priority scratch [nnz] (aliased by the dependency masks of the TD batch)
-    cc = r + N * 8;                          // strengths of the listed experiences
-    inh = cc + N * 8;                        // I [S]
+    cc = r + R * 8;                          // strengths of the listed experiences
+    inh = cc + cap * 8;                      // I [S]
     part = inh + S * 8;                      // scan partials
     cdf = part + (T + 32) * 8;               // random replay: m-fold sums of fl(1 / n_valid)
     l = cdf + (random_replay ? N * 8 : 0);   // experienced experiences: action << 16 | state, ascending flat index
-    rep = l + N * 4;                         // reactivated flat indices of one replay
+    rep = l + cap * 4;                       // reactivated flat indices of one replay
     msc = rep + ((B + 1) & ~1) * 4;          // next state of the listed experiences
-    mbits = msc + N * 2;                     // valid-action bits per state
+    mbits = msc + ((cap + 1) & ~1) * 2;      // valid-action bits per state
     bytes = (mbits + S + 15) & ~15;
+  }
+  // the largest list capacity whose layout fits into `limit` bytes
+  static int fit(int S, int A, int T, int B, bool random_replay, int limit) {
+    const int N = S * A;
+    if (ReplaySmem(S, A, T, B, random_replay).bytes <= limit) return N;
+    int lo = 0, hi = N;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) / 2;
+      if (ReplaySmem(S, A, T, B, random_replay, mid).bytes <= limit) lo = mid; else hi = mid - 1;
+    }
+    return lo;
   }
 };
 
@@ -268,7 +284,7 @@ __global__ void __launch_bounds__(256, 4) sfma_replay_kernel(const __grid_consta
   const int S = p.world.n_states, N = S * A, B = p.batch;
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n = blockIdx.x;
-  const ReplaySmem so(S, A, T, B, p.random_replay != 0);
+  const ReplaySmem so(S, A, T, B, p.random_replay != 0, ph.list_cap);
   double* R = reinterpret_cast<double*>(smem + so.r);
   double* Cc = reinterpret_cast<double*>(smem + so.cc);
   double* I = reinterpret_cast<double*>(smem + so.inh);
@@ -452,11 +468,16 @@ __global__ void __launch_bounds__(256, 4) sfma_replay_kernel(const __grid_consta
     int nnz;
     {
       const int chunk = (N + T - 1) / T;
-      const int lo = tid * chunk < N ? tid * chunk : N, hi = lo + chunk < N ? lo + chunk : N;
+      const int lo = tid * chunk < N ? tid * chunk : N;
+      int hi = lo + chunk < N ? lo + chunk : N;
       int cnt = 0;
 #pragma unroll 1
       for (int i = lo; i < hi; ++i) cnt += Cg[i] > 0.0 ? 1 : 0;
       int off = block_exclusive_scan_int(cnt, part, tid, T, nnz);
+      if (nnz > so.cap) {                                                  // more experienced (s, a) than the list holds
+        flags |= COBEL_FLAG_REPLAY_OVERFLOW;
+        nnz = 0; hi = lo;
+      }
 #pragma unroll 1
       for (int i = lo; i < hi; ++i) {
         const double c = Cg[i];
@@ -1069,14 +1090,17 @@ int launch(const CobelSFMAParams& p, cudaStream_t st) {
   // no strength modulation over all experiences), and the caller provided the carry scratch
   const bool track_t = p.recency != 0 || (p.learn && p.no_replay);
   const bool split = p.carry != nullptr && p.decay_strength == 1.0 && !track_t && !(p.mod_flags & COBEL_SFMA_MOD_REWARD);
+  // (state spaces whose tables exceed shared memory run on the split path only: its step kernel works on the tables
+  //  in HBM and its replay kernel stages just the list of experienced (s, a))
   if (split) {
     // CTA size of the replay kernel: its passes run over the compact list of experienced (s, a) -- a few hundred
     // entries -- and every warp repeats the block-wide combines, so a smaller CTA with more CTAs per SM wins
     // (20x20, 65536 agents: 7.9 / 8.5 / 6.2 x 10^8 agent-steps/s with 256 / 128 / 64 threads)
     int TR = N <= 128 ? 64 : N <= 4096 ? 128 : 256;
     if (const char* e = getenv("COBEL_SFMA_REPLAY_THREADS")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 256) TR = v; }
-    const ReplaySmem rso(S, A, TR, p.batch, p.random_replay != 0);
-    COBEL_REQUIRE(rso.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
+    const int cap = ReplaySmem::fit(S, A, TR, p.batch, p.random_replay != 0, 227 * 1024 - 512);
+    const ReplaySmem rso(S, A, TR, p.batch, p.random_replay != 0, cap);
+    COBEL_REQUIRE(cap >= 1 && rso.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
                   "SFMA replay of %d states x %d actions needs %d bytes of shared memory", S, A, rso.bytes);
     COBEL_CUDA_OK(cudaFuncSetAttribute(sfma_replay_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, rso.bytes));
     COBEL_CUDA_OK(cudaFuncSetAttribute(sfma_replay_kernel<A>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1085,17 +1109,17 @@ int launch(const CobelSFMAParams& p, cudaStream_t st) {
     auto replay = [&](SfmaPhase ph) { sfma_replay_kernel<A><<<(unsigned)p.n_agents, TR, rso.bytes, st>>>(p, ph); cobel_count_launch(); };
     // SfmaPhase{init, reset, n_trials, trial, start_replay}
     if (!p.learn) {
-      step(SfmaPhase{1, 1, p.trials, 0, 0});                       // test(): all trials in one launch
+      step(SfmaPhase{1, 1, p.trials, 0, 0, cap});                  // test(): all trials in one launch
     } else {
       for (int t = 0; t < p.trials; ++t) {
         if (p.start_replay) {                                      // agent/sfma.py:272-275: trace only, no Q updates
-          step(SfmaPhase{t == 0, 1, 0, t, 0});
-          replay(SfmaPhase{0, 0, 0, t, 1});
-          step(SfmaPhase{0, 0, 1, t, 0});
+          step(SfmaPhase{t == 0, 1, 0, t, 0, cap});
+          replay(SfmaPhase{0, 0, 0, t, 1, cap});
+          step(SfmaPhase{0, 0, 1, t, 0, cap});
         } else {
-          step(SfmaPhase{t == 0, 1, 1, t, 0});
+          step(SfmaPhase{t == 0, 1, 1, t, 0, cap});
         }
-        replay(SfmaPhase{0, 0, 0, t, 0});                          // agent/sfma.py:300-324 (no_replay keeps M.T: fused path)
+        replay(SfmaPhase{0, 0, 0, t, 0, cap});                          // agent/sfma.py:300-324 (no_replay keeps M.T: fused path)
       }
       // M.T.fill(0) after every trial with replay (agent/sfma.py:324); M.T is not tracked on this path
       if (p.trials > 0) COBEL_CUDA_OK(cudaMemsetAsync(p.T, 0, (size_t)p.n_agents * N * sizeof(double), st));
@@ -1131,12 +1155,13 @@ int replay_only(const CobelSFMAParams& p, const int32_t* state, int apply_update
   const int S = p.world.n_states, N = S * A;
   COBEL_REQUIRE(S <= 0x7FFF, COBEL_EUNSUPPORTED, "SFMA kernel supports at most 32767 states");
   const int T = N <= 128 ? 64 : N <= 4096 ? 128 : 256;
-  const ReplaySmem rso(S, A, T, p.batch, p.random_replay != 0);
-  COBEL_REQUIRE(rso.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
+  const int cap = ReplaySmem::fit(S, A, T, p.batch, p.random_replay != 0, 227 * 1024 - 512);
+  const ReplaySmem rso(S, A, T, p.batch, p.random_replay != 0, cap);
+  COBEL_REQUIRE(cap >= 1 && rso.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
                 "SFMA replay of %d states x %d actions needs %d bytes of shared memory", S, A, rso.bytes);
   COBEL_CUDA_OK(cudaFuncSetAttribute(sfma_replay_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, rso.bytes));
   sfma_set_carry_kernel<<<(unsigned)((p.n_agents + 127) / 128), 128, 0, st>>>(p.carry, state, p.n_agents);
-  sfma_replay_kernel<A><<<(unsigned)p.n_agents, T, rso.bytes, st>>>(p, SfmaPhase{0, 0, 0, 0, apply_updates == 1 ? 0 : (apply_updates == 2 ? 2 : 1)});
+  sfma_replay_kernel<A><<<(unsigned)p.n_agents, T, rso.bytes, st>>>(p, SfmaPhase{0, 0, 0, 0, apply_updates == 1 ? 0 : (apply_updates == 2 ? 2 : 1), cap});
   cobel_count_launch(2);
   COBEL_CUDA_OK(cudaGetLastError());
   return COBEL_OK;

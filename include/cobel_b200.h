@@ -105,7 +105,8 @@ enum {
   COBEL_FLAG_LOG_OVERFLOW   = 4,  /* QAgent experience log full */
   COBEL_FLAG_SINGULAR       = 8,  /* PMA: (I - gamma T) pivot underflow */
   COBEL_FLAG_VISITED_OVERFLOW = 16,/* compact SR: an agent visited more than max_visited distinct states */
-  COBEL_FLAG_BAND_VIOLATION = 32  /* PMA: T or a transition outside the band promised by sr_band */
+  COBEL_FLAG_BAND_VIOLATION = 32, /* PMA: T or a transition outside the band promised by sr_band */
+  COBEL_FLAG_REPLAY_OVERFLOW = 64 /* SFMA: more experienced (s, a) than the replay kernel's on-chip list holds */
 };
 
 /* ---- Dyna-Q: agent/dyna_q.py:140-330 + memory/dyna_q.py:62-157 ------------- */

@@ -331,3 +331,55 @@ def test_trajectory_monitor_and_occupancy_map_on_device():
     valid = pos[~torch.isnan(pos).any(dim=-1)].cpu().numpy()
     want = np.histogram2d(valid[:, 0], valid[:, 1], bins=(5, 5), range=[[0, 5], [0, 5]])[0]
     assert np.array_equal(occ.cpu().numpy(), want) and occ.sum().item() == float(res['n_steps'].sum().item())
+
+
+def test_recorded_run_in_chunked_launches_equals_one_launch():
+    """``record`` together with ``trials_per_launch``: the per-launch trace buffers are compacted per agent when the
+    launches are merged, so the merged run decodes exactly like a single launch (and ``trial_session`` counts over the
+    whole session)."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.monitor import TrajectoryMonitor
+    from cobel_rl_b200.policy import EpsilonGreedy
+    world = make_world('open5')
+
+    def run(chunk):
+        stream = cb.BatchStream(5, seed=77, device='cuda:0')
+        env = Gridworld(world, rng=stream)
+        seen = []
+        ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream),
+                   custom_callbacks={'on_trial_end': [lambda logs: seen.append((logs['trial'], logs['trial_session']))]})
+        ag.record = True
+        ag.trials_per_launch = chunk
+        res = ag.train(env, 7, 15, 4)
+        torch.cuda.synchronize()
+        return res, seen
+    one, seen_one = run(None)
+    many, seen_many = run(3)
+    assert seen_one == seen_many == [(t, t) for t in range(7)]
+    for k in ('n_steps', 'n_replay', 'trial_steps'):
+        assert torch.equal(one[k], many[k]), k
+    ns, nr = one['n_steps'], one['n_replay']
+    for i in range(5):
+        assert torch.equal(one['step_sa'][i, :ns[i]], many['step_sa'][i, :ns[i]])
+        assert torch.equal(one['step_next'][i, :ns[i]], many['step_next'][i, :ns[i]])
+        assert torch.equal(one['replay_idx'][i, :nr[i]], many['replay_idx'][i, :nr[i]])
+        calls = int((one['replay_len'][i] >= 0).sum())
+        assert torch.equal(one['replay_len'][i, :calls], many['replay_len'][i, :calls])
+        assert bool((many['step_sa'][i, ns[i]:] == -1).all())
+
+
+def test_zero_trial_sessions_are_no_ops_for_every_agent():
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import QAgent, SR
+    from cobel_rl_b200.policy import EpsilonGreedy
+    stream = cb.BatchStream(2, seed=1, device='cuda:0')
+    env = Gridworld(make_world('open5'), rng=stream)
+    k0 = stream.draw_count.clone()
+    for ag in (QAgent(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), rng=stream),
+               SR(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream))):
+        res = ag.train(env, 0, 10) if isinstance(ag, SR) else ag.train(env, 0, 10, 8)
+        assert res['trial_steps'].shape == (2, 0) and int(res['n_steps'].sum()) == 0
+    assert torch.equal(stream.draw_count, k0)

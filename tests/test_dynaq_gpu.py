@@ -91,28 +91,69 @@ def test_dynaq_results_independent_of_sharding():
     assert torch.equal(q1[100:140], q2) and torch.equal(s1[100:140], s2) and torch.equal(d1[100:140], d2)
 
 
-def test_dynaq_large_state_space_global_path():
-    """S*A too large for the staged shared-memory layout -> tables stay in global memory."""
+def _succ_world_tables(world):
+    """Oracle tables of a world built without its dense ``sas`` (large state spaces)."""
+    return {'S': world['states'], 'A': 4, 'succ': world['succ'], 'reward': world['rewards'].astype(np.float64),
+            'terminal': world['terminals'].astype(np.uint8), 'starts': world['starting_states'].astype(np.int32)}
+
+
+@pytest.mark.parametrize('shape', [(12, 12), (50, 50)])
+def test_dynaq_large_state_spaces(shape):
+    """12x12: the largest tables still staged in shared memory.  50x50 (2500 states, 180 KB of tables per agent): Q and
+    the memory stay in HBM / L2 (dynaq_warp_kernel<A, false, HBM>), only the replay's dependency masks are on chip
+    -- the reference has no limit on the state space (agent/dyna_q.py:128)."""
     import cobel_rl_b200 as cb
     from cobel_rl_b200.interface import Gridworld
     from cobel_rl_b200.agent import DynaQ
     from cobel_rl_b200.policy import EpsilonGreedy
     from cobel_rl_b200.misc.gridworld_tools import make_open_field
-    world = make_open_field(12, 12, 0, 1)
+    h, w = shape
+    world = make_open_field(h, w, 0, 1, dense_sas=False)
     stream = cb.BatchStream(3, seed=11, device='cuda:0')
     env = Gridworld(world, rng=stream)
     ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream))
     ag.record = True
     res = ag.train(env, 4, 60, 16)
+    rt = ag.test(env, 2, 40)
     torch.cuda.synchronize()
-    W = tb.compile_gridworld(world)
+    W = _succ_world_tables(world)
     for i in range(3):
         rng = tb.Draws(LazyStream(11, i), 1)
-        st = tb.dynaq_init(144, 4)
+        st = tb.dynaq_init(h * w, 4)
         rec = tb.dynaq_train(W, st, rng, 4, 60, 16).arrays()
+        rec2 = tb.tabular_test(W, st['Q'], rng, 2, 40, policy=('eps', 0.1)).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got.update(Q=ag.Q[i].cpu().numpy(), Mr=ag.M.rewards[i].cpu().numpy(), Ms=ag.M.states[i].cpu().numpy(),
+                   Mt=ag.M.terminals[i].cpu().numpy())
+        rec.update(Q=st['Q'], Mr=st['Mr'], Ms=st['Ms'], Mt=st['Mt'])
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'Q', 'Mr', 'Ms', 'Mt'], what='agent %d' % i)
+        assert_equal_records(unpack_run(rt, i, 4, W['succ'], W['reward']), rec2, ['states', 'actions', 'trial_steps'])
+        assert int(stream.draw_count[i]) == rng.k
+
+
+def test_qagent_large_state_space_hbm_path():
+    """QAgent on a 60x60 gridworld (3600 observation keys): the Q table stays in HBM / L2 (q_warp_kernel<A, false, HBM>)."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import QAgent
+    from cobel_rl_b200.policy import EpsilonGreedy
+    from cobel_rl_b200.misc.gridworld_tools import make_open_field
+    world = make_open_field(60, 60, 0, 1, dense_sas=False)
+    stream = cb.BatchStream(2, seed=13, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    ag = QAgent(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), None, 0.9, 0.8, rng=stream)
+    ag.record = True
+    res = ag.train(env, 3, 50, 16)
+    torch.cuda.synchronize()
+    W = _succ_world_tables(world)
+    for i in range(2):
+        rng = tb.Draws(LazyStream(13, i), 1)
+        st = tb.q_init(3600, 4)
+        rec = tb.q_train(W, st, rng, 3, 50, 16).arrays()
         got = unpack_run(res, i, 4, W['succ'], W['reward'])
         got['Q'] = ag.Q[i].cpu().numpy(); rec['Q'] = st['Q']
         assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'Q'], what='agent %d' % i)
+        assert int(stream.draw_count[i]) == rng.k
 
 
 def test_dynaq_user_stream():

@@ -160,3 +160,38 @@ def test_sfma_modulation_flags_vs_oracle(flags, mode):
         rec.update(Q=st['Q'], C=st['C'], I=st['I'], draws=rng.k)
         assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q', 'C', 'I', 'draws'],
                              what='agent %d %s' % (i, flags))
+
+
+def test_sfma_large_state_space_split_path():
+    """50x50 (2500 states, 10^4 experiences): the tables do not fit in shared memory -- the split path steps on the tables
+    in HBM (one thread per agent) and its replay kernel stages only the list of experienced (s, a); the reference has no
+    limit (memory/sfma.py:162-172).  Euclidean similarity (the DR metric would need the dense 200 MB sas)."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import SFMA
+    from cobel_rl_b200.memory import SFMAMemory
+    from cobel_rl_b200.memory.utils.metrics import Euclidean
+    from cobel_rl_b200.misc.gridworld_tools import make_open_field
+    from cobel_rl_b200.policy import EpsilonGreedy
+    world = make_open_field(50, 50, 0, 1, dense_sas=False)
+    metric = Euclidean(50, 50)
+    n, trials, steps, batch = 2, 3, 60, 16
+    stream = cb.BatchStream(n, seed=808, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = SFMAMemory(metric, 2500, 4, rng=stream)
+    ag = SFMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem, rng=stream)
+    ag.record = True
+    res = ag.train(env, trials, steps, batch)
+    torch.cuda.synchronize()
+    assert int(res['flags'].sum()) == 0
+    W = {'S': 2500, 'A': 4, 'succ': world['succ'], 'reward': world['rewards'].astype(np.float64),
+         'terminal': world['terminals'].astype(np.uint8), 'starts': world['starting_states'].astype(np.int32)}
+    for i in range(n):
+        rng = tb.Draws(LazyStream(808, i), 1)
+        st = tb.sfma_init(2500, 4)
+        rec = tb.sfma_train(W, st, metric.D, rng, trials, steps, batch).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got.update(Q=ag.Q[i].cpu().numpy(), C=mem.C[i].cpu().numpy(), I=mem.I[i].cpu().numpy(), draws=int(stream.draw_count[i]))
+        rec.update(Q=st['Q'], C=st['C'], I=st['I'], draws=rng.k)
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q', 'C', 'I', 'draws'],
+                             what='agent %d' % i)
