@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(kBandWarps * 32) pma_band_solve_kernel(const _
 // 2 S^2 bw operations instead of the S^3 of the dense Gauss-Jordan.
 // ---------------------------------------------------------------------------
 template <int BW>      // BW >= sr_band: length of the per-thread register window
-__global__ void __launch_bounds__(160) pma_sr_band_kernel(const __grid_constant__ CobelPMAParams p) {
+__global__ void __launch_bounds__(512) pma_sr_band_kernel(const __grid_constant__ CobelPMAParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int S = p.world.n_states, bw = p.sr_band, W = 2 * bw + 1, tid = threadIdx.x;
   const int64_t n = blockIdx.x;
@@ -871,8 +871,10 @@ struct MainPhase {
 // PLAIN = epsilon-greedy agent and memory policies from the tie-pattern tables, training with replay,
 // deterministic world, no optional trace buffers, generated stream: the per-row policy evaluation (fp64
 // divisions, exp) and the per-step checks are compiled out.
-template <int A, bool PLAIN>
-__global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __grid_constant__ CobelPMAParams p,
+// BIG = more than 1024 one-step backups or more than 160 states (up to 2048 / 512: 20x20 with 4 actions): two chunk
+// maxima per lane and a longer register window for the T row of a step; the common sizes keep the lean code.
+template <int A, bool PLAIN, bool BIG = false>
+__global__ void __launch_bounds__(kMainWarps * 32, BIG ? 1 : 4) pma_main_kernel(const __grid_constant__ CobelPMAParams p,
                                                                       const __grid_constant__ MainPhase ph) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int S = p.world.n_states, K = p.world.n_starts, N = S * A, B = p.batch;
@@ -894,11 +896,14 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
   double* rs = reinterpret_cast<double*>(blk + so.rs);         // M.rewards of the candidate sequence's elements
   uint8_t* mbits = blk + so.mbits;                             // [s] valid-action bits (all ones if unmasked)
   constexpr int kSt = 0x1FFF, kUm = 0x2000;
-  const int nch = so.np >> 5;                                  // chunks of 32 consecutive utilities (N <= 1024: at most 32)
+  static_assert(!(PLAIN && BIG), "the large-state instantiation is the generic kernel");
+  constexpr int kH = BIG ? 2 : 1;                              // chunk maxima per lane: chunk c lives in lane c & 31, slot c >> 5
+  constexpr int kTrow = BIG ? 16 : 5;                          // T-row entries per lane (S <= 512 / 160)
+  const int nch = so.np >> 5;                                  // chunks of 32 consecutive utilities (at most 32 kH)
   // flat backup index i = a*S + s (the reference's order, memory/pma.py:205) -> a, s, s*A + a without integer
-  // division: i < 1024 and S <= 160, so (i * ceil(2^20 / S)) >> 20 == i / S exactly
-  const uint32_t magicS = ((1u << 20) + (uint32_t)S - 1u) / (uint32_t)S;
-  auto act_of = [&](int i) -> int { return (int)(((uint32_t)i * magicS) >> 20); };
+  // division: i < 2048 and S <= 512, so (i * ceil(2^24 / S)) >> 24 == i / S exactly (and i * ceil(.) < 2^28)
+  const uint32_t magicS = ((1u << 24) + (uint32_t)S - 1u) / (uint32_t)S;
+  auto act_of = [&](int i) -> int { return (int)(((uint32_t)i * magicS) >> 24); };
   auto st_of = [&](int i) -> int { return i - act_of(i) * S; };
   auto sa_of = [&](int i) -> int { const int a_ = act_of(i); return (i - a_ * S) * A + a_; };
 
@@ -1023,8 +1028,14 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     }
     __syncwarp();
     int count = 0, last_seq = 0, ndst = -1;          // ndst < 0: first iteration, every backup is stale
-    unsigned dirty = nch >= 32 ? kFull : ((1u << nch) - 1u);   // chunks whose maximum has to be recomputed
-    int cm_hi = kKeyMinHi; unsigned cm_lo = 0;       // lane c: the largest key of chunk c
+    unsigned dirty[kH];                              // chunks whose maximum has to be recomputed
+    int cm_hi[kH]; unsigned cm_lo[kH];               // lane l, slot h: the largest key of chunk 32 h + l
+#pragma unroll
+    for (int h = 0; h < kH; ++h) {
+      const int left = nch - 32 * h;
+      dirty[h] = left >= 32 ? kFull : (left > 0 ? (1u << left) - 1u : 0u);
+      cm_hi[h] = kKeyMinHi; cm_lo[h] = 0;
+    }
     unsigned seqmask = 0;                            // lane w: bits of the states 32 w .. 32 w + 31 in performed[last_seq:]
     for (int it = 0; it < B; ++it) {
       // ---- (1) extension of the current sequence (memory/pma.py:219-235) -------------------------
@@ -1085,7 +1096,9 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
       }
       __syncwarp();
       double total = 0.0;                                  // gain of the candidate: its elements' gains added in order
-      unsigned myd = 0;
+      unsigned myd[kH];
+#pragma unroll
+      for (int h = 0; h < kH; ++h) myd[h] = 0;
 #pragma unroll 1
       for (int j0 = 0; j0 < n1 + nseq; j0 += 32) {
         const int j = j0 + lane;
@@ -1146,7 +1159,8 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
             g = g > min_gain ? g : min_gain;
             if (opt & COBEL_PMA_OPT_EQUAL_GAIN) g = 1.0;               // gain.fill(1), memory/pma.py:241-242
             ukey[i] = util_key(g, s, a);
-            myd |= 1u << (i >> 5);
+            if (!BIG || (i >> 10) == 0) myd[0] |= 1u << ((i >> 5) & 31);
+            else myd[kH - 1] |= 1u << ((i >> 5) & 31);
           } else if (original) {
             g = g > min_gain ? g : min_gain;
           }
@@ -1157,7 +1171,8 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
           for (int l = lo; l < hi; ++l) total = xadd(total, shfl_f64(g, l));
         }
       }
-      dirty |= __reduce_or_sync(kFull, myd);
+#pragma unroll
+      for (int h = 0; h < kH; ++h) dirty[h] |= __reduce_or_sync(kFull, myd[h]);
       __syncwarp();
       double gext = total > min_gain ? total : min_gain;
       if (opt & COBEL_PMA_OPT_EQUAL_GAIN) gext = 1.0;
@@ -1169,38 +1184,61 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         saved = ukey[ext];
         __syncwarp();
         if (lane == 0) ukey[ext] = util_key(gext, es, ea);
-        dirty |= 1u << (ext >> 5);
+        dirty[BIG ? (ext >> 10) : 0] |= 1u << ((ext >> 5) & 31);
         __syncwarp();
       }
       // chunk maxima are kept across iterations: only the chunks that received a new utility are reduced again
-      while (dirty) {
-        const int c = __ffs(dirty) - 1;
-        dirty &= dirty - 1;
-        const int2 m = warp_max_key(ukey[c * 32 + lane]);
-        if (lane == c) { cm_hi = m.y; cm_lo = (unsigned)m.x; }
+#pragma unroll
+      for (int h = 0; h < kH; ++h) {
+        while (dirty[h]) {
+          const int c = __ffs(dirty[h]) - 1;
+          dirty[h] &= dirty[h] - 1;
+          const int2 m = warp_max_key(ukey[(h * 32 + c) * 32 + lane]);
+          if (lane == c) { cm_hi[h] = m.y; cm_lo[h] = (unsigned)m.x; }
+        }
       }
-      const int2 cmine = make_int2((int)cm_lo, lane < nch ? cm_hi : kKeyMinHi);
-      const int2 umax = warp_max_key(cmine);
-      const bool cwin = cmine.y == umax.y && cmine.x == umax.x;          // chunk holds a maximum
-      unsigned tchunks = __ballot_sync(kFull, cwin);
-      const unsigned tchunks0 = tchunks;
+      int2 cmine[kH];
+#pragma unroll
+      for (int h = 0; h < kH; ++h) cmine[h] = make_int2((int)cm_lo[h], h * 32 + lane < nch ? cm_hi[h] : kKeyMinHi);
+      int2 lbest = cmine[0];
+      if (kH > 1 && (cmine[kH - 1].y > lbest.y || (cmine[kH - 1].y == lbest.y && (unsigned)cmine[kH - 1].x > (unsigned)lbest.x)))
+        lbest = cmine[kH - 1];
+      const int2 umax = warp_max_key(lbest);
       // the largest utility below the maximum: over the other chunks' maxima and the rest of the winning chunks
-      int2 second = warp_max_key(cwin ? make_int2(0, kKeyMinHi) : cmine);
-      // ties in flat-index order: lane c keeps the tie ballot of chunk c
-      unsigned mytb = 0, onlyb = 0;
-      const int c0 = __ffs(tchunks) - 1;
-      while (tchunks) {
-        const int c = __ffs(tchunks) - 1;
-        tchunks &= tchunks - 1;
-        const int2 k = ukey[c * 32 + lane];
-        const bool eq = k.y == umax.y && k.x == umax.x;
-        const unsigned b = __ballot_sync(kFull, eq);
-        const int2 r2 = warp_max_key(eq ? make_int2(0, kKeyMinHi) : k);
-        if (r2.y > second.y || (r2.y == second.y && (unsigned)r2.x > (unsigned)second.x)) second = r2;
-        mytb = lane == c ? b : mytb;
-        onlyb = b;
+      bool cwin[kH];
+      unsigned tch[kH];
+      int2 lsec = make_int2(0, kKeyMinHi);
+#pragma unroll
+      for (int h = 0; h < kH; ++h) {
+        cwin[h] = cmine[h].y == umax.y && cmine[h].x == umax.x;          // chunk holds a maximum
+        tch[h] = __ballot_sync(kFull, cwin[h]);
+        if (!cwin[h] && (cmine[h].y > lsec.y || (cmine[h].y == lsec.y && (unsigned)cmine[h].x > (unsigned)lsec.x))) lsec = cmine[h];
       }
-      const int ktot = __reduce_add_sync(kFull, __popc(mytb));
+      int2 second = warp_max_key(lsec);
+      // ties in flat-index order: lane l, slot h keeps the tie ballot of chunk 32 h + l
+      unsigned mytb[kH];
+      unsigned onlyb = 0;
+      const int c0 = (tch[0] || kH == 1) ? __ffs(tch[0]) - 1 : 32 + __ffs(tch[kH - 1]) - 1;
+#pragma unroll
+      for (int h = 0; h < kH; ++h) {
+        mytb[h] = 0;
+        unsigned t = tch[h];
+        while (t) {
+          const int c = __ffs(t) - 1;
+          t &= t - 1;
+          const int2 k = ukey[(h * 32 + c) * 32 + lane];
+          const bool eq = k.y == umax.y && k.x == umax.x;
+          const unsigned b = __ballot_sync(kFull, eq);
+          const int2 r2 = warp_max_key(eq ? make_int2(0, kKeyMinHi) : k);
+          if (r2.y > second.y || (r2.y == second.y && (unsigned)r2.x > (unsigned)second.x)) second = r2;
+          mytb[h] = lane == c ? b : mytb[h];
+          if (!onlyb) onlyb = b;
+        }
+      }
+      int mycnt = 0;
+#pragma unroll
+      for (int h = 0; h < kH; ++h) mycnt += __popc(mytb[h]);
+      const int ktot = __reduce_add_sync(kFull, mycnt);
       {
         const double vmax = key_value(umax);
         if (second.y != kKeyMinHi && vmax != 0.0) {
@@ -1238,25 +1276,29 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         }
         // the pick-th tie in flat-index order: walk the winning chunks (ascending) until their tie counts cover it
         chosen = 0;
-        unsigned tc = tchunks0;
         int base = 0;
-        while (tc) {
-          const int c = __ffs(tc) - 1;
-          tc &= tc - 1;
-          const unsigned b = __shfl_sync(kFull, mytb, c);
-          const int nb = __popc(b);
-          if (pick < base + nb) {
-            const unsigned sel = __ballot_sync(kFull, (b >> lane & 1u) && __popc(b & ((1u << lane) - 1u)) == pick - base);
-            chosen = c * 32 + __ffs(sel) - 1;
-            break;
+        bool found = false;
+#pragma unroll
+        for (int h = 0; h < kH; ++h) {
+          unsigned tc = tch[h];
+          while (tc && !found) {
+            const int c = __ffs(tc) - 1;
+            tc &= tc - 1;
+            const unsigned b = __shfl_sync(kFull, mytb[h], c);
+            const int nb = __popc(b);
+            if (pick < base + nb) {
+              const unsigned sel = __ballot_sync(kFull, (b >> lane & 1u) && __popc(b & ((1u << lane) - 1u)) == pick - base);
+              chosen = (h * 32 + c) * 32 + __ffs(sel) - 1;
+              found = true;
+            }
+            base += nb;
           }
-          base += nb;
         }
       }
       if (ext >= 0) {
         __syncwarp();
         if (lane == 0) ukey[ext] = saved;
-        dirty = 1u << (ext >> 5);
+        dirty[BIG ? (ext >> 10) : 0] = 1u << ((ext >> 5) & 31);
       }
       // ---- (5) apply the chosen (n-step) update: PMAMemory.update_q, memory/pma.py:452-496 --------
       {
@@ -1352,9 +1394,9 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
     for (;; ++step) {
       win.ensure(2, lane);
       // T[s] is updated at the end of the step (M.store): issue its HBM loads now, behind the action selection
-      double trow[5];                                  // S <= 160: at most 5 entries per lane
+      double trow[kTrow];                              // at most kTrow entries per lane
 #pragma unroll
-      for (int x = 0; x < 5; ++x) { const int j = lane + 32 * x; trow[x] = (learn && j < S) ? Tg[(size_t)s * S + j] : 0.0; }
+      for (int x = 0; x < kTrow; ++x) { const int j = lane + 32 * x; trow[x] = (learn && j < S) ? Tg[(size_t)s * S + j] : 0.0; }
       double row[A];
       load_row<A>(Q + s * A, row);
       const double ua = win.next();
@@ -1383,7 +1425,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
         const double m0 = Mr[s * A + a];
         const double m1 = xadd(m0, xmul(mlr, xsub(r, m0)));
 #pragma unroll
-        for (int x = 0; x < 5; ++x) {                  // T[s] += lr_T * (onehot(s') - T[s]), memory/pma.py:162-165
+        for (int x = 0; x < kTrow; ++x) {              // T[s] += lr_T * (onehot(s') - T[s]), memory/pma.py:162-165
           const int j = lane + 32 * x;
           if (j < S) Tg[(size_t)s * S + j] = xadd(trow[x], xmul(p.lr_T, xsub(j == s2 ? 1.0 : 0.0, trow[x])));
         }
@@ -1434,23 +1476,29 @@ __global__ void __launch_bounds__(kMainWarps * 32, 4) pma_main_kernel(const __gr
 template <int A>
 int run(const CobelPMAParams& p, cudaStream_t st) {
   const int S = p.world.n_states;
-  COBEL_REQUIRE(S <= 160 && S * A <= 1024, COBEL_EUNSUPPORTED,
-                "PMA kernels support at most 160 states (register-tiled S x S eliminations), got %d", S);
+  COBEL_REQUIRE(S <= 512 && S * A <= 2048, COBEL_EUNSUPPORTED,
+                "PMA kernels support at most 512 states and 2048 one-step backups, got %d states x %d actions", S, A);
+  const bool big = S > 160 || S * A > 1024;             // pma_main_kernel<A, false, BIG>
   const MainSmem so(S, A);
   const size_t sm_main = (size_t)kMainWarps * so.bytes;
   COBEL_REQUIRE(sm_main <= 227 * 1024, COBEL_EUNSUPPORTED, "PMA: %d states x %d actions do not fit in shared memory", S, A);
   const bool tabs = p.n_tab > 0 && A <= 4;
   COBEL_REQUIRE(p.n_tab == 0 || (p.tab_kind && p.tab_param && p.tab_scratch), COBEL_EINVAL,
                 "n_tab > 0 needs tab_kind, tab_param and tab_scratch[n_tab, COBEL_PMA_TAB_DOUBLES(A)]");
-  const bool plain = tabs && p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.mem_policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn &&
+  const bool plain = !big && tabs && p.policy.kind == COBEL_POLICY_EPS_GREEDY && p.mem_policy.kind == COBEL_POLICY_EPS_GREEDY && p.learn &&
                      !p.no_replay && !p.options && !p.world.tp_off && !p.trace.step_sa && !p.trace.replay_idx &&
                      !p.trace.replay_len && !p.stream.user_stream;
   const bool do_replay = p.learn && !p.no_replay;
   const bool band = do_replay && p.sr_band >= 0;
+  COBEL_REQUIRE(!big || !do_replay || band, COBEL_EUNSUPPORTED,
+                "PMA: more than 160 states need the banded update_sr (sr_band >= 0; the dense S x S eliminations are "
+                "register-tiled for S <= 160), got %d states", S);
   const int tile = S <= 7 * 16 ? 7 : 10;
   const size_t sm_sr = (size_t)(4 * (tile * 16 + 2) + ((S + 1) & ~1) + S * S) * 8;
-  if (tile == 7) COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
-  else COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
+  if (!big) {
+    if (tile == 7) COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
+    else COBEL_CUDA_OK(cudaFuncSetAttribute(pma_sr_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sr));
+  }
   if constexpr (A <= 4) {
     if (tabs) {                                        // the tie-pattern policy tables of this call
       pma_policy_table_kernel<A><<<(unsigned)p.n_tab + 1, 256, 0, st>>>(p.tab_kind, p.tab_param, p.tab_scratch);
@@ -1468,6 +1516,7 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
     if constexpr (A <= 4) {
       if (plain) return go(pma_main_kernel<A, true>);
     }
+    if (big) return go(pma_main_kernel<A, false, true>);
     return go(pma_main_kernel<A, false>);
   };
   auto sr_launch = [&](int final_only) {
@@ -1518,6 +1567,7 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
            p.sr_band <= 24 ? go(pma_sr_band_kernel<24>) : go(pma_sr_band_kernel<32>);
       if (rc) return rc;
     } else {
+      COBEL_REQUIRE(!big, COBEL_EUNSUPPORTED, "PMA: the band factors of %d states do not fit in shared memory", S);
       sr_launch(1);
     }
   } else {

@@ -250,8 +250,19 @@ def test_unsupported_shapes_and_options_fail_loudly():
     ag = DynaQ(env5.observation_space, env5.action_space, EpsilonGreedy(0.1, rng=stream))
     with pytest.raises(NotImplementedError):
         ag.train(env5, 2, 5, 4)
-    # PMA: the S x S successor representation must fit the register-tiled kernels (S <= 160)
+    # PMA beyond 160 states runs with the banded update_sr only: the dense S x S eliminations are register-tiled for
+    # S <= 160 (13x13 = 169 states trains fine on the banded path, see test_pma_gpu.py for 20x20)
     world = make_open_field(13, 13, 0, 1)
+    stream = cb.BatchStream(2, seed=1, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = PMAMemory(world['sas'], EpsilonGreedy(0.1, rng=stream), rng=stream)
+    pma = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem)
+    pma.train(env, 1, 5, 4)
+    mem.sr_band_max = -1                  # force the dense path
+    with pytest.raises(NotImplementedError):
+        pma.train(env, 1, 5, 4)
+    # and beyond 512 states / 2048 one-step backups not at all
+    world = make_open_field(23, 23, 0, 1)
     stream = cb.BatchStream(2, seed=1, device='cuda:0')
     env = Gridworld(world, rng=stream)
     mem = PMAMemory(world['sas'], EpsilonGreedy(0.1, rng=stream), rng=stream)

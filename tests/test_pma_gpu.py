@@ -210,3 +210,41 @@ def test_pma_on_other_grid_shapes_vs_oracle(shape):
         rec.update(Q=st['Q'], T=st['T'], SR=st['SR'], draws=rng.k)
         assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q', 'T', 'SR', 'draws'],
                              rtol=RTOL, what='%s agent %d' % (shape, i))
+
+
+def test_pma_20x20_large_state_space():
+    """PMA on a 20x20 walled gridworld (400 states, 1600 one-step backups, band 20): pma_main_kernel<A, false, BIG> with
+    two chunk maxima per lane; the reference has no limit on the state space (memory/pma.py:139-141).  Integer
+    sequences and Q bit-equal to the oracle, SR against its dense LAPACK inverse."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import PMA
+    from cobel_rl_b200.memory import PMAMemory
+    from cobel_rl_b200.misc import gridworld_tools as mg
+    from cobel_rl_b200.policy import EpsilonGreedy
+    walls = [(5, 6), (6, 5), (25, 26), (26, 25), (45, 46), (46, 45), (208, 228), (228, 208), (209, 229), (229, 209)]
+    world = mg.make_gridworld(20, 20, terminals=[19], rewards=np.array([[19, 10.0]]), goals=[19], starting_states=[210],
+                              invalid_transitions=walls)
+    W = tb.compile_gridworld(world)
+    n, trials, steps, batch = 2, 2, 70, 16
+    stream = cb.BatchStream(n, seed=2020, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = PMAMemory(world['sas'], EpsilonGreedy(0.1, rng=stream), 0.9, 0.9, 0.9, 0.99, rng=stream)
+    ag = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem)
+    ag.mask_actions = True
+    ag.action_mask = tb.valid_move_mask(W['succ'])
+    ag.record = True
+    assert mem.sr_band(env.transition_band)[0] == 20
+    res = ag.train(env, trials, steps, batch)
+    torch.cuda.synchronize()
+    assert int(res['flags'].sum()) == 0
+    for i in range(n):
+        rng = tb.Draws(LazyStream(2020, i), 1)
+        st = tb.pma_init(tb.t0_from_succ(W['succ']), 400, 4)
+        st['action_mask'] = tb.valid_move_mask(W['succ'])
+        rec = tb.pma_train(W, st, rng, trials, steps, batch, gamma_q=0.99, mask_actions=True).arrays()
+        got = unpack_run(res, i, 4, W['succ'], W['reward'])
+        got.update(Q=ag.Q[i].cpu().numpy(), T=mem.T[i].cpu().numpy(), SR=mem.SR[i].cpu().numpy(), draws=int(stream.draw_count[i]))
+        rec.update(Q=st['Q'], T=st['T'], SR=st['SR'], draws=rng.k)
+        assert_equal_records(got, rec, ['states', 'actions', 'trial_steps', 'replay', 'replay_len', 'Q', 'T', 'SR', 'draws'],
+                             rtol=RTOL, what='agent %d' % i)
