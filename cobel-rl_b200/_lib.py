@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcobel_b200.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_f64p = C.c_void_p   # device pointers travel as raw addresses
 c_ptr = C.c_void_p

@@ -40,6 +40,7 @@
 // LAPACK's, which only matters if two distinct utilities are closer than that -- the smallest
 // relative gap seen is reported per agent (`min_gap`) as a certificate.
 #include "warp_agent.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -553,17 +554,20 @@ constexpr int kBandWarps = 8;
 struct BandSmem {                                     // per warp (agent)
   int ring, x, w, bytes;
   __host__ __device__ BandSmem(int S, int bw) {
+    // the right-hand side `w` of a row solve aliases the ring: the ring is dead once the factors are in the scratch
+    const int ringb = band_ring_rows(bw) * (2 * bw + 2) * 8, vecb = ((S + 1) & ~1) * 8;
     ring = 0;
-    x = ring + band_ring_rows(bw) * (2 * bw + 2) * 8;
-    w = x + ((S + 1) & ~1) * 8;
-    bytes = (w + ((S + 1) & ~1) * 8 + 15) & ~15;
+    w = 0;
+    x = ringb > vecb ? ringb : vecb;
+    bytes = (x + vecb + 15) & ~15;
   }
 };
 
 // (A one-thread-per-agent factor kernel -- window of bw + 2 rows lane-interleaved in shared memory, 5.5
 //  instructions per element update, 3x fewer instructions per agent -- measured 1.28 ms against 1.0 ms for this one
 //  at 16384 agents: 32 KB of window per 16 agents leave 1.75 warps per scheduler on strictly dependent steps.)
-__global__ void __launch_bounds__(kBandWarps * 32) pma_band_factor_kernel(const __grid_constant__ CobelPMAParams p) {
+__global__ void __launch_bounds__(kBandWarps * 32) pma_band_factor_kernel(const __grid_constant__ CobelPMAParams p,
+                                                                         const int solve_start) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int S = p.world.n_states, bw = p.sr_band, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n = (int64_t)blockIdx.x * kBandWarps + warp;
@@ -587,6 +591,17 @@ __global__ void __launch_bounds__(kBandWarps * 32) pma_band_factor_kernel(const 
     double* w = reinterpret_cast<double*>(blk + so.w);
     band_solve_row(fac, w, S, bw, (int)p.carry[n * 8 + 0], x, lane);
     double* need = p.need_scratch + (size_t)n * S;
+#pragma unroll 1
+    for (int e = lane; e < S; e += 32) need[e] = x[e];
+  }
+  if (solve_start) {
+    // a single starting state: the next trial's awake replay needs SR[start], known before the reset draw -- its
+    // row goes to the second plane of need_scratch and the end replay, the reset, the start replay and the steps
+    // of the next trial run in ONE launch of the main kernel
+    double* w = reinterpret_cast<double*>(blk + so.w);
+    __syncwarp();
+    band_solve_row(fac, w, S, bw, __ldg(p.world.starts), x, lane);
+    double* need = p.need_scratch + (size_t)(p.n_agents + n) * S;
 #pragma unroll 1
     for (int e = lane; e < S; e += 32) need[e] = x[e];
   }
@@ -639,35 +654,49 @@ __global__ void __launch_bounds__(512) pma_sr_band_kernel(const __grid_constant_
   if (i0 >= S) return;
   double* col = p.SR + (size_t)n * S * S + min(c, S - 1);          // element i of this thread's column: col[i * S]
   const bool live = c < S;
-  double w[BW];                                                    // the last BW solution entries: w[d-1] = y_{i-d} / x_{i+d}
+  // The last BW solution entries live in a register window whose rotation is static: the loops advance in chunks
+  // of BW fully unrolled steps, step u of a chunk writes slot u and reads y_{i-d} / x_{i+d} from slot (u - d) mod BW
+  // (no shifting moves; the factors of a step are BW / 2 LDS.128).
+  double w[BW];
 #pragma unroll
   for (int d = 0; d < BW; ++d) w[d] = 0.0;
-#pragma unroll 2
-  for (int i = i0; i < S; ++i) {                                   // L y = e_c (unit diagonal; multipliers l[i][i-d] at offset -d)
-    const double* f = fac + (size_t)i * WP + BW;
-    double acc = i == c ? 1.0 : 0.0;
+#pragma unroll 1
+  for (int ib = i0; ib < S; ib += BW) {                            // L y = e_c (unit diagonal; multipliers l[i][i-d] at offset -d)
 #pragma unroll
-    for (int d = 1; d <= BW; ++d) acc = fma(-f[-d], w[d - 1], acc);
-    if (live) col[(size_t)i * S] = acc;
+    for (int u = 0; u < BW; ++u) {
+      const int i = ib + u;
+      if (i < S) {
+        const double* f = fac + (size_t)i * WP + BW;
+        double acc = i == c ? 1.0 : 0.0;
 #pragma unroll
-    for (int d = BW - 1; d > 0; --d) w[d] = w[d - 1];
-    w[0] = acc;
+        for (int d = 1; d <= BW; ++d) acc = fma(-f[-d], w[(u - d + 2 * BW) % BW], acc);
+        if (live) col[(size_t)i * S] = acc;
+        w[u] = acc;
+      }
+    }
   }
 #pragma unroll
   for (int d = 0; d < BW; ++d) w[d] = 0.0;
-  double ynext = live ? col[(size_t)(S - 1) * S] : 0.0;
-#pragma unroll 2
-  for (int i = S - 1; i >= 0; --i) {                               // U x = y (the diagonal holds 1 / pivot)
-    const double* f = fac + (size_t)i * WP + BW;
-    double acc = ynext;
-    ynext = (live && i - 1 >= i0) ? col[(size_t)(i - 1) * S] : 0.0;   // y_i = 0 above the warp's first column
+  // y_i = 0 above the warp's first column; the loads of y run two steps ahead of the recurrence
+  auto yld = [&](int i) -> double { return (live && i >= i0) ? col[(size_t)i * S] : 0.0; };
+  double y0 = yld(S - 1), y1 = yld(S - 2);
+#pragma unroll 1
+  for (int ib = S - 1; ib >= 0; ib -= BW) {                        // U x = y (the diagonal holds 1 / pivot)
 #pragma unroll
-    for (int d = 1; d <= BW; ++d) acc = fma(-f[d], w[d - 1], acc);
-    const double xi = acc * f[0];
-    if (live) col[(size_t)i * S] = xi;
+    for (int u = 0; u < BW; ++u) {
+      const int i = ib - u;
+      if (i >= 0) {
+        const double* f = fac + (size_t)i * WP + BW;
+        double acc = y0;
+        y0 = y1;
+        y1 = yld(i - 2);
 #pragma unroll
-    for (int d = BW - 1; d > 0; --d) w[d] = w[d - 1];
-    w[0] = xi;
+        for (int d = 1; d <= BW; ++d) acc = fma(-f[d], w[(u - d + 2 * BW) % BW], acc);
+        const double xi = acc * f[0];
+        if (live) col[(size_t)i * S] = xi;
+        w[u] = xi;
+      }
+    }
   }
 }
 
@@ -833,7 +862,7 @@ COBEL_DEV int2 warp_max_key(int2 k) {
 // pma_main_kernel: one warp per agent.
 // ---------------------------------------------------------------------------
 struct MainSmem {      // byte offsets inside one agent's shared-memory block
-  int q, mr, need, pk, mbits, ukey, poff, pitems, list, perf, dst, rs, bytes;
+  int q, mr, need, pk, mbits, ukey, poff, pitems, list, perf, dst, rs, bar, bytes;
   int np;              // utility entries padded to a multiple of 32 (chunks of one entry per lane)
   static constexpr int kListCap = 256;     // stale-gain list; larger sets fall back to a full pass
   __host__ __device__ MainSmem(int S, int A) {
@@ -852,7 +881,8 @@ struct MainSmem {      // byte offsets inside one agent's shared-memory block
     perf = list + kListCap * 2;
     dst = perf + (kMaxSeq + 2) * 2;
     rs = (dst + (kMaxSeq + 2) * 2 + 7) & ~7;
-    bytes = (rs + (kMaxSeq + 2) * 8 + 15) & ~15;
+    bar = rs + (kMaxSeq + 2) * 8;            // mbarrier of the bulk stage-in
+    bytes = (bar + 8 + 15) & ~15;
   }
 };
 
@@ -865,7 +895,8 @@ struct MainPhase {
   int reset;            // draw the start state of the next trial (else it comes from carry[4])
   int n_trials;         // trials run by this launch (several only without replays; later ones reset themselves)
   int trial_first;      // index of the first trial run by this launch
-  int scratch_need;     // banded update_sr: both replays read their need vector from need_scratch
+  int scratch_need;     // banded update_sr: both replays read their need vector from need_scratch (1: its first plane;
+                        // 2: the end replay from the first, the start replay from the second plane)
 };
 
 // PLAIN = epsilon-greedy agent and memory policies from the tie-pattern tables, training with replay,
@@ -911,10 +942,24 @@ __global__ void __launch_bounds__(kMainWarps * 32, BIG ? 1 : 4) pma_main_kernel(
   double* Tg = p.T + (size_t)n * S * S;
   const double* SRg = p.SR + (size_t)n * S * S;
   const uint8_t* amask = p.action_mask ? p.action_mask + n * p.mask_agent_stride : nullptr;
+  // Stage-in: Q and M.rewards arrive by two bulk asynchronous copies (TMA 1-D path) issued by lane 0, while the lanes
+  // pack M.states | update_mask | M.terminals; rows that are not 16-byte multiples take the plain loop.
+  uint64_t* bar = reinterpret_cast<uint64_t*>(blk + so.bar);
+  const bool bulk = (N & 1) == 0 && aligned16(p.Q) && aligned16(p.Mr);
+  if (bulk) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      mbar_fence_init();
+      mbar_expect_tx(bar, 2u * (unsigned)N * 8u);
+      bulk_load(Q, p.Q + g0, (unsigned)N * 8u, bar);
+      bulk_load(Mr, p.Mr + g0, (unsigned)N * 8u, bar);
+    }
+  } else {
 #pragma unroll 1
+    for (int e = lane; e < N; e += 32) { Q[e] = p.Q[g0 + e]; Mr[e] = p.Mr[g0 + e]; }
+  }
+#pragma unroll 4
   for (int e = lane; e < N; e += 32) {
-    Q[e] = p.Q[g0 + e];
-    Mr[e] = p.Mr[g0 + e];
     const int s_ = e / A, a_ = e - s_ * A;
     Pk[e] = (uint16_t)(p.Ms[g0 + e] | (p.update_mask[g0 + a_ * S + s_] ? kUm : 0) | ((p.Mt[g0 + e] ? 1 : 0) << 15));
   }
@@ -1373,6 +1418,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, BIG ? 1 : 4) pma_main_kernel(
   // (agent/pma.py:248-256), stage 1 = [reset] + start-of-trial replay (206-213) + online steps.
   const int bw = p.sr_band;
   const double* nscr = p.need_scratch + (size_t)n * S;
+  if (bulk) mbar_wait(bar, 0);                                  // Q and M.rewards have landed
   int trial = ph.trial_first, ntr = ph.n_trials;
   int s = ph.init_carry ? 0 : (int)carry[4];
   bool reset = ph.reset != 0;
@@ -1388,7 +1434,8 @@ __global__ void __launch_bounds__(kMainWarps * 32, BIG ? 1 : 4) pma_main_kernel(
       s = __ldg(p.world.starts + draw_integer(win.next(), K));
     }
     if (ntr == 0) break;
-    if (do_replay) replay(ph.scratch_need ? nscr : SRg + (size_t)s * S);     // awake replay, need = SR[start]
+    if (do_replay)                                                           // awake replay, need = SR[start]
+      replay(ph.scratch_need == 2 ? nscr + (size_t)p.n_agents * S : ph.scratch_need ? nscr : SRg + (size_t)s * S);
     double treward = 0.0;
     int step = 0, last = -1;
     for (;; ++step) {
@@ -1454,12 +1501,26 @@ __global__ void __launch_bounds__(kMainWarps * 32, BIG ? 1 : 4) pma_main_kernel(
 
   __syncwarp();
   if (learn) {
+    // Stage-out: a launch without online steps (an end-of-trial replay) has changed Q only
+    const bool stepped = ph.n_trials > 0;
+    if (bulk) {
+      fence_async_smem();                                       // the bulk stores read what the lanes wrote
+      __syncwarp();
+      if (lane == 0) {
+        bulk_store_issue(p.Q + g0, Q, (unsigned)N * 8u);
+        if (stepped) bulk_store_issue(p.Mr + g0, Mr, (unsigned)N * 8u);
+        bulk_commit();
+      }
+    } else {
 #pragma unroll 1
-    for (int e = lane; e < N; e += 32) {
-      p.Q[g0 + e] = Q[e];
-      p.Mr[g0 + e] = Mr[e];
-      p.Ms[g0 + e] = Pk[e] & kSt;
-      p.Mt[g0 + e] = Pk[e] >> 15;
+      for (int e = lane; e < N; e += 32) { p.Q[g0 + e] = Q[e]; if (stepped) p.Mr[g0 + e] = Mr[e]; }
+    }
+    if (stepped) {
+#pragma unroll 4
+      for (int e = lane; e < N; e += 32) {
+        p.Ms[g0 + e] = Pk[e] & kSt;
+        p.Mt[g0 + e] = Pk[e] >> 15;
+      }
     }
   }
   flags = __reduce_or_sync(kFull, flags);
@@ -1470,6 +1531,7 @@ __global__ void __launch_bounds__(kMainWarps * 32, BIG ? 1 : 4) pma_main_kernel(
     tr.n_replay[n] += nrep - nrep0;
     if (tr.flags && flags) tr.flags[n] |= flags;
     if (p.min_gap && gap_num < 1e300) p.min_gap[n] = fmin(p.min_gap[n], gap_num / gap_den);
+    if (learn && bulk) bulk_store_wait();                       // shared memory must outlive the bulk stores
   }
 }
 
@@ -1533,6 +1595,7 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
     //   main(reset, start replay from the caller's SR, steps of trial 0)
     //   trial t: factor(update_sr; need of the end replay) -> main(end replay t, reset t+1)
     //            -> solve(need = SR[start]) -> main(start replay, steps of trial t+1)
+    //   (a world with ONE starting state: factor also solves SR[start], and the two main launches are one)
     // and SR = inv(I - gamma T) once, densely, from the last factors
     const unsigned grid_band = (unsigned)((p.n_agents + kBandWarps - 1) / kBandWarps);
     const BandSmem bso(S, p.sr_band);
@@ -1542,10 +1605,15 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
     pma_band_check_kernel<<<(unsigned)p.n_agents, 256, 0, st>>>(p);
     cobel_count_launch();
     rc = main_launch(MainPhase{1, 0, 1, 1, 0, 0});
+    const bool one_start = p.world.n_starts == 1;      // the start row is known before the reset draw
     for (int t = 0; t < p.trials && !rc; ++t) {
       const int more = t + 1 < p.trials ? 1 : 0;
-      pma_band_factor_kernel<<<grid_band, kBandWarps * 32, sm_bandk, st>>>(p);
+      pma_band_factor_kernel<<<grid_band, kBandWarps * 32, sm_bandk, st>>>(p, one_start && more);
       cobel_count_launch();
+      if (one_start) {                                 // end replay t, reset, start replay and steps of trial t + 1
+        rc = main_launch(MainPhase{0, 1, more, more, t + 1, 2});
+        continue;
+      }
       rc = main_launch(MainPhase{0, 1, more, 0, t + 1, 1});
       if (rc || !more) break;
       pma_band_solve_kernel<<<grid_band, kBandWarps * 32, sm_bandk, st>>>(p, 4);
@@ -1553,7 +1621,8 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
       rc = main_launch(MainPhase{0, 0, 0, 1, t + 1, 1});
     }
     if (rc) return rc;
-    const int bwp = p.sr_band <= 4 ? 4 : p.sr_band <= 8 ? 8 : p.sr_band <= 12 ? 12 : p.sr_band <= 16 ? 16 : p.sr_band <= 24 ? 24 : 32;
+    const int bwp = p.sr_band <= 4 ? 4 : p.sr_band <= 6 ? 6 : p.sr_band <= 8 ? 8 : p.sr_band <= 10 ? 10 : p.sr_band <= 12 ? 12 :
+                    p.sr_band <= 16 ? 16 : p.sr_band <= 24 ? 24 : 32;
     const size_t sm_band = (size_t)S * (2 * bwp + 2) * 8;
     if (sm_band <= 227 * 1024) {
       auto go = [&](auto kernel) -> int {
@@ -1562,7 +1631,8 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
         cobel_count_launch();
         return COBEL_OK;
       };
-      rc = p.sr_band <= 4 ? go(pma_sr_band_kernel<4>) : p.sr_band <= 8 ? go(pma_sr_band_kernel<8>) :
+      rc = p.sr_band <= 4 ? go(pma_sr_band_kernel<4>) : p.sr_band <= 6 ? go(pma_sr_band_kernel<6>) :
+           p.sr_band <= 8 ? go(pma_sr_band_kernel<8>) : p.sr_band <= 10 ? go(pma_sr_band_kernel<10>) :
            p.sr_band <= 12 ? go(pma_sr_band_kernel<12>) : p.sr_band <= 16 ? go(pma_sr_band_kernel<16>) :
            p.sr_band <= 24 ? go(pma_sr_band_kernel<24>) : go(pma_sr_band_kernel<32>);
       if (rc) return rc;

@@ -15,6 +15,7 @@
 // bytes); rewards / model / Q scratch live in shared memory.
 #include <cstdlib>
 #include "warp_agent.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -219,38 +220,6 @@ __global__ void __launch_bounds__(256) sr_kernel(const __grid_constant__ CobelSR
 // Rows must be 16-byte multiples (S even); odd S and state spaces whose rows do not fit in shared memory take
 // sr_kernel.
 // ---------------------------------------------------------------------------
-COBEL_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-COBEL_DEV void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-COBEL_DEV void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-COBEL_DEV void mbar_wait(uint64_t* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// global -> shared, completion signalled on the mbarrier (SASS: UBLKCP.S.G + SYNCS)
-COBEL_DEV void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// shared -> global (SASS: UBLKCP.G.S)
-COBEL_DEV void bulk_store(void* dst_gmem, const void* src_smem, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-COBEL_DEV void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-COBEL_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 struct SRTmaSmem {
   int rew, rows, urow, acc, leaf, q, model, bars, bytes;
   __host__ __device__ SRTmaSmem(int S, int A, int nl) {

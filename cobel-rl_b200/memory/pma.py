@@ -55,7 +55,7 @@ class PMAMemory(TableMemory):
         self._update_mask = torch.zeros((n, S * self.nb_actions), dtype=torch.uint8, device=dev)
         self._min_gap = torch.full((n,), float('inf'), dtype=torch.float64, device=dev)
         self._carry = torch.zeros((n, 8), dtype=torch.int64, device=dev)            # kernel scratch
-        self._need_scratch = torch.zeros((n, S), dtype=torch.float64, device=dev)   # kernel scratch
+        self._need_scratch = torch.zeros((2, n, S), dtype=torch.float64, device=dev)   # kernel scratch
         self._band_T = self._matrix_band(self._T0)     # half bandwidth of T; None = must be re-measured
         self._band_scratch = None
         self.sr_band_max = 24                          # wider T: dense update_sr every trial (csrc/pma.cu)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define COBEL_ABI_VERSION 3
+#define COBEL_ABI_VERSION 4
 
 enum {
   COBEL_OK = 0,
@@ -295,7 +295,8 @@ typedef struct CobelPMAParams {
   int64_t  pow_stride;       /* 0 = one table for all agents, COBEL_PMA_MAX_SEQ+2 = one per agent */
   double*  min_gap;          /* optional [N] in/out: smallest relative gap between the two largest distinct utilities */
   int64_t* carry;            /* scratch [N,8]: per-agent state carried between the launches of one call */
-  double*  need_scratch;     /* scratch [N,S]: stationary `need` of agents whose trial timed out */
+  double*  need_scratch;     /* scratch [2,N,S]: the `need` vector of the next replay call (an SR row from the banded solve or the
+                                stationary distribution of a timed-out trial); second plane: SR[start] of the next trial */
   double   lr_T;             /* M.learning_rate_T (0.9) */
   double   min_gain;         /* M.min_gain (1e-6) */
   int32_t  min_gain_original;/* M.min_gain_mode == 'original' */
