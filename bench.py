@@ -43,20 +43,25 @@ WORKLOADS = {
         metric='agent-steps/sec incl. replay', unit='agent-steps/s', kernel='dynaq_warp_kernel<4,PLAIN>',
         agents_per_gpu=4096, trials=500, steps=50, batch=32, world='open5', bytes_per_unit=2066,
         unit_key='n_steps', cpu_trials=500),
+    'dynaq64k': dict(
+        desc='Dyna-Q throughput regime: 65536 agents/GPU (two agents per warp), 5x5 open field, 500 trials x <=50 steps, batch 32',
+        metric='agent-steps/sec incl. replay', unit='agent-steps/s', kernel='dynaq_pair_kernel<4>',
+        agents_per_gpu=65536, trials=500, steps=50, batch=32, world='open5', bytes_per_unit=2066,
+        unit_key='n_steps', cpu_trials=500, like='dynaq'),
     'pma': dict(
         desc='C3: 16384 PMA agents/GPU, 10x10 gridworld with walls, 4 trials x <=100 steps, replay batch 32 at '
              'trial start and end',
-        metric='PMA replay updates/sec', unit='replay-updates/s', kernel='pma_main_kernel<4,PLAIN,BAND> + pma_band_check_kernel + pma_sr_band_kernel<12>',
+        metric='PMA replay updates/sec', unit='replay-updates/s', kernel='pma_main_kernel<4,PLAIN> + pma_band_factor_kernel + pma_sr_band_kernel<10> + pma_band_check_kernel',
         agents_per_gpu=16384, trials=4, steps=100, batch=32, world='walls10', bytes_per_unit=23 * 400 + 8 * 100,
         unit_key='n_replay', cpu_trials=4),
     'sfma': dict(
         desc='C4: 65536 SFMA agents/GPU, 20x20 open field, DR metric, default mode, 4 trials x <=200 steps, batch 32',
-        metric='agent-steps/sec incl. replay', unit='agent-steps/s', kernel='sfma_kernel<4>',
+        metric='agent-steps/sec incl. replay', unit='agent-steps/s', kernel='sfma_step_kernel<4> + sfma_replay_kernel<4>',
         agents_per_gpu=65536, trials=4, steps=200, batch=32, world='open20', bytes_per_unit=138,
         unit_key='n_steps', cpu_trials=4),
     'sr': dict(
         desc='SR agents (dense S x S), 20x20 open field, 4096 agents/GPU, 4 trials x <=64 steps',
-        metric='agent-steps/sec', unit='agent-steps/s', kernel='sr_kernel<4>',
+        metric='agent-steps/sec', unit='agent-steps/s', kernel='sr_tma_kernel<4>',
         agents_per_gpu=4096, trials=4, steps=64, batch=0, world='open20', bytes_per_unit=8 * 400 * 8 + 24,
         unit_key='n_steps', cpu_trials=4),
     'sr100': dict(
@@ -74,7 +79,7 @@ WORKLOADS = {
 
 
 # agents per host core in the cpu_baseline leg: sized for roughly 10-20 s of CPU work per workload
-CPU_AGENTS_PER_CORE = {'dynaq': 16, 'pma': 12, 'q': 16, 'sr': 8, 'sfma': 4, 'sr100': 1}
+CPU_AGENTS_PER_CORE = {'dynaq': 16, 'dynaq64k': 16, 'pma': 12, 'q': 16, 'sr': 8, 'sfma': 4, 'sr100': 1}
 
 
 def peaks():
@@ -95,6 +100,18 @@ def measured_traffic(name, agents_per_gpu):
     if not t or t.get('agents_per_gpu') != agents_per_gpu:
         return None
     return t['bytes_per_launch']
+
+
+def measured_issue(name, agents_per_gpu):
+    """Warp-instructions per unit of the workload's kernels from the committed ncu counters (profiles/issue.json,
+    written by profiles/collect_counters.py), or None if no capture exists for this configuration."""
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'issue.json'))).get(name)
+    except (OSError, ValueError):
+        return None
+    if not t or t.get('agents_per_gpu') != agents_per_gpu:
+        return None
+    return t
 
 
 def make_world(name):
@@ -330,8 +347,9 @@ class Job:
         from cobel_rl_b200 import agent as AG, memory as MEM
         from cobel_rl_b200.interface import Gridworld, Topology
         from cobel_rl_b200.policy import EpsilonGreedy
-        self.torch, self.name, self.wl, self.dev = torch, name, WORKLOADS[name], dev
+        self.torch, self.wl, self.dev = torch, WORKLOADS[name], dev
         wl = self.wl
+        self.name = name = wl.get('like', name)
         self.stream = st = cb.BatchStream(n_local, seed=SEED, device=dev, agent_id_base=lo)
         if name == 'q':
             from cobel_rl_b200.misc.topology_tools import linear_track
@@ -422,7 +440,7 @@ class Job:
         return sum(v.numel() * v.element_size() for v in self.host_out.values())
 
 
-def measure(job, k, warmup, cdist, dev, flush, e2e=True):
+def measure(job, k, warmup, cdist, dev, flush, e2e=True, n_total=None):
     """Returns dict(ms kernel-only, ms e2e, per-rank units of one step, launches, wall)."""
     import torch
     from cobel_rl_b200 import _lib
@@ -474,10 +492,22 @@ def measure(job, k, warmup, cdist, dev, flush, e2e=True):
         ms2, _, res2 = timed(job.step_e2e, None)
         assert float(res2[job.wl['unit_key']].sum().item()) == units
         out['ms_e2e'] = sum(ms2) / len(ms2)
+        if n_total is not None:
+            # the path's only collective: the final all-gather of the per-agent statistics (one NCCL call), warmed,
+            # then timed inside the end-to-end step
+            def e2e_gather():
+                r = job.step_e2e()
+                out['gathered'] = cdist.gather_results(r, n_total)
+                return r
+            for _ in range(2):
+                e2e_gather()
+            torch.cuda.synchronize(dev)
+            ms3, _, _ = timed(e2e_gather, None)
+            out['ms_e2e_gather'] = sum(ms3) / len(ms3)
     return out
 
 
-def result_block(name, m, world, peak, peak_src, job, t_step, t_e2e, units_total):
+def result_block(name, m, world, peak, peak_src, job, t_step, t_e2e, units_total, clocks=None):
     wl = WORKLOADS[name]
     achieved = wl['bytes_per_unit'] * m['units'] / (m['ms'] * 1e-3) / 1e9
     blk = {
@@ -496,10 +526,23 @@ def result_block(name, m, world, peak, peak_src, job, t_step, t_e2e, units_total
                              '(DESIGN.md, profiles/)'},
         'gpu_launches': m['launches'],
     }
+    iss = measured_issue(name, wl['agents_per_gpu'])
+    if iss:
+        # what actually bounds these kernels: warp-instruction issue.  instr/unit from the committed ncu counters of
+        # this configuration x the units of this run / (SM sub-partitions x SM clock x measured time)
+        smsp = 4 * job.torch.cuda.get_device_properties(job.dev).multi_processor_count
+        mhz = (clocks or {}).get('sm_mhz') or iss.get('sm_mhz') or 1965.0
+        ipc = iss['warp_instr_per_unit'] * m['units'] / (smsp * mhz * 1e6 * m['ms'] * 1e-3)
+        blk['roofline']['issue'] = {'warp_instr_per_unit': iss['warp_instr_per_unit'], 'achieved': ipc, 'peak': 1.0,
+                                    'unit': 'warp-instructions/cycle/SM sub-partition', 'frac': ipc,
+                                    'sm_mhz': mhz, 'source': iss.get('source')}
     if t_e2e is not None:
         blk['e2e'] = {'value': units_total / (t_e2e * 1e-3), 'unit': wl['unit'], 'h2d_bytes_per_step': job.h2d_bytes(),
                       'd2h_bytes_per_step': job.d2h_bytes(), 'ms_per_step': t_e2e}
     return blk
+
+
+EXTRAS = ['pma', 'dynaq64k', 'q', 'sr', 'sfma', 'sr100']     # reported under their own keys next to the headline
 
 
 def run_ours(args):
@@ -512,8 +555,10 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
     peak, peak_src = peaks()
-    names = [args.workload] + (['pma'] if args.workload == 'dynaq' and not args.no_pma else [])
-    blocks, clocks = {}, None
+    names = [args.workload]
+    if args.workload == 'dynaq' and not args.no_pma:
+        names += ['pma'] if args.extras == 'pma' else (EXTRAS if args.extras == 'all' else [])
+    blocks, head_clocks = {}, None
     for name in names:
         wl = WORKLOADS[name]
         if wl.get('scaling') == 'strong':
@@ -525,31 +570,46 @@ def run_ours(args):
             lo, hi = cdist.shard_range(n_local * world, rank, world)
         n_total = int(cdist.sum_over_ranks(n_local, dev))
         job = Job(name, dev, lo, n_local)
+        if args.profile_one:
+            # one step between cudaProfilerStart / Stop (ncu --profile-from-start off): profiles/collect_counters.py
+            for _ in range(max(args.warmup, 3)):
+                job.reset(); job.step()
+            job.reset()
+            torch.cuda.synchronize(dev)
+            torch.cuda.profiler.start()
+            res = job.step()
+            torch.cuda.synchronize(dev)
+            torch.cuda.profiler.stop()
+            print(json.dumps({'workload': name, 'agents_per_gpu': wl['agents_per_gpu'],
+                              'units': float(res[wl['unit_key']].sum().item())}))
+            return
         sampler = ClockSampler(local)
-        if rank == 0 and name == names[0]:
+        if rank == 0:
             sampler.start()
         k = args.steps if name == names[0] else max(3, min(args.steps, 5))
-        m = measure(job, k, args.warmup, cdist, dev, flush)
-        if rank == 0 and name == names[0]:
-            clocks = sampler.stop()
-        # the only collective of the path: final all-gather of per-agent statistics
-        torch.cuda.synchronize(dev)
-        g0 = time.perf_counter()
-        gathered = cdist.gather_results(m['res'], n_total)
-        torch.cuda.synchronize(dev)
-        gather_ms = 1e3 * (time.perf_counter() - g0)
-        assert gathered['n_steps'].shape[0] == n_total
+        m = measure(job, k, args.warmup, cdist, dev, flush, n_total=n_total if world > 1 else None)
+        clocks = sampler.stop() if rank == 0 else None
+        if name == names[0]:
+            head_clocks = clocks
         t_step = cdist.max_over_ranks(m['ms'], dev)
         t_e2e = cdist.max_over_ranks(m['ms_e2e'], dev)
+        t_e2e_g = cdist.max_over_ranks(m['ms_e2e_gather'], dev) if 'ms_e2e_gather' in m else None
+        if 'gathered' in m:
+            assert m['gathered']['n_steps'].shape[0] == n_total
         units_total = cdist.sum_over_ranks(m['units'], dev)
         steps_total = cdist.sum_over_ranks(m['steps_units'], dev)
         replay_total = cdist.sum_over_ranks(m['replay_units'], dev)
         if rank == 0:
-            blk = result_block(name, m, world, peak, peak_src, job, t_step, t_e2e, units_total)
+            blk = result_block(name, m, world, peak, peak_src, job, t_step, t_e2e, units_total, clocks)
             blk['config'].update(agent_steps_per_bench_step=steps_total, replay_updates_per_bench_step=replay_total,
-                                 final_all_gather_ms=gather_ms, wall_s_incl_flush_and_reset=m['wall'])
+                                 wall_s_incl_flush_and_reset=m['wall'])
+            if t_e2e_g is not None:
+                # e2e plus the final NCCL all-gather of the per-agent statistics (one collective, warmed)
+                blk['e2e_with_gather'] = {'value': units_total / (t_e2e_g * 1e-3), 'unit': wl['unit'],
+                                          'ms_per_step': t_e2e_g, 'gather_ms': t_e2e_g - t_e2e}
+            blk['clocks'] = clocks
             blocks[name] = blk
-        del job, gathered, m
+        del job, m
         torch.cuda.empty_cache()
     if rank != 0:
         return
@@ -559,16 +619,19 @@ def run_ours(args):
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': head['ms_per_step'],
         'higher_is_better': True, 'scaling': WORKLOADS[names[0]].get('scaling', 'weak'), 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic', 'config': head['config'], 'roofline': head['roofline'], 'e2e': head['e2e'],
-        'gpu_launches': head['gpu_launches'], 'clocks': clocks,
+        'gpu_launches': head['gpu_launches'], 'clocks': head_clocks,
     }
+    if 'e2e_with_gather' in head:
+        out['e2e_with_gather'] = head['e2e_with_gather']
     if world == 1 and not args.no_cpu:
         cb = cpu_run(names[0], CPU_AGENTS_PER_CORE.get(names[0], 1))
         out['cpu_baseline'] = {k: v for k, v in cb.items() if k not in ('seconds', 'units')}
     for name in names[1:]:
         blk = blocks[name]
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and name == 'pma':
             cb = cpu_run(name, CPU_AGENTS_PER_CORE.get(name, 1))
             blk['cpu_baseline'] = {k: v for k, v in cb.items() if k not in ('seconds', 'units')}
+        blk['scaling'] = WORKLOADS[name].get('scaling', 'weak')
         out[name] = blk
     print(json.dumps(out))
 
@@ -582,7 +645,11 @@ def main():
     ap.add_argument('--workload', default='dynaq', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--agents', type=int, default=0, help='override agents per GPU (profiling only; not the headline config)')
-    ap.add_argument('--no-pma', action='store_true', help='skip the second headline metric (PMA replay-updates/s)')
+    ap.add_argument('--no-pma', action='store_true', help='headline workload only (no extra workloads)')
+    ap.add_argument('--extras', default='all', choices=['all', 'pma', 'none'],
+                    help='extra workloads reported under their own keys next to the Dyna-Q headline: all = PMA (the second '
+                         'headline metric), Dyna-Q at 65536 agents, QAgent, dense SR, SFMA C4, compact SR C5')
+    ap.add_argument('--profile-one', action='store_true', help='one step between cudaProfilerStart/Stop, for ncu')
     args = ap.parse_args()
     if args.agents:
         for w in WORKLOADS.values():

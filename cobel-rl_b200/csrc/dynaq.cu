@@ -15,6 +15,7 @@
 //     sequential 32-update chain collapses to about five rounds with bit-identical results.
 // (v1 of this kernel used one thread per agent: 180 warp-instructions per update at one
 //  instruction per 5 cycles, profiles/r1_dynaq_v1_thread_per_agent.txt.)
+#include <cstdlib>
 #include "warp_agent.cuh"
 
 namespace {
@@ -236,6 +237,213 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, HBM ? 1 : 7) dynaq_warp_ker
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// dynaq_pair_kernel: the PLAIN case with TWO AGENTS PER WARP (16 lanes each), A <= 4.
+// The online part of a step (action selection, environment step, store, online update, stream refill) is
+// warp-uniform work: with one agent per warp all 32 lanes repeat it, 151 of the 389 warp-instructions of an
+// agent-step (profiles/r1_dynaq_v7_plain.txt).  Here each half-warp runs its own agent -- own trial / step
+// counters, own tables, own stream -- so that work is issued once per two agents, and the replay batch of 32 is
+// applied as two level-parallel passes of 16 (lane = update; the passes of the two agents share the rounds).
+// The level-parallel routine is the one of the warp-per-agent kernel: its dependency masks live in per-agent
+// arrays and hold warp lane bits, so the two halves never see each other.
+// Stream: a ring of 128 draws per agent in shared memory, refilled 32 draws at a time (one Philox block per lane
+// of the half) whenever fewer than a step's 34 are left -- every generated draw is consumed.
+// ---------------------------------------------------------------------------
+constexpr int kPairWarps = 2;          // warps per CTA (4 agents)
+constexpr int kRing = 128;             // draws in an agent's ring
+
+struct PairSmem {       // byte offsets inside one agent's shared-memory block
+  int q, mr, mx, wm, rm, ptab, ring, bytes;
+  __host__ __device__ PairSmem(int S, int A) {
+    const int SA = S * A;
+    q = 0;
+    mr = q + SA * 8;
+    wm = mr + SA * 8;
+    rm = wm + S * 4;
+    mx = rm + S * 4;
+    ptab = (mx + SA * 2 + 15) & ~15;
+    ring = ptab + kEpsTabDoubles * 8;
+    bytes = ring + kRing * 8;
+  }
+};
+
+template <int A>
+__global__ void __launch_bounds__(kPairWarps * 32, 14) dynaq_pair_kernel(const __grid_constant__ CobelDynaQParams p) {
+  static_assert(A <= 4, "tie-pattern table");
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int S = p.world.n_states, K = p.world.n_starts, SA = S * A;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, h = lane & 15;
+  const WorldSmem wo(S, A, K);
+  const PairSmem ao(S, A);
+  double* rew_s = reinterpret_cast<double*>(smem + wo.rew);
+  int32_t* succ_s = reinterpret_cast<int32_t*>(smem + wo.succ);
+  int32_t* starts_s = reinterpret_cast<int32_t*>(smem + wo.starts);
+  uint8_t* term_s = smem + wo.term;
+  for (int e = threadIdx.x; e < SA; e += blockDim.x) succ_s[e] = p.world.succ[e];
+  for (int e = threadIdx.x; e < S; e += blockDim.x) { rew_s[e] = p.world.reward[e]; term_s[e] = p.world.terminal[e]; }
+  for (int e = threadIdx.x; e < K; e += blockDim.x) starts_s[e] = p.world.starts[e];
+  __syncthreads();
+
+  const int64_t n = ((int64_t)blockIdx.x * kPairWarps + warp) * 2 + half;
+  const bool mine = n < p.n_agents;                   // a half without an agent idles on zeroed tables
+  const int64_t nn = mine ? n : p.n_agents - 1;
+  unsigned char* blk = smem + wo.bytes + (size_t)(warp * 2 + half) * ao.bytes;
+  const size_t g0 = (size_t)nn * SA;
+  double* Q = reinterpret_cast<double*>(blk + ao.q);
+  double* Mr = reinterpret_cast<double*>(blk + ao.mr);
+  uint16_t* Mx = reinterpret_cast<uint16_t*>(blk + ao.mx);     // next state | non-terminal << 15
+  uint32_t* wm = reinterpret_cast<uint32_t*>(blk + ao.wm);
+  uint32_t* rm = reinterpret_cast<uint32_t*>(blk + ao.rm);
+  double* ptab = reinterpret_cast<double*>(blk + ao.ptab);
+  double* ring = reinterpret_cast<double*>(blk + ao.ring);
+  for (int e = h; e < SA; e += 16) {
+    Q[e] = mine ? p.Q[g0 + e] : 0.0;
+    Mr[e] = mine ? p.Mr[g0 + e] : 0.0;
+    Mx[e] = mine ? (uint16_t)(p.Ms[g0 + e] | ((p.Mt[g0 + e] ? 1 : 0) << 15)) : (uint16_t)0;
+  }
+  for (int e = h; e < S; e += 16) { wm[e] = 0; rm[e] = 0; }
+  for (int e = h; e < kRing; e += 16) ring[e] = 0.0;
+  const double lr = p.lr[nn], gamma = p.gamma[nn], mlr = p.mem_lr[nn];
+  {
+    // the agent's 2^A - 1 normalised CDFs by tie pattern (see eps_cdf_table_init): lane h = pattern h
+    const double eps = p.policy.param[nn];
+    const int pat = h & ((1 << A) - 1), k = __popc(pat);
+    const double base = xdiv(eps, (double)A);
+    const double tie = xdiv(xsub(1.0, eps), (double)(k > 0 ? k : 1));
+    const double top = xadd(base, tie), low = xadd(base, 0.0);
+    double cdf[A];
+    double c = (pat & 1) ? top : low;
+    cdf[0] = c;
+#pragma unroll
+    for (int a = 1; a < A; ++a) { c = xadd(c, (pat >> a & 1) ? top : low); cdf[a] = c; }
+    if (c != 1.0) {
+#pragma unroll
+      for (int a = 0; a < A; ++a) cdf[a] = xdiv(cdf[a], c);
+    }
+    if (h > 0 && h < (1 << A)) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) ptab[pat * 4 + a] = a < A ? cdf[a] : 2.0;
+    }
+  }
+  // stream state of the half: the ring holds draws [gen - 128, gen), the next draw is gen - avail
+  const uint64_t agent = (uint64_t)(p.stream.agent_id_base + nn);
+  const uint32_t key0 = (uint32_t)p.stream.seed, key1 = (uint32_t)(p.stream.seed >> 32);
+  const uint64_t pos0 = (uint64_t)p.stream.draw_count[nn];
+  uint64_t gblk = (pos0 & ~31ull) >> 1;               // Philox block of ring slot wr
+  int wr = 0;                                         // ring slot that the next refill writes (multiple of 32)
+  int rd = (int)(pos0 & 31ull);                       // ring slot of the next draw
+  int avail = -rd;                                    // generated draws not yet consumed
+  const CobelTrace& tr = p.trace;
+  bool live = mine && p.trials > 0;
+  bool fresh = true;                                  // the next step starts a trial
+  int s = 0, step = 0, trial = 0;
+  int nsteps = 0;
+  double treward = 0.0;
+  __syncwarp();
+
+  while (__any_sync(kFull, live)) {
+    // ---- stream: at least one step's draws (reset + action + 32 replay indices) ----
+    for (;;) {
+      const bool need = live && avail < 34;
+      if (!__any_sync(kFull, need)) break;
+      const uint64_t b = gblk + (uint64_t)h;
+      uint32_t o[4];
+      philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)agent, (uint32_t)(agent >> 32), key0, key1, o);
+      if (need) {
+        reinterpret_cast<double2*>(ring)[(wr >> 1) + h] = make_double2(u53(o[0], o[1]), u53(o[2], o[3]));
+        gblk += 16; wr = (wr + 32) & (kRing - 1); avail += 32;
+      }
+    }
+    __syncwarp();
+    // ---- interface/gridworld.py:142 (reset), policy, environment ----
+    if (fresh) {
+      if (live) { s = starts_s[draw_integer(ring[rd], K)]; rd = (rd + 1) & (kRing - 1); --avail; }
+      fresh = false; step = 0; treward = 0.0;
+    }
+    double row[A];
+    load_row<A>(Q + s * A, row);
+    const double ua = ring[rd];
+    int a;
+    {
+      const double m = row_max<A>(row);
+      uint32_t ties = 0;
+#pragma unroll
+      for (int x = 0; x < A; ++x) ties |= (row[x] == m ? 1u : 0u) << x;
+      const double edge = ptab[ties * 4 + (h & 3)];
+      const unsigned bal = __ballot_sync(kFull, h < A - 1 && edge <= ua);
+      a = __popc((bal >> (half * 16)) & 0xFFFFu);
+    }
+    const int sa = s * A + a;
+    const int s2 = succ_s[sa];
+    const double r = rew_s[s2];
+    const int end = term_s[s2];
+    const int nt = 1 - end;
+    {
+      // memory/dyna_q.py:92-96 (store first), then agent/dyna_q.py:275-301 (online update)
+      const double m0 = Mr[sa];
+      const double m1 = xadd(m0, xmul(mlr, xsub(r, m0)));
+      double row2[A];
+      load_row<A>(Q + s2 * A, row2);
+      const double q = Q[sa];
+      const double g = nt ? gamma : 0.0;
+      double td = xadd(r, xmul(g, row_max<A>(row2)));
+      td = xsub(td, q);
+      const double qn = xadd(q, xmul(lr, td));
+      __syncwarp();
+      if (live && h == 0) {
+        Mr[sa] = m1;
+        Mx[sa] = (uint16_t)(s2 | (nt << 15));
+        Q[sa] = qn;
+      }
+      __syncwarp();
+    }
+    // ---- replay: memory/dyna_q.py:137-157 + agent/dyna_q.py:329-330, 32 updates as two passes of 16 ----
+#pragma unroll 1
+    for (int b0 = 0; b0 < 32; b0 += 16) {
+      const double u = ring[(rd + 1 + b0 + h) & (kRing - 1)];
+      const int i = draw_integer(u, SA);
+      const int rs = i / A, ra = i - rs * A;
+      const double rr = Mr[i];
+      const uint16_t v = Mx[i];
+      td_batch_level_parallel<A>(Q, wm, rm, S, lane, live, rs, ra, rr, v & 0x7FFF, v >> 15, lr, gamma);
+    }
+    // ---- bookkeeping of the half, branch-free (the two halves end their trials at different steps) ----
+    {
+      const bool fin = end || step + 1 == p.steps;
+      const double tw = xadd(treward, r);
+      if (live && fin && h == 0) {                       // logs['steps'] = index of the last step
+        tr.trial_steps[n * p.trials + trial] = step;
+        tr.trial_reward[n * p.trials + trial] = tw;
+      }
+      const int adv = live ? 33 : 0;
+      rd = (rd + adv) & (kRing - 1); avail -= adv;
+      nsteps += live ? 1 : 0;
+      treward = tw;
+      trial += (live && fin) ? 1 : 0;
+      fresh = fin;
+      step = step + 1;
+      s = s2;
+      live = live && trial < p.trials;
+    }
+  }
+
+  __syncwarp();
+  if (mine) {
+    for (int e = h; e < SA; e += 16) {
+      p.Q[g0 + e] = Q[e];
+      p.Mr[g0 + e] = Mr[e];
+      p.Ms[g0 + e] = Mx[e] & 0x7FFF;
+      p.Mt[g0 + e] = Mx[e] >> 15;
+    }
+    if (h == 0) {
+      p.stream.draw_count[n] = (int64_t)(gblk * 2) - (int64_t)avail;
+      tr.n_steps[n] += nsteps;
+      tr.n_replay[n] += (int64_t)nsteps * 32;
+    }
+  }
+}
+
 template <int A>
 int launch(const CobelDynaQParams& p, cudaStream_t st) {
   const int S = p.world.n_states, K = p.world.n_starts;
@@ -260,6 +468,26 @@ int launch(const CobelDynaQParams& p, cudaStream_t st) {
     return COBEL_OK;
   }
   const unsigned grid = (unsigned)((p.n_agents + kWarpsPerCta - 1) / kWarpsPerCta);
+  if constexpr (A <= 4) {
+    // the production case: two agents per warp (COBEL_DYNAQ_PAIR=0 keeps the warp-per-agent kernel, for A/B runs)
+    const PairSmem po(S, A);
+    const size_t smp = (size_t)wo.bytes + (size_t)kPairWarps * 2 * po.bytes;
+    // It pays once the machine is full either way: with fewer agents than two waves of the warp-per-agent kernel
+    // the halved number of warps costs more issue rate than the shared instructions save (4096 agents: 1.39e9
+    // against 1.58e9 agent-steps/s; 16384: 2.26e9 against 2.05e9; 262144: 2.66e9 against 2.27e9).
+    // COBEL_DYNAQ_PAIR=0 / 1 forces one kernel or the other (A/B runs).
+    static const int pair_env = [] { const char* e = getenv("COBEL_DYNAQ_PAIR"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+    static const int n_sm = [] { int d = 0, v = 148; if (cudaGetDevice(&d) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+    const bool pair_on = pair_env >= 0 ? pair_env == 1 : p.n_agents >= (int64_t)2 * 7 * kWarpsPerCta * n_sm;
+    if (plain && pair_on && smp <= 227 * 1024 && S <= 0x7FFF) {
+      const int64_t per_cta = kPairWarps * 2;
+      COBEL_CUDA_OK(cudaFuncSetAttribute(dynaq_pair_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp));
+      dynaq_pair_kernel<A><<<(unsigned)((p.n_agents + per_cta - 1) / per_cta), kPairWarps * 32, smp, st>>>(p);
+      cobel_count_launch();
+      COBEL_CUDA_OK(cudaGetLastError());
+      return COBEL_OK;
+    }
+  }
   if (plain) {
     COBEL_CUDA_OK(cudaFuncSetAttribute(dynaq_warp_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dynaq_warp_kernel<A, true><<<grid, kWarpsPerCta * 32, sm, st>>>(p);

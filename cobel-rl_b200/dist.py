@@ -56,8 +56,27 @@ def gather_agents(t, n_total=None):
 
 
 def gather_results(res, n_total=None, keys=('trial_steps', 'trial_reward', 'n_steps', 'n_replay')):
-    """The final collective: all-gather the per-agent statistics of a RunResult."""
-    return {k: gather_agents(res[k], n_total) for k in keys if k in res}
+    """The final collective: all-gather the per-agent statistics of a RunResult -- ONE collective for all keys (the
+    fields of an agent are packed into one byte record, ``all_gather_into_tensor`` when the shards are equal)."""
+    keys = [k for k in keys if k in res]
+    if not dist.is_initialized() or dist.get_world_size() == 1 or not keys:
+        return {k: res[k] for k in keys}
+    n_local = res[keys[0]].shape[0]
+    parts = [res[k].contiguous().reshape(n_local, -1).view(torch.uint8) for k in keys]
+    widths = [p.shape[1] for p in parts]
+    rec = torch.cat(parts, dim=1) if len(parts) > 1 else parts[0]
+    world = dist.get_world_size()
+    if n_total is not None and n_total == n_local * world:
+        out = torch.empty((n_total, rec.shape[1]), dtype=torch.uint8, device=rec.device)
+        dist.all_gather_into_tensor(out, rec.contiguous())
+    else:
+        out = gather_agents(rec, n_total)
+    got, off = {}, 0
+    for k, w in zip(keys, widths):
+        t = res[k]
+        got[k] = out[:, off:off + w].contiguous().view(t.dtype).reshape((out.shape[0],) + tuple(t.shape[1:]))
+        off += w
+    return got
 
 
 def max_over_ranks(x, device):

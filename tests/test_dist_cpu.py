@@ -39,14 +39,21 @@ def _worker(rank, world, port, n_total, q):
 
 
 def test_gather_world2_gloo():
+    _gather_world2(11)      # odd: ranks hold 6 and 5 agents (padded all-gather)
+
+
+def test_gather_world2_gloo_equal_shards():
+    _gather_world2(12)      # equal shards: one all_gather_into_tensor of the packed per-agent records
+
+
+def _gather_world2(n_total):
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    n_total = 11        # odd: ranks hold 6 and 5 agents
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted(q.get(timeout=120) for _ in procs)
     for p in procs:
         p.join(60)
-    assert out == [(0, True, 2.0, 11.0), (1, True, 2.0, 11.0)]
+    assert out == [(0, True, 2.0, float(n_total)), (1, True, 2.0, float(n_total))]
