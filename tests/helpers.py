@@ -263,3 +263,71 @@ def cuda_case(name, n_extra=2, device='cuda:0'):
         assert not a, 'unused case arguments %s' % a
         return out
     raise ValueError(kind)
+
+
+# --------------------------------------------------------------------------- #
+# full-size runs: the oracle on a SAMPLE of agents, one process per host core
+# --------------------------------------------------------------------------- #
+
+def sample_agents(n, per_group, k=32):
+    """``k`` agent ids spread over the whole range: both ends, the last (possibly partial) CTA / warp group of
+    ``per_group`` agents, and an even spread in between."""
+    ids = {0, 1, n - 1, n - 2, max(n - per_group, 0), max(n - per_group - 1, 0), n // 2, n // 2 + 1}
+    k = min(k, n)
+    step = max(n // k, 1)
+    i = 0
+    while len(ids) < k:
+        ids.add(min(i * step + (i * 7) % per_group, n - 1) if i < 2 * k else i - 2 * k)
+        i += 1
+    return sorted(ids)
+
+
+def _oracle_sample_worker(job):
+    kind, seed, g, cfg = job
+    import numpy as np
+    from oracle import tabular as tb
+    from oracle.philox import LazyStream
+    rng = tb.Draws(LazyStream(seed, g), 1)
+    if kind == 'sr100':
+        from cobel_rl_b200.misc.gridworld_tools import make_open_field
+        world = make_open_field(100, 100, 0, 1, dense_sas=False)
+        W = {'S': 10000, 'A': 4, 'succ': world['succ'], 'reward': world['rewards'].astype(np.float64),
+             'terminal': world['terminals'].astype(np.uint8), 'starts': world['starting_states'].astype(np.int32)}
+        st = tb.sr_init(10000, 4)
+        rec = tb.sr_train(W, st, rng, cfg['trials'], cfg['steps']).arrays()
+        nzr, nzc = np.nonzero(st['SR'] - np.eye(10000))
+        return {'trial_steps': rec['trial_steps'], 'draws': rng.k, 'SR_offdiag': (nzr, nzc, st['SR'][nzr, nzc]),
+                'SR_diag': np.diag(st['SR']).copy()}
+    if 'world_fn' in cfg:
+        from cobel_rl_b200.misc import gridworld_tools
+        world = getattr(gridworld_tools, cfg['world_fn'][0])(*cfg['world_fn'][1])
+    else:
+        world = make_world(cfg['world'])
+    W = tb.compile_gridworld(world)
+    S, A = W['S'], W['A']
+    if kind == 'dynaq':
+        st = tb.dynaq_init(S, A)
+        rec = tb.dynaq_train(W, st, rng, cfg['trials'], cfg['steps'], cfg['batch']).arrays()
+        return {'trial_steps': rec['trial_steps'], 'draws': rng.k, 'Q': st['Q'], 'Mr': st['Mr']}
+    if kind == 'pma':
+        st = tb.pma_init(tb.t0_from_succ(W['succ']), S, A)
+        rec = tb.pma_train(W, st, rng, cfg['trials'], cfg['steps'], cfg['batch'], gamma_q=0.99, mask_actions=True).arrays()
+        return {'trial_steps': rec['trial_steps'], 'draws': rng.k, 'Q': st['Q'], 'SR': st['SR'], 'T': st['T']}
+    if kind == 'sfma':
+        from cobel_rl_b200.memory.utils.metrics import DR
+        D = DR(world['width'], world['height'], world['sas'], 0.9, world['invalid_transitions']).D
+        st = tb.sfma_init(S, A)
+        rec = tb.sfma_train(W, st, D, rng, cfg['trials'], cfg['steps'], cfg['batch'], mode=cfg.get('mode', 'default'),
+                            mask_actions=True).arrays()
+        return {'trial_steps': rec['trial_steps'], 'draws': rng.k, 'Q': st['Q'], 'C': st['C']}
+    raise ValueError(kind)
+
+
+def oracle_sample(kind, seed, agent_ids, **cfg):
+    """{agent id: oracle result} for a sample of agents of a full-size run, computed on all host cores."""
+    import multiprocessing as mp
+    jobs = [(kind, seed, int(g), cfg) for g in agent_ids]
+    procs = min(len(jobs), os.cpu_count() or 1, 16)
+    with mp.get_context('spawn').Pool(procs) as pool:
+        out = pool.map(_oracle_sample_worker, jobs, chunksize=1)
+    return dict(zip([int(g) for g in agent_ids], out))

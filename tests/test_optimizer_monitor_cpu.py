@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from cobel_rl_b200.monitor import EscapeLatencyMonitor, RewardMonitor
-from cobel_rl_b200.optimizer import GridSearchOptimizer
+from cobel_rl_b200.optimizer import EAOptimizer, GridSearchOptimizer
 
 PARAMS = {'x_1': [0, 1, 2, 3, 4], 'x_2': [0., 0.1, 0.2, 0.3, 0.4], 'x_3': np.array([0.9, 0.5, 0.6, 0.7, 0.8])}
 
@@ -54,6 +54,73 @@ def test_batched_fit_equals_per_run_fit(tmp_path):
     opt3 = GridSearchOptimizer(str(tmp_path) + '/', PARAMS, nb_runs=3, max_agents=60)
     fit3 = opt3.fit(sim_batch, {'task_1': {}}, data, loss, overwrite=True)
     assert fit3 == fit and max(calls) <= 60 and sum(calls) == 375
+
+
+EA_TASKS = {'t1': {'x': 1.0}, 't2': {'x': -2.0}}
+EA_DATA = {'t1': 0.3 * 1.0 + 0.5, 't2': 0.3 * -2.0 + 0.5}
+
+
+def _ea_loss(sim, data):
+    return float(sum((np.mean(sim[t]) - data[t]) ** 2 for t in sim))
+
+
+def _ea_params(rng):
+    return {'a': {'param_type': float, 'init_range': {'low': -1, 'high': 1}, 'mutator': (rng.normal, {'scale': 0.05})},
+            'b': {'param_type': float, 'param_range': {'a_min': 0.0, 'a_max': 1.0}, 'mutator': (rng.normal, {'scale': 0.05})}}
+
+
+def test_ea_optimizer_reference_constructor_cannot_run(reference, tmp_path):
+    """optimizer/evolution.py:73-75: the default mutator is a set literal holding a dict."""
+    from cobel.optimizer.evolution import EAOptimizer as Ref
+    with pytest.raises(TypeError, match='unhashable'):
+        Ref(str(tmp_path) + '/', _ea_params(np.random.default_rng(0)), 1, 1, np.random.default_rng(0))
+
+
+def test_ea_optimizer_matches_reference_fit_method(reference, tmp_path):
+    """The reference's unmodified ``fit`` (on an object whose constructor is bypassed) against the batched back-end
+    in ``bookkeeping='reference'`` mode: same run_<r>.pkl files, same returned fit, same rng consumption."""
+    import os
+    import pickle
+    from cobel.optimizer.evolution import EAOptimizer as Ref
+    d_ref, d_our = str(tmp_path) + '/ref/', str(tmp_path) + '/our/'
+    os.makedirs(d_ref); os.makedirs(d_our)
+    rng_ref, rng_our = np.random.default_rng(11), np.random.default_rng(11)
+    ref = object.__new__(Ref)
+    import copy
+    ref.parameters = copy.deepcopy(_ea_params(rng_ref))      # evolution.py:65 (a bound mutator gets its own copy of the generator)
+    for p in ref.parameters.values():               # what evolution.py:68-72 would have filled in
+        p.setdefault('init_range', {'low': -1, 'high': 1})
+        p.setdefault('param_range', {'a_min': None, 'a_max': None})
+    ref.file_path, ref.nb_runs, ref.population_size, ref.rng, ref.present_files = d_ref, 2, 3, rng_ref, []
+    calls = []
+    f_ref = ref.fit(lambda task, ind: ind['a'] * task['x'] + ind['b'], EA_TASKS, EA_DATA, _ea_loss, generations=6, individuals=5)
+
+    def sim_batch(task, params):
+        calls.append(len(params['_run']))
+        return params['a'] * task['x'] + params['b']
+    ours = EAOptimizer(d_our, _ea_params(rng_our), 2, 3, rng_our, bookkeeping='reference')
+    f_our = ours.fit(sim_batch, EA_TASKS, EA_DATA, _ea_loss, generations=6, individuals=5)
+    assert f_our == f_ref and len(f_ref) >= 1
+    assert calls == [5 * 3] * (2 * 6 * 2)            # one batched call per task and generation: individuals x repetitions
+    for r in range(2):
+        assert pickle.load(open(d_our + 'run_%d.pkl' % r, 'rb')) == pickle.load(open(d_ref + 'run_%d.pkl' % r, 'rb'))
+    assert rng_our.uniform() == rng_ref.uniform()    # same number of draws consumed
+
+
+def test_ea_optimizer_intended_bookkeeping_converges_and_resumes(tmp_path):
+    rng = np.random.default_rng(5)
+    d = str(tmp_path) + '/'
+    opt = EAOptimizer(d, _ea_params(rng), nb_runs=1, population_size=2, rng=rng)
+    fit = opt.fit(lambda task, p: p['a'] * task['x'] + p['b'], EA_TASKS, EA_DATA, _ea_loss, generations=60, individuals=12)
+    (a, b), f = next(iter(fit.items()))
+    assert f < 1e-3 and abs(a - 0.3) < 0.05 and abs(b - 0.5) < 0.05 and 0.0 <= b <= 1.0
+    import pickle
+    hist = pickle.load(open(d + 'run_0.pkl', 'rb'))
+    assert len(hist) == 60 and all(hist[i + 1][1] <= hist[i][1] for i in range(59))      # elitist: never worse
+    # default mutator (the reference's is not constructible): rng.normal(value, 0.1); and resume from run_0.pkl
+    opt2 = EAOptimizer(d, {'a': {'param_type': float}, 'b': {'param_type': float}}, rng=np.random.default_rng(1))
+    assert opt2.parameters['a']['mutator'][1] == {'scale': 0.1}
+    assert opt2.fit(None, EA_TASKS, EA_DATA, _ea_loss) == fit
 
 
 def test_monitors_from_callbacks_and_results():
