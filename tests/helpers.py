@@ -295,7 +295,9 @@ def _oracle_sample_worker(job):
              'terminal': world['terminals'].astype(np.uint8), 'starts': world['starting_states'].astype(np.int32)}
         st = tb.sr_init(10000, 4)
         rec = tb.sr_train(W, st, rng, cfg['trials'], cfg['steps']).arrays()
-        nzr, nzc = np.nonzero(st['SR'] - np.eye(10000))
+        nzr, nzc = np.nonzero(st['SR'])
+        keep = nzr != nzc
+        nzr, nzc = nzr[keep], nzc[keep]
         return {'trial_steps': rec['trial_steps'], 'draws': rng.k, 'SR_offdiag': (nzr, nzc, st['SR'][nzr, nzc]),
                 'SR_diag': np.diag(st['SR']).copy()}
     if 'world_fn' in cfg:
