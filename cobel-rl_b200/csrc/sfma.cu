@@ -514,6 +514,8 @@ __global__ void __launch_bounds__(256, 4) sfma_replay_kernel(const __grid_consta
     for (int e = tid; e < S; e += T) I[e] = 0.0;                           // sfma.py:277
     __syncthreads();
     int count = 0;
+    const int nw = T >> 5, chunk = (nnz + T - 1) / T;
+    const int clo = tid * chunk < nnz ? tid * chunk : nnz, chi = clo + chunk < nnz ? clo + chunk : nnz;
     for (int it = 0; it < B; ++it) {
       if (mf & COBEL_SFMA_D_NORMALIZE) {                                   // np.amax(D[current_state])
         const double* Dc = D + (size_t)cur * S;
@@ -527,9 +529,13 @@ __global__ void __launch_bounds__(256, 4) sfma_replay_kernel(const __grid_consta
         for (int w = 1; w < (T >> 5); ++w) dmax = part[w] > dmax ? part[w] : dmax;
         __syncthreads();
       }
+      // Every thread owns a contiguous chunk [clo, chi) of the list for all passes of a reactivation, so the priority,
+      // the exp() and the partial sums of its entries need no barrier in between; a reactivation costs four block
+      // barriers (max / scan / owner / inhibition) instead of the dozen of a textbook block-wide sampler -- barrier
+      // stalls were 4.6 warps per issued instruction in this kernel (profiles/r2_sfma_split_replay.txt).
       double lmax = 0.0;
 #pragma unroll 1
-      for (int j = tid; j < nnz; j += T) {
+      for (int j = clo; j < chi; ++j) {
         const uint32_t l = L[j];
         const int sp = l & 0xFFFF;
         const double cn = (mf & COBEL_SFMA_C_NORMALIZE) ? xdiv(Cc[j], cmax) : Cc[j];
@@ -540,11 +546,16 @@ __global__ void __launch_bounds__(256, 4) sfma_replay_kernel(const __grid_consta
       }
       // block max (R >= 0): all-zero <=> np.sum(R) == 0 (sfma.py:316)
       for (int d = 16; d > 0; d >>= 1) { const double o = shfl_f64_xor(lmax, d); lmax = o > lmax ? o : lmax; }
-      if (lane == 0) part[warp] = lmax;
-      __syncthreads();
-      double m = part[0];
-      for (int w = 1; w < (T >> 5); ++w) m = part[w] > m ? part[w] : m;
-      __syncthreads();
+      double* pmax = part + T + (it & 1) * 8;
+      if (lane == 0) pmax[warp] = lmax;
+      if (warp == 0 && !p.deterministic) {                                 // the draw is consumed only if a replay follows
+        win.ensure(1, lane);
+        const double u = win.peek(0);
+        if (lane == 0) sh.u = u;
+      }
+      __syncthreads();                                                     // (1)
+      double m = pmax[0];
+      for (int w = 1; w < nw; ++w) m = pmax[w] > m ? pmax[w] : m;
       if (!(m > 0.0)) break;
       int jsel;
       if (p.deterministic) {                                               // argmax(R): first maximum
@@ -556,16 +567,58 @@ __global__ void __launch_bounds__(256, 4) sfma_replay_kernel(const __grid_consta
         jsel = sh.idx;
         __syncthreads();
       } else {
+        if (warp == 0) win.advance(1);
         // probs ~ exp(beta * R / max) - 1  (softmax(R, -1, beta), sfma.py:349-373); exp(0) - 1 == 0 exactly
+        double local = 0.0;
 #pragma unroll 1
-        for (int j = tid; j < nnz; j += T) { const double r = R[j]; R[j] = r > 0.0 ? xadd(exp(xmul((mf & COBEL_SFMA_R_RAW) ? r : xdiv(r, m), beta)), -1.0) : 0.0; }
-        if (warp == 0) {
-          win.ensure(1, lane);
-          const double u = win.next();
-          if (lane == 0) sh.u = u;
+        for (int j = clo; j < chi; ++j) {
+          const double r = R[j];
+          const double w = r > 0.0 ? xadd(exp(xmul((mf & COBEL_SFMA_R_RAW) ? r : xdiv(r, m), beta)), -1.0) : 0.0;
+          R[j] = w;
+          local += w;
         }
-        __syncthreads();
-        jsel = block_sample(R, nnz, sh.u, part, &sh, tid, T, flags);
+        // inverse-CDF draw (NumPy: searchsorted(cumsum(p) / cumsum(p)[-1], u, 'right')): exclusive scan of the
+        // chunk sums, the first chunk whose running sum passes u * total owns the draw
+        double inc = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const double o = shfl_f64_up(inc, d); if (lane >= d) inc += o; }
+        double* psum = part + T + 16;
+        if (lane == 31) psum[warp] = inc;
+        __syncthreads();                                                   // (2)
+        double off = 0.0, total = 0.0;
+        for (int w = 0; w < nw; ++w) { if (w < warp) off += psum[w]; total += psum[w]; }
+        const double excl = off + (inc - local);
+        const double target = sh.u * total, tol = 1e-12 * total;
+        const unsigned pass = __ballot_sync(kFull, local > 0.0 && excl + local > target);
+        int* pc = reinterpret_cast<int*>(part + T + 24);
+        if (lane == 0) pc[warp] = pass ? warp * 32 + __ffs(pass) - 1 : 0x7fffffff;
+        part[tid] = excl;
+        __syncthreads();                                                   // (3)
+        int owner = pc[0];
+        for (int w = 1; w < nw; ++w) owner = pc[w] < owner ? pc[w] : owner;
+        bool near = false;
+        if (owner == 0x7fffffff) {                                         // u * total rounded up to the total: the last positive weight
+          jsel = nnz - 1;
+          while (jsel > 0 && !(R[jsel] > 0.0)) --jsel;
+          near = true;
+        } else {                                                           // every thread walks the owner's chunk (broadcast reads)
+          const int olo = owner * chunk < nnz ? owner * chunk : nnz, ohi = olo + chunk < nnz ? olo + chunk : nnz;
+          double acc = part[owner];
+          int found = -1, lastpos = olo;
+          near = fabs(acc - target) < tol;
+#pragma unroll 1
+          for (int i = olo; i < ohi; ++i) {
+            const double w = R[i];
+            if (!(w > 0.0)) continue;
+            lastpos = i;
+            acc += w;
+            if (fabs(acc - target) < tol) near = true;
+            if (found < 0 && acc > target) found = i;
+          }
+          jsel = found >= 0 ? found : lastpos;
+          if (found < 0) near = true;
+        }
+        if (near) flags |= COBEL_FLAG_CDF_NEAR_TIE;
       }
       const uint32_t l = L[jsel];
       action = l >> 16;
@@ -829,6 +882,8 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     for (int e = tid; e < S; e += T) I[e] = 0.0;                           // sfma.py:277
     __syncthreads();
     int count = 0;
+    const int nw = T >> 5, chunk = (nnz + T - 1) / T;
+    const int clo = tid * chunk < nnz ? tid * chunk : nnz, chi = clo + chunk < nnz ? clo + chunk : nnz;
     for (int it = 0; it < B; ++it) {
       if (mf & COBEL_SFMA_D_NORMALIZE) {                                   // np.amax(D[current_state])
         const double* Dc = D + (size_t)cur * S;

@@ -137,3 +137,79 @@ def cross(nb_nodes_arm, nb_nodes_width, spacing=1.0, rotation=0.0):
         x, y = R @ (np.array((ticks[ix], ticks[iy])) * scale - offset)
         node['pose'] = (float(x), float(y), 0.0, 0.0, 0.0, 0.0)
     return nodes, list(nodes.keys())
+
+
+# ---------------------------------------------------------------------------
+# remove_obstructed_neighbors (topology_tools.py:472-505).  The reference delegates the geometry to shapely
+# (intersects(LineString, buffer(MultiPolygon, d))); shapely is not part of this image, so the predicate is written
+# out: an edge is obstructed if its segment comes within ``buffer_distance`` of an obstacle polygon (closed set;
+# d = 0: touches or crosses it).  shapely's buffer approximates the rounded corners of the offset region by 8
+# segments per quarter circle, so the two predicates can differ only for an edge that passes a convex obstacle
+# corner at a distance within 0.5 % below ``buffer_distance``.
+# ---------------------------------------------------------------------------
+def _rings(obstacle):
+    """[exterior, hole, ...] vertex arrays of an obstacle: an ``[n, 2]`` vertex list, or any object with shapely's
+    ``exterior.coords`` / ``interiors`` attributes."""
+    if hasattr(obstacle, 'exterior'):
+        rings = [np.asarray(obstacle.exterior.coords, dtype=np.float64)[:, :2]]
+        rings += [np.asarray(r.coords, dtype=np.float64)[:, :2] for r in getattr(obstacle, 'interiors', [])]
+    else:
+        rings = [np.asarray(obstacle, dtype=np.float64).reshape(-1, 2)]
+    return [r[:-1] if len(r) > 1 and np.array_equal(r[0], r[-1]) else r for r in rings]
+
+
+def _inside(pt, ring):
+    """Even-odd rule; points on the boundary are caught by the distance test."""
+    x, y = pt
+    x0, y0 = ring[:, 0], ring[:, 1]
+    x1, y1 = np.roll(x0, -1), np.roll(y0, -1)
+    cross = (y0 > y) != (y1 > y)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        xs = x0 + (y - y0) * (x1 - x0) / (y1 - y0)
+    return bool(np.count_nonzero(cross & (x < xs)) % 2)
+
+
+def _point_segment_distance(p, a, b):
+    ab = b - a
+    den = float(ab @ ab)
+    t = 0.0 if den == 0.0 else min(1.0, max(0.0, float((p - a) @ ab) / den))
+    return float(np.linalg.norm(p - (a + t * ab)))
+
+
+def _segments_cross(p1, p2, q1, q2):
+    def orient(a, b, c):
+        return (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0])
+    d1, d2, d3, d4 = orient(q1, q2, p1), orient(q1, q2, p2), orient(p1, p2, q1), orient(p1, p2, q2)
+    return ((d1 > 0) != (d2 > 0)) and ((d3 > 0) != (d4 > 0)) and d1 != 0 and d2 != 0 and d3 != 0 and d4 != 0
+
+
+def _segment_polygon_distance(p1, p2, rings):
+    """0 if the segment touches, crosses or lies inside the polygon (exterior minus holes), else the distance."""
+    inside = _inside(p1, rings[0]) and not any(_inside(p1, h) for h in rings[1:])
+    if inside:
+        return 0.0
+    best = np.inf
+    for ring in rings:
+        for a, b in zip(ring, np.roll(ring, -1, axis=0)):
+            if _segments_cross(p1, p2, a, b):
+                return 0.0
+            best = min(best, _point_segment_distance(p1, a, b), _point_segment_distance(p2, a, b),
+                       _point_segment_distance(a, p1, p2), _point_segment_distance(b, p1, p2))
+    return best
+
+
+def remove_obstructed_neighbors(nodes, obstacles, buffer_distance=0.0):
+    """topology_tools.py:472-505: edges whose straight line comes within ``buffer_distance`` of an obstacle are
+    redirected to the node itself.  ``obstacles``: polygons as ``[n, 2]`` vertex lists (or shapely-like objects);
+    the z-coordinate is ignored, as in the reference."""
+    import copy
+    assert buffer_distance >= 0, 'The buffer distance has to be non-negative!'
+    nodes_updated = copy.deepcopy(nodes)
+    polys = [_rings(o) for o in obstacles]
+    for n, node in nodes_updated.items():
+        pos_1 = np.array(node['pose'], dtype=np.float64)[:2]
+        for i, neighbor in enumerate(node['neighbors']):
+            pos_2 = np.array(nodes_updated[neighbor]['pose'][:2], dtype=np.float64)
+            if any(_segment_polygon_distance(pos_1, pos_2, rings) <= buffer_distance for rings in polys):
+                node['neighbors'][i] = n
+    return nodes_updated

@@ -1,6 +1,7 @@
 """CPU (build container only: needs /root/reference): the product's world / graph builders produce
 exactly the reference's WorldDicts and node dictionaries (keys, dtypes, values, neighbour order)."""
 import numpy as np
+import pytest
 
 from cobel_rl_b200.misc import gridworld_tools as mg, topology_tools as mt
 from cobel_rl_b200.memory.utils import metrics as mm
@@ -139,3 +140,36 @@ def test_pickled_world_round_trip(reference, tmp_path):
     mg.save_world(world, tmp_path / 'again.pkl')
     again = mg.load_world(tmp_path / 'again.pkl')
     same_world(again, world)
+
+
+def test_remove_obstructed_neighbors_known_answers():
+    """misc/topology_tools.py:472-505 (the reference needs shapely, which this image does not have: the predicate
+    is checked against hand-derived answers on a 5 x 5 grid graph)."""
+    from cobel_rl_b200.misc import topology_tools as tt
+    nodes, _ = tt.grid(5, (0.0, 4.0))
+    wall = [[1.4, -0.5], [1.6, -0.5], [1.6, 2.5], [1.4, 2.5]]        # between the columns x = 1 and x = 2, rows y <= 2
+    upd = tt.remove_obstructed_neighbors(nodes, [wall])
+    cut = {(n, i) for n in nodes for i in range(4) if nodes[n]['neighbors'][i] != upd[n]['neighbors'][i]}
+    by_pos = {nodes[n]['pose'][:2]: n for n in nodes}
+    want = set()
+    for y in (0.0, 1.0, 2.0):
+        want |= {(by_pos[(1.0, y)], 2), (by_pos[(2.0, y)], 0)}          # right of x = 1, left of x = 2
+    assert cut == want
+    assert all(upd[n]['neighbors'][i] == n for n, i in cut)             # obstructed edges point back to the node
+    assert nodes[by_pos[(1.0, 0.0)]]['neighbors'][2] == by_pos[(2.0, 0.0)]      # the input graph is not modified
+    # the edge (1,3)-(2,3) passes the wall's top edge at distance 0.5: cut from buffer 0.5 on, not below
+    e = (by_pos[(1.0, 3.0)], 2)
+    assert tt.remove_obstructed_neighbors(nodes, [wall], 0.49)[e[0]]['neighbors'][2] == by_pos[(2.0, 3.0)]
+    assert tt.remove_obstructed_neighbors(nodes, [wall], 0.5)[e[0]]['neighbors'][2] == e[0]
+    # an edge that ends inside an obstacle, a shapely-like polygon object with a hole, and the assertion
+    class Ring:
+        def __init__(self, c): self.coords = c
+    class Poly:
+        exterior = Ring([(2.5, 2.5), (4.5, 2.5), (4.5, 4.5), (2.5, 4.5), (2.5, 2.5)])
+        interiors = [Ring([(3.6, 3.6), (4.4, 3.6), (4.4, 4.4), (3.6, 4.4), (3.6, 3.6)])]
+    upd = tt.remove_obstructed_neighbors(nodes, [Poly()])
+    assert upd[by_pos[(2.0, 3.0)]]['neighbors'][2] == by_pos[(2.0, 3.0)]        # (2,3) -> (3,3) enters the polygon
+    assert upd[by_pos[(3.0, 3.0)]]['neighbors'][1] == by_pos[(3.0, 3.0)]        # inside -> inside
+    assert upd[by_pos[(0.0, 0.0)]]['neighbors'] == nodes[by_pos[(0.0, 0.0)]]['neighbors']
+    with pytest.raises(AssertionError):
+        tt.remove_obstructed_neighbors(nodes, [wall], -1.0)
