@@ -195,3 +195,38 @@ def test_bad_arguments_raise():
     ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream))
     with pytest.raises(AssertionError):
         ag.train(env, 3, 0, 32)          # steps must be positive
+
+
+def test_integration_md_binding_stub_reproduces_the_golden(monkeypatch):
+    """The reference-side ctypes binding shown in INTEGRATION.md (section 2), executed as written: its
+    ``dynaq_train_b200`` drives ``cobel_dynaq_run`` for copies of a reference-shaped agent object and agent 0 must land
+    on the golden vector that the unmodified reference produced for the same stream."""
+    import os
+    import types
+    import torch
+    import __graft_entry__ as g
+    from oracle import cases
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    block = text.split('```python')[2].split('```')[0]
+    monkeypatch.setenv('COBEL_B200_LIB', g.LIB)
+    ns = {}
+    exec(compile(block, 'INTEGRATION.md', 'exec'), ns)
+    kind, wname, agent_id, args = cases.CASES['dynaq_open5_eps']
+    assert agent_id == 0
+    world = make_world(wname)
+    S = world['states']
+    # what the reference's DynaQ / DynaQMemory hold after construction (agent/dyna_q.py:106-138, memory/dyna_q.py:62-75)
+    mem = types.SimpleNamespace(rewards=np.zeros((S, 4)), states=np.tile(np.arange(S).reshape(S, 1), 4).astype(int),
+                                terminals=np.zeros((S, 4)).astype(int), learning_rate=0.9)
+    agent = types.SimpleNamespace(Q=np.zeros((S, 4)), M=mem, learning_rate=0.99, gamma=0.99,
+                                  policy=types.SimpleNamespace(epsilon=args['policy'][1]))
+    Q, (Mr, Ms, Mt), tsteps, trew = ns['dynaq_train_b200'](agent, world, args['trials'], args['steps'], args['batch'],
+                                                           3, cases.SEED)
+    torch.cuda.synchronize()
+    gold = load_golden('dynaq_open5_eps')
+    assert np.array_equal(Q[0].cpu().numpy(), gold['Q']) and np.array_equal(Mr[0].cpu().numpy(), gold['Mr'])
+    assert np.array_equal(Ms[0].cpu().numpy(), gold['Ms']) and np.array_equal(Mt[0].cpu().numpy(), gold['Mt'])
+    assert np.array_equal(tsteps[0].cpu().numpy(), gold['trial_steps'])
+    assert np.array_equal(trew[0].cpu().numpy(), gold['trial_reward'])
+    assert not np.array_equal(Q[1].cpu().numpy(), gold['Q'])         # the other copies follow their own streams
