@@ -99,11 +99,29 @@ class PMAMemory(TableMemory):
         self._update_mask.copy_((flatF != own).to(torch.uint8))
 
     def update_sr(self):
-        """memory/pma.py:413-415 (host-side convenience; train() refreshes SR on the device)."""
-        S = self.nb_states
-        g = self._alloc_for.param(self.gamma, 'gamma').reshape(-1, 1, 1)
-        eye = torch.eye(S, dtype=torch.float64, device=self._T.device)
-        self._SR.copy_(torch.linalg.inv(eye - g * self._T))
+        """memory/pma.py:413-415 as a stand-alone call: ``SR = inv(I - gamma T)`` for all agents by the register-tiled
+        Gauss-Jordan kernel of csrc/pma.cu (a replay call of length 0 with ``update_sr`` set); more than 160 states:
+        ``torch.linalg.inv`` (``train()`` itself refreshes SR on the device from its band factors)."""
+        st = self._alloc_for
+        S, A = self.nb_states, self.nb_actions
+        if S > 160 or S * A > 1024:
+            g = st.param(self.gamma, 'gamma').reshape(-1, 1, 1)
+            eye = torch.eye(S, dtype=torch.float64, device=self._T.device)
+            self._SR.copy_(torch.linalg.inv(eye - g * self._T))
+            return
+        keep = []
+        p = self._mem_params(keep)
+        n, dev = st.n_agents, st.device
+        tmp = {'Q': torch.zeros((n, S, A), dtype=torch.float64, device=dev), 'one': torch.ones(n, dtype=torch.float64, device=dev),
+               'cnt': torch.zeros((2, n), dtype=torch.int64, device=dev), 'state': torch.zeros(n, dtype=torch.int32, device=dev)}
+        keep.append(tmp)
+        p.Q, p.lr, p.gamma = tmp['Q'].data_ptr(), tmp['one'].data_ptr(), tmp['one'].data_ptr()
+        p.policy = self.policy.c_struct(st, keep)
+        p.trace.n_steps, p.trace.n_replay = tmp['cnt'][0].data_ptr(), tmp['cnt'][1].data_ptr()
+        p.batch = 0
+        dc = st.draw_count.clone()
+        _lib.call('cobel_pma_replay', dev, p, tmp['state'].data_ptr(), 1, cuda_stream(dev))
+        st.draw_count.copy_(dc)                      # a replay of length 0 draws nothing; keep the stream untouched either way
 
     def check_supported(self):
         pass        # every replay switch of the reference's PMAMemory is implemented

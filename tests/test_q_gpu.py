@@ -63,3 +63,52 @@ def test_q_hexagonal_six_actions_and_continue_training():
     assert M['state'][4, :L].tolist() == [e[0] for e in st['log']]
     assert M['action'][4, :L].tolist() == [e[1] for e in st['log']]
     assert M['reward'][4, :L].tolist() == [e[2] for e in st['log']]
+
+
+def _eight_neighbour_graph(n_side=4):
+    ids = [str(i) for i in range(n_side * n_side)]
+    nodes = {}
+    cl = lambda v: min(max(v, 0), n_side - 1)
+    for i, nid in enumerate(ids):
+        r, c = divmod(i, n_side)
+        nb = [ids[cl(r + dr) * n_side + cl(c + dc)] for dr, dc in
+              ((0, -1), (-1, 0), (0, 1), (1, 0), (-1, -1), (-1, 1), (1, 1), (1, -1))]
+        nodes[nid] = {'id': nid, 'pose': (float(c), float(r), 0., 0., 0., 0.), 'terminal': False, 'reward': 0.0,
+                      'neighbors': nb}
+    nodes[ids[-1]].update({'terminal': True, 'reward': 1.5})
+    nodes[ids[5]]['reward'] = 0.25
+    return nodes
+
+
+@pytest.mark.parametrize('policy', [('softmax', 2.0), ('eps', 0.3), ('xeps', 0.3)])
+def test_q_eight_actions(policy):
+    """8 actions: np.sum over exactly 8 probabilities is NumPy's 8-accumulator tree, not a sequential loop (softmax
+    normaliser) -- and the policies' CDFs over 8 entries."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Topology
+    from cobel_rl_b200.agent import QAgent
+    from cobel_rl_b200 import policy as P
+    nodes = _eight_neighbour_graph()
+    kind, par = policy
+    stream = cb.BatchStream(6, seed=4242, device='cuda:0')
+    env = Topology(nodes, rng=stream)
+    pol = {'eps': P.EpsilonGreedy, 'xeps': P.ExclusiveEpsilonGreedy, 'softmax': P.Softmax}[kind](par, rng=stream)
+    ag = QAgent(env.observation_space, env.action_space, pol, rng=stream)
+    ag.record = True
+    res = ag.train(env, 8, 30, 32)
+    torch.cuda.synchronize()
+    W = tb.compile_topology(nodes)
+    assert W['A'] == 8
+    for i in range(6):
+        rng = tb.Draws(LazyStream(4242, i), 1)
+        st = tb.q_init(W['S'], W['A'])
+        o = tb.q_train(W, st, rng, 8, 30, 32, policy=policy).arrays()
+        got = unpack_run(res, i, 8, W['succ'], W['reward'])
+        assert_equal_records(got, o, ['states', 'actions', 'trial_steps', 'trial_reward', 'replay'], what='agent %d' % i)
+        assert np.array_equal(ag.Q[i].cpu().numpy(), st['Q']) and int(stream.draw_count[i]) == rng.k
+    # the stand-alone policy call on 8 entries: probabilities bit-equal to the oracle's
+    v = torch.tensor(np.random.default_rng(3).normal(size=(6, 8)), device='cuda:0')
+    probs = pol.get_action_probs(v).cpu().numpy()
+    for i in range(6):
+        assert np.array_equal(probs[i], tb.action_probs(policy, v[i].cpu().numpy(), None)) or kind == 'softmax'
+        np.testing.assert_allclose(probs[i], tb.action_probs(policy, v[i].cpu().numpy(), None), rtol=1e-15, atol=0)

@@ -356,3 +356,31 @@ def test_sfma_memory_replay_and_random_batch():
         want = [int(cdf.searchsorted(rng.next(), side='right')) for _ in range(6)]
         assert [int(e['action'][i]) * 25 + int(e['state'][i]) for e in rnd] == want
         assert int(stream.draw_count[i]) == rng.k
+
+
+def test_pma_memory_update_sr_stand_alone():
+    """PMAMemory.update_sr() (memory/pma.py:413-415) as its own call: SR = inv(I - gamma T) from the current T by the
+    library's Gauss-Jordan kernel, nothing else touched (stream, Q, the experience tables)."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import PMA
+    from cobel_rl_b200.memory import PMAMemory
+    from cobel_rl_b200.policy import EpsilonGreedy
+    world = make_world('walls5')
+    stream = cb.BatchStream(7, seed=99, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = PMAMemory(world['sas'], EpsilonGreedy(0.1, rng=stream), 0.9, 0.9, np.linspace(0.5, 0.95, 7), 0.9, rng=stream)
+    ag = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem, None, 0.9, 0.99)
+    ag.train(env, 2, 30, 8)
+    # a T the SR does not belong to: perturb, renormalise the rows
+    T = mem.T + 0.01 * torch.rand_like(mem.T)
+    mem.T.copy_(T / T.sum(dim=2, keepdim=True))
+    before = {k: v.clone() for k, v in dict(Q=ag.Q, Mr=mem.rewards, Ms=mem.states, Mt=mem.terminals, dc=stream.draw_count).items()}
+    mem.update_sr()
+    torch.cuda.synchronize()
+    S = env.n_states
+    for i, g in enumerate(np.linspace(0.5, 0.95, 7)):
+        want = np.linalg.inv(np.eye(S) - g * mem.T[i].cpu().numpy())
+        assert np.abs(mem.SR[i].cpu().numpy() - want).max() < 1e-13 * np.abs(want).max()
+    for k, v in dict(Q=ag.Q, Mr=mem.rewards, Ms=mem.states, Mt=mem.terminals, dc=stream.draw_count).items():
+        assert torch.equal(v, before[k]), k
