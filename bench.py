@@ -395,10 +395,15 @@ class Job:
                           'T': mem._T, 'SR': mem._SR}
         # per-agent state small enough to keep pristine device + pinned host copies of (everything except the
         # S x S matrices, which are re-broadcast on the device from one pristine matrix)
-        self.big = {k: v[0].clone() for k, v in self.state.items() if v.dim() == 3 and v[0].numel() >= 2500}
+        # Tables whose initial content is the same for every agent (a fresh agent's zero Q table, the memory's initial
+        # model, T and SR of the world) travel to the device as ONE template and are broadcast there; what differs per
+        # agent (here: the stream positions; in a sweep also the hyper-parameter vectors) is uploaded per agent.
+        same = {k: bool((v == v[0:1]).all().item()) for k, v in self.state.items()}
+        self.big = {k: v[0].clone() for k, v in self.state.items() if same[k] and v.dim() >= 2}
         self.init = {k: v.clone() for k, v in self.state.items() if k not in self.big}
         self.host_in = {k: v.cpu().pin_memory() for k, v in self.init.items()}
         self.host_big = {k: v.cpu().pin_memory() for k, v in self.big.items()}
+        self.host_draws = torch.ones(n_local, dtype=torch.int64).pin_memory()     # draw 0: the environment constructor
         tr = wl['trials']
         self.host_out = {'trial_steps': torch.empty((n_local, tr), dtype=torch.int32).pin_memory(),
                          'trial_reward': torch.empty((n_local, tr), dtype=torch.float64).pin_memory()}
@@ -428,7 +433,7 @@ class Job:
             self.state[k].copy_(v, non_blocking=True)
         for k, v in self.host_big.items():
             self.state[k].copy_(v.to(self.dev, non_blocking=True).unsqueeze(0).expand_as(self.state[k]))
-        self.stream.draw_count.fill_(1)
+        self.stream.draw_count.copy_(self.host_draws, non_blocking=True)
         res = self._train()
         self.host_out[self.out_key].copy_(self.state[self.out_key], non_blocking=True)
         self.host_out['trial_steps'].copy_(res['trial_steps'], non_blocking=True)
@@ -436,7 +441,7 @@ class Job:
         return res
 
     def h2d_bytes(self):
-        return sum(v.numel() * v.element_size() for v in list(self.host_in.values()) + list(self.host_big.values()))
+        return sum(v.numel() * v.element_size() for v in list(self.host_in.values()) + list(self.host_big.values()) + [self.host_draws])
 
     def d2h_bytes(self):
         return sum(v.numel() * v.element_size() for v in self.host_out.values())
@@ -540,7 +545,10 @@ def result_block(name, m, world, peak, peak_src, job, t_step, t_e2e, units_total
                                     'sm_mhz': mhz, 'source': iss.get('source')}
     if t_e2e is not None:
         blk['e2e'] = {'value': units_total / (t_e2e * 1e-3), 'unit': wl['unit'], 'h2d_bytes_per_step': job.h2d_bytes(),
-                      'd2h_bytes_per_step': job.d2h_bytes(), 'ms_per_step': t_e2e}
+                      'd2h_bytes_per_step': job.d2h_bytes(), 'ms_per_step': t_e2e,
+                      'note': 'per step, from pinned host memory: one template of every table whose initial content is the '
+                              'same for all agents (broadcast on the device) + the per-agent stream positions; back to '
+                              'the host: the per-agent result table and per-trial statistics of ALL agents'}
     return blk
 
 

@@ -91,7 +91,7 @@ class PMAParams(C.Structure):
                 ('lr_T', C.c_double), ('min_gain', C.c_double),
                 ('min_gain_original', C.c_int32), ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32),
                 ('no_replay', C.c_int32), ('learn', C.c_int32), ('sr_band', C.c_int32), ('options', C.c_int32),
-                ('band_scratch', c_ptr), ('n_tab', C.c_int32), ('reserved3', C.c_int32), ('tab_kind', c_ptr),
+                ('band_scratch', c_ptr), ('n_tab', C.c_int32), ('band_trusted', C.c_int32), ('tab_kind', c_ptr),
                 ('tab_param', c_ptr), ('tab_of_agent', c_ptr), ('tab_scratch', c_ptr)]
 
 

@@ -88,8 +88,9 @@ class PMA(Agent):
         for t0, n_tr in self._chunks(trials):
             keep = []
             tr, res = self._make_trace(n_tr, steps, 0, 2 if (learn and not no_replay) else 0, batch_size, keep)
-            band, bscratch = M.sr_band(interface.transition_band) if (learn and not no_replay) else (-1, None)
+            band, bscratch, trusted = M.sr_band(interface.transition_band) if (learn and not no_replay) else (-1, None, False)
             p = self._params(interface.c_world(), pol, tr, n_tr, steps, batch_size, no_replay, learn, band, bscratch, keep)
+            p.band_trusted = 1 if trusted else 0
             _lib.call('cobel_pma_run', st.device, p, launch_stream(st))
             self._check_flags(res)
             if band >= 0 and bool((res['flags'] & 32).any()):      # COBEL_FLAG_BAND_VIOLATION

@@ -1602,8 +1602,10 @@ int run(const CobelPMAParams& p, cudaStream_t st) {
     const size_t sm_bandk = (size_t)kBandWarps * bso.bytes;
     COBEL_CUDA_OK(cudaFuncSetAttribute(pma_band_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_bandk));
     COBEL_CUDA_OK(cudaFuncSetAttribute(pma_band_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_bandk));
-    pma_band_check_kernel<<<(unsigned)p.n_agents, 256, 0, st>>>(p);
-    cobel_count_launch();
+    if (!p.band_trusted) {                             // the caller's band guarantee on the initial T
+      pma_band_check_kernel<<<(unsigned)p.n_agents, 256, 0, st>>>(p);
+      cobel_count_launch();
+    }
     rc = main_launch(MainPhase{1, 0, 1, 1, 0, 0});
     const bool one_start = p.world.n_starts == 1;      // the start row is known before the reset draw
     for (int t = 0; t < p.trials && !rc; ++t) {

@@ -72,20 +72,23 @@ class PMAMemory(TableMemory):
         return self._view(self._T)
 
     def sr_band(self, world_band):
-        """Half bandwidth that T keeps during a run (its own and the world's transitions), or -1 for the dense
-        update_sr; allocates the factorisation scratch."""
+        """``(band, scratch, trusted)``: the half bandwidth that T keeps during a run (its own and the world's
+        transitions), or -1 for the dense update_sr; allocates the factorisation scratch.  ``trusted``: T has not been
+        handed out since this object last measured it or a kernel last enforced the band on it, so the library's
+        streaming check of T (``pma_band_check_kernel``) can be skipped."""
+        trusted = self._band_T is not None
         if self._band_T is None:
             nz = (self._T != 0).any(dim=0).nonzero()
             self._band_T = int((nz[:, 0] - nz[:, 1]).abs().max().item()) if nz.numel() else 0
         bw = max(self._band_T, int(world_band))
         S = self.nb_states
         if bw > self.sr_band_max or 2 * bw + 1 >= S:
-            return -1, None
+            return -1, None, False
         self._band_T = bw                              # experienced transitions stay inside the world's band
         n = self._T.shape[0] * S * (2 * bw + 1)
         if self._band_scratch is None or self._band_scratch.numel() < n:
             self._band_scratch = torch.empty(n, dtype=torch.float64, device=self._T.device)
-        return bw, self._band_scratch
+        return bw, self._band_scratch, trusted
 
     SR = property(lambda self: self._view(self._SR))
     update_mask = property(lambda self: self._view(self._update_mask).bool())

@@ -32,7 +32,8 @@ class SFMAMemory(TableMemory):
         self.mode = 'default'
         self.blend = 0.1
         self.interpolation_fwd, self.interpolation_rev = 0.5, 0.5
-        # options of the reference that the B200 path does not implement (must stay at their defaults)
+        # strength-modulation and normalisation switches (memory/sfma.py:216-236, 283-288, 319-320): implemented in-kernel
+        # (COBEL_SFMA_MOD_*), except error_mod / error_mod_local (see check_supported)
         self.C_normalize = False
         self.D_normalize = False
         self.R_normalize = True

@@ -319,7 +319,8 @@ typedef struct CobelPMAParams {
    * (kind, parameter) -- with exactly the per-row operations -- and a gain evaluation becomes a row maximum,
    * A compares and one table row.  n_tab = 0: probabilities are evaluated per row (any policy, any A). */
   int32_t  n_tab;            /* number of tables */
-  int32_t  reserved3;
+  int32_t  band_trusted;     /* 1: the caller vouches that the initial T lies inside sr_band (e.g. it was left by a previous call of this
+                                library, which enforces the band on every transition) -- the streaming check of T is skipped */
   const int32_t* tab_kind;   /* [n_tab] COBEL_POLICY_* of table t (a Softmax entry leaves its table unused) */
   const double*  tab_param;  /* [n_tab] its epsilon */
   const int32_t* tab_of_agent;/* optional [N,2]: tables of (agent.policy, M.policy) of agent n; NULL = (0, n_tab-1) */

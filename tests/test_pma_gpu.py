@@ -131,9 +131,14 @@ def test_pma_band_violation_is_reported():
     ag = PMA(env.observation_space, env.action_space, EpsilonGreedy(0.1, rng=stream), mem)
     assert env.transition_band == 10
     real = mem.sr_band
-    mem.sr_band = lambda wb: (3, real(wb)[1])            # lie: the world's band is 10
+    mem.sr_band = lambda wb: (3, real(wb)[1], False)     # lie: the world's band is 10 (and T is not vouched for)
     with pytest.raises(_lib.CobelError, match='band'):
         ag.train(env, 1, 20, 4)
+    # a T written through the public view is re-measured and checked by the library again
+    mem.sr_band = real
+    assert mem.sr_band(10)[2] is True
+    mem.T[0, 0, 99] = 0.5                                 # far outside the band of 10: the dense update_sr takes over
+    assert mem.sr_band(10)[2] is False and mem.sr_band(10)[0] == -1
 
 
 @pytest.mark.parametrize('opts', [dict(equal_need=True), dict(equal_gain=True), dict(ignore_barriers=False),
