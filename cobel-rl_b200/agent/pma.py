@@ -92,9 +92,7 @@ class PMA(Agent):
             p = self._params(interface.c_world(), pol, tr, n_tr, steps, batch_size, no_replay, learn, band, bscratch, keep)
             p.band_trusted = 1 if trusted else 0
             _lib.call('cobel_pma_run', st.device, p, launch_stream(st))
-            self._check_flags(res)
-            if band >= 0 and bool((res['flags'] & 32).any()):      # COBEL_FLAG_BAND_VIOLATION
-                raise _lib.CobelError('PMA: T or a transition left the band of %d assumed by the banded update_sr' % band)
+            self._check_flags(res)                                 # incl. COBEL_FLAG_BAND_VIOLATION (one sync per launch)
             self._fire_trial_callbacks(res, self.current_trial, (1, 1) if (learn and not no_replay) else (0, 0), session_first=t0)
             self.current_trial += n_tr
             results.append(res)

@@ -163,8 +163,13 @@ class PMAMemory(TableMemory):
             # not the kernel's default assignment (agent: table 0, memory: the last one)
             tof = torch.stack([c if torch.is_tensor(c) else torch.full((stream.n_agents,), c, dtype=torch.int32, device=dev)
                                for c in cols], dim=1).contiguous()
-        tkind = torch.tensor(kinds, dtype=torch.int32, device=dev)
-        tpar = torch.tensor(params, dtype=torch.float64, device=dev)
+        tcache = self.__dict__.setdefault('_tab_cache', {})
+        tkey = (tuple(kinds), tuple(params), str(dev))
+        if tkey not in tcache:
+            if len(tcache) >= 16:
+                tcache.clear()
+            tcache[tkey] = (torch.tensor(kinds, dtype=torch.int32, device=dev), torch.tensor(params, dtype=torch.float64, device=dev))
+        tkind, tpar = tcache[tkey]
         n = n_tab * _lib.pma_tab_doubles(n_actions) + 1024      # + COBEL_PMA_TIE_DOUBLES
         if getattr(self, '_tab_scratch', None) is None or self._tab_scratch.numel() < n:
             self._tab_scratch = torch.empty(n, dtype=torch.float64, device=dev)
@@ -305,6 +310,17 @@ class PMAMemory(TableMemory):
         """``float(gamma) ** k`` for k = 0..MAX_SEQ+1 with Python's pow, like the reference
         (memory/pma.py:310,315,485,491).  Returns (sr table, q table, per-agent stride)."""
         L = _lib.PMA_MAX_SEQ + 2
+        gq = self.gamma_q if q_gamma is None else q_gamma
+        if isinstance(self.gamma, (int, float)) and isinstance(gq, (int, float)):      # scalars: built once per pair
+            cache = self.__dict__.setdefault('_pow_cache', {})
+            key = (float(self.gamma), float(gq), str(stream.device))
+            if key not in cache:
+                if len(cache) >= 16:
+                    cache.clear()
+                cache[key] = tuple(torch.tensor([[float(g) ** k for k in range(L)]], dtype=torch.float64, device=stream.device)
+                                   for g in key[:2])
+            ta, tb = cache[key]
+            return ta, tb, 0
 
         def table(x):
             v = stream.param(x, 'gamma').cpu().numpy()

@@ -65,6 +65,14 @@ class BatchStream:
 
     def param(self, x, name='parameter'):
         """Broadcast a scalar / sequence / tensor hyper-parameter to a ``[N]`` fp64 device tensor."""
+        if isinstance(x, (int, float)):                 # the common case: one value for all agents -- built once per value
+            cache = self.__dict__.setdefault('_param_cache', {})
+            t = cache.get(float(x))
+            if t is None:
+                if len(cache) >= 64:
+                    cache.clear()
+                t = cache[float(x)] = torch.full((self.n_agents,), float(x), dtype=torch.float64, device=self.device)
+            return t
         t = torch.as_tensor(x, dtype=torch.float64).to(self.device).reshape(-1)
         if t.numel() == 1:
             t = t.expand(self.n_agents)
