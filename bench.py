@@ -116,17 +116,24 @@ def measured_issue(name, agents_per_gpu):
     return t
 
 
+# the bench worlds (the same definitions the parity cases use, oracle/cases.py; restated here so that the measured arm
+# imports nothing from oracle/)
+WALLS_10x10 = [(4, 5), (5, 4), (14, 15), (15, 14), (24, 25), (25, 24), (34, 35), (35, 34),
+               (62, 72), (72, 62), (63, 73), (73, 63)]
+
+
 def make_world(name):
     from cobel_rl_b200.misc.gridworld_tools import make_gridworld, make_open_field
-    from oracle.cases import world_args
     if name == 'open20':
         return make_open_field(20, 20, 0, 1)
     if name == 'open100':
         return make_open_field(100, 100, 0, 1, dense_sas=False)
-    h, w, kw = world_args(name)
-    kw = dict(kw)
-    kw.pop('slippery', None)
-    return make_gridworld(h, w, **kw)
+    if name == 'open5':       # config C2, demo/gridworld/demo_dyna_q.py:41
+        return make_gridworld(5, 5, terminals=[0], rewards=np.array([[0, 1]]), goals=[0])
+    if name == 'walls10':     # config C3
+        return make_gridworld(10, 10, terminals=[9], rewards=np.array([[9, 10]]), goals=[9], starting_states=[57],
+                              invalid_transitions=WALLS_10x10)
+    raise KeyError(name)
 
 
 class ClockSampler:
