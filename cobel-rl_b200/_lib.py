@@ -75,7 +75,7 @@ class SFMAParams(C.Structure):
                 ('trials', C.c_int32), ('steps', C.c_int32), ('batch', C.c_int32), ('nb_replays', C.c_int32),
                 ('start_replay', C.c_int32), ('random_replay', C.c_int32), ('dynamic', C.c_int32),
                 ('no_replay', C.c_int32), ('learn', C.c_int32), ('td_acc', c_ptr), ('trial_mode', c_ptr),
-                ('reward_modulation', C.c_double), ('mod_flags', C.c_int32), ('reserved2', C.c_int32), ('carry', c_ptr)]
+                ('reward_modulation', C.c_double), ('mod_flags', C.c_int32), ('exp_bound', C.c_int32), ('carry', c_ptr)]
 
 
 PMA_MAX_SEQ = 64

@@ -230,8 +230,6 @@ class Agent(abc.ABC):
         fl = res['flags']
         if not fl.numel() or int(fl.max().item()) == 0:
             return
-        if self.record and bool((fl & 1).any()):
-            raise _lib.CobelError('trace buffer overflow (internal sizing error)')
         if bool((fl & 32).any()):      # COBEL_FLAG_BAND_VIOLATION (a violated band promise also derails the eliminations)
             raise _lib.CobelError('PMA: T or a transition left the band assumed by the banded update_sr')
         if bool((fl & 8).any()):       # COBEL_FLAG_SINGULAR
@@ -240,6 +238,8 @@ class Agent(abc.ABC):
         if bool((fl & 64).any()):      # COBEL_FLAG_REPLAY_OVERFLOW
             raise _lib.CobelError('SFMA: an agent has experienced more (state, action) pairs than the replay kernel can '
                                   'stage in shared memory for this state space')
+        if self.record and bool((fl & 1).any()):
+            raise _lib.CobelError('trace buffer overflow (internal sizing error)')
         if bool((fl & 2).any()):       # COBEL_FLAG_CDF_NEAR_TIE: exp() / prefix sums are not bit-identical to NumPy's
             import warnings
             warnings.warn('SFMA replay: %d agent(s) drew within 1e-12 of a CDF bin edge; their sampled indices may '

@@ -1161,7 +1161,22 @@ int launch(const CobelSFMAParams& p, cudaStream_t st) {
     COBEL_CUDA_OK(cudaFuncSetAttribute(sfma_replay_kernel<A>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const unsigned grid_step = (unsigned)((p.n_agents + 63) / 64);
     auto step = [&](SfmaPhase ph) { sfma_step_kernel<A><<<grid_step, 64, 0, st>>>(p, ph); cobel_count_launch(); };
-    auto replay = [&](SfmaPhase ph) { sfma_replay_kernel<A><<<(unsigned)p.n_agents, TR, rso.bytes, st>>>(p, ph); cobel_count_launch(); };
+    // The list of experienced (s, a) of a replay holds at most what the agent had when the call started plus one new
+    // pair per step taken since (A with state_mod): with the caller's bound (exp_bound) a launch stages that many entries instead of
+    // S*A -- at C4 22 KB instead of 40 KB per agent, 8 instead of 5 resident CTAs per SM.
+    auto replay = [&](SfmaPhase ph) {
+      int lc = cap;
+      if (p.exp_bound > 0) {
+        // (state_mod strengthens every action of the visited state: up to A new entries per step, memory/sfma.py:234-236)
+        const long long per_step = (p.mod_flags & COBEL_SFMA_MOD_STATE) ? A : 1;
+        const long long bound = (long long)p.exp_bound - 1 + (long long)(ph.trial + (ph.start_replay ? 0 : 1)) * p.steps * per_step;
+        if (bound < lc) lc = bound < 1 ? 1 : (int)bound;
+      }
+      const ReplaySmem ls(S, A, TR, p.batch, p.random_replay != 0, lc);
+      ph.list_cap = lc;
+      sfma_replay_kernel<A><<<(unsigned)p.n_agents, TR, ls.bytes, st>>>(p, ph);
+      cobel_count_launch();
+    };
     // SfmaPhase{init, reset, n_trials, trial, start_replay}
     if (!p.learn) {
       step(SfmaPhase{1, 1, p.trials, 0, 0, cap});                  // test(): all trials in one launch

@@ -252,7 +252,9 @@ typedef struct CobelSFMAParams {
   int32_t* trial_mode;       /* optional [N,trials] out: replay mode chosen at the end of each trial (dynamic) */
   double   reward_modulation;/* M.reward_modulation (1.0) */
   int32_t  mod_flags;        /* COBEL_SFMA_MOD_* bits: strength modulation and normalisation switches */
-  int32_t  reserved2;
+  int32_t  exp_bound;        /* 1 + an upper bound on the number of (s, a) with C > 0 that any agent holds when the call starts; 0 =
+                                unknown.  The split path sizes the replay kernel's on-chip list by exp_bound - 1 + the steps taken
+                                so far instead of S*A: less shared memory per agent, more agents per SM */
   int64_t* carry;            /* optional scratch [N,4]: per-agent state between the launches of the split path (one
                                 thread per agent for the online steps, one CTA per agent for the replays); NULL = the
                                 fused one-CTA-per-agent kernel */
