@@ -1149,10 +1149,12 @@ int launch(const CobelSFMAParams& p, cudaStream_t st) {
   //  in HBM and its replay kernel stages just the list of experienced (s, a))
   if (split) {
     // CTA size of the replay kernel: its passes run over the compact list of experienced (s, a) -- a few hundred
-    // entries -- and every warp repeats the block-wide combines, so a smaller CTA with more CTAs per SM wins
-    // (20x20, 65536 agents: 7.9 / 8.5 / 6.2 x 10^8 agent-steps/s with 256 / 128 / 64 threads)
+    // entries -- and every warp repeats the block-wide combines, so a small CTA with more CTAs per SM wins (20x20,
+    // 65536 agents, lists of <= 800 entries: 0.88 / 1.19 / 1.11 / 0.73 x 10^9 agent-steps/s with 32 / 64 / 128 / 256
+    // threads); chosen per launch from the length bound of the list
     int TR = N <= 128 ? 64 : N <= 4096 ? 128 : 256;
-    if (const char* e = getenv("COBEL_SFMA_REPLAY_THREADS")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 256) TR = v; }
+    bool tr_forced = false;
+    if (const char* e = getenv("COBEL_SFMA_REPLAY_THREADS")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) { TR = v; tr_forced = true; } }
     const int cap = ReplaySmem::fit(S, A, TR, p.batch, p.random_replay != 0, 227 * 1024 - 512);
     const ReplaySmem rso(S, A, TR, p.batch, p.random_replay != 0, cap);
     COBEL_REQUIRE(cap >= 1 && rso.bytes <= 227 * 1024, COBEL_EUNSUPPORTED,
@@ -1172,9 +1174,10 @@ int launch(const CobelSFMAParams& p, cudaStream_t st) {
         const long long bound = (long long)p.exp_bound - 1 + (long long)(ph.trial + (ph.start_replay ? 0 : 1)) * p.steps * per_step;
         if (bound < lc) lc = bound < 1 ? 1 : (int)bound;
       }
-      const ReplaySmem ls(S, A, TR, p.batch, p.random_replay != 0, lc);
+      const int tr = (tr_forced || lc > cap) ? TR : (lc <= 1024 ? 64 : TR);
+      const ReplaySmem ls(S, A, tr, p.batch, p.random_replay != 0, lc);
       ph.list_cap = lc;
-      sfma_replay_kernel<A><<<(unsigned)p.n_agents, TR, ls.bytes, st>>>(p, ph);
+      sfma_replay_kernel<A><<<(unsigned)p.n_agents, tr, ls.bytes, st>>>(p, ph);
       cobel_count_launch();
     };
     // SfmaPhase{init, reset, n_trials, trial, start_replay}
