@@ -198,9 +198,13 @@ __global__ void __launch_bounds__(64) sfma_step_kernel(const __grid_constant__ C
     double tdacc = p.td_acc ? p.td_acc[n] : 0.0;
     double treward = 0.0;
     int step = 0, last = -1;
+    // The tables live in HBM and a step touches a handful of their entries, so what a step costs is its DEPENDENT
+    // DRAM round trips: all loads of a step that do not depend on one another (M.rewards[s,a], C[a,s], Q[s',:]) are
+    // issued together as soon as the action is known, before any store, and the row Q[s',:] is carried over as the
+    // next step's Q[s,:] -- one round trip per step instead of four.
+    double row[A];
+    load_row_t<A>(Q + (size_t)s * A, row);
     for (;; ++step) {
-      double row[A];
-      load_row_t<A>(Q + (size_t)s * A, row);
       const int a = select_action_thread<A>(row, mask_bits<A>(amask, s), kind, par, rng.next());
       const int s2 = p.world.tp_off ? stochastic_successor_t(p.world, s * A + a, rng.next()) : __ldg(p.world.succ + s * A + a);
       const double r = __ldg(p.world.reward + s2);
@@ -211,23 +215,57 @@ __global__ void __launch_bounds__(64) sfma_step_kernel(const __grid_constant__ C
         else flags |= COBEL_FLAG_TRACE_OVERFLOW;
       }
       ++nsteps;
+      double row2[A];
       if (learn) {
         // SFMAMemory.store (memory/sfma.py:206-215; decay_strength == 1 and M.T is not tracked on this path), then
         // SFMA.update_q (agent/sfma.py:423-458): max over the unmasked actions of s'
-        const double m0 = Mr[s * A + a];
-        Mr[s * A + a] = xadd(m0, xmul(mlr, xsub(r, m0)));
+        const double m0 = Mr[s * A + a];                           // ---- loads ----
+        double cs[A];
+        if (mf & COBEL_SFMA_MOD_STATE) {
+#pragma unroll
+          for (int x = 0; x < A; ++x) cs[x] = C[x * S + s];
+        } else {
+          cs[0] = C[a * S + s];
+        }
+        load_row_t<A>(Q + (size_t)s2 * A, row2);
+        const uint32_t mb2 = mask_bits<A>(amask, s2);
+        Mr[s * A + a] = xadd(m0, xmul(mlr, xsub(r, m0)));          // ---- stores ----
         Ms[s * A + a] = s2;
         Mt[s * A + a] = nt;
-        double c = xadd(C[a * S + s], p.c_step);
-        if (mf & COBEL_SFMA_MOD_REWARD_LOCAL) c = xadd(c, xmul(r, p.reward_modulation));   // memory/sfma.py:216-218
-        C[a * S + s] = c;
-        if (mf & COBEL_SFMA_MOD_STATE) {                                                    // memory/sfma.py:233-236
+        if (mf & COBEL_SFMA_MOD_STATE) {                           // memory/sfma.py:233-236: every action of s, after the store
 #pragma unroll
-          for (int x = 0; x < A; ++x) C[x * S + s] = xadd(C[x * S + s], 1.0);
+          for (int x = 0; x < A; ++x) {
+            double c = cs[x];
+            if (x == a) {
+              c = xadd(c, p.c_step);
+              if (mf & COBEL_SFMA_MOD_REWARD_LOCAL) c = xadd(c, xmul(r, p.reward_modulation));
+            }
+            C[x * S + s] = xadd(c, 1.0);
+          }
+        } else {
+          double c = xadd(cs[0], p.c_step);
+          if (mf & COBEL_SFMA_MOD_REWARD_LOCAL) c = xadd(c, xmul(r, p.reward_modulation));   // memory/sfma.py:216-218
+          C[a * S + s] = c;
         }
-        const double td = td_update_thread<A>(Q, s, a, r, s2, nt, lr, gamma, mask_bits<A>(amask, s2));
+        // td = r + (gamma * terminal) * max_{valid} Q[s'] - Q[s,a]; Q[s,a] += lr * td  (Q[s,:] is `row`)
+        double mx = -__longlong_as_double(0x7FF0000000000000ll);
+#pragma unroll
+        for (int x = 0; x < A; ++x) mx = (mb2 >> x & 1u) ? xmax(mx, row2[x]) : mx;
+        const double q = pick_reg<A>(row, a);
+        double td = xadd(r, xmul(nt ? gamma : 0.0, mx));
+        td = xsub(td, q);
+        const double qn = xadd(q, xmul(lr, td));
+        Q[(size_t)s * A + a] = qn;
+        if (s2 == s) {                                             // the carried row must see the update
+#pragma unroll
+          for (int x = 0; x < A; ++x) row2[x] = x == a ? qn : row2[x];
+        }
         tdacc = xadd(tdacc, fabs(td));
+      } else {
+        load_row_t<A>(Q + (size_t)s2 * A, row2);
       }
+#pragma unroll
+      for (int x = 0; x < A; ++x) row[x] = row2[x];
       s = s2;
       treward = xadd(treward, r);
       if (end) last = s2;
