@@ -230,3 +230,36 @@ def test_integration_md_binding_stub_reproduces_the_golden(monkeypatch):
     assert np.array_equal(tsteps[0].cpu().numpy(), gold['trial_steps'])
     assert np.array_equal(trew[0].cpu().numpy(), gold['trial_reward'])
     assert not np.array_equal(Q[1].cpu().numpy(), gold['Q'])         # the other copies follow their own streams
+
+
+def test_pair_kernel_per_agent_hyper_parameters_and_walls():
+    """The two-agents-per-warp kernel (selected from two waves of agents on) with a parameter sweep on the agent axis
+    (epsilon, learning rates, gamma differ per agent: per-half CDF tables and constants) on a walled world with a
+    fixed start state, against the oracle on agents spread over the range; 9001 agents = a half-empty last warp."""
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.agent import DynaQ
+    from cobel_rl_b200.memory import DynaQMemory
+    from cobel_rl_b200.policy import EpsilonGreedy
+    n, trials, steps, batch = 9001, 30, 40, 32
+    g = np.random.default_rng(5)
+    eps, lr, gm, mlr = g.uniform(0.02, 0.5, n), g.uniform(0.3, 1.0, n), g.uniform(0.5, 0.99, n), g.uniform(0.2, 1.0, n)
+    world = make_world('walls5')
+    stream = cb.BatchStream(n, seed=31337, device='cuda:0')
+    env = Gridworld(world, rng=stream)
+    mem = DynaQMemory(env.n_states, 4, mlr, rng=stream)
+    ag = DynaQ(env.observation_space, env.action_space, EpsilonGreedy(eps, rng=stream), None, lr, gm, mem)
+    res = ag.train(env, trials, steps, batch)
+    torch.cuda.synchronize()
+    assert torch.equal(res['n_replay'], res['n_steps'] * batch)
+    W = tb.compile_gridworld(world)
+    for i in (0, 1, 2, 4499, 4500, 8998, 8999, 9000):
+        rng = tb.Draws(LazyStream(31337, i), 1)
+        st = tb.dynaq_init(25, 4)
+        rec = tb.dynaq_train(W, st, rng, trials, steps, batch, policy=('eps', float(eps[i])), lr=float(lr[i]),
+                             gamma=float(gm[i]), mem_lr=float(mlr[i])).arrays()
+        assert np.array_equal(rec['trial_steps'], res['trial_steps'][i].cpu().numpy()), 'agent %d' % i
+        assert np.array_equal(rec['trial_reward'], res['trial_reward'][i].cpu().numpy())
+        assert np.array_equal(st['Q'], ag.Q[i].cpu().numpy()) and np.array_equal(st['Mr'], mem.rewards[i].cpu().numpy())
+        assert np.array_equal(st['Ms'], mem.states[i].cpu().numpy()) and np.array_equal(st['Mt'], mem.terminals[i].cpu().numpy())
+        assert rng.k == int(stream.draw_count[i])
