@@ -315,8 +315,11 @@ struct ReplaySmem {
   }
 };
 
+#ifndef SFMA_REPLAY_MINB
+#define SFMA_REPLAY_MINB 4
+#endif
 template <int A>
-__global__ void __launch_bounds__(256, 4) sfma_replay_kernel(const __grid_constant__ CobelSFMAParams p, const __grid_constant__ SfmaPhase ph) {
+__global__ void __launch_bounds__(256, SFMA_REPLAY_MINB) sfma_replay_kernel(const __grid_constant__ CobelSFMAParams p, const __grid_constant__ SfmaPhase ph) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ BlockShared sh;
   const int S = p.world.n_states, N = S * A, B = p.batch;
@@ -920,8 +923,6 @@ __global__ void __launch_bounds__(256) sfma_kernel(const __grid_constant__ Cobel
     for (int e = tid; e < S; e += T) I[e] = 0.0;                           // sfma.py:277
     __syncthreads();
     int count = 0;
-    const int nw = T >> 5, chunk = (nnz + T - 1) / T;
-    const int clo = tid * chunk < nnz ? tid * chunk : nnz, chi = clo + chunk < nnz ? clo + chunk : nnz;
     for (int it = 0; it < B; ++it) {
       if (mf & COBEL_SFMA_D_NORMALIZE) {                                   // np.amax(D[current_state])
         const double* Dc = D + (size_t)cur * S;
