@@ -82,3 +82,49 @@ def test_hybrid_matches_reference_golden(name):
     # the other agents learned their own networks (different streams and initial weights)
     qa = ag.predict_on_batch(np.arange(env.n_states))
     assert float((qa[0] - qa[local]).abs().max()) > 1e-6 and float((qa[2] - qa[local]).abs().max()) > 1e-6
+
+
+def _hybrid_env(n=2, seed=5):
+    import cobel_rl_b200 as cb
+    from cobel_rl_b200.interface import Gridworld
+    from cobel_rl_b200.policy import EpsilonGreedy
+    stream = cb.BatchStream(n, seed=seed, device='cuda:0')
+    env = Gridworld(make_world(WORLD), rng=stream)
+    return stream, env, EpsilonGreedy(0.1, rng=stream), EpsilonGreedy(0.0, rng=stream)
+
+
+def test_dyna_dqn_option_sweep_like_the_reference_unit_test():
+    """unit_tests/test_dyna_dqn.py:36-87: every combination of test policy, action mask, DDQN and target-update rule
+    runs through train() and test(); additionally the Q predictions stay finite and the memory has been filled."""
+    from itertools import product
+    from cobel_rl_b200.agent import DynaDQN
+    from cobel_rl_b200.network import BatchedTorchNetwork
+    for use_test_policy, mask_actions, ddqn, target_update in product([True, False], [True, False], [True, False], [0.001, 10]):
+        stream, env, pol, pol_test = _hybrid_env()
+        net = BatchedTorchNetwork([seeded(4, 10 + i) for i in range(2)], device='cuda:0')
+        ag = DynaDQN(env.observation_space, env.action_space, pol, net, policy_test=pol_test if use_test_policy else None)
+        ag.target_update, ag.mask_actions, ag.DDQN = target_update, mask_actions, ddqn
+        ag.train(env, 2, 8, 8)
+        ag.test(env, 1, 8)
+        q = ag.predict_on_batch(np.arange(25))
+        assert q.shape == (2, 25, 4) and bool(torch.isfinite(q).all())
+        assert int((ag.M.terminals != 0).sum()) > 0 and ag.current_trial == 3
+
+
+def test_dyna_dsr_option_sweep_like_the_reference_unit_test():
+    """unit_tests/test_dyna_dsr.py:34-100: DR / follow-up state / terminality / target-update combinations."""
+    from itertools import product
+    from cobel_rl_b200.agent import DynaDSR
+    from cobel_rl_b200.network import BatchedTorchNetwork
+    for mask_actions, use_dr, follow_up, ignore_term, target_update in product([True, False], [True, False], [True, False],
+                                                                             [True, False], [0.001, 10]):
+        stream, env, pol, pol_test = _hybrid_env()
+        sr = BatchedTorchNetwork([seeded(25, 20 + i) for i in range(2)], device='cuda:0')
+        rw = BatchedTorchNetwork([seeded(1, 40 + i) for i in range(2)], device='cuda:0')
+        ag = DynaDSR(env.observation_space, env.action_space, pol, sr, rw, policy_test=pol_test)
+        ag.target_update, ag.mask_actions = target_update, mask_actions
+        ag.use_DR, ag.use_follow_up_state, ag.ignore_terminality = use_dr, follow_up, ignore_term
+        ag.train(env, 2, 6, 8)
+        ag.test(env, 1, 6)
+        q = ag.predict_on_batch(np.arange(25))
+        assert q.shape == (2, 25, 4) and bool(torch.isfinite(q).all())
