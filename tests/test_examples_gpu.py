@@ -28,3 +28,13 @@ def test_topology_demo(template):
     agent, trace = demo_topology.simulation(template, 32, 120)
     assert trace.shape == (32, 120) and trace[:, -10:].mean() < trace[:, :10].mean()
     assert agent.Q.shape[0] == 32
+
+
+def test_dyna_dqn_demo_learns():
+    """examples/demo_dyna_dqn.py (demo/gridworld/demo_dyna_dqn.py for N agents): the batch of Dyna-DQN agents learns."""
+    import demo_dyna_dqn
+    agent, trace = demo_dyna_dqn.simulation(32, 40)
+    assert trace.shape == (32, 40)
+    assert trace[:, -10:].mean() < 0.7 * trace[:, :10].mean(), 'escape latency should drop with training'
+    q = agent.predict_on_batch(np.arange(25))
+    assert q.shape == (32, 25, 4) and bool(q.isfinite().all())
